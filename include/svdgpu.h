@@ -1,0 +1,168 @@
+/* svdgpu.h -- C ABI of the B200 SGD trainer for SVDFeature's hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.
+ * It is what a reference-side ISVDTrainer implementation binds (see
+ * svdfeature_b200/csrc/gpu_trainer.cpp and INTEGRATION.md).  All reference
+ * citations are relative to the reference root; "base.h" is
+ * solvers/base-solver/apex_svd_base.h, "model.h" is apex_svd_model.h.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from svdgpu_last_error().  (The reference's own convention --
+ *     print + exit(-1), apex-utils/apex_utils.h:47-50 -- is re-established by
+ *     the C++ trainer on top of this ABI.)
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - one handle = one CUDA device = one host thread at a time (the reference's
+ *     trainer is single-threaded too, svd_feature.cpp:231-247).
+ *   - there is NO CPU fallback: without a CUDA device svdgpu_create fails.
+ */
+#ifndef SVDGPU_H_
+#define SVDGPU_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svdgpu svdgpu_t;             /* one trainer on one GPU            */
+typedef struct svdgpu_batch svdgpu_batch_t; /* an instance batch resident in HBM */
+
+/* Model shape: the fields of SVDModelParam (model.h:373-450) and SVDTypeParam
+ * (model.h:242-261) the hot path depends on. */
+typedef struct {
+  int num_user;
+  int num_item;
+  int num_global;
+  int num_ufeedback; /* rows of W_ufeedback; used only when format_type == 1 */
+  int num_factor;    /* k */
+  int no_user_bias;
+  int active_type; /* model.h:61-79: 0 linear, 1 sigmoid-L2, 2 sigmoid-likelihood,
+                      3 sigmoid-rank, 5 smooth hinge, 6 hinge-L2, 7 = 3          */
+  int format_type; /* model.h:50-57: 0 random order, 1 user grouped (SVD++)     */
+} svdgpu_shape;
+
+/* Training hyper-parameters: SVDTrainParam (model.h:291-344) + base_score
+ * (already passed through calc_base_score, model.h:220-237, as the model file
+ * stores it). */
+typedef struct {
+  float learning_rate;
+  float wd_user, wd_item;
+  float wd_user_bias, wd_item_bias;
+  float wd_global;
+  int reg_method;  /* base.h:211-283: 0 L2 decay (supported), 1/3 L1, 2 projection */
+  int reg_global;  /* base.h:188-210: 0 L2 decay (supported), 1 L1                  */
+  unsigned num_regfree_global;
+  float scale_lr_ufeedback, wd_ufeedback, wd_ufeedback_bias; /* base.h:512-520 */
+  float base_score;
+} svdgpu_hparams;
+
+/* How instances of one call are ordered against each other. */
+enum {
+  /* Ordered data-flow: every row (user/item/global/feedback) carries a version
+   * counter and each instance waits for exactly the writers that precede it in
+   * input order.  Result is bit-identical to the reference's sequential loop
+   * (base.h:456-462) for active_type 0/5/6; 1-ulp-of-expf close for sigmoid types. */
+  SVDGPU_MODE_EXACT = 0,
+  /* Hogwild: one lane group per instance, no ordering between instances of a
+   * call; per-instance arithmetic is unchanged.  Throughput mode. */
+  SVDGPU_MODE_HOGWILD = 1
+};
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* replaces: SVDFeature ctor + SVDModel::alloc_space (base.h:102-109, model.h:511-556) */
+int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device);
+void svdgpu_destroy(svdgpu_t *h);
+/* message of the last failure on this handle (h may be NULL for create failures) */
+const char *svdgpu_last_error(const svdgpu_t *h);
+
+/* ---- configuration ----------------------------------------------------- */
+/* replaces: SVDTrainParam::set_param (model.h:350-368) + set_round's lr decay (base.h:470-478) */
+int svdgpu_set_hparams(svdgpu_t *h, const svdgpu_hparams *hp);
+int svdgpu_set_mode(svdgpu_t *h, int mode);
+/* Tunables, by name:
+ *   "scatter_user", "scatter_item" : 0 plain store, 1 red.global.add of the delta (hogwild)
+ *   "exact_dot"   : 1 keep the reference's 4-lane dot order in hogwild mode (default 1)
+ *   "lanes"       : lanes per instance in hogwild mode (0 = auto = pitch/4, max 32)
+ *   "chunk_rows"  : rows per launch for host-pointer calls
+ *   "ctas_per_sm" : persistent CTAs per SM (0 = auto) */
+int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
+/* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
+int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);
+
+/* ---- model transfer ---------------------------------------------------- */
+/* Layout = SVDModel's slabs (model.h:481-556): ui_bias[rows], W_uiset[rows][pitch],
+ * g_bias[num_global] with rows = ustart + num_user + num_item, ustart =
+ * num_ufeedback when format_type == 1 else 0; feedback rows first, then user
+ * rows, then item rows.  pitch_floats is the host row stride in floats
+ * (>= num_factor).  replaces: rand_init / load_from_file / save_to_file targets. */
+int svdgpu_upload_model(svdgpu_t *h, const float *ui_bias, const float *W_uiset,
+                        size_t pitch_floats, const float *g_bias);
+int svdgpu_download_model(svdgpu_t *h, float *ui_bias, float *W_uiset, size_t pitch_floats,
+                          float *g_bias);
+
+/* ---- the hot path, host buffers ---------------------------------------- */
+/* One SVDFeatureCSR batch (apex_svd_data.h:34-231): row r owns feature segments
+ * global [row_ptr[3r],row_ptr[3r+1]), user [..3r+1,3r+2), item [..3r+2,3r+3) of
+ * index/value.  replaces: for each row ISVDTrainer::update(Elem) ->
+ * SVDFeature::update_inner (base.h:456-466). */
+int svdgpu_update_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
+                      const unsigned *index, const float *value);
+/* replaces: for each row ISVDTrainer::predict(Elem) -> SVDFeature::pred (base.h:445-454,467-469) */
+int svdgpu_predict_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
+                       const unsigned *index, const float *value, float *out);
+/* User-grouped input (SVDPlusBlock, apex_svd_data.h:376-466): block b owns rows
+ * [blk_row_off[b], blk_row_off[b+1]) of the CSR and feedback entries
+ * [blk_fb_off[b], blk_fb_off[b+1]); blk_tag (svdpp_tag, may be NULL = DEFAULT).
+ * replaces: for each block SVDPPFeature::update(SVDPlusBlock) (base.h:568-582). */
+int svdgpu_update_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off,
+                         const int *blk_fb_off, const int *blk_tag, const unsigned *fb_index,
+                         const float *fb_value, const int *row_ptr, const float *label,
+                         const unsigned *index, const float *value);
+/* replaces: SVDPPFeature::predict(vector<float>&, SVDPlusBlock) (base.h:583-591) */
+int svdgpu_predict_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off,
+                          const int *blk_fb_off, const int *blk_tag, const unsigned *fb_index,
+                          const float *fb_value, const int *row_ptr, const float *label,
+                          const unsigned *index, const float *value, float *out);
+
+/* ---- the hot path, batches resident in HBM ----------------------------- */
+/* Copy a CSR batch to the device once and train on it every round (the
+ * reference re-reads its buffer file each round, svd_feature.cpp:245-246). */
+int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const int *row_ptr,
+                        const float *label, const unsigned *index, const float *value);
+/* optional: attach user-group structure to a resident batch */
+int svdgpu_batch_set_ugroup(svdgpu_t *h, svdgpu_batch_t *b, int num_block, const int *blk_row_off,
+                            const int *blk_fb_off, const int *blk_tag, const unsigned *fb_index,
+                            const float *fb_value);
+/* rows [row_begin,row_end) (blocks [begin,end) for a user-grouped batch) */
+int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end);
+/* out_host may be NULL (predictions stay on the device; see svdgpu_batch_pred_ptr) */
+int svdgpu_batch_predict(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float *out_host);
+void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b);
+
+/* ---- synchronisation, timing, introspection ---------------------------- */
+/* wait for all queued work; reports device-side input errors (index out of
+ * bound -- the reference's assert_true at base.h:320,327,343) */
+int svdgpu_sync(svdgpu_t *h);
+/* CUDA-event stopwatch on the launch stream */
+int svdgpu_timer_start(svdgpu_t *h);
+int svdgpu_timer_stop(svdgpu_t *h, float *elapsed_ms);
+/* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm" */
+long long svdgpu_get_counter(const svdgpu_t *h, const char *name);
+/* device pointers of the model slabs (for peer / collective plumbing): 0 ui_bias,
+ * 1 W_uiset, 2 g_bias; *pitch_floats receives the device row stride */
+void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats);
+
+/* ---- multi-GPU: replicated item side, user rows sharded by hash(user) ---- */
+/* Snapshot the replicated slabs (item rows, item bias, g_bias[, feedback rows]). */
+int svdgpu_items_snapshot(svdgpu_t *h);
+/* Pack delta = current - snapshot into one contiguous device buffer; returns its
+ * device pointer and length in floats (the buffer a NCCL all-reduce runs on). */
+int svdgpu_items_pack_delta(svdgpu_t *h, void **dev_ptr, size_t *num_floats);
+/* current = snapshot + scale * (reduced delta); then re-snapshot. */
+int svdgpu_items_apply_delta(svdgpu_t *h, float scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDGPU_H_ */

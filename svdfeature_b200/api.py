@@ -1,0 +1,388 @@
+"""ctypes bindings of the native libraries (no compute happens in Python).
+
+``SvdGpu``     -- thin wrapper over the C ABI of include/svdgpu.h (libsvdgpu.so)
+``GpuTrainer`` -- the C++ ``GpuSVDFeature : ISVDTrainer`` (libsvdf_gpu.so) driven
+                  through the same ``svdtr_*`` shim the reference is wrapped with,
+                  so a test can run the reference and the GPU trainer with
+                  identical calls.
+
+Both fail loudly when the CUDA library is missing or no GPU is present: there
+is no CPU fallback in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_GPU = os.path.join(HERE, "libsvdgpu.so")
+LIB_TRAINER = os.path.join(HERE, "libsvdf_gpu.so")
+
+MODE_EXACT, MODE_HOGWILD = 0, 1
+
+_i32p = C.POINTER(C.c_int)
+_f32p = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint)
+_vp = C.c_void_p
+
+
+class Shape(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "num_user", "num_item", "num_global", "num_ufeedback", "num_factor", "no_user_bias",
+        "active_type", "format_type")]
+
+
+class HParams(C.Structure):
+    _fields_ = [
+        ("learning_rate", C.c_float), ("wd_user", C.c_float), ("wd_item", C.c_float),
+        ("wd_user_bias", C.c_float), ("wd_item_bias", C.c_float), ("wd_global", C.c_float),
+        ("reg_method", C.c_int), ("reg_global", C.c_int), ("num_regfree_global", C.c_uint),
+        ("scale_lr_ufeedback", C.c_float), ("wd_ufeedback", C.c_float),
+        ("wd_ufeedback_bias", C.c_float), ("base_score", C.c_float)]
+
+
+# every symbol include/svdgpu.h declares: (restype, argtypes)
+SVDGPU_SYMBOLS = {
+    "svdgpu_create": (C.c_int, [C.POINTER(_vp), C.POINTER(Shape), C.c_int]),
+    "svdgpu_destroy": (None, [_vp]),
+    "svdgpu_last_error": (C.c_char_p, [_vp]),
+    "svdgpu_set_hparams": (C.c_int, [_vp, C.POINTER(HParams)]),
+    "svdgpu_set_mode": (C.c_int, [_vp, C.c_int]),
+    "svdgpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
+    "svdgpu_set_stream": (C.c_int, [_vp, _vp]),
+    "svdgpu_upload_model": (C.c_int, [_vp, _f32p, _f32p, C.c_size_t, _f32p]),
+    "svdgpu_download_model": (C.c_int, [_vp, _f32p, _f32p, C.c_size_t, _f32p]),
+    "svdgpu_update_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "svdgpu_predict_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "svdgpu_update_ugroup": (C.c_int, [_vp, C.c_int] + [_vp] * 9),
+    "svdgpu_predict_ugroup": (C.c_int, [_vp, C.c_int] + [_vp] * 10),
+    "svdgpu_batch_create": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp, _vp]),
+    "svdgpu_batch_set_ugroup": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 5),
+    "svdgpu_batch_update": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "svdgpu_batch_predict": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    "svdgpu_batch_destroy": (None, [_vp, _vp]),
+    "svdgpu_sync": (C.c_int, [_vp]),
+    "svdgpu_timer_start": (C.c_int, [_vp]),
+    "svdgpu_timer_stop": (C.c_int, [_vp, _f32p]),
+    "svdgpu_get_counter": (C.c_longlong, [_vp, C.c_char_p]),
+    "svdgpu_device_ptr": (_vp, [_vp, C.c_int, C.POINTER(C.c_size_t)]),
+    "svdgpu_items_snapshot": (C.c_int, [_vp]),
+    "svdgpu_items_pack_delta": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "svdgpu_items_apply_delta": (C.c_int, [_vp, C.c_float]),
+}
+
+_lib = None
+_tlib = None
+
+
+class SvdGpuError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libsvdgpu.so and declare every symbol of include/svdgpu.h."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_GPU):
+            raise SvdGpuError(
+                "native library %s is missing: run `python -m svdfeature_b200.build` "
+                "(there is no CPU fallback)" % LIB_GPU)
+        lib = C.CDLL(LIB_GPU, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SVDGPU_SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    """Address of a numpy array / torch tensor (host memory) or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (e.g. pinned host memory)
+        assert a.is_contiguous()
+        return a.data_ptr()
+    return a
+
+
+class Batch:
+    def __init__(self, owner, handle, num_row):
+        self.owner, self.h, self.num_row = owner, handle, num_row
+        self.num_unit = None
+
+    def close(self):
+        if self.h:
+            self.owner.lib.svdgpu_batch_destroy(self.owner.h, self.h)
+            self.h = None
+
+
+class SvdGpu:
+    """One trainer on one GPU: the C ABI, one method per entry point."""
+
+    def __init__(self, num_user, num_item, num_factor, num_global=0, num_ufeedback=0, no_user_bias=0,
+                 active_type=0, format_type=0, device=0):
+        self.lib = load_library()
+        self.shape = Shape(num_user, num_item, num_global, num_ufeedback, num_factor, no_user_bias,
+                           active_type, format_type)
+        h = _vp()
+        if self.lib.svdgpu_create(C.byref(h), C.byref(self.shape), device) != 0:
+            raise SvdGpuError(self.lib.svdgpu_last_error(None).decode())
+        self.h = h
+        self.ustart = num_ufeedback if format_type == 1 else 0
+        self.rows = self.ustart + num_user + num_item
+        self.pitch = (num_factor + 3) // 4 * 4
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SvdGpuError(self.lib.svdgpu_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.svdgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # configuration
+    def set_hparams(self, **kw):
+        hp = HParams(learning_rate=0.01, scale_lr_ufeedback=1.0)
+        for k, v in kw.items():
+            setattr(hp, k, v)
+        self.hp = hp
+        self._ck(self.lib.svdgpu_set_hparams(self.h, C.byref(hp)))
+
+    def set_mode(self, mode):
+        self._ck(self.lib.svdgpu_set_mode(self.h, mode))
+
+    def set_option(self, name, value):
+        self._ck(self.lib.svdgpu_set_option(self.h, name.encode(), int(value)))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.svdgpu_set_stream(self.h, cuda_stream))
+
+    # model
+    def upload(self, ui_bias, W, g_bias):
+        assert W.dtype == np.float32 and ui_bias.dtype == np.float32 and g_bias.dtype == np.float32
+        W = np.ascontiguousarray(W)
+        pitch = W.shape[1] if W.ndim == 2 else self.pitch
+        self._ck(self.lib.svdgpu_upload_model(
+            self.h, ui_bias.ctypes.data_as(_f32p), W.ctypes.data_as(_f32p), pitch,
+            g_bias.ctypes.data_as(_f32p)))
+
+    def download(self):
+        ub = np.zeros(max(self.rows, 1), np.float32)
+        W = np.zeros((max(self.rows, 1), self.pitch), np.float32)
+        gb = np.zeros(max(self.shape.num_global, 1), np.float32)
+        self._ck(self.lib.svdgpu_download_model(
+            self.h, ub.ctypes.data_as(_f32p), W.ctypes.data_as(_f32p), self.pitch,
+            gb.ctypes.data_as(_f32p)))
+        return ub[:self.rows], W[:self.rows], gb[:self.shape.num_global]
+
+    # hot path, host buffers
+    def update_csr(self, csr):
+        rp, lb, ix, vl = csr
+        self._ck(self.lib.svdgpu_update_csr(self.h, len(lb), _ptr(rp), _ptr(lb), _ptr(ix), _ptr(vl)))
+
+    def predict_csr(self, csr):
+        rp, lb, ix, vl = csr
+        out = np.empty(len(lb), np.float32)
+        self._ck(self.lib.svdgpu_predict_csr(self.h, len(lb), _ptr(rp), _ptr(lb), _ptr(ix), _ptr(vl),
+                                             _ptr(out)))
+        return out
+
+    def update_ugroup(self, ug):
+        bro, bfo, tag, fi, fv, rp, lb, ix, vl = ug
+        self._ck(self.lib.svdgpu_update_ugroup(self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag),
+                                               _ptr(fi), _ptr(fv), _ptr(rp), _ptr(lb), _ptr(ix), _ptr(vl)))
+
+    def predict_ugroup(self, ug):
+        bro, bfo, tag, fi, fv, rp, lb, ix, vl = ug
+        out = np.empty(len(lb), np.float32)
+        self._ck(self.lib.svdgpu_predict_ugroup(self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag),
+                                                _ptr(fi), _ptr(fv), _ptr(rp), _ptr(lb), _ptr(ix),
+                                                _ptr(vl), _ptr(out)))
+        return out
+
+    # hot path, resident batches
+    def batch_create(self, csr, ugroup=None):
+        rp, lb, ix, vl = csr
+        b = _vp()
+        self._ck(self.lib.svdgpu_batch_create(self.h, C.byref(b), len(lb), _ptr(rp), _ptr(lb), _ptr(ix),
+                                              _ptr(vl)))
+        batch = Batch(self, b, len(lb))
+        if ugroup is not None:
+            bro, bfo, tag, fi, fv = ugroup
+            self._ck(self.lib.svdgpu_batch_set_ugroup(self.h, b, len(bro) - 1, _ptr(bro), _ptr(bfo),
+                                                      _ptr(tag), _ptr(fi), _ptr(fv)))
+            batch.num_unit = len(bro) - 1 if tag is None or not np.any(tag) else None
+        return batch
+
+    def batch_update(self, batch, begin=0, end=None):
+        if end is None:
+            end = batch.num_unit if batch.num_unit is not None else batch.num_row
+        self._ck(self.lib.svdgpu_batch_update(self.h, batch.h, begin, end))
+
+    def batch_predict(self, batch, begin=0, end=None, fetch=True):
+        if end is None:
+            end = batch.num_unit if batch.num_unit is not None else batch.num_row
+        n = batch.num_row if batch.num_unit is not None else end - begin
+        out = np.empty(n, np.float32) if fetch else None
+        self._ck(self.lib.svdgpu_batch_predict(self.h, batch.h, begin, end, _ptr(out)))
+        return out
+
+    # sync / timing / introspection
+    def sync(self):
+        self._ck(self.lib.svdgpu_sync(self.h))
+
+    def timer_start(self):
+        self._ck(self.lib.svdgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.svdgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def counter(self, name):
+        return int(self.lib.svdgpu_get_counter(self.h, name.encode()))
+
+    def device_ptr(self, which):
+        pitch = C.c_size_t()
+        p = self.lib.svdgpu_device_ptr(self.h, which, C.byref(pitch))
+        return p, pitch.value
+
+    # multi-GPU exchange
+    def items_snapshot(self):
+        self._ck(self.lib.svdgpu_items_snapshot(self.h))
+
+    def items_pack_delta(self):
+        p, n = _vp(), C.c_size_t()
+        self._ck(self.lib.svdgpu_items_pack_delta(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def items_apply_delta(self, scale=1.0):
+        self._ck(self.lib.svdgpu_items_apply_delta(self.h, scale))
+
+
+# ---------------------------------------------------------------------------
+# the C++ ISVDTrainer implementation behind the svdtr_* shim
+# ---------------------------------------------------------------------------
+def load_trainer_library():
+    global _tlib
+    if _tlib is None:
+        load_library()
+        if not os.path.exists(LIB_TRAINER):
+            raise SvdGpuError("native library %s is missing: run `python -m svdfeature_b200.build`" % LIB_TRAINER)
+        lib = C.CDLL(LIB_TRAINER)
+        vp = _vp
+        sig = {
+            "svdtr_create": (vp, [C.c_int, C.c_int, C.c_int]),
+            "svdtr_destroy": (None, [vp]),
+            "svdtr_seed": (None, [C.c_uint]),
+            "svdtr_set_param": (None, [vp, C.c_char_p, C.c_char_p]),
+            "svdtr_init_model": (None, [vp]),
+            "svdtr_init_trainer": (None, [vp]),
+            "svdtr_set_round": (None, [vp, C.c_int]),
+            "svdtr_finish_round": (None, [vp]),
+            "svdtr_save_model": (C.c_int, [vp, C.c_char_p]),
+            "svdtr_load_model": (C.c_int, [vp, C.c_char_p]),
+            "svdtr_sync": (None, [vp]),
+            "svdtr_gpu_handle": (vp, [vp]),
+        }
+        for base in ("svdtr_update_csr", "svdtr_update_csr_bulk"):
+            sig[base] = (None, [vp, C.c_int] + [vp] * 4)
+        for base in ("svdtr_predict_csr", "svdtr_predict_csr_bulk"):
+            sig[base] = (None, [vp, C.c_int] + [vp] * 5)
+        for base in ("svdtr_update_ugroup", "svdtr_update_ugroup_bulk"):
+            sig[base] = (None, [vp, C.c_int] + [vp] * 9)
+        for base in ("svdtr_predict_ugroup", "svdtr_predict_ugroup_bulk"):
+            sig[base] = (None, [vp, C.c_int] + [vp] * 10)
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _tlib = lib
+    return _tlib
+
+
+class GpuTrainer:
+    """ISVDTrainer on the GPU.  ``bulk=False`` drives the per-row virtuals
+    (``update(Elem)`` / ``update(SVDPlusBlock)``) exactly like svd_feature.cpp:231-247;
+    ``bulk=True`` hands whole batches over in one call."""
+
+    def __init__(self, format_type=2, active_type=0, extend_type=0, params=None, bulk=True):
+        self.lib = load_trainer_library()
+        self.h = self.lib.svdtr_create(format_type, active_type, extend_type)
+        self.sfx = "_bulk" if bulk else ""
+        if params:
+            self.set_params(params)
+
+    def set_params(self, params):
+        for k, v in params.items():
+            self.lib.svdtr_set_param(self.h, str(k).encode(), str(v).encode())
+
+    def init(self, seed=10):
+        self.lib.svdtr_seed(seed)
+        self.lib.svdtr_init_model(self.h)
+        self.lib.svdtr_init_trainer(self.h)
+
+    def set_round(self, r):
+        self.lib.svdtr_set_round(self.h, int(r))
+
+    def finish_round(self):
+        self.lib.svdtr_finish_round(self.h)
+
+    def update_csr(self, csr):
+        rp, lb, ix, vl = csr
+        getattr(self.lib, "svdtr_update_csr" + self.sfx)(self.h, len(lb), _ptr(rp), _ptr(lb), _ptr(ix), _ptr(vl))
+
+    def predict_csr(self, csr):
+        rp, lb, ix, vl = csr
+        out = np.empty(len(lb), np.float32)
+        getattr(self.lib, "svdtr_predict_csr" + self.sfx)(self.h, len(lb), _ptr(rp), _ptr(lb), _ptr(ix),
+                                                          _ptr(vl), _ptr(out))
+        return out
+
+    def update_ugroup(self, ug):
+        bro, bfo, tag, fi, fv, rp, lb, ix, vl = ug
+        getattr(self.lib, "svdtr_update_ugroup" + self.sfx)(
+            self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag), _ptr(fi), _ptr(fv), _ptr(rp),
+            _ptr(lb), _ptr(ix), _ptr(vl))
+
+    def predict_ugroup(self, ug):
+        bro, bfo, tag, fi, fv, rp, lb, ix, vl = ug
+        out = np.empty(len(lb), np.float32)
+        getattr(self.lib, "svdtr_predict_ugroup" + self.sfx)(
+            self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag), _ptr(fi), _ptr(fv), _ptr(rp),
+            _ptr(lb), _ptr(ix), _ptr(vl), _ptr(out))
+        return out
+
+    def save_model(self, path):
+        assert self.lib.svdtr_save_model(self.h, path.encode()) == 0
+
+    def load_model(self, path):
+        assert self.lib.svdtr_load_model(self.h, path.encode()) == 0
+
+    def model_bytes(self, tmpdir):
+        path = os.path.join(str(tmpdir), "m_gpu_%d.model" % id(self))
+        self.save_model(path)
+        with open(path, "rb") as f:
+            return f.read()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.svdtr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

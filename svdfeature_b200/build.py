@@ -1,0 +1,81 @@
+"""In-tree build of the native libraries (sm_100a only).
+
+    libsvdgpu.so    -- CUDA kernels + the C ABI of include/svdgpu.h
+    libsvdf_gpu.so  -- the C++ ISVDTrainer implementation (gpu_trainer.cpp) behind the
+                       same C shim the reference is wrapped with (trainer_cabi.cpp)
+
+nvcc cross-compiles without a GPU; the .so files are git-ignored but travel to
+the GPU box with the tree.  ``python -m svdfeature_b200.build`` rebuilds.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_GPU = os.path.join(HERE, "libsvdgpu.so")
+LIB_TRAINER = os.path.join(HERE, "libsvdf_gpu.so")
+REFERENCE_ROOT = "/root/reference"
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",  # the reference never fuses multiply-add (built -msse2); parity needs the same
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
+    "-Xptxas", "-v",
+    "-shared", "-cudart", "shared",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _sources(*names):
+    return [os.path.join(CSRC, n) for n in names]
+
+
+def build_gpu(force=False, verbose=False):
+    deps = _sources("svdgpu_api.cu", "svdgpu_kernels.cuh", "svdgpu_device.cuh") + [
+        os.path.join(ROOT, "include", "svdgpu.h")]
+    if not force and not _newer(LIB_GPU, deps):
+        return LIB_GPU
+    cmd = [NVCC] + NVCC_FLAGS + ["-o", LIB_GPU, os.path.join(CSRC, "svdgpu_api.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+        f.write(log)
+    if res.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed for libsvdgpu.so")
+    if verbose:
+        print(log)
+    return LIB_GPU
+
+
+def build_trainer(force=False):
+    src = _sources("gpu_trainer.cpp", "trainer_cabi.cpp")
+    if not all(os.path.exists(s) for s in src):
+        return None
+    deps = src + _sources("apex_compat.h") + [os.path.join(ROOT, "include", "svdgpu.h")]
+    if not force and not _newer(LIB_TRAINER, deps):
+        return LIB_TRAINER
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
+           "-I", os.path.join(ROOT, "include"), "-o", LIB_TRAINER] + src + [
+        "-L", HERE, "-lsvdgpu", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return LIB_TRAINER
+
+
+def build_all(force=False, verbose=False):
+    build_gpu(force, verbose)
+    build_trainer(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)

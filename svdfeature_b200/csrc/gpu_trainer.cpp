@@ -1,0 +1,521 @@
+// gpu_trainer.cpp -- the reference's solver seam, implemented on the B200.
+//
+// `GpuSVDFeature` is an apex_svd::ISVDTrainer (apex_svd.h:33-107) and this file
+// defines apex_svd::create_svd_trainer (apex_svd.h:212), i.e. it takes the place
+// of the reference's apex_svd.cpp at link time exactly as
+// solvers/example/Makefile:17-23 documents for custom solvers.  It covers what
+// SVDFeature and SVDPPFeature (solvers/base-solver/apex_svd_base.h:79-592) do:
+// same set_param keys, same call order, same model-file bytes
+// (apex_svd_model.h:570-660), same error convention (message on stderr, exit(-1)).
+//
+// The class owns no arithmetic.  Model initialisation and file I/O are host work
+// (they are not on the hot path and must reproduce glibc rand() draws); every
+// update/predict goes through the C ABI of include/svdgpu.h to the CUDA kernels.
+#ifdef SVDGPU_WITH_REFERENCE_HEADERS
+#include "apex_svd.h"
+#else
+#include "apex_compat.h"
+#endif
+
+#include "svdgpu.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+// On-disk model header: SVDModelParam, apex_svd_model.h:373-450 (17 fields in
+// declaration order, then int reserved[247]; 1056 bytes).
+struct ModelHeader {
+  int32_t num_user, num_item, num_factor, num_global;
+  float u_init_sigma, i_init_sigma, base_score;
+  int32_t no_user_bias, num_ufeedback;
+  float ufeedback_init_sigma;
+  int32_t num_randinit_ufactor, num_randinit_ifactor;
+  int32_t common_latent_space, user_nonnegative, common_feedback_space, extend_flag, item_nonnegative;
+  int32_t reserved[247];
+};
+static_assert(sizeof(ModelHeader) == 1056, "model header must stay 1056 bytes");
+
+// apex-tensor/apex_random.h:53-77 (uniform in (0,1) from rand(); Marsaglia polar,
+// second variate discarded)
+inline double next_double2() { return ((double)rand() + 1.0) / ((double)RAND_MAX + 2.0); }
+inline double sample_normal() {
+  double x, y, s;
+  do {
+    x = 2 * next_double2() - 1.0;
+    y = 2 * next_double2() - 1.0;
+    s = x * x + y * y;
+  } while (s >= 1.0 || s == 0.0);
+  return x * std::sqrt(-2.0 * std::log(s) / s);
+}
+
+// apex_svd_model.h:220-237
+float transform_base_score(float base_score, int active_type) {
+  switch (active_type) {
+    case 0: case 5: case 6: return base_score;
+    case 1: case 2: case 3: case 7:
+      apex_utils::assert_true(base_score > 0.0f && base_score < 1.0f, "sigmoid range constrain");
+      return -logf(1.0f / base_score - 1.0f);
+    default: apex_utils::error("unkown active type"); return 0.0f;
+  }
+}
+
+void check(svdgpu_t *h, int rc) {
+  if (rc != 0) apex_utils::error(svdgpu_last_error(h));
+}
+
+// growable SoA staging for the per-row / per-block API
+struct CsrStage {
+  std::vector<int> row_ptr;
+  std::vector<float> label;
+  std::vector<unsigned> index;
+  std::vector<float> value;
+  CsrStage() { row_ptr.push_back(0); }
+  void clear() {
+    row_ptr.assign(1, 0);
+    label.clear();
+    index.clear();
+    value.clear();
+  }
+  int num_row() const { return (int)label.size(); }
+  void push(const apex_svd::SVDFeatureCSR::Elem &e) {
+    label.push_back(e.label);
+    index.insert(index.end(), e.index_global, e.index_global + e.num_global);
+    value.insert(value.end(), e.value_global, e.value_global + e.num_global);
+    row_ptr.push_back((int)index.size());
+    index.insert(index.end(), e.index_ufactor, e.index_ufactor + e.num_ufactor);
+    value.insert(value.end(), e.value_ufactor, e.value_ufactor + e.num_ufactor);
+    row_ptr.push_back((int)index.size());
+    index.insert(index.end(), e.index_ifactor, e.index_ifactor + e.num_ifactor);
+    value.insert(value.end(), e.value_ifactor, e.value_ifactor + e.num_ifactor);
+    row_ptr.push_back((int)index.size());
+  }
+};
+
+}  // namespace
+
+namespace apex_svd {
+
+class GpuSVDFeature : public ISVDTrainer {
+ public:
+  explicit GpuSVDFeature(const SVDTypeParam &mtype) : mtype_(mtype) {
+    memset(&mp_, 0, sizeof(mp_));
+    mp_.u_init_sigma = mp_.i_init_sigma = 0.01f;  // model.h:436-450
+    mp_.base_score = 0.5f;
+    memset(&hp_, 0, sizeof(hp_));
+    hp_.learning_rate = 0.01f;  // model.h:334-344
+    hp_.scale_lr_ufeedback = 1.0f;
+    svdpp_ = (mtype.extend_type == 1 || mtype.format_type == svd_type::USER_GROUP_FORMAT);
+    blk_row_off_.push_back(0);
+    blk_fb_off_.push_back(0);
+  }
+  virtual ~GpuSVDFeature() {
+    if (h_) svdgpu_destroy(h_);
+  }
+
+  // ---- model related interface (base.h:126-173) ---------------------------
+  virtual void set_param(const char *name, const char *val) {
+    if (!strcmp(name, "feature_user") || !strcmp(name, "feature_item")) {
+      if (strcmp(val, "NULL"))
+        apex_utils::error("feature_user/feature_item side features are not supported by the GPU trainer");
+    }
+    if (!strncmp(name, "up:", 3) || !strncmp(name, "ip:", 3) || !strncmp(name, "uip:", 4) || !strncmp(name, "gp:", 3))
+      apex_utils::error("ranged weight decay (up:/ip:/uip:/gp:) is not supported by the GPU trainer");
+    // SVDTrainParam::set_param, model.h:350-368
+    if (!strcmp("learning_rate", name)) hp_.learning_rate = (float)atof(val);
+    if (!strcmp("wd_user", name)) hp_.wd_user = (float)atof(val);
+    if (!strcmp("wd_item", name)) hp_.wd_item = (float)atof(val);
+    if (!strcmp("wd_uiset", name)) hp_.wd_user = hp_.wd_item = (float)atof(val);
+    if (!strcmp("wd_user_bias", name)) hp_.wd_user_bias = (float)atof(val);
+    if (!strcmp("wd_item_bias", name)) hp_.wd_item_bias = (float)atof(val);
+    if (!strcmp("wd_uiset_bias", name)) hp_.wd_user_bias = hp_.wd_item_bias = (float)atof(val);
+    if (!strcmp("wd_global", name)) hp_.wd_global = (float)atof(val);
+    if (!strcmp("reg_method", name)) hp_.reg_method = atoi(val);
+    if (!strcmp("reg_global", name)) hp_.reg_global = atoi(val);
+    if (!strcmp("num_regfree_global", name)) hp_.num_regfree_global = (unsigned)atoi(val);
+    if (!strcmp("decay_learning_rate", name)) decay_learning_rate_ = atoi(val);
+    if (!strcmp("decay_rate", name)) decay_rate_ = (float)atof(val);
+    if (!strcmp("scale_lr_ufeedback", name)) hp_.scale_lr_ufeedback = (float)atof(val);
+    if (!strcmp("wd_ufeedback", name)) hp_.wd_ufeedback = (float)atof(val);
+    if (!strcmp("wd_ufeedback_bias", name)) hp_.wd_ufeedback_bias = (float)atof(val);
+    // GPU-side keys (new; the reference ignores unknown keys, so one config serves both)
+    if (!strcmp("gpu:device", name)) device_ = atoi(val);
+    if (!strcmp("gpu:mode", name)) {
+      if (!strcmp(val, "exact") || !strcmp(val, "0")) mode_ = SVDGPU_MODE_EXACT;
+      else if (!strcmp(val, "hogwild") || !strcmp(val, "1")) mode_ = SVDGPU_MODE_HOGWILD;
+      else apex_utils::error("gpu:mode must be exact or hogwild");
+    }
+    if (!strcmp("gpu:batch", name)) batch_rows_ = atoi(val) > 0 ? atoi(val) : batch_rows_;
+    if (!strncmp("gpu:opt:", name, 8)) options_.push_back(std::make_pair(std::string(name + 8), atoll(val)));
+    if (h_) {
+      push_hparams();
+      if (!strcmp("gpu:mode", name)) check(h_, svdgpu_set_mode(h_, mode_));
+      if (!strncmp("gpu:opt:", name, 8)) check(h_, svdgpu_set_option(h_, name + 8, atoll(val)));
+    }
+    if (space_allocated_) return;  // base.h:133-135
+    // SVDModelParam::set_param, model.h:456-476
+    if (!strcmp("num_user", name)) mp_.num_user = atoi(val);
+    if (!strcmp("num_item", name)) mp_.num_item = atoi(val);
+    if (!strcmp("num_uiset", name)) mp_.num_user = mp_.num_item = atoi(val);
+    if (!strcmp("num_global", name)) mp_.num_global = atoi(val);
+    if (!strcmp("num_factor", name)) mp_.num_factor = atoi(val);
+    if (!strcmp("u_init_sigma", name)) mp_.u_init_sigma = (float)atof(val);
+    if (!strcmp("i_init_sigma", name)) mp_.i_init_sigma = (float)atof(val);
+    if (!strcmp("ui_init_sigma", name)) mp_.u_init_sigma = mp_.i_init_sigma = (float)atof(val);
+    if (!strcmp("base_score", name)) mp_.base_score = (float)atof(val);
+    if (!strcmp("no_user_bias", name)) mp_.no_user_bias = atoi(val);
+    if (!strcmp("num_ufeedback", name)) mp_.num_ufeedback = atoi(val);
+    if (!strcmp("num_randinit_ufactor", name)) mp_.num_randinit_ufactor = atoi(val);
+    if (!strcmp("num_randinit_ifactor", name)) mp_.num_randinit_ifactor = atoi(val);
+    if (!strcmp("num_randinit_uifactor", name)) mp_.num_randinit_ifactor = mp_.num_randinit_ufactor = atoi(val);
+    if (!strcmp("ufeedback_init_sigma", name)) mp_.ufeedback_init_sigma = (float)atof(val);
+    if (!strcmp("common_latent_space", name)) mp_.common_latent_space = atoi(val);
+    if (!strcmp("common_feedback_space", name)) mp_.common_feedback_space = atoi(val);
+    if (!strcmp("user_nonnegative", name)) mp_.user_nonnegative = atoi(val);
+    if (!strcmp("item_nonnegative", name)) mp_.item_nonnegative = atoi(val);
+  }
+
+  virtual void load_model(FILE *fi) {  // model.h:570-633
+    flush();
+    if (fread(&mp_, sizeof(ModelHeader), 1, fi) != 1) {
+      printf("error loading CF SVD model\n");
+      exit(-1);
+    }
+    alloc_host();
+    read_1d(&ui_bias_[ustart_], mp_.num_user, fi);
+    read_2d(&W_[(size_t)ustart_ * pitch_], mp_.num_user, fi);
+    read_1d(&ui_bias_[ustart_ + mp_.num_user], mp_.num_item, fi);
+    read_2d(&W_[(size_t)(ustart_ + mp_.num_user) * pitch_], mp_.num_item, fi);
+    read_1d(g_bias_.data(), mp_.num_global, fi);
+    if (mtype_.format_type == svd_type::USER_GROUP_FORMAT) {
+      read_1d(ui_bias_.data(), mp_.num_ufeedback, fi);
+      read_2d(W_.data(), mp_.num_ufeedback, fi);
+    }
+    if (h_) {
+      ensure_handle();  // shape may have changed
+      upload();
+    }
+  }
+
+  virtual void save_model(FILE *fo) {  // model.h:638-660
+    flush();
+    if (h_) check(h_, svdgpu_download_model(h_, ui_bias_.data(), W_.data(), (size_t)pitch_, g_bias_.data()));
+    fwrite(&mp_, sizeof(ModelHeader), 1, fo);
+    write_1d(&ui_bias_[ustart_], mp_.num_user, fo);
+    write_2d(&W_[(size_t)ustart_ * pitch_], mp_.num_user, fo);
+    write_1d(&ui_bias_[ustart_ + mp_.num_user], mp_.num_item, fo);
+    write_2d(&W_[(size_t)(ustart_ + mp_.num_user) * pitch_], mp_.num_item, fo);
+    write_1d(g_bias_.data(), mp_.num_global, fo);
+    if (mtype_.format_type == svd_type::USER_GROUP_FORMAT) {
+      write_1d(ui_bias_.data(), mp_.num_ufeedback, fo);
+      write_2d(W_.data(), mp_.num_ufeedback, fo);
+    }
+  }
+
+  virtual void init_model(void) {  // base.h:146-149; model.h:665-705 rand_init
+    alloc_host();
+    mp_.base_score = transform_base_score(mp_.base_score, mtype_.active_type);
+    const int k = mp_.num_factor;
+    {
+      const int ny = mp_.num_randinit_ufactor != 0 ? mp_.num_randinit_ufactor : mp_.num_user;
+      float *base = &W_[(size_t)ustart_ * pitch_];
+      for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < k; ++x) base[(size_t)y * pitch_ + x] = (float)sample_normal() * mp_.u_init_sigma;
+    }
+    {
+      const int ny = mp_.num_randinit_ifactor != 0 ? mp_.num_randinit_ifactor : mp_.num_item;
+      float *base = &W_[(size_t)(ustart_ + mp_.num_user) * pitch_];
+      for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < k; ++x) base[(size_t)y * pitch_ + x] = (float)sample_normal() * mp_.i_init_sigma;
+    }
+    if (mtype_.format_type == svd_type::USER_GROUP_FORMAT) {
+      for (int y = 0; y < mp_.num_ufeedback; ++y)
+        for (int x = 0; x < k; ++x)
+          W_[(size_t)y * pitch_ + x] = (float)sample_normal() * mp_.ufeedback_init_sigma;
+    }
+  }
+
+  virtual void init_trainer(void) {  // base.h:151-173
+    apex_utils::assert_true(space_allocated_ != 0, "init_trainer: no model (call init_model or load_model first)");
+    ensure_handle();
+    upload();
+    init_end_ = 1;
+  }
+
+  // ---- training interface ---------------------------------------------------
+  virtual void set_round(int nround) {  // base.h:470-478
+    if (decay_learning_rate_ != 0) {
+      apex_utils::assert_true(round_counter_ <= nround, "round counter restriction");
+      flush();
+      while (round_counter_ < nround) {
+        hp_.learning_rate *= decay_rate_;
+        round_counter_++;
+      }
+      if (h_) push_hparams();
+    }
+  }
+  virtual void finish_round(void) { flush(); }
+
+  virtual void update(const SVDFeatureCSR::Elem &feature) {  // base.h:464-466
+    apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
+    if (svdpp_) apex_utils::error("GPU trainer: a user-grouped model takes SVDPlusBlock input");
+    rows_.push(feature);  // the Elem aliases the loader's buffer: copy now (apex_buffer_loader.h:212-226)
+    if (rows_.num_row() >= batch_rows_) flush();
+  }
+  virtual float predict(const SVDFeatureCSR::Elem &feature) {  // base.h:467-469
+    apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
+    if (svdpp_) apex_utils::error("GPU trainer: a user-grouped model takes SVDPlusBlock input");
+    flush();
+    CsrStage one;
+    one.push(feature);
+    float out = 0.0f;
+    check(h_, svdgpu_predict_csr(h_, 1, one.row_ptr.data(), one.label.data(), one.index.data(),
+                                 one.value.data(), &out));
+    return out;
+  }
+
+  virtual void update(const SVDPlusBlock &data) {  // base.h:568-582
+    apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
+    if (!svdpp_) apex_utils::error("GPU trainer: a random-order model takes SVDFeatureCSR::Elem input");
+    push_block(data);
+    const bool closed = data.extend_tag == svdpp_tag::DEFAULT || data.extend_tag == svdpp_tag::END_TAG;
+    if (closed && rows_.num_row() >= batch_rows_) flush();
+  }
+  virtual void predict(std::vector<float> &pred, const SVDPlusBlock &data) {  // base.h:583-591
+    apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
+    if (!svdpp_) apex_utils::error("GPU trainer: a random-order model takes SVDFeatureCSR::Elem input");
+    flush();
+    // a MIDDLE/END block predicts with the feedback sum of its START block in the
+    // reference (trainer state); here each call is self-contained, which is the same
+    // for DEFAULT blocks and for split users carrying their feedback list in every block.
+    push_block(data);
+    blk_tag_.back() = svdpp_tag::DEFAULT;
+    pred.resize((size_t)rows_.num_row());
+    check(h_, svdgpu_predict_ugroup(h_, 1, blk_row_off_.data(), blk_fb_off_.data(), blk_tag_.data(),
+                                    fb_index_.data(), fb_value_.data(), rows_.row_ptr.data(),
+                                    rows_.label.data(), rows_.index.data(), rows_.value.data(),
+                                    pred.data()));
+    clear_stage();
+  }
+
+  // ---- bulk extensions (whole batches in one call) ----------
+  void update_batch(const SVDFeatureCSR &c) {
+    apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
+    if (svdpp_) apex_utils::error("GPU trainer: a user-grouped model takes SVDPlusBlock input");
+    flush();
+    check(h_, svdgpu_update_csr(h_, c.num_row, c.row_ptr, c.row_label, c.feat_index, c.feat_value));
+  }
+  void predict_batch(const SVDFeatureCSR &c, float *out) {
+    apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
+    flush();
+    check(h_, svdgpu_predict_csr(h_, c.num_row, c.row_ptr, c.row_label, c.feat_index, c.feat_value, out));
+  }
+  void update_ugroup_batch(int num_block, const int *blk_row_off, const int *blk_fb_off, const int *blk_tag,
+                           const unsigned *fb_index, const float *fb_value, const SVDFeatureCSR &c) {
+    apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
+    flush();
+    check(h_, svdgpu_update_ugroup(h_, num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value,
+                                   c.row_ptr, c.row_label, c.feat_index, c.feat_value));
+  }
+  void predict_ugroup_batch(int num_block, const int *blk_row_off, const int *blk_fb_off, const int *blk_tag,
+                            const unsigned *fb_index, const float *fb_value, const SVDFeatureCSR &c,
+                            float *out) {
+    apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
+    flush();
+    check(h_, svdgpu_predict_ugroup(h_, num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value,
+                                    c.row_ptr, c.row_label, c.feat_index, c.feat_value, out));
+  }
+  svdgpu_t *handle() { return h_; }
+  void sync() {
+    flush();
+    if (h_) check(h_, svdgpu_sync(h_));
+  }
+
+ private:
+  void alloc_host() {  // model.h:511-556 (separate index spaces only)
+    if (mp_.common_latent_space != 0 || mp_.common_feedback_space != 0)
+      apex_utils::error("common_latent_space / common_feedback_space are not supported by the GPU trainer");
+    if (mp_.user_nonnegative != 0 || mp_.item_nonnegative != 0)
+      apex_utils::error("user_nonnegative / item_nonnegative are not supported by the GPU trainer");
+    ustart_ = (mtype_.format_type == svd_type::USER_GROUP_FORMAT) ? mp_.num_ufeedback : 0;
+    rows_total_ = (size_t)ustart_ + (size_t)mp_.num_user + (size_t)mp_.num_item;
+    pitch_ = ((mp_.num_factor + 3) >> 2) << 2;
+    ui_bias_.assign(rows_total_ ? rows_total_ : 1, 0.0f);
+    W_.assign((rows_total_ ? rows_total_ : 1) * (size_t)(pitch_ ? pitch_ : 1), 0.0f);
+    g_bias_.assign(mp_.num_global > 0 ? (size_t)mp_.num_global : 1, 0.0f);
+    space_allocated_ = 1;
+  }
+  void ensure_handle() {
+    svdgpu_shape s;
+    s.num_user = mp_.num_user;
+    s.num_item = mp_.num_item;
+    s.num_global = mp_.num_global;
+    s.num_ufeedback = mp_.num_ufeedback;
+    s.num_factor = mp_.num_factor;
+    s.no_user_bias = mp_.no_user_bias;
+    s.active_type = mtype_.active_type;
+    s.format_type = svdpp_ ? 1 : 0;
+    if (h_ && !memcmp(&s, &shape_, sizeof(s))) return;
+    if (h_) svdgpu_destroy(h_);
+    h_ = NULL;
+    if (svdpp_ && mtype_.format_type != svd_type::USER_GROUP_FORMAT)
+      apex_utils::error("GPU trainer: extend_type=1 needs format_type=1 (user-grouped input)");
+    if (svdgpu_create(&h_, &s, device_) != 0) apex_utils::error(svdgpu_last_error(NULL));
+    shape_ = s;
+    check(h_, svdgpu_set_mode(h_, mode_));
+    for (size_t i = 0; i < options_.size(); ++i)
+      check(h_, svdgpu_set_option(h_, options_[i].first.c_str(), options_[i].second));
+    push_hparams();
+  }
+  void push_hparams() {
+    hp_.base_score = mp_.base_score;
+    check(h_, svdgpu_set_hparams(h_, &hp_));
+  }
+  void upload() { check(h_, svdgpu_upload_model(h_, ui_bias_.data(), W_.data(), (size_t)pitch_, g_bias_.data())); }
+
+  void push_block(const SVDPlusBlock &b) {
+    fb_index_.insert(fb_index_.end(), b.index_ufeedback, b.index_ufeedback + b.num_ufeedback);
+    fb_value_.insert(fb_value_.end(), b.value_ufeedback, b.value_ufeedback + b.num_ufeedback);
+    blk_fb_off_.push_back((int)fb_index_.size());
+    for (int r = 0; r < b.data.num_row; ++r) rows_.push(b.data[r]);
+    blk_row_off_.push_back(rows_.num_row());
+    blk_tag_.push_back(b.extend_tag);
+  }
+  void clear_stage() {
+    rows_.clear();
+    blk_row_off_.assign(1, 0);
+    blk_fb_off_.assign(1, 0);
+    blk_tag_.clear();
+    fb_index_.clear();
+    fb_value_.clear();
+  }
+  void flush() {
+    if (!h_) return;
+    if (svdpp_) {
+      if (!blk_tag_.empty())
+        check(h_, svdgpu_update_ugroup(h_, (int)blk_tag_.size(), blk_row_off_.data(), blk_fb_off_.data(),
+                                       blk_tag_.data(), fb_index_.data(), fb_value_.data(),
+                                       rows_.row_ptr.data(), rows_.label.data(), rows_.index.data(),
+                                       rows_.value.data()));
+    } else if (rows_.num_row() > 0) {
+      check(h_, svdgpu_update_csr(h_, rows_.num_row(), rows_.row_ptr.data(), rows_.label.data(),
+                                  rows_.index.data(), rows_.value.data()));
+    }
+    clear_stage();
+  }
+
+  // tensor records, apex-tensor/apex_tensor_cpu_inline_common.h:72-88
+  void write_1d(const float *p, int n, FILE *fo) {
+    int32_t h = n;
+    fwrite(&h, 4, 1, fo);
+    if (n > 0) fwrite(p, 4, (size_t)n, fo);
+  }
+  void write_2d(const float *p, int y_max, FILE *fo) {
+    int32_t h[2] = {mp_.num_factor, y_max};
+    fwrite(h, 4, 2, fo);
+    for (int y = 0; y < y_max; ++y) fwrite(p + (size_t)y * pitch_, 4, (size_t)mp_.num_factor, fo);
+  }
+  void read_1d(float *p, int n, FILE *fi) {
+    int32_t h = 0;
+    apex_utils::assert_true(fread(&h, 4, 1, fi) == 1 && h == n, "tensor::load_from_file");
+    if (n > 0) apex_utils::assert_true(fread(p, 4, (size_t)n, fi) == (size_t)n, "tensor::load_from_file");
+  }
+  void read_2d(float *p, int y_max, FILE *fi) {
+    int32_t h[2] = {0, 0};
+    apex_utils::assert_true(fread(h, 4, 2, fi) == 2 && h[0] == mp_.num_factor && h[1] == y_max,
+                            "tensor::load_from_file");
+    for (int y = 0; y < y_max; ++y)
+      if (mp_.num_factor > 0)
+        apex_utils::assert_true(fread(p + (size_t)y * pitch_, 4, (size_t)mp_.num_factor, fi) == (size_t)mp_.num_factor,
+                                "tensor::load_from_file");
+  }
+
+  SVDTypeParam mtype_;
+  ModelHeader mp_;
+  svdgpu_hparams hp_;
+  svdgpu_shape shape_;
+  int decay_learning_rate_ = 0;
+  float decay_rate_ = 1.0f;
+  int round_counter_ = 0;
+  int init_end_ = 0, space_allocated_ = 0;
+  bool svdpp_ = false;
+  int device_ = 0, mode_ = SVDGPU_MODE_EXACT;
+  int batch_rows_ = 1 << 20;
+  std::vector<std::pair<std::string, long long> > options_;
+  svdgpu_t *h_ = NULL;
+  // host mirror of the model (init, load/save)
+  int ustart_ = 0, pitch_ = 0;
+  size_t rows_total_ = 0;
+  std::vector<float> ui_bias_, W_, g_bias_;
+  // staged input
+  CsrStage rows_;
+  std::vector<int> blk_row_off_, blk_fb_off_, blk_tag_;
+  std::vector<unsigned> fb_index_;
+  std::vector<float> fb_value_;
+};
+
+// apex_svd.cpp:32-45 -- the link-time seam
+ISVDTrainer *create_svd_trainer(SVDTypeParam mtype) {
+  if (mtype.extend_type == 2 || mtype.extend_type == 15 || mtype.extend_type == 30 || mtype.extend_type == 31)
+    apex_utils::error("GPU trainer: extend_type 2/15/30/31 solvers (multi-imfb, bilinear, gbrt) are CPU-only in the reference and not provided here");
+  return new GpuSVDFeature(mtype);
+}
+
+}  // namespace apex_svd
+
+// ---- bulk C entry points (GPU trainer only; same handle as trainer_cabi.cpp) ----
+namespace {
+struct ShimHandle {  // must match trainer_cabi.cpp's Handle
+  apex_svd::SVDTypeParam mtype;
+  apex_svd::ISVDTrainer *tr;
+};
+apex_svd::GpuSVDFeature *gpu_of(void *hv) {
+  return static_cast<apex_svd::GpuSVDFeature *>(static_cast<ShimHandle *>(hv)->tr);
+}
+apex_svd::SVDFeatureCSR view(int num_row, const int *row_ptr, const float *label, const unsigned *index,
+                             const float *value) {
+  apex_svd::SVDFeatureCSR c;
+  c.num_row = num_row;
+  c.num_val = num_row > 0 ? row_ptr[3 * (size_t)num_row] - row_ptr[0] : 0;
+  c.row_ptr = const_cast<int *>(row_ptr);
+  c.row_label = const_cast<float *>(label);
+  c.feat_index = const_cast<unsigned *>(index);
+  c.feat_value = const_cast<float *>(value);
+  return c;
+}
+}  // namespace
+
+extern "C" {
+void svdtr_update_csr_bulk(void *hv, int num_row, const int *row_ptr, const float *label,
+                           const unsigned *index, const float *value) {
+  gpu_of(hv)->update_batch(view(num_row, row_ptr, label, index, value));
+}
+void svdtr_predict_csr_bulk(void *hv, int num_row, const int *row_ptr, const float *label,
+                            const unsigned *index, const float *value, float *out) {
+  gpu_of(hv)->predict_batch(view(num_row, row_ptr, label, index, value), out);
+}
+void svdtr_update_ugroup_bulk(void *hv, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                              const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                              const int *row_ptr, const float *label, const unsigned *index,
+                              const float *value) {
+  const int n = num_block > 0 ? blk_row_off[num_block] : 0;
+  gpu_of(hv)->update_ugroup_batch(num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value,
+                                  view(n, row_ptr, label, index, value));
+}
+void svdtr_predict_ugroup_bulk(void *hv, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                               const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                               const int *row_ptr, const float *label, const unsigned *index,
+                               const float *value, float *out) {
+  const int n = num_block > 0 ? blk_row_off[num_block] : 0;
+  gpu_of(hv)->predict_ugroup_batch(num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value,
+                                   view(n, row_ptr, label, index, value), out);
+}
+void svdtr_sync(void *hv) { gpu_of(hv)->sync(); }
+void *svdtr_gpu_handle(void *hv) { return gpu_of(hv)->handle(); }
+}

@@ -1,0 +1,1108 @@
+// svdgpu_api.cu -- implementation of include/svdgpu.h: handle, HBM layout,
+// host<->device staging, ticket computation for the ordered mode and kernel
+// dispatch.  No CPU compute path exists here: every update/predict call ends in
+// a kernel launch or fails.
+#include "../../include/svdgpu.h"
+#include "svdgpu_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace svdk;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+struct HostBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+// One staging slot for host-pointer calls: pinned mirrors + device arrays.
+struct Slot {
+  HostBuf h_rp, h_label, h_index, h_value, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
+  DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
+  cudaEvent_t done = nullptr;  // last kernel that read this slot
+  bool used = false;
+};
+}  // namespace
+
+struct svdgpu_batch {
+  int num_row = 0;
+  long long num_val = 0;
+  DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_pred;
+  bool has_ticket = false;
+  // user-group structure
+  bool ugroup = false;
+  int num_block = 0, num_unit = 0;
+  DevBuf d_unit_off, d_blk_row_off, d_blk_fb_off, d_fbi, d_fbv, d_fbt, d_order;
+  std::vector<int> unit_off;  // host copy: block range of each unit
+};
+
+struct svdgpu {
+  svdgpu_shape shape;
+  svdgpu_hparams hp;
+  bool hp_set = false;
+  int device = 0;
+  int num_sm = 0;
+  int mode = SVDGPU_MODE_HOGWILD;
+  int scatter_user = SCATTER_STORE, scatter_item = SCATTER_RED;
+  int exact_dot = 1;
+  int lanes_opt = 0;
+  int chunk_rows = 1 << 20;
+  int ctas_per_sm = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+  DevModel dm;
+  DevHP dhp;
+  size_t rows = 0;
+  int *d_err = nullptr;
+  unsigned *d_counter = nullptr;
+  Slot slot[2];
+  int cur_slot = 0;
+  // multi-GPU exchange
+  DeltaPlan plan;
+  float *d_snap = nullptr, *d_delta = nullptr;
+  // host scratch for tickets
+  std::vector<unsigned> cnt_ui, cnt_g;
+  std::string err;
+  long long n_launch = 0, n_inst = 0, n_h2d = 0, n_d2h = 0;
+};
+
+namespace {
+
+int fail(svdgpu *h, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return 1;
+}
+
+#define CU(h, call)                                                                     \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int dev_reserve(svdgpu *h, DevBuf &b, size_t bytes) {
+  bytes += 64;  // bulk copies read 16-byte windows past the last element
+  if (bytes <= b.cap) return 0;
+  if (b.p) CU(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = bytes + bytes / 4;
+  CU(h, cudaMalloc(&b.p, cap));
+  b.cap = cap;
+  return 0;
+}
+int host_reserve(svdgpu *h, HostBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) CU(h, cudaFreeHost(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = bytes + bytes / 4 + 64;
+  CU(h, cudaMallocHost(&b.p, cap));
+  b.cap = cap;
+  return 0;
+}
+void dev_free(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+void host_free(HostBuf &b) {
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// H2D of a host array: straight from the caller's memory when it is pinned,
+// else through the slot's pinned mirror.
+int h2d(svdgpu *h, DevBuf &d, HostBuf &stage, const void *src, size_t bytes) {
+  if (dev_reserve(h, d, bytes)) return 1;
+  if (bytes == 0) return 0;
+  const void *from = src;
+  if (!is_pinned(src)) {
+    if (host_reserve(h, stage, bytes)) return 1;
+    memcpy(stage.p, src, bytes);
+    from = stage.p;
+  }
+  CU(h, cudaMemcpyAsync(d.p, from, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->n_h2d += (long long)bytes;
+  return 0;
+}
+
+// ---- hyper-parameters -> device constants (all fp32, reference expressions) ----
+bool is_one_host(float s) { return !(std::fabs((double)(s - 1.0f)) > 1e-6); }
+
+void refresh_hp(svdgpu *h) {
+  const svdgpu_hparams &p = h->hp;
+  DevHP &d = h->dhp;
+  d.lr = p.learning_rate;
+  volatile float lu = p.learning_rate * p.wd_user;  // base.h:213-214
+  volatile float li = p.learning_rate * p.wd_item;  // base.h:253-254
+  d.du = 1.0f - lu;
+  d.di = 1.0f - li;
+  d.du_skip = is_one_host(d.du);
+  d.di_skip = is_one_host(d.di);
+  volatile float lub = p.learning_rate * p.wd_user_bias;  // base.h:248
+  volatile float lib = p.learning_rate * p.wd_item_bias;  // base.h:282
+  d.dub = 1.0f - lub;
+  d.dib = 1.0f - lib;
+  volatile float lg = p.learning_rate * p.wd_global;  // base.h:189,192
+  d.dg = 1.0f - lg;
+  d.regfree = p.num_regfree_global;
+  d.base_score = p.base_score;
+  volatile float lrfb = p.learning_rate * p.scale_lr_ufeedback;  // base.h:513
+  d.lr_fb = lrfb;
+  volatile float lf = lrfb * p.wd_ufeedback;  // base.h:515
+  d.dfb = 1.0f - lf;
+  d.dfb_skip = is_one_host(d.dfb);
+  volatile float lfb = lrfb * p.wd_ufeedback_bias;  // base.h:518
+  d.dfbb = 1.0f - lfb;
+}
+
+// ---- kernel dispatch ---------------------------------------------------------
+struct Geometry {
+  int lanes, vec;
+};
+int pick_geometry(svdgpu *h, Geometry &g) {
+  const int chunks = h->dm.pitch / 4;
+  int lanes = h->lanes_opt;
+  if (lanes == 0) {
+    lanes = 4;
+    while (lanes < chunks && lanes < 32) lanes <<= 1;
+  }
+  if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+    return fail(h, "option lanes must be 0, 4, 8, 16 or 32");
+  int vec = (chunks + lanes - 1) / lanes;
+  if (vec <= 1) vec = 1;
+  else if (vec <= 2) vec = 2;
+  else if (vec <= 4) vec = 4;
+  else return fail(h, "num_factor %d needs more than 4 float4 chunks per lane with %d lanes (max k = %d)",
+                   h->shape.num_factor, lanes, lanes * 16);
+  g.lanes = lanes;
+  g.vec = vec;
+  return 0;
+}
+
+// Calls F<LANES,VEC>::run(args...) for the supported geometries.
+template <template <int, int> class F, typename... A>
+int dispatch_geometry(svdgpu *h, const Geometry &g, A... a) {
+#define GEO(L, V) \
+  if (g.lanes == L && g.vec == V) return F<L, V>::run(h, a...);
+  GEO(4, 1) GEO(8, 1) GEO(16, 1) GEO(32, 1) GEO(32, 2) GEO(32, 4) GEO(8, 2) GEO(16, 2)
+#undef GEO
+  return fail(h, "no kernel instantiated for lanes=%d vec=%d", g.lanes, g.vec);
+}
+
+template <typename K>
+int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid) {
+  int per_sm = 0;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (h->ctas_per_sm > 0) per_sm = std::min(per_sm, h->ctas_per_sm);
+  long long gmax = (long long)per_sm * h->num_sm;
+  *grid = (int)std::max(1LL, std::min(gmax, work_items));
+  return 0;
+}
+
+template <int L, int V>
+struct LaunchStream {
+  static int run(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
+    const long long ntile = ((long long)(r1 - r0) + HW_TILE - 1) / HW_TILE;
+    int grid = 1;
+#define GO(ED, TR)                                                                           \
+  {                                                                                          \
+    auto k = k_stream<L, V, ED, TR>;                                                         \
+    if (grid_for(h, k, HW_THREADS, ntile, &grid)) return 1;                                  \
+    k<<<grid, HW_THREADS, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,       \
+                                          h->scatter_item, pred, h->d_err);                  \
+  }
+    if (train) {
+      if (h->exact_dot) GO(true, true) else GO(false, true)
+    } else {
+      GO(true, false)
+    }
+#undef GO
+    CU(h, cudaGetLastError());
+    h->n_launch++;
+    return 0;
+  }
+};
+
+template <int L, int V>
+struct LaunchExact {
+  static int run(svdgpu *h, const DevCsr &csr, int r0, int r1) {
+    auto k = k_exact<L, V>;
+    int grid = 1;
+    if (grid_for(h, k, EX_WARPS * 32, ((long long)(r1 - r0) + EX_WARPS - 1) / EX_WARPS, &grid)) return 1;
+    CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
+    CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
+    CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
+    k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->d_counter, h->d_err);
+    CU(h, cudaGetLastError());
+    h->n_launch++;
+    return 0;
+  }
+};
+
+template <int L, int V>
+struct LaunchUgroup {
+  static int run(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0, int u1, bool train,
+                 bool ordered, float *pred) {
+    int grid = 1;
+    CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
+#define GO(ED, ORD, TR)                                                                         \
+  {                                                                                             \
+    auto k = k_ugroup<L, V, ED, ORD, TR>;                                                       \
+    const int gpw = ORD ? 1 : 32 / L;                                                           \
+    if (grid_for(h, k, EX_WARPS * 32, ((long long)(u1 - u0) + EX_WARPS * gpw - 1) / (EX_WARPS * gpw), &grid)) \
+      return 1;                                                                                 \
+    k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, ug, u0, u1, h->scatter_user,   \
+                                             h->scatter_item, h->d_counter, pred, h->d_err);    \
+  }
+    if (!train) {
+      GO(true, false, false)
+    } else if (ordered) {
+      CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
+      CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
+      GO(true, true, true)
+    } else {
+      if (h->exact_dot) GO(true, false, true) else GO(false, false, true)
+    }
+#undef GO
+    CU(h, cudaGetLastError());
+    h->n_launch++;
+    return 0;
+  }
+};
+
+// ---- input validation + tickets (ordered mode) --------------------------------
+// ticket[f] = how many earlier feature occurrences (in input order, earlier
+// instances only) touched the same row; the kernel waits for the row's version
+// counter to reach it.  Also the reference's index asserts (base.h:320,327,343).
+int validate_csr(svdgpu *h, int num_row, const int *row_ptr) {
+  if (num_row < 0) return fail(h, "num_row < 0");
+  for (long long i = 0; i < 3LL * num_row; ++i)
+    if (row_ptr[i + 1] < row_ptr[i]) return fail(h, "row_ptr must be non-decreasing");
+  return 0;
+}
+
+int make_tickets(svdgpu *h, int r0, int r1, const int *row_ptr, const unsigned *index,
+                 unsigned *ticket /* indexed from row_ptr[3*r0] */) {
+  const int base = row_ptr[3LL * r0];
+  const unsigned nu = (unsigned)h->shape.num_user, ni = (unsigned)h->shape.num_item,
+                 ng = (unsigned)h->shape.num_global;
+  unsigned *cu = h->cnt_ui.data() + h->dm.user_off, *ci = h->cnt_ui.data() + h->dm.item_off,
+           *cg = h->cnt_g.data();
+  for (int r = r0; r < r1; ++r) {
+    const int *p = row_ptr + 3LL * r;
+    for (int f = p[0]; f < p[1]; ++f) {
+      if (index[f] >= ng) return fail(h, "global feature index exceed setting");
+      ticket[f - base] = cg[index[f]];
+    }
+    for (int f = p[1]; f < p[2]; ++f) {
+      if (index[f] >= nu) return fail(h, "user feature index exceed bound");
+      ticket[f - base] = cu[index[f]];
+    }
+    for (int f = p[2]; f < p[3]; ++f) {
+      if (index[f] >= ni) return fail(h, "item feature index exceed bound");
+      ticket[f - base] = ci[index[f]];
+    }
+    for (int f = p[0]; f < p[1]; ++f) cg[index[f]]++;
+    for (int f = p[1]; f < p[2]; ++f) cu[index[f]]++;
+    for (int f = p[2]; f < p[3]; ++f) ci[index[f]]++;
+  }
+  return 0;
+}
+
+void reset_ticket_counters(svdgpu *h) {
+  h->cnt_ui.assign(std::max<size_t>(h->rows, 1), 0u);
+  h->cnt_g.assign((size_t)std::max(h->shape.num_global, 1), 0u);
+}
+
+int check_ready(svdgpu *h) {
+  if (!h) return 1;
+  if (!h->hp_set) return fail(h, "svdgpu_set_hparams has not been called");
+  if (h->hp.reg_method != 0)
+    return fail(h, "reg_method=%d is not supported on the GPU path (only 0: L2 decay)", h->hp.reg_method);
+  if (h->hp.reg_global != 0)
+    return fail(h, "reg_global=%d is not supported on the GPU path (only 0: L2 decay)", h->hp.reg_global);
+  return 0;
+}
+
+Slot &next_slot(svdgpu *h) {
+  Slot &s = h->slot[h->cur_slot];
+  h->cur_slot ^= 1;
+  if (s.used) cudaEventSynchronize(s.done);
+  return s;
+}
+int slot_done(svdgpu *h, Slot &s) {
+  CU(h, cudaEventRecord(s.done, h->stream));
+  s.used = true;
+  return 0;
+}
+
+// units = maximal runs DEFAULT | START (MIDDLE)* END
+int build_units(svdgpu *h, int num_block, const int *blk_tag, std::vector<int> &unit_off) {
+  unit_off.clear();
+  unit_off.push_back(0);
+  bool open = false;
+  for (int b = 0; b < num_block; ++b) {
+    const int tag = blk_tag ? blk_tag[b] : 0;
+    if (tag == 0) {
+      if (open) return fail(h, "DEFAULT block inside a START..END run");
+      unit_off.push_back(b + 1);
+    } else if (tag == 1) {
+      if (open) return fail(h, "START block inside a START..END run");
+      open = true;
+    } else if (tag == 2) {
+      if (!open) return fail(h, "END block without START");
+      open = false;
+      unit_off.push_back(b + 1);
+    } else if (tag == 3) {
+      if (!open) return fail(h, "MIDDLE block without START");
+    } else {
+      return fail(h, "unknown extend_tag %d", tag);
+    }
+  }
+  if (open) return fail(h, "START..END run not closed inside the call");
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+const char *svdgpu_last_error(const svdgpu_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
+  if (!out || !shape) return fail(nullptr, "svdgpu_create: null argument");
+  *out = nullptr;
+  if (shape->num_user < 0 || shape->num_item < 0 || shape->num_global < 0 || shape->num_ufeedback < 0 ||
+      shape->num_factor <= 0)
+    return fail(nullptr, "svdgpu_create: bad shape");
+  switch (shape->active_type) {
+    case 0: case 1: case 2: case 3: case 5: case 6: case 7: break;
+    default: return fail(nullptr, "unkown active type");
+  }
+  if (shape->format_type != 0 && shape->format_type != 1)
+    return fail(nullptr, "svdgpu_create: format_type must be 0 (random order) or 1 (user group)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, "svdgpu_create: no CUDA device (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, "svdgpu_create: device %d out of range", device);
+  svdgpu *h = new svdgpu();
+  h->shape = *shape;
+  h->device = device;
+#define CUC(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      fail(nullptr, "%s failed: %s", #call, cudaGetErrorString(e_));                     \
+      svdgpu_destroy(h);                                                                 \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+  CUC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, device));
+  h->num_sm = prop.multiProcessorCount;
+  CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CUC(cudaEventCreate(&h->ev0));
+  CUC(cudaEventCreate(&h->ev1));
+  CUC(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming));
+
+  DevModel &m = h->dm;
+  memset(&m, 0, sizeof(m));
+  m.k = shape->num_factor;
+  m.pitch = ((shape->num_factor + 3) >> 2) << 2;  // sse.h:26-27: 16-byte row pitch
+  m.num_user = shape->num_user;
+  m.num_item = shape->num_item;
+  m.num_global = shape->num_global;
+  m.num_ufeedback = shape->format_type == 1 ? shape->num_ufeedback : 0;
+  m.user_off = m.num_ufeedback;                  // model.h:513
+  m.item_off = m.user_off + shape->num_user;     // model.h:533-534
+  m.no_user_bias = shape->no_user_bias;
+  m.active_type = shape->active_type;
+  h->rows = (size_t)m.item_off + (size_t)shape->num_item;
+  const size_t wbytes = std::max<size_t>(h->rows, 1) * m.pitch * sizeof(float);
+  CUC(cudaMalloc(&m.W, wbytes));
+  CUC(cudaMemset(m.W, 0, wbytes));
+  CUC(cudaMalloc(&m.bias, std::max<size_t>(h->rows, 1) * sizeof(float)));
+  CUC(cudaMemset(m.bias, 0, std::max<size_t>(h->rows, 1) * sizeof(float)));
+  CUC(cudaMalloc(&m.g_bias, (size_t)std::max(shape->num_global, 1) * sizeof(float)));
+  CUC(cudaMemset(m.g_bias, 0, (size_t)std::max(shape->num_global, 1) * sizeof(float)));
+  CUC(cudaMalloc(&m.ver_ui, std::max<size_t>(h->rows, 1) * sizeof(unsigned)));
+  CUC(cudaMalloc(&m.ver_g, (size_t)std::max(shape->num_global, 1) * sizeof(unsigned)));
+  CUC(cudaMalloc(&h->d_err, sizeof(int)));
+  CUC(cudaMemset(h->d_err, 0, sizeof(int)));
+  CUC(cudaMalloc(&h->d_counter, sizeof(unsigned)));
+#undef CUC
+  Geometry g;
+  if (pick_geometry(h, g)) {
+    g_create_error = h->err;
+    svdgpu_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+void svdgpu_destroy(svdgpu_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->dm.W);
+  cudaFree(h->dm.bias);
+  cudaFree(h->dm.g_bias);
+  cudaFree(h->dm.ver_ui);
+  cudaFree(h->dm.ver_g);
+  cudaFree(h->d_err);
+  cudaFree(h->d_counter);
+  cudaFree(h->d_snap);
+  cudaFree(h->d_delta);
+  for (int i = 0; i < 2; ++i) {
+    Slot &s = h->slot[i];
+    HostBuf *hb[] = {&s.h_rp, &s.h_label, &s.h_index, &s.h_value, &s.h_ticket, &s.h_misc, &s.h_fbi, &s.h_fbv, &s.h_fbt};
+    for (HostBuf *b : hb) host_free(*b);
+    DevBuf *db[] = {&s.d_rp, &s.d_label, &s.d_index, &s.d_value, &s.d_ticket, &s.d_misc, &s.d_fbi, &s.d_fbv, &s.d_fbt, &s.d_pred};
+    for (DevBuf *b : db) dev_free(*b);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int svdgpu_set_hparams(svdgpu_t *h, const svdgpu_hparams *hp) {
+  if (!h || !hp) return 1;
+  h->hp = *hp;
+  h->hp_set = true;
+  refresh_hp(h);
+  return 0;
+}
+
+int svdgpu_set_mode(svdgpu_t *h, int mode) {
+  if (!h) return 1;
+  if (mode != SVDGPU_MODE_EXACT && mode != SVDGPU_MODE_HOGWILD) return fail(h, "unknown mode %d", mode);
+  h->mode = mode;
+  return 0;
+}
+
+int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
+  if (!h || !name) return 1;
+  if (!strcmp(name, "scatter_user")) h->scatter_user = v ? SCATTER_RED : SCATTER_STORE;
+  else if (!strcmp(name, "scatter_item")) h->scatter_item = v ? SCATTER_RED : SCATTER_STORE;
+  else if (!strcmp(name, "exact_dot")) h->exact_dot = v ? 1 : 0;
+  else if (!strcmp(name, "lanes")) {
+    const int old = h->lanes_opt;
+    h->lanes_opt = (int)v;
+    Geometry g;
+    if (pick_geometry(h, g)) {
+      h->lanes_opt = old;
+      return 1;
+    }
+  } else if (!strcmp(name, "chunk_rows")) {
+    if (v < 1) return fail(h, "chunk_rows must be >= 1");
+    h->chunk_rows = (int)std::min<long long>(v, 1LL << 28);
+  } else if (!strcmp(name, "ctas_per_sm")) h->ctas_per_sm = (int)v;
+  else return fail(h, "unknown option '%s'", name);
+  return 0;
+}
+
+int svdgpu_set_stream(svdgpu_t *h, void *s) {
+  if (!h) return 1;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return 0;
+}
+
+int svdgpu_upload_model(svdgpu_t *h, const float *ui_bias, const float *W, size_t pitch_floats,
+                        const float *g_bias) {
+  if (!h) return 1;
+  CU(h, cudaSetDevice(h->device));
+  const DevModel &m = h->dm;
+  if (pitch_floats < (size_t)m.k) return fail(h, "upload_model: pitch %zu < num_factor %d", pitch_floats, m.k);
+  if (h->rows) {
+    CU(h, cudaMemsetAsync(m.W, 0, h->rows * m.pitch * sizeof(float), h->stream));
+    CU(h, cudaMemcpy2DAsync(m.W, m.pitch * sizeof(float), W, pitch_floats * sizeof(float),
+                            m.k * sizeof(float), h->rows, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(m.bias, ui_bias, h->rows * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (m.num_global)
+    CU(h, cudaMemcpyAsync(m.g_bias, g_bias, (size_t)m.num_global * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int svdgpu_download_model(svdgpu_t *h, float *ui_bias, float *W, size_t pitch_floats, float *g_bias) {
+  if (!h) return 1;
+  CU(h, cudaSetDevice(h->device));
+  const DevModel &m = h->dm;
+  if (pitch_floats < (size_t)m.k) return fail(h, "download_model: pitch %zu < num_factor %d", pitch_floats, m.k);
+  if (svdgpu_sync(h)) return 1;
+  if (h->rows) {
+    CU(h, cudaMemcpy2DAsync(W, pitch_floats * sizeof(float), m.W, m.pitch * sizeof(float),
+                            m.k * sizeof(float), h->rows, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(ui_bias, m.bias, h->rows * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (m.num_global)
+    CU(h, cudaMemcpyAsync(g_bias, m.g_bias, (size_t)m.num_global * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int svdgpu_sync(svdgpu_t *h) {
+  if (!h) return 1;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  int e = 0;
+  CU(h, cudaMemcpy(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e != 0) {
+    CU(h, cudaMemset(h->d_err, 0, sizeof(int)));
+    switch (e) {  // the reference's assert messages, base.h:320,327,343,530
+      case ERR_GLOBAL_INDEX: return fail(h, "global feature index exceed setting");
+      case ERR_USER_INDEX: return fail(h, "user feature index exceed bound");
+      case ERR_ITEM_INDEX: return fail(h, "item feature index exceed bound");
+      case ERR_FB_INDEX: return fail(h, "ufeedback id exceed bound");
+      default: return fail(h, "device error %d", e);
+    }
+  }
+  return 0;
+}
+
+int svdgpu_timer_start(svdgpu_t *h) {
+  if (!h) return 1;
+  CU(h, cudaEventRecord(h->ev0, h->stream));
+  return 0;
+}
+int svdgpu_timer_stop(svdgpu_t *h, float *ms) {
+  if (!h || !ms) return 1;
+  CU(h, cudaEventRecord(h->ev1, h->stream));
+  CU(h, cudaEventSynchronize(h->ev1));
+  CU(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+
+long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
+  if (!h || !name) return -1;
+  if (!strcmp(name, "kernel_launches")) return h->n_launch;
+  if (!strcmp(name, "instances")) return h->n_inst;
+  if (!strcmp(name, "h2d_bytes")) return h->n_h2d;
+  if (!strcmp(name, "d2h_bytes")) return h->n_d2h;
+  if (!strcmp(name, "num_sm")) return h->num_sm;
+  if (!strcmp(name, "lanes")) {
+    Geometry g;
+    return pick_geometry(const_cast<svdgpu *>(h), g) ? -1 : g.lanes;
+  }
+  return -1;
+}
+
+void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats) {
+  if (!h) return nullptr;
+  if (pitch_floats) *pitch_floats = (size_t)h->dm.pitch;
+  switch (which) {
+    case 0: return h->dm.bias;
+    case 1: return h->dm.W;
+    case 2: return h->dm.g_bias;
+    default: return nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// random-order CSR, host buffers
+// ---------------------------------------------------------------------------
+static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
+                        const unsigned *index, const float *value, float *out, bool train) {
+  if (check_ready(h)) return 1;
+  CU(h, cudaSetDevice(h->device));
+  if (num_row == 0) return 0;
+  if (!row_ptr || !label || (row_ptr[3LL * num_row] > row_ptr[0] && (!index || !value)))
+    return fail(h, "null input array");
+  if (validate_csr(h, num_row, row_ptr)) return 1;
+  Geometry geo;
+  if (pick_geometry(h, geo)) return 1;
+  const bool exact = train && h->mode == SVDGPU_MODE_EXACT;
+  for (int r0 = 0; r0 < num_row; r0 += h->chunk_rows) {
+    const int r1 = (int)std::min<long long>(num_row, (long long)r0 + h->chunk_rows);
+    const int n = r1 - r0;
+    const int v0 = row_ptr[3LL * r0], v1 = row_ptr[3LL * r1];
+    const size_t nv = (size_t)(v1 - v0);
+    Slot &s = next_slot(h);
+    if (h2d(h, s.d_rp, s.h_rp, row_ptr + 3LL * r0, (3 * (size_t)n + 1) * 4)) return 1;
+    if (h2d(h, s.d_label, s.h_label, label + r0, (size_t)n * 4)) return 1;
+    if (h2d(h, s.d_index, s.h_index, index + v0, nv * 4)) return 1;
+    if (h2d(h, s.d_value, s.h_value, value + v0, nv * 4)) return 1;
+    DevCsr csr;
+    csr.row_ptr = (const int *)s.d_rp.p;
+    csr.label = (const float *)s.d_label.p;
+    csr.index = (const unsigned *)s.d_index.p;
+    csr.value = (const float *)s.d_value.p;
+    csr.ticket = nullptr;
+    csr.val_base = v0;
+    if (exact) {
+      if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
+      reset_ticket_counters(h);
+      if (make_tickets(h, r0, r1, row_ptr, index, (unsigned *)s.h_ticket.p)) return 1;
+      if (dev_reserve(h, s.d_ticket, nv * 4)) return 1;
+      if (nv) CU(h, cudaMemcpyAsync(s.d_ticket.p, s.h_ticket.p, nv * 4, cudaMemcpyHostToDevice, h->stream));
+      h->n_h2d += (long long)nv * 4;
+      csr.ticket = (const unsigned *)s.d_ticket.p;
+      // row_ptr on the device is the slice [3*r0, 3*r1]: rows are 0..n there
+      if (dispatch_geometry<LaunchExact>(h, geo, csr, 0, n)) return 1;
+    } else {
+      float *pred = nullptr;
+      if (!train) {
+        if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
+        pred = (float *)s.d_pred.p;
+      }
+      if (dispatch_geometry<LaunchStream>(h, geo, csr, 0, n, train, pred)) return 1;
+      if (!train) {
+        CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        h->n_d2h += (long long)n * 4;
+      }
+    }
+    if (slot_done(h, s)) return 1;
+    h->n_inst += n;
+  }
+  // host arrays are borrowed for the call only: wait until the copies have read them
+  CU(h, cudaEventRecord(h->ev_copy, h->stream));
+  CU(h, cudaEventSynchronize(h->ev_copy));
+  return 0;
+}
+
+int svdgpu_update_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
+                      const unsigned *index, const float *value) {
+  return run_csr_host(h, num_row, row_ptr, label, index, value, nullptr, true);
+}
+
+int svdgpu_predict_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
+                       const unsigned *index, const float *value, float *out) {
+  if (h && num_row > 0 && !out) return fail(h, "predict: null output");
+  if (run_csr_host(h, num_row, row_ptr, label, index, value, out, false)) return 1;
+  return svdgpu_sync(h);
+}
+
+// ---------------------------------------------------------------------------
+// user-grouped input, host buffers
+// ---------------------------------------------------------------------------
+static int fb_tickets(svdgpu *h, const std::vector<int> &unit_off, int u0, int u1, const int *blk_row_off,
+                      const int *blk_fb_off, const unsigned *fb_index, const int *row_ptr,
+                      const unsigned *index, unsigned *fb_ticket, int fb_base, unsigned *ticket,
+                      int row0) {
+  // sequential order: unit gather (holds its feedback rows) -> rows -> scatter
+  unsigned *cf = h->cnt_ui.data();  // feedback rows are rows [0,num_ufeedback) of the slab
+  for (int u = u0; u < u1; ++u) {
+    const int b0 = unit_off[u], b1 = unit_off[u + 1];
+    const int f0 = blk_fb_off[b0], f1 = blk_fb_off[b0 + 1];
+    for (int f = f0; f < f1; ++f) {
+      if (fb_index[f] >= (unsigned)h->dm.num_ufeedback) return fail(h, "ufeedback id exceed bound");
+      fb_ticket[f - fb_base] = cf[fb_index[f]];
+    }
+    if (make_tickets(h, blk_row_off[b0], blk_row_off[b1], row_ptr, index,
+                     ticket + (row_ptr[3LL * blk_row_off[b0]] - row_ptr[3LL * row0])))
+      return 1;
+    for (int f = f0; f < f1; ++f) cf[fb_index[f]]++;
+  }
+  return 0;
+}
+
+static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                           const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                           const int *row_ptr, const float *label, const unsigned *index,
+                           const float *value, float *out, bool train) {
+  if (check_ready(h)) return 1;
+  CU(h, cudaSetDevice(h->device));
+  if (h->shape.format_type != 1) return fail(h, "user-grouped input needs format_type=1 (trainer was created for random order)");
+  if (num_block == 0) return 0;
+  if (!blk_row_off || !blk_fb_off || !row_ptr || !label) return fail(h, "null input array");
+  const int num_row = blk_row_off[num_block];
+  if (blk_row_off[0] != 0 || blk_fb_off[0] != 0) return fail(h, "block offsets must start at 0");
+  for (int b = 0; b < num_block; ++b)
+    if (blk_row_off[b + 1] < blk_row_off[b] || blk_fb_off[b + 1] < blk_fb_off[b])
+      return fail(h, "block offsets must be non-decreasing");
+  if (validate_csr(h, num_row, row_ptr)) return 1;
+  std::vector<int> unit_off;
+  if (build_units(h, num_block, blk_tag, unit_off)) return 1;
+  const int num_unit = (int)unit_off.size() - 1;
+  Geometry geo;
+  if (pick_geometry(h, geo)) return 1;
+  const bool exact = train && h->mode == SVDGPU_MODE_EXACT;
+
+  int u0 = 0;
+  while (u0 < num_unit) {
+    // chunk = as many whole units as fit in chunk_rows rows (at least one)
+    int u1 = u0 + 1;
+    while (u1 < num_unit && blk_row_off[unit_off[u1 + 1]] - blk_row_off[unit_off[u0]] <= h->chunk_rows) ++u1;
+    const int b0 = unit_off[u0], b1 = unit_off[u1];
+    const int r0 = blk_row_off[b0], r1 = blk_row_off[b1];
+    const int n = r1 - r0;
+    const int v0 = row_ptr[3LL * r0], v1 = row_ptr[3LL * r1];
+    const size_t nv = (size_t)(v1 - v0);
+    const int fb0 = blk_fb_off[b0], fb1 = blk_fb_off[b1];
+    const size_t nfb = (size_t)(fb1 - fb0);
+    Slot &s = next_slot(h);
+    if (h2d(h, s.d_rp, s.h_rp, row_ptr + 3LL * r0, (3 * (size_t)n + 1) * 4)) return 1;
+    if (h2d(h, s.d_label, s.h_label, label + r0, (size_t)n * 4)) return 1;
+    if (h2d(h, s.d_index, s.h_index, index + v0, nv * 4)) return 1;
+    if (h2d(h, s.d_value, s.h_value, value + v0, nv * 4)) return 1;
+    if (h2d(h, s.d_fbi, s.h_fbi, fb_index + fb0, nfb * 4)) return 1;
+    if (h2d(h, s.d_fbv, s.h_fbv, fb_value + fb0, nfb * 4)) return 1;
+    // misc = unit_off (relative blocks) | blk_row_off | blk_fb_off | order
+    const int nu = u1 - u0, nb = b1 - b0;
+    const size_t misc_ints = (size_t)(nu + 1) + 2 * (size_t)(nb + 1) + (size_t)nu;
+    if (host_reserve(h, s.h_misc, misc_ints * 4)) return 1;
+    int *mi = (int *)s.h_misc.p;
+    int *m_unit = mi, *m_row = mi + (nu + 1), *m_fb = m_row + (nb + 1), *m_order = m_fb + (nb + 1);
+    for (int u = 0; u <= nu; ++u) m_unit[u] = unit_off[u0 + u] - b0;
+    for (int b = 0; b <= nb; ++b) {
+      m_row[b] = blk_row_off[b0 + b];
+      m_fb[b] = blk_fb_off[b0 + b];
+    }
+    // longest units first (Hogwild only; the ordered mode keeps input order)
+    std::iota(m_order, m_order + nu, 0);
+    std::stable_sort(m_order, m_order + nu, [&](int a, int b) {
+      return (m_row[m_unit[a + 1]] - m_row[m_unit[a]]) > (m_row[m_unit[b + 1]] - m_row[m_unit[b]]);
+    });
+    if (dev_reserve(h, s.d_misc, misc_ints * 4)) return 1;
+    CU(h, cudaMemcpyAsync(s.d_misc.p, mi, misc_ints * 4, cudaMemcpyHostToDevice, h->stream));
+    h->n_h2d += (long long)misc_ints * 4;
+
+    DevCsr csr;
+    csr.row_ptr = (const int *)s.d_rp.p;
+    csr.label = (const float *)s.d_label.p;
+    csr.index = (const unsigned *)s.d_index.p;
+    csr.value = (const float *)s.d_value.p;
+    csr.ticket = nullptr;
+    csr.val_base = v0;
+    DevUgroup ug;
+    const int *dmi = (const int *)s.d_misc.p;
+    ug.unit_off = dmi;
+    ug.blk_row_off = dmi + (nu + 1);
+    ug.blk_fb_off = ug.blk_row_off + (nb + 1);
+    ug.order = ug.blk_fb_off + (nb + 1);
+    ug.fb_index = (const unsigned *)s.d_fbi.p;
+    ug.fb_value = (const float *)s.d_fbv.p;
+    ug.fb_ticket = nullptr;
+    ug.row_base = r0;
+    ug.fb_base = fb0;
+    if (exact) {
+      if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
+      if (host_reserve(h, s.h_fbt, nfb * 4 + 4)) return 1;
+      reset_ticket_counters(h);
+      if (fb_tickets(h, unit_off, u0, u1, blk_row_off, blk_fb_off, fb_index, row_ptr, index,
+                     (unsigned *)s.h_fbt.p, fb0, (unsigned *)s.h_ticket.p, r0))
+        return 1;
+      if (dev_reserve(h, s.d_ticket, nv * 4)) return 1;
+      if (dev_reserve(h, s.d_fbt, nfb * 4)) return 1;
+      if (nv) CU(h, cudaMemcpyAsync(s.d_ticket.p, s.h_ticket.p, nv * 4, cudaMemcpyHostToDevice, h->stream));
+      if (nfb) CU(h, cudaMemcpyAsync(s.d_fbt.p, s.h_fbt.p, nfb * 4, cudaMemcpyHostToDevice, h->stream));
+      h->n_h2d += (long long)(nv + nfb) * 4;
+      csr.ticket = (const unsigned *)s.d_ticket.p;
+      ug.fb_ticket = (const unsigned *)s.d_fbt.p;
+    }
+    float *pred = nullptr;
+    if (!train) {
+      if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
+      pred = (float *)s.d_pred.p;
+    }
+    if (dispatch_geometry<LaunchUgroup>(h, geo, csr, ug, 0, nu, train, exact, pred)) return 1;
+    if (!train && n) {
+      CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+      h->n_d2h += (long long)n * 4;
+    }
+    if (slot_done(h, s)) return 1;
+    h->n_inst += n;
+    u0 = u1;
+  }
+  CU(h, cudaEventRecord(h->ev_copy, h->stream));
+  CU(h, cudaEventSynchronize(h->ev_copy));
+  return 0;
+}
+
+int svdgpu_update_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                         const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                         const int *row_ptr, const float *label, const unsigned *index,
+                         const float *value) {
+  return run_ugroup_host(h, num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value, row_ptr,
+                         label, index, value, nullptr, true);
+}
+int svdgpu_predict_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                          const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                          const int *row_ptr, const float *label, const unsigned *index,
+                          const float *value, float *out) {
+  if (h && num_block > 0 && !out) return fail(h, "predict: null output");
+  if (run_ugroup_host(h, num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value, row_ptr,
+                      label, index, value, out, false))
+    return 1;
+  return svdgpu_sync(h);
+}
+
+// ---------------------------------------------------------------------------
+// resident batches
+// ---------------------------------------------------------------------------
+static int upload_plain(svdgpu *h, DevBuf &d, const void *src, size_t bytes) {
+  if (dev_reserve(h, d, bytes)) return 1;
+  if (bytes) {
+    CU(h, cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->n_h2d += (long long)bytes;
+  }
+  return 0;
+}
+
+int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const int *row_ptr,
+                        const float *label, const unsigned *index, const float *value) {
+  if (!h || !out) return 1;
+  *out = nullptr;
+  CU(h, cudaSetDevice(h->device));
+  if (num_row < 0 || !row_ptr || (num_row > 0 && !label)) return fail(h, "batch_create: bad arguments");
+  if (validate_csr(h, num_row, row_ptr)) return 1;
+  if (row_ptr[0] != 0) return fail(h, "batch_create: row_ptr[0] must be 0");
+  svdgpu_batch *b = new svdgpu_batch();
+  b->num_row = num_row;
+  b->num_val = row_ptr[3LL * num_row];
+  const size_t nv = (size_t)b->num_val;
+  int rc = 0;
+  rc |= upload_plain(h, b->d_rp, row_ptr, (3 * (size_t)num_row + 1) * 4);
+  rc |= upload_plain(h, b->d_label, label, (size_t)num_row * 4);
+  rc |= upload_plain(h, b->d_index, index, nv * 4);
+  rc |= upload_plain(h, b->d_value, value, nv * 4);
+  if (!rc && h->mode == SVDGPU_MODE_EXACT && h->shape.format_type == 0) {
+    std::vector<unsigned> tk(nv + 1);
+    reset_ticket_counters(h);
+    rc |= make_tickets(h, 0, num_row, row_ptr, index, tk.data());
+    if (!rc) rc |= upload_plain(h, b->d_ticket, tk.data(), nv * 4);
+    if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
+    b->has_ticket = !rc;
+  }
+  if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
+  if (rc) {
+    svdgpu_batch_destroy(h, b);
+    return 1;
+  }
+  *out = b;
+  return 0;
+}
+
+int svdgpu_batch_set_ugroup(svdgpu_t *h, svdgpu_batch_t *b, int num_block, const int *blk_row_off,
+                            const int *blk_fb_off, const int *blk_tag, const unsigned *fb_index,
+                            const float *fb_value) {
+  if (!h || !b) return 1;
+  CU(h, cudaSetDevice(h->device));
+  if (h->shape.format_type != 1) return fail(h, "user-grouped input needs format_type=1");
+  if (num_block < 0 || !blk_row_off || !blk_fb_off) return fail(h, "batch_set_ugroup: bad arguments");
+  if (blk_row_off[0] != 0 || blk_fb_off[0] != 0 || blk_row_off[num_block] != b->num_row)
+    return fail(h, "batch_set_ugroup: block offsets must cover the batch rows");
+  if (build_units(h, num_block, blk_tag, b->unit_off)) return 1;
+  b->num_block = num_block;
+  b->num_unit = (int)b->unit_off.size() - 1;
+  const size_t nfb = (size_t)blk_fb_off[num_block];
+  std::vector<int> order(b->num_unit);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    return (blk_row_off[b->unit_off[x + 1]] - blk_row_off[b->unit_off[x]]) >
+           (blk_row_off[b->unit_off[y + 1]] - blk_row_off[b->unit_off[y]]);
+  });
+  int rc = 0;
+  rc |= upload_plain(h, b->d_unit_off, b->unit_off.data(), b->unit_off.size() * 4);
+  rc |= upload_plain(h, b->d_blk_row_off, blk_row_off, ((size_t)num_block + 1) * 4);
+  rc |= upload_plain(h, b->d_blk_fb_off, blk_fb_off, ((size_t)num_block + 1) * 4);
+  rc |= upload_plain(h, b->d_fbi, fb_index, nfb * 4);
+  rc |= upload_plain(h, b->d_fbv, fb_value, nfb * 4);
+  rc |= upload_plain(h, b->d_order, order.data(), order.size() * 4);
+  if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
+  if (rc) return fail(h, "batch_set_ugroup: upload failed");
+  b->ugroup = true;
+  return 0;
+}
+
+static DevCsr batch_csr(const svdgpu_batch *b) {
+  DevCsr c;
+  c.row_ptr = (const int *)b->d_rp.p;
+  c.label = (const float *)b->d_label.p;
+  c.index = (const unsigned *)b->d_index.p;
+  c.value = (const float *)b->d_value.p;
+  c.ticket = b->has_ticket ? (const unsigned *)b->d_ticket.p : nullptr;
+  c.val_base = 0;
+  return c;
+}
+static DevUgroup batch_ug(const svdgpu_batch *b) {
+  DevUgroup u;
+  u.unit_off = (const int *)b->d_unit_off.p;
+  u.blk_row_off = (const int *)b->d_blk_row_off.p;
+  u.blk_fb_off = (const int *)b->d_blk_fb_off.p;
+  u.fb_index = (const unsigned *)b->d_fbi.p;
+  u.fb_value = (const float *)b->d_fbv.p;
+  u.fb_ticket = nullptr;
+  u.order = (const int *)b->d_order.p;
+  u.row_base = 0;
+  u.fb_base = 0;
+  return u;
+}
+
+int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
+  if (check_ready(h)) return 1;
+  if (!b) return fail(h, "null batch");
+  CU(h, cudaSetDevice(h->device));
+  Geometry geo;
+  if (pick_geometry(h, geo)) return 1;
+  if (b->ugroup) {
+    if (begin < 0 || end > b->num_unit || begin > end) return fail(h, "batch_update: unit range out of bounds");
+    if (begin == end) return 0;
+    if (h->mode == SVDGPU_MODE_EXACT)
+      return fail(h, "ordered mode on a resident user-grouped batch is not supported; use svdgpu_update_ugroup");
+    // the LPT order array covers the whole batch: partial ranges run in input order
+    DevUgroup ug = batch_ug(b);
+    if (begin != 0 || end != b->num_unit) ug.order = nullptr;
+    if (dispatch_geometry<LaunchUgroup>(h, geo, batch_csr(b), ug, begin, end, true, false, (float *)nullptr)) return 1;
+    h->n_inst += b->num_row;
+    return 0;
+  }
+  if (begin < 0 || end > b->num_row || begin > end) return fail(h, "batch_update: row range out of bounds");
+  if (begin == end) return 0;
+  if (h->mode == SVDGPU_MODE_EXACT) {
+    if (!b->has_ticket) return fail(h, "batch was created in hogwild mode: no tickets for the ordered mode");
+    if (begin != 0 || end != b->num_row)
+      return fail(h, "ordered mode needs the whole resident batch (tickets are per batch)");
+    if (dispatch_geometry<LaunchExact>(h, geo, batch_csr(b), begin, end)) return 1;
+  } else {
+    if (dispatch_geometry<LaunchStream>(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
+  }
+  h->n_inst += end - begin;
+  return 0;
+}
+
+int svdgpu_batch_predict(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float *out_host) {
+  if (check_ready(h)) return 1;
+  if (!b) return fail(h, "null batch");
+  CU(h, cudaSetDevice(h->device));
+  Geometry geo;
+  if (pick_geometry(h, geo)) return 1;
+  if (dev_reserve(h, b->d_pred, (size_t)std::max(b->num_row, 1) * 4)) return 1;
+  float *pred = (float *)b->d_pred.p;
+  int r0 = begin, r1 = end;
+  if (b->ugroup) {
+    if (begin < 0 || end > b->num_unit || begin > end) return fail(h, "batch_predict: unit range out of bounds");
+    if (begin == end) return 0;
+    DevUgroup ug = batch_ug(b);
+    ug.order = nullptr;
+    if (dispatch_geometry<LaunchUgroup>(h, geo, batch_csr(b), ug, begin, end, false, false, pred)) return 1;
+    // rows covered by the unit range (host copy of the offsets is not kept: copy all rows)
+    r0 = 0;
+    r1 = b->num_row;
+  } else {
+    if (begin < 0 || end > b->num_row || begin > end) return fail(h, "batch_predict: row range out of bounds");
+    if (begin == end) return 0;
+    if (dispatch_geometry<LaunchStream>(h, geo, batch_csr(b), begin, end, false, pred + begin)) return 1;
+  }
+  if (out_host) {
+    CU(h, cudaMemcpyAsync(out_host, pred + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, h->stream));
+    h->n_d2h += (long long)(r1 - r0) * 4;
+    return svdgpu_sync(h);
+  }
+  return 0;
+}
+
+void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b) {
+  if (!b) return;
+  if (h) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+  }
+  DevBuf *db[] = {&b->d_rp, &b->d_label, &b->d_index, &b->d_value, &b->d_ticket, &b->d_pred,
+                  &b->d_unit_off, &b->d_blk_row_off, &b->d_blk_fb_off, &b->d_fbi, &b->d_fbv, &b->d_fbt, &b->d_order};
+  for (DevBuf *d : db) dev_free(*d);
+  delete b;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU exchange of the replicated slabs
+// ---------------------------------------------------------------------------
+static int ensure_plan(svdgpu *h) {
+  if (h->d_snap) return 0;
+  const DevModel &m = h->dm;
+  DeltaPlan &p = h->plan;
+  p.nseg = 0;
+  long long off = 0;
+  auto add = [&](float *cur, long long n) {
+    if (n <= 0) return;
+    p.seg[p.nseg].cur = cur;
+    p.seg[p.nseg].n = n;
+    p.seg[p.nseg].off = off;
+    off += (n + 3) & ~3LL;
+    p.nseg++;
+  };
+  add(m.W + (size_t)m.item_off * m.pitch, (long long)m.num_item * m.pitch);  // W_item
+  add(m.bias + m.item_off, m.num_item);                                      // i_bias
+  add(m.g_bias, m.num_global);                                               // g_bias
+  add(m.W, (long long)m.num_ufeedback * m.pitch);                            // W_ufeedback
+  add(m.bias, m.num_ufeedback);                                              // ufeedback_bias
+  p.total = off;
+  CU(h, cudaMalloc(&h->d_snap, std::max<long long>(off, 4) * sizeof(float)));
+  CU(h, cudaMalloc(&h->d_delta, std::max<long long>(off, 4) * sizeof(float)));
+  CU(h, cudaMemsetAsync(h->d_delta, 0, std::max<long long>(off, 4) * sizeof(float), h->stream));
+  return 0;
+}
+static int run_delta(svdgpu *h, int mode, float scale) {
+  if (ensure_plan(h)) return 1;
+  k_delta<<<h->num_sm * 4, 256, 0, h->stream>>>(h->plan, h->d_snap, h->d_delta, mode, scale);
+  CU(h, cudaGetLastError());
+  h->n_launch++;
+  return 0;
+}
+int svdgpu_items_snapshot(svdgpu_t *h) {
+  if (!h) return 1;
+  CU(h, cudaSetDevice(h->device));
+  return run_delta(h, 0, 0.f);
+}
+int svdgpu_items_pack_delta(svdgpu_t *h, void **dev_ptr, size_t *num_floats) {
+  if (!h || !dev_ptr || !num_floats) return 1;
+  CU(h, cudaSetDevice(h->device));
+  if (!h->d_snap) return fail(h, "items_pack_delta: call svdgpu_items_snapshot first");
+  if (run_delta(h, 1, 0.f)) return 1;
+  *dev_ptr = h->d_delta;
+  *num_floats = (size_t)h->plan.total;
+  return 0;
+}
+int svdgpu_items_apply_delta(svdgpu_t *h, float scale) {
+  if (!h) return 1;
+  CU(h, cudaSetDevice(h->device));
+  if (!h->d_snap) return fail(h, "items_apply_delta: call svdgpu_items_snapshot first");
+  return run_delta(h, 2, scale);
+}
+
+}  // extern "C"

@@ -1,0 +1,576 @@
+// svdgpu_device.cuh -- device code of the SGD hot path (sm_100a).
+//
+// One lane GROUP (LANES = pitch/4 lanes, <= 32, each lane owning VEC float4
+// chunks of a factor row) executes one training instance: the whole of
+// SVDFeature::update_inner (base.h:456-462) -- bias gather, row gather, dot,
+// loss gradient, scatter update, L2 decay -- with the rows held in registers
+// (the reference makes ~7 passes over k floats through memory).
+//
+// Arithmetic contract (identical to oracle/svdf_oracle.c and the reference):
+//   fp32 rows, separate multiply and add (compiled with --fmad=false), fp64
+//   accumulation of base+bias+dot in the reference's order, the |s-1|<=1e-6
+//   "scalar is one" shortcut, and -- when EXACT_DOT -- the reference's 4-lane
+//   strided dot order (sse.h:289-317).  File:line citations use the short names
+//   base.h = solvers/base-solver/apex_svd_base.h, model.h = apex_svd_model.h,
+//   sse.h = apex-tensor/apex_tensor_sse.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svdk {
+
+// ---------------------------------------------------------------------------
+// parameter blocks passed by value to every kernel
+// ---------------------------------------------------------------------------
+struct DevModel {
+  float *W;           // [rows][pitch]   feedback rows | user rows | item rows
+  float *bias;        // [rows]
+  float *g_bias;      // [num_global]
+  unsigned *ver_ui;   // [rows]          row version counters (exact mode)
+  unsigned *ver_g;    // [num_global]
+  int pitch;          // floats per row, multiple of 4
+  int k;              // num_factor
+  int num_user, num_item, num_global, num_ufeedback;
+  int user_off, item_off;  // first user / item row in the slab
+  int no_user_bias;
+  int active_type;
+};
+
+struct DevHP {
+  float lr;
+  float du, di;       // 1 - lr*wd_user, 1 - lr*wd_item              (base.h:216,257)
+  float dub, dib;     // 1 - lr*wd_user_bias, 1 - lr*wd_item_bias    (base.h:248,282)
+  float dg;           // 1 - lr*wd_global                            (base.h:192)
+  int du_skip, di_skip;  // row decay skipped: |d-1| <= 1e-6         (sse.h:231-242)
+  unsigned regfree;   // num_regfree_global                          (base.h:190)
+  float base_score;
+  float lr_fb;        // lr * scale_lr_ufeedback                     (base.h:513)
+  float dfb;          // 1 - lr_fb*wd_ufeedback                      (base.h:515)
+  int dfb_skip;
+  float dfbb;         // 1 - lr_fb*wd_ufeedback_bias                 (base.h:518)
+};
+
+// A CSR batch in HBM.  index/value/ticket hold the elements [val_base, ...) of
+// the caller's arrays, so a row_ptr value p addresses index[p - val_base].
+struct DevCsr {
+  const int *row_ptr;
+  const float *label;
+  const unsigned *index;
+  const float *value;
+  const unsigned *ticket;  // exact mode: row version each feature waits for
+  int val_base;
+};
+
+enum { SCATTER_STORE = 0, SCATTER_RED = 1 };
+enum { ERR_NONE = 0, ERR_GLOBAL_INDEX = 1, ERR_USER_INDEX = 2, ERR_ITEM_INDEX = 3, ERR_FB_INDEX = 4 };
+
+// ---------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldcg4(const float *p) {
+  return __ldcg(reinterpret_cast<const float4 *>(p));
+}
+__device__ __forceinline__ void stcg4(float *p, float4 v) {
+  __stcg(reinterpret_cast<float4 *>(p), v);
+}
+// vector reduction into global memory (sm_90+): one 16-byte atomic add per lane
+__device__ __forceinline__ void red4(float *p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void red1(float *p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared (TMA unit, SASS UBLKCP), completion
+// signalled on an mbarrier.  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// scalar pieces of the reference
+// ---------------------------------------------------------------------------
+// sse.h:231-242: a row scaled by s with |s-1| <= 1e-6 is not multiplied
+__device__ __forceinline__ bool scalar_is_one(float s) {
+  return !(fabs((double)__fsub_rn(s, 1.0f)) > 1e-6);
+}
+// expf: the reference calls glibc expf (<= 0.502 ulp).  exp() in fp64 rounded to
+// fp32 is correctly rounded in all but ~1e-8 of cases, i.e. equal to glibc's in
+// all but the ~0.2% of arguments where glibc itself is 1 ulp off.
+__device__ __forceinline__ float ref_expf(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float sigmoidf_ref(float x) {
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, ref_expf(-x)));
+}
+// model.h:112-123
+__device__ __forceinline__ float map_active(float sum, int type) {
+  return (type == 1 || type == 2) ? sigmoidf_ref(sum) : sum;
+}
+__device__ __forceinline__ float smooth_hinge_grad(float z) {  // model.h:90-94
+  if (z > 1.0f) return 0.0f;
+  if (z < 0.0f) return 1.0f;
+  return __fsub_rn(1.0f, z);
+}
+// model.h:132-156
+__device__ __forceinline__ float cal_grad(float r, float pred, int type) {
+  switch (type) {
+    case 1: return __fmul_rn(__fmul_rn(__fsub_rn(r, pred), pred), __fsub_rn(1.0f, pred));
+    case 3:
+    case 7: return __fsub_rn(r, sigmoidf_ref(pred));
+    case 5:
+      if (r > 0.5f) return smooth_hinge_grad(__fsub_rn(pred, 0.5f));
+      return -smooth_hinge_grad(__fsub_rn(0.5f, pred));
+    case 6:
+      if (r > 0.5f) return pred > 1.0f ? 0.0f : __fsub_rn(r, pred);
+      return pred < 0.0f ? 0.0f : __fsub_rn(r, pred);
+    default: return __fsub_rn(r, pred);  // 0 and 2
+  }
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// t + w*s with the reference's shortcut (row_add_scaled in the oracle)
+__device__ __forceinline__ float4 f4_add_scaled(float4 t, float4 w, float s, bool one) {
+  if (one) {
+    t.x = __fadd_rn(t.x, w.x); t.y = __fadd_rn(t.y, w.y);
+    t.z = __fadd_rn(t.z, w.z); t.w = __fadd_rn(t.w, w.w);
+  } else {
+    t.x = __fadd_rn(t.x, __fmul_rn(w.x, s)); t.y = __fadd_rn(t.y, __fmul_rn(w.y, s));
+    t.z = __fadd_rn(t.z, __fmul_rn(w.z, s)); t.w = __fadd_rn(t.w, __fmul_rn(w.w, s));
+  }
+  return t;
+}
+__device__ __forceinline__ float4 f4_scale(float4 t, float s) {
+  t.x = __fmul_rn(t.x, s); t.y = __fmul_rn(t.y, s);
+  t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s);
+  return t;
+}
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) {
+  return make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z),
+                     __fsub_rn(a.w, b.w));
+}
+
+// ---------------------------------------------------------------------------
+// the lane group
+// ---------------------------------------------------------------------------
+template <int LANES, int VEC>
+struct Group {
+  static constexpr int NCH = LANES * VEC;     // float4 chunks per row covered
+  static constexpr int DOT_STRIDE = NCH + 4;  // padded component stride in smem
+  static constexpr int DOT_FLOATS = 4 * DOT_STRIDE;
+
+  int gl;          // lane within the group
+  unsigned gmask;  // lanes of this group
+  float *dot_s;    // DOT_FLOATS floats of shared scratch private to the group
+
+  __device__ __forceinline__ void gsync() const { __syncwarp(gmask); }
+  template <typename T>
+  __device__ __forceinline__ T bcast(T v, int src) const {
+    return __shfl_sync(gmask, v, src, LANES);
+  }
+
+  // ---- row access ------------------------------------------------------
+  __device__ __forceinline__ void load_row(const DevModel &m, size_t row, float4 (&w)[VEC]) const {
+    const float *p = m.W + row * (size_t)m.pitch;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = gl + v * LANES;
+      w[v] = (4 * c < m.pitch) ? ldcg4(p + 4 * c) : f4_zero();
+    }
+  }
+  __device__ __forceinline__ void store_row(const DevModel &m, size_t row, const float4 (&w)[VEC]) const {
+    float *p = m.W + row * (size_t)m.pitch;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = gl + v * LANES;
+      if (4 * c < m.pitch) stcg4(p + 4 * c, w[v]);
+    }
+  }
+  __device__ __forceinline__ void red_row(const DevModel &m, size_t row, const float4 (&nw)[VEC],
+                                          const float4 (&old)[VEC]) const {
+    float *p = m.W + row * (size_t)m.pitch;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = gl + v * LANES;
+      if (4 * c < m.pitch) red4(p + 4 * c, f4_sub(nw[v], old[v]));
+    }
+  }
+
+  // ---- dot product -------------------------------------------------------
+  // Reference order (sse.h:289-317): the k/4 SSE vectors a[4i..4i+3]*b[4i..4i+3]
+  // are accumulated in order i = 0,1,2,... into one 4-wide accumulator, which is
+  // then folded (l0+l2)+(l1+l3); k%4 tail elements are added serially after.
+  // Chunk (v,lane) of this group IS SSE vector i = v*LANES + lane, so component c
+  // of every chunk goes to dot_s[c*DOT_STRIDE + i] and lane c adds its NCH values
+  // in order.
+  template <bool EXACT>
+  __device__ __forceinline__ float dot(const DevModel &m, const float4 (&a)[VEC],
+                                       const float4 (&b)[VEC]) const {
+    if (EXACT) {
+      const int nfull = m.k >> 2;  // full SSE vectors
+      gsync();
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int i = gl + v * LANES;
+        dot_s[0 * DOT_STRIDE + i] = __fmul_rn(a[v].x, b[v].x);
+        dot_s[1 * DOT_STRIDE + i] = __fmul_rn(a[v].y, b[v].y);
+        dot_s[2 * DOT_STRIDE + i] = __fmul_rn(a[v].z, b[v].z);
+        dot_s[3 * DOT_STRIDE + i] = __fmul_rn(a[v].w, b[v].w);
+      }
+      gsync();
+      float acc = 0.0f;
+      if (gl < 4) {
+        const float *src = dot_s + gl * DOT_STRIDE;
+        int i = 0;
+        for (; i + 4 <= nfull; i += 4) {
+          const float4 q = *reinterpret_cast<const float4 *>(src + i);
+          acc = __fadd_rn(acc, q.x); acc = __fadd_rn(acc, q.y);
+          acc = __fadd_rn(acc, q.z); acc = __fadd_rn(acc, q.w);
+        }
+        for (; i < nfull; ++i) acc = __fadd_rn(acc, src[i]);
+      }
+      const float l0 = bcast(acc, 0), l1 = bcast(acc, 1), l2 = bcast(acc, 2), l3 = bcast(acc, 3);
+      float sum = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
+      const int tail = m.k & 3;  // elements nfull*4 .. k-1 live in chunk nfull
+      for (int t = 0; t < tail; ++t) sum = __fadd_rn(sum, dot_s[t * DOT_STRIDE + nfull]);
+      return sum;
+    } else {
+      float acc = 0.0f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float s = __fadd_rn(__fadd_rn(__fmul_rn(a[v].x, b[v].x), __fmul_rn(a[v].z, b[v].z)),
+                            __fadd_rn(__fmul_rn(a[v].y, b[v].y), __fmul_rn(a[v].w, b[v].w)));
+        acc = __fadd_rn(acc, s);
+      }
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, o, LANES));
+      return acc;
+    }
+  }
+
+  // ---- ordered fp64 sum of val[f]*table[off+idx[f]] over f in [beg,end) -----
+  // base.h:318-322,325-334,340-350: each product is fp32, the running sum fp64,
+  // added in feature order.  Lanes fetch LANES features at a time; the adds are
+  // replayed in order through shuffles so every lane ends with the same sum.
+  __device__ __forceinline__ double bias_sum(double sum, const float *table, int off,
+                                            const unsigned *idx, const float *val, int beg,
+                                            int end) const {
+    for (int base = beg; base < end; base += LANES) {
+      const int f = base + gl;
+      float p = 0.0f;
+      if (f < end) p = __fmul_rn(val[f], __ldcg(table + off + idx[f]));
+      const int cnt = min(LANES, end - base);
+      for (int j = 0; j < cnt; ++j) sum = __dadd_rn(sum, (double)bcast(p, j));
+    }
+    return sum;
+  }
+
+  // any duplicate index inside [beg,end)?  (sequential semantics matter then)
+  __device__ __forceinline__ bool has_dup(const unsigned *idx, int beg, int end) const {
+    const int n = end - beg;
+    if (n <= 1) return false;
+    if (n > LANES) return true;  // conservative: take the unfused path
+    const unsigned mine = (gl < n) ? idx[beg + gl] : 0xffffffffu;
+    bool dup = false;
+    for (int j = 0; j < n - 1; ++j) {
+      const unsigned other = bcast(mine, j);
+      dup |= (gl > j && gl < n && other == mine);
+    }
+    return __any_sync(gmask, dup);
+  }
+
+  // scalar table RMW over a feature segment: x += lrerr*val (if upd), x *= decay (if dec)
+  // parallel over lanes when the segment has no duplicate index, else serial on lane 0.
+  __device__ __forceinline__ void scalar_seg(float *table, int off, const unsigned *idx,
+                                             const float *val, int beg, int end, float lrerr,
+                                             float decay, bool upd, bool dec, unsigned regfree,
+                                             bool parallel, int scatter) const {
+    if (parallel) {
+      for (int f = beg + gl; f < end; f += LANES) {
+        float *p = table + off + idx[f];
+        const float x0 = __ldcg(p);
+        float x = x0;
+        if (upd) x = __fadd_rn(x, __fmul_rn(lrerr, val[f]));
+        if (dec && idx[f] >= regfree) x = __fmul_rn(x, decay);
+        if (scatter == SCATTER_RED) red1(p, __fsub_rn(x, x0));
+        else __stcg(p, x);
+      }
+    } else {
+      if (gl == 0) {
+        for (int f = beg; f < end; ++f) {
+          float *p = table + off + idx[f];
+          float x = __ldcg(p);
+          if (upd) x = __fadd_rn(x, __fmul_rn(lrerr, val[f]));
+          if (dec && idx[f] >= regfree) x = __fmul_rn(x, decay);
+          __stcg(p, x);
+        }
+      }
+      gsync();
+    }
+  }
+};
+
+// SVD++ per-user state carried across the rows of one block (base.h:486-488)
+template <int VEC>
+struct FbState {
+  float4 fb[VEC];  // tmp_ufeedback (this lane's chunks)
+  float fb_bias;   // tmp_ufeedback_bias
+  float norm;      // norm_ufeedback
+};
+
+// ---------------------------------------------------------------------------
+// one training / prediction instance
+// ---------------------------------------------------------------------------
+// idx/val are addressed with ABSOLUTE row_ptr values (the caller pre-offsets the
+// pointers); rp0..rp3 are the four segment bounds of the row.
+// Returns the prediction (base.h:445-454); when TRAIN also applies the update.
+template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, bool SVDPP>
+__device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, const DevModel &m,
+                                                  const DevHP &hp, int rp0, int rp1, int rp2,
+                                                  int rp3, float label, const unsigned *idx,
+                                                  const float *val, int scatter_user,
+                                                  int scatter_item, FbState<VEC> *fbs,
+                                                  int *err_flag) {
+  // ---- index bounds (base.h:320,327,343: assert_true -> error) -------------
+  {
+    int bad = 0;
+    for (int f = rp0 + g.gl; f < rp3; f += LANES) {
+      const unsigned id = idx[f];
+      if (f < rp1) { if (id >= (unsigned)m.num_global) bad = ERR_GLOBAL_INDEX; }
+      else if (f < rp2) { if (id >= (unsigned)m.num_user) bad = ERR_USER_INDEX; }
+      else { if (id >= (unsigned)m.num_item) bad = ERR_ITEM_INDEX; }
+    }
+    if (__any_sync(g.gmask, bad != 0)) {
+      if (bad) atomicCAS(err_flag, 0, bad);
+      return 0.0f;
+    }
+  }
+
+  // ---- calc_bias (base.h:313-353) ------------------------------------------
+  double bsum = 0.0;
+  bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
+  if (!m.no_user_bias) {
+    bsum = g.bias_sum(bsum, m.bias, m.user_off, idx, val, rp1, rp2);
+    if (SVDPP) bsum = __dadd_rn(bsum, (double)fbs->fb_bias);  // get_bias_svdpp, base.h:509-511
+  }
+  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, rp2, rp3);
+
+  // ---- prepare_tmp (base.h:354-381) ----------------------------------------
+  float4 tu[VEC], ti[VEC], wu0[VEC], wi0[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    tu[v] = SVDPP ? fbs->fb[v] : f4_zero();  // prepare_svdpp, base.h:430-432 / 506-508
+    ti[v] = f4_zero();
+    wu0[v] = f4_zero();
+    wi0[v] = f4_zero();
+  }
+  for (int f = rp1; f < rp2; ++f) {
+    float4 w[VEC];
+    g.load_row(m, (size_t)m.user_off + idx[f], w);
+    const float s = val[f];
+    const bool one = scalar_is_one(s);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      tu[v] = f4_add_scaled(tu[v], w[v], s, one);
+      if (f == rp1) wu0[v] = w[v];
+    }
+  }
+  for (int f = rp2; f < rp3; ++f) {
+    float4 w[VEC];
+    g.load_row(m, (size_t)m.item_off + idx[f], w);
+    const float s = val[f];
+    const bool one = scalar_is_one(s);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      ti[v] = f4_add_scaled(ti[v], w[v], s, one);
+      if (f == rp2) wi0[v] = w[v];
+    }
+  }
+
+  // ---- pred (base.h:445-454) ------------------------------------------------
+  const float d = g.template dot<EXACT_DOT>(m, tu, ti);
+  double sum = __dadd_rn((double)hp.base_score, bsum);
+  sum = __dadd_rn(sum, (double)d);
+  const float pred = map_active((float)sum, m.active_type);
+  if (!TRAIN) return pred;
+
+  // ---- update_no_decay + regularize(after) (base.h:383-427, 286-311) --------
+  const float err = cal_grad(label, pred, m.active_type);
+  const float lrerr = __fmul_rn(hp.lr, err);
+
+  const bool dup_g = g.has_dup(idx, rp0, rp1);
+  const bool dup_u = g.has_dup(idx, rp1, rp2);
+  const bool dup_i = g.has_dup(idx, rp2, rp3);
+  const bool fused = !(dup_u || dup_i);
+
+  // globals: g_bias[gid] += lr*err*gval ; later g_bias[gid] *= 1-lr*wd_global
+  if (rp1 > rp0)
+    g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, lrerr, hp.dg, true, !dup_g, hp.regfree, !dup_g,
+                 dup_g ? SCATTER_STORE : scatter_item);
+
+  if (fused) {
+    // every touched row appears once: update and decay in one register pass
+    for (int f = rp1; f < rp2; ++f) {
+      const size_t row = (size_t)m.user_off + idx[f];
+      float4 w[VEC], nw[VEC];
+      if (f == rp1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v] = wu0[v];
+      } else {
+        g.load_row(m, row, w);
+      }
+      const float sc = __fmul_rn(lrerr, val[f]);
+      const bool one = scalar_is_one(sc);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        nw[v] = f4_add_scaled(w[v], ti[v], sc, one);
+        if (!hp.du_skip) nw[v] = f4_scale(nw[v], hp.du);
+      }
+      if (scatter_user == SCATTER_RED) g.red_row(m, row, nw, w);
+      else g.store_row(m, row, nw);
+    }
+    if (!m.no_user_bias)
+      g.scalar_seg(m.bias, m.user_off, idx, val, rp1, rp2, lrerr, hp.dub, true, true, 0u, true,
+                   scatter_user);
+    for (int f = rp2; f < rp3; ++f) {
+      const size_t row = (size_t)m.item_off + idx[f];
+      float4 w[VEC], nw[VEC];
+      if (f == rp2) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v] = wi0[v];
+      } else {
+        g.load_row(m, row, w);
+      }
+      const float sc = __fmul_rn(lrerr, val[f]);
+      const bool one = scalar_is_one(sc);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        nw[v] = f4_add_scaled(w[v], tu[v], sc, one);
+        if (!hp.di_skip) nw[v] = f4_scale(nw[v], hp.di);
+      }
+      if (scatter_item == SCATTER_RED) g.red_row(m, row, nw, w);
+      else g.store_row(m, row, nw);
+    }
+    g.scalar_seg(m.bias, m.item_off, idx, val, rp2, rp3, lrerr, hp.dib, true, true, 0u, true,
+                 scatter_item);
+  } else {
+    // a row index repeats inside this instance: replay the reference's passes
+    // through memory in its order (all updates, then all decays).
+    for (int f = rp1; f < rp2; ++f) {
+      const size_t row = (size_t)m.user_off + idx[f];
+      float4 w[VEC];
+      g.load_row(m, row, w);
+      const float sc = __fmul_rn(lrerr, val[f]);
+      const bool one = scalar_is_one(sc);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = f4_add_scaled(w[v], ti[v], sc, one);
+      g.store_row(m, row, w);
+    }
+    if (!m.no_user_bias)
+      g.scalar_seg(m.bias, m.user_off, idx, val, rp1, rp2, lrerr, 0.f, true, false, 0u, false,
+                   SCATTER_STORE);
+    for (int f = rp2; f < rp3; ++f) {
+      const size_t row = (size_t)m.item_off + idx[f];
+      float4 w[VEC];
+      g.load_row(m, row, w);
+      const float sc = __fmul_rn(lrerr, val[f]);
+      const bool one = scalar_is_one(sc);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = f4_add_scaled(w[v], tu[v], sc, one);
+      g.store_row(m, row, w);
+    }
+    g.scalar_seg(m.bias, m.item_off, idx, val, rp2, rp3, lrerr, 0.f, true, false, 0u, false,
+                 SCATTER_STORE);
+  }
+
+  // ---- update_svdpp (base.h:512-520) -----------------------------------------
+  if (SVDPP) {
+    const float s = __fmul_rn(__fmul_rn(hp.lr_fb, err), fbs->norm);
+    const bool one = scalar_is_one(s);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      fbs->fb[v] = f4_add_scaled(fbs->fb[v], ti[v], s, one);
+      if (!hp.dfb_skip) fbs->fb[v] = f4_scale(fbs->fb[v], hp.dfb);
+    }
+    if (!m.no_user_bias) {
+      fbs->fb_bias = __fadd_rn(fbs->fb_bias, s);
+      fbs->fb_bias = __fmul_rn(fbs->fb_bias, hp.dfbb);
+    }
+  }
+
+  // ---- regularize(after) for the unfused cases --------------------------------
+  if (dup_g) g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, 0.f, hp.dg, false, true, hp.regfree, false,
+                          SCATTER_STORE);
+  if (!fused) {
+    for (int f = rp1; f < rp2; ++f) {
+      const size_t row = (size_t)m.user_off + idx[f];
+      if (!hp.du_skip) {
+        float4 w[VEC];
+        g.load_row(m, row, w);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v] = f4_scale(w[v], hp.du);
+        g.store_row(m, row, w);
+      }
+      if (!m.no_user_bias)
+        g.scalar_seg(m.bias, m.user_off, idx, val, f, f + 1, 0.f, hp.dub, false, true, 0u, false,
+                     SCATTER_STORE);
+    }
+    for (int f = rp2; f < rp3; ++f) {
+      const size_t row = (size_t)m.item_off + idx[f];
+      if (!hp.di_skip) {
+        float4 w[VEC];
+        g.load_row(m, row, w);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v] = f4_scale(w[v], hp.di);
+        g.store_row(m, row, w);
+      }
+      g.scalar_seg(m.bias, m.item_off, idx, val, f, f + 1, 0.f, hp.dib, false, true, 0u, false,
+                   SCATTER_STORE);
+    }
+  }
+  return pred;
+}
+
+}  // namespace svdk

@@ -1,0 +1,57 @@
+"""Pin the C restatement (oracle/liboracle.so) bit-for-bit against the UNMODIFIED
+reference compiled into oracle/_ref (built from /root/reference by oracle/Makefile).
+CPU only."""
+import numpy as np
+import pytest
+
+import _cases
+from _oracle import COracle, RefTrainer, have_ref, build_oracle
+
+build_oracle()
+CASES = _cases.cases()
+
+
+def _train(cls, fmt, act, params, data, kind, tmp, rounds=2):
+    t = cls(fmt, act, 0, params)
+    t.init(10)
+    for r in range(rounds):
+        t.set_round(r)
+        (t.update_csr if kind == "csr" else t.update_ugroup)(data)
+    pred = (t.predict_csr if kind == "csr" else t.predict_ugroup)(data)
+    return t.model_bytes(tmp), pred
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_compiled_reference(name, tmp_path):
+    fmt, act, params, data, kind = CASES[name]
+    mo, po = _train(COracle, fmt, act, params, data, kind, tmp_path)
+    mr, pr = _train(RefTrainer, fmt, act, params, data, kind, tmp_path)
+    assert mo == mr, "model bytes differ"
+    assert np.array_equal(po, pr), "predictions differ"
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("reg_method,reg_global", [(1, 1), (2, 0), (3, 0)])
+def test_oracle_other_regularisers(reg_method, reg_global, tmp_path):
+    fmt, act, params, data, kind = CASES["general_k13_dups"]
+    params = dict(params, reg_method=reg_method, reg_global=reg_global)
+    mo, po = _train(COracle, fmt, act, params, data, kind, tmp_path)
+    mr, pr = _train(RefTrainer, fmt, act, params, data, kind, tmp_path)
+    assert mo == mr and np.array_equal(po, pr)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_oracle_loads_reference_model_file(tmp_path):
+    fmt, act, params, data, kind = CASES["svdpp_k16"]
+    r = RefTrainer(fmt, act, 0, params)
+    r.init(10)
+    r.update_ugroup(data)
+    path = str(tmp_path / "ref.model")
+    r.save_model(path)
+    o = COracle(fmt, act, 0, params)
+    o.load_model(path)
+    o.init_trainer = None
+    o.lib.svdo_init_trainer(o.h)
+    assert np.array_equal(o.predict_ugroup(data), r.predict_ugroup(data))
+    assert o.model_bytes(tmp_path) == open(path, "rb").read()
