@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- SGD training instances/sec of the SVDFeature hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Netflix-shaped basicMF, 480k users x 18k items,
+k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch of
+--rows-per-step ratings (default 5M, i.e. 20 steps = one epoch).  Prints ONE JSON line.
+
+  value      whole-job instances/s with the batches resident in HBM (device-timed, CUDA
+             events on the launch stream, max over ranks)
+  e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D of every
+             step's batch and a D2H read of a probe prediction inside the timed region
+  roofline   dominant kernel (k_stream): algorithmic bytes (1072 B/instance)
+             / measured launch time vs the measured HBM copy peak
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) timed on the host, 1 thread,
+             on a bounded prefix of the same workload
+
+N>1 (torchrun): users are hash-partitioned (user mod N) so user rows are private to a
+rank; item rows/bias are replicated and their deltas are all-reduced over NCCL every
+step.  Weak scaling: every rank processes --rows-per-step rows per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_USER, NUM_ITEM, K = 480000, 18000, 64
+TOTAL_ROWS = 100_000_000
+HP = dict(learning_rate=0.005, wd_user=0.004, wd_item=0.004, base_score=3.6)
+BYTES_PER_INSTANCE = 8 * K * 2 + 8 * 2 + 16 + 8 * 2  # = 1072, SURVEY.md section 8(d)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------
+# synthetic Netflix-shaped ratings
+# ---------------------------------------------------------------------------
+def marginals(seed=10):
+    from svdfeature_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    ucdf = synth.lognormal_cdf(NUM_USER, 1.0, rng)
+    icdf = synth.zipf_cdf(NUM_ITEM, 1.0, 70.0)
+    iperm = rng.permutation(NUM_ITEM)
+    return ucdf, icdf, iperm
+
+
+def gen_rows_torch(n, seed, device, rank=0, world=1):
+    """(row_ptr, label, index, value) as torch tensors on `device`; users of rank r are
+    the ids congruent to r mod world (hash partition)."""
+    import torch
+
+    ucdf, icdf, iperm = marginals()
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    ucdf_t = torch.from_numpy(ucdf).to(device)
+    icdf_t = torch.from_numpy(icdf).to(device)
+    iperm_t = torch.from_numpy(iperm.astype(np.int64)).to(device)
+    u = torch.searchsorted(ucdf_t, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=NUM_USER - 1)
+    if world > 1:
+        u = (u // world) * world + rank
+        u = torch.where(u >= NUM_USER, u - world, u)
+    it = iperm_t[torch.searchsorted(icdf_t, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=NUM_ITEM - 1)]
+    lab = torch.clamp(torch.round(3.6 + 1.1 * torch.randn(n, generator=g, device=device)), 1, 5).float()
+    index = torch.stack([u, it], 1).reshape(-1).to(torch.int32)  # ids < 2^31: same bits as uint32
+    value = torch.ones(2 * n, device=device, dtype=torch.float32)
+    base = torch.arange(n, device=device, dtype=torch.int64) * 2
+    row_ptr = torch.empty(3 * n + 1, device=device, dtype=torch.int32)
+    row_ptr[0:3 * n:3] = base.int()
+    row_ptr[1:3 * n:3] = base.int()
+    row_ptr[2:3 * n:3] = (base + 1).int()
+    row_ptr[3 * n] = 2 * n
+    return row_ptr, lab, index, value
+
+
+def gen_rows_numpy(n, seed):
+    from svdfeature_b200 import synth
+
+    return synth.basic_mf(n, NUM_USER, NUM_ITEM, seed=seed, zipf_s=1.0, zipf_q=70.0, user_sigma=1.0)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline (the ONLY place bench.py touches oracle/)
+# ---------------------------------------------------------------------------
+def ref_trainer():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import COracle, RefTrainer, have_ref
+
+    params = dict(num_user=NUM_USER, num_item=NUM_ITEM, num_factor=K, **HP)
+    if have_ref():
+        t, kind = RefTrainer(0, 0, 0, params), "reference"
+    else:
+        t, kind = COracle(0, 0, 0, params), "port"
+    t.init(10)
+    return t, kind
+
+
+def time_cpu(rows_total, rows_per_call):
+    """instances/s of the reference's single-threaded update() loop on host cores."""
+    t, kind = ref_trainer()
+    data = gen_rows_numpy(rows_total, seed=10)
+    warm = min(rows_per_call, rows_total)
+    t.update_csr((data[0][:3 * warm + 1], data[1][:warm], data[2], data[3]))  # touch the model once
+    t0 = time.perf_counter()
+    done = 0
+    for r0 in range(0, rows_total, rows_per_call):
+        r1 = min(rows_total, r0 + rows_per_call)
+        t.update_csr((data[0][3 * r0:3 * r1 + 1], data[1][r0:r1], data[2], data[3]))
+        done += r1 - r0
+    dt = time.perf_counter() - t0
+    return done / dt, kind, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.ref_rows_per_step
+    t, kind = ref_trainer()
+    nchunk = 4
+    data = gen_rows_numpy(rows * nchunk, seed=10)
+
+    def step(s):
+        c = s % nchunk
+        r0, r1 = c * rows, (c + 1) * rows
+        t.update_csr((data[0][3 * r0:3 * r1 + 1], data[1][r0:r1], data[2], data[3]))
+
+    for s in range(args.warmup):
+        step(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(args.warmup + s)
+    dt = time.perf_counter() - t0
+    v = rows * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "sgd_training_instances_per_sec", "value": v, "unit": "instances/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(rows, "cpu"),
+        "cpu_baseline": {"value": v, "unit": "instances/s", "cores": 1, "kind": kind,
+                         "sample": "%d steps x %d ratings of the 480kx18k k=64 stream, ISVDTrainer::update loop, 1 thread of %d host cores"
+                                   % (args.steps, rows, os.cpu_count())},
+        "e2e": {"value": v, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(rows_per_step, mode):
+    return {"workload": "configs[1] Netflix-shaped basicMF: 480k users x 18k items, k=64, 100M synthetic ratings "
+                        "(users lognormal, items Zipf-Mandelbrot s=1 q=70, shuffled)",
+            "rows_per_step": rows_per_step, "mode": mode, "l2_policy": "inputs larger than L2 (batch+model > 126 MB per step)",
+            "hparams": HP}
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="hogwild", choices=["hogwild", "exact"])
+    ap.add_argument("--rows-per-step", type=int, default=5_000_000)
+    ap.add_argument("--ref-rows-per-step", type=int, default=2_000_000)
+    ap.add_argument("--cpu-rows", type=int, default=20_000_000, help="rows of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to svdgpu_set_option")
+    ap.add_argument("--allreduce-every", type=int, default=1)
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    from svdfeature_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    rows = args.rows_per_step
+    nchunk = max(1, min(TOTAL_ROWS // rows, args.steps + args.warmup))
+    total = rows * nchunk
+    t_setup = time.perf_counter()
+    rp, lab, idx, val = gen_rows_torch(total, seed=10 + rank, device=dev, rank=rank, world=world)
+    # the C ABI takes host pointers: stage the stream in pinned host memory once
+    host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (rp, lab, idx, val)]
+    torch.cuda.synchronize()
+    del rp, lab, idx, val
+    torch.cuda.empty_cache()
+    h_rp, h_lab, h_idx, h_val = host
+
+    g = api.SvdGpu(NUM_USER, NUM_ITEM, K, device=local)
+    g.set_hparams(**HP)
+    g.set_mode(api.MODE_HOGWILD if args.mode == "hogwild" else api.MODE_EXACT)
+    for o in args.opt:
+        name, v = o.split("=")
+        g.set_option(name, int(v))
+    stream = torch.cuda.Stream(device=dev)
+    g.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(10)
+    rows_model = NUM_USER + NUM_ITEM
+    W0 = (rng.standard_normal((rows_model, K)) * 0.01).astype(np.float32)  # N(0, 0.01^2) as rand_init
+    g.upload(np.zeros(rows_model, np.float32), W0, np.zeros(1, np.float32))
+
+    # ---- resident batches (value) ----
+    if args.mode == "exact":
+        batches = []
+        for c in range(nchunk):
+            sl = (h_rp[3 * c * rows:3 * (c + 1) * rows + 1] - int(h_rp[3 * c * rows])).contiguous().numpy()
+            batches.append(g.batch_create((sl, h_lab[c * rows:(c + 1) * rows].numpy(),
+                                           h_idx[2 * c * rows:2 * (c + 1) * rows].numpy(),
+                                           h_val[2 * c * rows:2 * (c + 1) * rows].numpy())))
+
+        def step(s):
+            g.batch_update(batches[s % nchunk])
+    else:
+        batch = g.batch_create((h_rp, h_lab, h_idx, h_val))
+
+        def step(s):
+            c = s % nchunk
+            g.batch_update(batch, c * rows, (c + 1) * rows)
+    log("[rank %d] setup %.1fs: %d rows in %d chunks" % (rank, time.perf_counter() - t_setup, total, nchunk))
+
+    use_allreduce = world > 1
+
+    def exchange():
+        if not use_allreduce:
+            return
+        p, n = g.items_pack_delta()
+        t = _as_tensor(p, n, dev)
+        dist.all_reduce(t)
+        g.items_apply_delta(1.0)
+
+    with torch.cuda.stream(stream):
+        if use_allreduce:
+            g.items_snapshot()
+        for s in range(args.warmup):
+            step(s)
+            if (s + 1) % args.allreduce_every == 0:
+                exchange()
+        g.sync()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        l0 = g.counter("kernel_launches")
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for s in range(args.steps):
+            step(args.warmup + s)
+            if (s + 1) % args.allreduce_every == 0:
+                exchange()
+        ev1.record(stream)
+        g.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        clk = clocks.stop() if rank == 0 else None
+        ms = ev0.elapsed_time(ev1)
+        launches = g.counter("kernel_launches") - l0
+
+        # kernel-only duration of k_stream launches (roofline numerator), same stream
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s in range(args.steps):
+            kev[s][0].record(stream)
+            step(args.warmup + s)
+            kev[s][1].record(stream)
+        g.sync()
+        kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    if dist:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * rows * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e and args.mode == "hogwild":
+        probe_n = 1024
+        probe = (h_rp[:3 * probe_n + 1].numpy(), h_lab[:probe_n].numpy(), h_idx.numpy(), h_val.numpy())
+
+        def e2e_step(s):
+            c = s % nchunk
+            r0, r1 = c * rows, (c + 1) * rows
+            g.update_csr((h_rp[3 * r0:3 * r1 + 1], h_lab[r0:r1], h_idx, h_val))
+            if use_allreduce:
+                with torch.cuda.stream(stream):
+                    exchange()
+            return g.predict_csr(probe)  # D2H read of the step's result (probe predictions)
+
+        g.set_option("chunk_rows", 1 << 20)
+        for s in range(max(1, args.warmup)):
+            e2e_step(s)
+        g.sync()
+        if dist:
+            dist.barrier()
+        h0, d0 = g.counter("h2d_bytes"), g.counter("d2h_bytes")
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            e2e_step(args.warmup + s)
+        g.sync()
+        dt = time.perf_counter() - t0
+        if dist:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": world * rows * args.steps / dt, "unit": "instances/s",
+               "h2d_bytes_per_step": (g.counter("h2d_bytes") - h0) // args.steps,
+               "d2h_bytes_per_step": (g.counter("d2h_bytes") - d0) // args.steps,
+               "timing": "wall clock around K calls of svdgpu_update_csr (pinned host buffers) + probe predict"}
+
+    if dist:
+        dist.barrier()
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = rows * BYTES_PER_INSTANCE / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_stream" if args.mode == "hogwild" else "k_exact",
+                "algorithmic_bytes_per_instance": BYTES_PER_INSTANCE, "launch_ms": kms, "peak_source": peak_src,
+                "frac_of_nominal_8000": achieved / 8000.0}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, kind, dt = time_cpu(args.cpu_rows, 1_000_000)
+        cpu = {"value": v, "unit": "instances/s", "cores": 1, "kind": kind,
+               "sample": "first %d ratings of the same stream, ISVDTrainer::update loop, %.1f s, 1 thread of %d host cores"
+                         % (args.cpu_rows, dt, os.cpu_count())}
+
+    line = {
+        "metric": "sgd_training_instances_per_sec", "value": value, "unit": "instances/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(rows, args.mode), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    if world > 1:
+        line["config"]["parallelism"] = "user-hash shards x%d, item-side delta allreduce (NCCL) every %d step(s)" % (
+            world, args.allreduce_every)
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+class _DevArray:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def _as_tensor(ptr, n, dev):
+    import torch
+
+    return torch.as_tensor(_DevArray(ptr, n), device=dev)
+
+
+if __name__ == "__main__":
+    main()
