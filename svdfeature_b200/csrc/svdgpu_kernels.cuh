@@ -350,11 +350,12 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
   const unsigned *tk = ORDERED ? csr.ticket - csr.val_base : nullptr;
   const int *row_ptr = csr.row_ptr - 3 * (long long)ug.row_base;
   const float *label = csr.label - ug.row_base;
+  if (ORDERED) scatter_user = scatter_item = SCATTER_STORE;  // ordered results must not depend on atomics
 
   for (;;) {
     unsigned n = 0;
     if (g.gl == 0) n = atomicAdd(counter, 1u);
-    n = g.bcast(n, gw * LANES);
+    n = g.bcast(n, 0);
     if ((long long)unit_begin + n >= unit_end) break;
     int u = unit_begin + (int)n;
     if (!ORDERED && ug.order) u = ug.order[u];

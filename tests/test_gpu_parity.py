@@ -142,12 +142,27 @@ def test_hogwild_statistical_parity(native):
     assert abs(rmse_o - rmse_g) <= 1e-3, (rmse_o, rmse_g)
 
 
-def test_hogwild_ugroup_close(native):
-    o, g, data, kind = _pair(native, "svdpp_k16", native.MODE_HOGWILD)
-    _step(o, data, kind)
-    _step(g, data, kind)
-    po, pg = _pred(o, data, kind), _pred(g, data, kind)
+def test_hogwild_ugroup_statistical_parity(native):
+    """SVD++ blocks, Hogwild across users (rows of a user stay sequential)."""
+    nu, ni, n = 20000, 2000, 300000
+    params = dict(num_user=nu, num_item=ni, num_factor=32, learning_rate=0.005, wd_user=0.004, wd_item=0.004,
+                  base_score=3.6, num_ufeedback=ni, wd_ufeedback=0.004, ufeedback_init_sigma=0.01)
+    train = synth.user_grouped(n, nu, ni, avg_fb=30, seed=31)
+    o = COracle(1, 0, 0, params)
+    o.init(10)
+    g = native.SvdGpu(**_cases.shape_of(params, 1, 0))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_mode(native.MODE_HOGWILD)
+    g.upload(*[a.copy() for a in o.arrays()])
+    for _ in range(2):
+        o.update_ugroup(train)
+        g.update_ugroup(train)
+    po, pg = o.predict_ugroup(train), g.predict_ugroup(train)
+    lab = train[6]
+    rmse_o = float(np.sqrt(np.mean((po - lab) ** 2)))
+    rmse_g = float(np.sqrt(np.mean((pg - lab) ** 2)))
     assert float(np.sqrt(np.mean((po - pg) ** 2))) <= 2e-2
+    assert abs(rmse_o - rmse_g) <= 2e-3, (rmse_o, rmse_g)
 
 
 def test_resident_batch_matches_host_path(native):
