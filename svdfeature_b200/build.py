@@ -40,21 +40,38 @@ def _sources(*names):
     return [os.path.join(CSRC, n) for n in names]
 
 
+GPU_UNITS = ["svdgpu_api.cu", "svdgpu_stream.cu", "svdgpu_ordered.cu"]
+GPU_HEADERS = ["svdgpu_internal.h", "svdgpu_device.cuh"]
+
+
 def build_gpu(force=False, verbose=False):
-    deps = _sources("svdgpu_api.cu", "svdgpu_kernels.cuh", "svdgpu_device.cuh") + [
-        os.path.join(ROOT, "include", "svdgpu.h")]
-    if not force and not _newer(LIB_GPU, deps):
-        return LIB_GPU
-    cmd = [NVCC] + NVCC_FLAGS + ["-o", LIB_GPU, os.path.join(CSRC, "svdgpu_api.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
-        f.write(log)
-    if res.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed for libsvdgpu.so")
-    if verbose:
-        print(log)
+    """nvcc -c every unit in parallel (one process each), then link libsvdgpu.so."""
+    hdrs = _sources(*GPU_HEADERS) + [os.path.join(ROOT, "include", "svdgpu.h")]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs, logs = [], [], []
+    for unit in GPU_UNITS:
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _newer(obj, [src] + hdrs):
+            cmd = [NVCC] + [f for f in NVCC_FLAGS if f not in ("-shared",)] + ["-c", "-o", obj, src]
+            if os.environ.get("SVDGPU_TUNE_BUILD"):  # fewer template instances: quick kernel iteration only
+                cmd.insert(1, "-DSVDGPU_TUNE_BUILD")
+            procs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for unit, p in procs:
+        log, _ = p.communicate()
+        logs.append("==== %s\n%s" % (unit, log))
+        if p.returncode != 0:
+            sys.stderr.write(log)
+            raise RuntimeError("nvcc failed for %s" % unit)
+    if logs:
+        with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+            f.write("\n".join(logs))
+        if verbose:
+            print("\n".join(logs))
+    if procs or not os.path.exists(LIB_GPU):
+        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-o", LIB_GPU] + objs)
     return LIB_GPU
 
 

@@ -2,8 +2,7 @@
 // host<->device staging, ticket computation for the ordered mode and kernel
 // dispatch.  No CPU compute path exists here: every update/predict call ends in
 // a kernel launch or fails.
-#include "../../include/svdgpu.h"
-#include "svdgpu_kernels.cuh"
+#include "svdgpu_internal.h"
 
 #include <algorithm>
 #include <cmath>
@@ -18,23 +17,6 @@ using namespace svdk;
 
 namespace {
 thread_local std::string g_create_error;
-
-struct DevBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-};
-struct HostBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-};
-
-// One staging slot for host-pointer calls: pinned mirrors + device arrays.
-struct Slot {
-  HostBuf h_rp, h_label, h_index, h_value, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
-  DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
-  cudaEvent_t done = nullptr;  // last kernel that read this slot
-  bool used = false;
-};
 }  // namespace
 
 struct svdgpu_batch {
@@ -49,38 +31,11 @@ struct svdgpu_batch {
   std::vector<int> unit_off;  // host copy: block range of each unit
 };
 
-struct svdgpu {
-  svdgpu_shape shape;
-  svdgpu_hparams hp;
-  bool hp_set = false;
-  int device = 0;
-  int num_sm = 0;
-  int mode = SVDGPU_MODE_HOGWILD;
-  int scatter_user = SCATTER_STORE, scatter_item = SCATTER_RED;
-  int exact_dot = 1;
-  int lanes_opt = 0;
-  int chunk_rows = 1 << 20;
-  int ctas_per_sm = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
-  DevModel dm;
-  DevHP dhp;
-  size_t rows = 0;
-  int *d_err = nullptr;
-  unsigned *d_counter = nullptr;
-  Slot slot[2];
-  int cur_slot = 0;
-  // multi-GPU exchange
-  DeltaPlan plan;
-  float *d_snap = nullptr, *d_delta = nullptr;
-  // host scratch for tickets
-  std::vector<unsigned> cnt_ui, cnt_g;
-  std::string err;
-  long long n_launch = 0, n_inst = 0, n_h2d = 0, n_d2h = 0;
-};
-
 namespace {
 
+}  // namespace
+
+namespace svdk {
 int fail(svdgpu *h, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -91,13 +46,9 @@ int fail(svdgpu *h, const char *fmt, ...) {
   else g_create_error = buf;
   return 1;
 }
+}  // namespace svdk
 
-#define CU(h, call)                                                                     \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess)                                                              \
-      return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
+namespace {
 
 int dev_reserve(svdgpu *h, DevBuf &b, size_t bytes) {
   bytes += 64;  // bulk copies read 16-byte windows past the last element
@@ -186,16 +137,15 @@ void refresh_hp(svdgpu *h) {
   d.dfbb = 1.0f - lfb;
 }
 
-// ---- kernel dispatch ---------------------------------------------------------
-struct Geometry {
-  int lanes, vec;
-};
+// ---- lane geometry -----------------------------------------------------------
+// chunks = pitch/4 float4 per row.  Automatic choice: two chunks per lane (measured
+// fastest on B200: more instances per warp, same bytes in flight), at least 4 lanes.
 int pick_geometry(svdgpu *h, Geometry &g) {
   const int chunks = h->dm.pitch / 4;
   int lanes = h->lanes_opt;
   if (lanes == 0) {
     lanes = 4;
-    while (lanes < chunks && lanes < 32) lanes <<= 1;
+    while (lanes * 2 < chunks && lanes < 32) lanes <<= 1;
   }
   if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
     return fail(h, "option lanes must be 0, 4, 8, 16 or 32");
@@ -209,98 +159,6 @@ int pick_geometry(svdgpu *h, Geometry &g) {
   g.vec = vec;
   return 0;
 }
-
-// Calls F<LANES,VEC>::run(args...) for the supported geometries.
-template <template <int, int> class F, typename... A>
-int dispatch_geometry(svdgpu *h, const Geometry &g, A... a) {
-#define GEO(L, V) \
-  if (g.lanes == L && g.vec == V) return F<L, V>::run(h, a...);
-  GEO(4, 1) GEO(8, 1) GEO(16, 1) GEO(32, 1) GEO(32, 2) GEO(32, 4) GEO(8, 2) GEO(16, 2)
-#undef GEO
-  return fail(h, "no kernel instantiated for lanes=%d vec=%d", g.lanes, g.vec);
-}
-
-template <typename K>
-int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid) {
-  int per_sm = 0;
-  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
-  if (per_sm < 1) per_sm = 1;
-  if (h->ctas_per_sm > 0) per_sm = std::min(per_sm, h->ctas_per_sm);
-  long long gmax = (long long)per_sm * h->num_sm;
-  *grid = (int)std::max(1LL, std::min(gmax, work_items));
-  return 0;
-}
-
-template <int L, int V>
-struct LaunchStream {
-  static int run(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
-    const long long ntile = ((long long)(r1 - r0) + HW_TILE - 1) / HW_TILE;
-    int grid = 1;
-#define GO(ED, TR)                                                                           \
-  {                                                                                          \
-    auto k = k_stream<L, V, ED, TR>;                                                         \
-    if (grid_for(h, k, HW_THREADS, ntile, &grid)) return 1;                                  \
-    k<<<grid, HW_THREADS, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,       \
-                                          h->scatter_item, pred, h->d_err);                  \
-  }
-    if (train) {
-      if (h->exact_dot) GO(true, true) else GO(false, true)
-    } else {
-      GO(true, false)
-    }
-#undef GO
-    CU(h, cudaGetLastError());
-    h->n_launch++;
-    return 0;
-  }
-};
-
-template <int L, int V>
-struct LaunchExact {
-  static int run(svdgpu *h, const DevCsr &csr, int r0, int r1) {
-    auto k = k_exact<L, V>;
-    int grid = 1;
-    if (grid_for(h, k, EX_WARPS * 32, ((long long)(r1 - r0) + EX_WARPS - 1) / EX_WARPS, &grid)) return 1;
-    CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
-    CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
-    CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
-    k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->d_counter, h->d_err);
-    CU(h, cudaGetLastError());
-    h->n_launch++;
-    return 0;
-  }
-};
-
-template <int L, int V>
-struct LaunchUgroup {
-  static int run(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0, int u1, bool train,
-                 bool ordered, float *pred) {
-    int grid = 1;
-    CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
-#define GO(ED, ORD, TR)                                                                         \
-  {                                                                                             \
-    auto k = k_ugroup<L, V, ED, ORD, TR>;                                                       \
-    const int gpw = ORD ? 1 : 32 / L;                                                           \
-    if (grid_for(h, k, EX_WARPS * 32, ((long long)(u1 - u0) + EX_WARPS * gpw - 1) / (EX_WARPS * gpw), &grid)) \
-      return 1;                                                                                 \
-    k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, ug, u0, u1, h->scatter_user,   \
-                                             h->scatter_item, h->d_counter, pred, h->d_err);    \
-  }
-    if (!train) {
-      GO(true, false, false)
-    } else if (ordered) {
-      CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
-      CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
-      GO(true, true, true)
-    } else {
-      if (h->exact_dot) GO(true, false, true) else GO(false, false, true)
-    }
-#undef GO
-    CU(h, cudaGetLastError());
-    h->n_launch++;
-    return 0;
-  }
-};
 
 // ---- input validation + tickets (ordered mode) --------------------------------
 // ticket[f] = how many earlier feature occurrences (in input order, earlier
@@ -366,6 +224,21 @@ int slot_done(svdgpu *h, Slot &s) {
   CU(h, cudaEventRecord(s.done, h->stream));
   s.used = true;
   return 0;
+}
+
+// Hogwild unit order: input order (it is the SGD order the caller shuffled), except that
+// the rare very long users (> 8x the mean, >= 512 rows) start first so that none of them
+// becomes the tail of the launch.
+template <typename SizeOf>
+void unit_order(int nu, SizeOf size_of, int *order) {
+  long long total = 0;
+  for (int u = 0; u < nu; ++u) total += size_of(u);
+  const long long thr = std::max<long long>(512, nu > 0 ? 8 * total / nu : 0);
+  int n = 0;
+  for (int u = 0; u < nu; ++u)
+    if (size_of(u) > thr) order[n++] = u;
+  for (int u = 0; u < nu; ++u)
+    if (!(size_of(u) > thr)) order[n++] = u;
 }
 
 // units = maximal runs DEFAULT | START (MIDDLE)* END
@@ -683,14 +556,14 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
       h->n_h2d += (long long)nv * 4;
       csr.ticket = (const unsigned *)s.d_ticket.p;
       // row_ptr on the device is the slice [3*r0, 3*r1]: rows are 0..n there
-      if (dispatch_geometry<LaunchExact>(h, geo, csr, 0, n)) return 1;
+      if (launch_exact(h, geo, csr, 0, n)) return 1;
     } else {
       float *pred = nullptr;
       if (!train) {
         if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
         pred = (float *)s.d_pred.p;
       }
-      if (dispatch_geometry<LaunchStream>(h, geo, csr, 0, n, train, pred)) return 1;
+      if (launch_stream(h, geo, csr, 0, n, train, pred)) return 1;
       if (!train) {
         CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
         h->n_d2h += (long long)n * 4;
@@ -793,11 +666,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
       m_row[b] = blk_row_off[b0 + b];
       m_fb[b] = blk_fb_off[b0 + b];
     }
-    // longest units first (Hogwild only; the ordered mode keeps input order)
-    std::iota(m_order, m_order + nu, 0);
-    std::stable_sort(m_order, m_order + nu, [&](int a, int b) {
-      return (m_row[m_unit[a + 1]] - m_row[m_unit[a]]) > (m_row[m_unit[b + 1]] - m_row[m_unit[b]]);
-    });
+    unit_order(nu, [&](int u) { return (long long)(m_row[m_unit[u + 1]] - m_row[m_unit[u]]); }, m_order);
     if (dev_reserve(h, s.d_misc, misc_ints * 4)) return 1;
     CU(h, cudaMemcpyAsync(s.d_misc.p, mi, misc_ints * 4, cudaMemcpyHostToDevice, h->stream));
     h->n_h2d += (long long)misc_ints * 4;
@@ -840,7 +709,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
       if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
       pred = (float *)s.d_pred.p;
     }
-    if (dispatch_geometry<LaunchUgroup>(h, geo, csr, ug, 0, nu, train, exact, pred)) return 1;
+    if (launch_ugroup(h, geo, csr, ug, 0, nu, train, exact, pred)) return 1;
     if (!train && n) {
       CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
       h->n_d2h += (long long)n * 4;
@@ -931,12 +800,10 @@ int svdgpu_batch_set_ugroup(svdgpu_t *h, svdgpu_batch_t *b, int num_block, const
   b->num_block = num_block;
   b->num_unit = (int)b->unit_off.size() - 1;
   const size_t nfb = (size_t)blk_fb_off[num_block];
-  std::vector<int> order(b->num_unit);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-    return (blk_row_off[b->unit_off[x + 1]] - blk_row_off[b->unit_off[x]]) >
-           (blk_row_off[b->unit_off[y + 1]] - blk_row_off[b->unit_off[y]]);
-  });
+  std::vector<int> order((size_t)std::max(b->num_unit, 1));
+  unit_order(b->num_unit, [&](int u) {
+    return (long long)(blk_row_off[b->unit_off[u + 1]] - blk_row_off[b->unit_off[u]]);
+  }, order.data());
   int rc = 0;
   rc |= upload_plain(h, b->d_unit_off, b->unit_off.data(), b->unit_off.size() * 4);
   rc |= upload_plain(h, b->d_blk_row_off, blk_row_off, ((size_t)num_block + 1) * 4);
@@ -988,7 +855,7 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
     // the LPT order array covers the whole batch: partial ranges run in input order
     DevUgroup ug = batch_ug(b);
     if (begin != 0 || end != b->num_unit) ug.order = nullptr;
-    if (dispatch_geometry<LaunchUgroup>(h, geo, batch_csr(b), ug, begin, end, true, false, (float *)nullptr)) return 1;
+    if (launch_ugroup(h, geo, batch_csr(b), ug, begin, end, true, false, (float *)nullptr)) return 1;
     h->n_inst += b->num_row;
     return 0;
   }
@@ -998,9 +865,9 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
     if (!b->has_ticket) return fail(h, "batch was created in hogwild mode: no tickets for the ordered mode");
     if (begin != 0 || end != b->num_row)
       return fail(h, "ordered mode needs the whole resident batch (tickets are per batch)");
-    if (dispatch_geometry<LaunchExact>(h, geo, batch_csr(b), begin, end)) return 1;
+    if (launch_exact(h, geo, batch_csr(b), begin, end)) return 1;
   } else {
-    if (dispatch_geometry<LaunchStream>(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
+    if (launch_stream(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
   }
   h->n_inst += end - begin;
   return 0;
@@ -1020,14 +887,14 @@ int svdgpu_batch_predict(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, flo
     if (begin == end) return 0;
     DevUgroup ug = batch_ug(b);
     ug.order = nullptr;
-    if (dispatch_geometry<LaunchUgroup>(h, geo, batch_csr(b), ug, begin, end, false, false, pred)) return 1;
+    if (launch_ugroup(h, geo, batch_csr(b), ug, begin, end, false, false, pred)) return 1;
     // rows covered by the unit range (host copy of the offsets is not kept: copy all rows)
     r0 = 0;
     r1 = b->num_row;
   } else {
     if (begin < 0 || end > b->num_row || begin > end) return fail(h, "batch_predict: row range out of bounds");
     if (begin == end) return 0;
-    if (dispatch_geometry<LaunchStream>(h, geo, batch_csr(b), begin, end, false, pred + begin)) return 1;
+    if (launch_stream(h, geo, batch_csr(b), begin, end, false, pred + begin)) return 1;
   }
   if (out_host) {
     CU(h, cudaMemcpyAsync(out_host, pred + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1079,10 +946,7 @@ static int ensure_plan(svdgpu *h) {
 }
 static int run_delta(svdgpu *h, int mode, float scale) {
   if (ensure_plan(h)) return 1;
-  k_delta<<<h->num_sm * 4, 256, 0, h->stream>>>(h->plan, h->d_snap, h->d_delta, mode, scale);
-  CU(h, cudaGetLastError());
-  h->n_launch++;
-  return 0;
+  return launch_delta(h, mode, scale);
 }
 int svdgpu_items_snapshot(svdgpu_t *h) {
   if (!h) return 1;

@@ -136,7 +136,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // ---------------------------------------------------------------------------
 // sse.h:231-242: a row scaled by s with |s-1| <= 1e-6 is not multiplied
 __device__ __forceinline__ bool scalar_is_one(float s) {
-  return !(fabs((double)__fsub_rn(s, 1.0f)) > 1e-6);
+  // fabs((double)(s-1.0f)) > 1e-6  <=>  fabsf(s-1.0f) > 1e-6f, because (float)1e-6 < 1e-6
+  return !(fabsf(__fsub_rn(s, 1.0f)) > 1e-6f);
 }
 // expf: the reference calls glibc expf (<= 0.502 ulp).  exp() in fp64 rounded to
 // fp32 is correctly rounded in all but ~1e-8 of cases, i.e. equal to glibc's in

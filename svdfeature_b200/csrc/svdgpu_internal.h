@@ -1,0 +1,114 @@
+// svdgpu_internal.h -- handle layout and launcher entry points shared by the
+// translation units of libsvdgpu.so (not part of the public ABI).
+#pragma once
+#include "../../include/svdgpu.h"
+#include "svdgpu_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+struct HostBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+// One staging slot for host-pointer calls: pinned mirrors + device arrays.
+struct Slot {
+  HostBuf h_rp, h_label, h_index, h_value, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
+  DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
+  cudaEvent_t done = nullptr;  // last kernel that read this slot
+  bool used = false;
+};
+
+namespace svdk {
+struct DeltaSeg {
+  float *cur;     // live slab segment
+  long long n;    // floats
+  long long off;  // offset in the packed buffers
+};
+struct DeltaPlan {
+  DeltaSeg seg[5];
+  int nseg;
+  long long total;
+};
+// A "unit" is one user's consecutive blocks: a DEFAULT block, or START..END
+// (apex_svd_data.h:353-371).  unit_off[u]..unit_off[u+1] are its blocks.
+struct DevUgroup {
+  const int *unit_off;     // [num_unit+1] block ranges
+  const int *blk_row_off;  // [num_block+1]
+  const int *blk_fb_off;   // [num_block+1]
+  const unsigned *fb_index;
+  const float *fb_value;
+  const unsigned *fb_ticket;  // ordered mode
+  const int *order;           // hogwild: unit processing order (longest first), may be null
+  int row_base;               // blk_row_off values are absolute rows; csr arrays start at row_base
+  int fb_base;                // blk_fb_off values are absolute; fb arrays start at fb_base
+};
+struct Geometry {
+  int lanes, vec;
+};
+}  // namespace svdk
+
+struct svdgpu {
+  svdgpu_shape shape;
+  svdgpu_hparams hp;
+  bool hp_set = false;
+  int device = 0;
+  int num_sm = 0;
+  int mode = SVDGPU_MODE_HOGWILD;
+  int scatter_user = svdk::SCATTER_RED, scatter_item = svdk::SCATTER_RED;
+  int exact_dot = 0;  // Hogwild default: tree-order dot (the ordered mode always uses the reference order)
+  int lanes_opt = 0;
+  int chunk_rows = 1 << 20;
+  int ctas_per_sm = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+  svdk::DevModel dm;
+  svdk::DevHP dhp;
+  size_t rows = 0;
+  int *d_err = nullptr;
+  unsigned *d_counter = nullptr;
+  Slot slot[2];
+  int cur_slot = 0;
+  // multi-GPU exchange
+  svdk::DeltaPlan plan;
+  float *d_snap = nullptr, *d_delta = nullptr;
+  // host scratch for tickets
+  std::vector<unsigned> cnt_ui, cnt_g;
+  std::string err;
+  long long n_launch = 0, n_inst = 0, n_h2d = 0, n_d2h = 0;
+};
+
+namespace svdk {
+int fail(svdgpu *h, const char *fmt, ...);
+
+#define CU(h, call)                                                                                 \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return svdk::fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename K>
+int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid) {
+  int per_sm = 0;
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (h->ctas_per_sm > 0) per_sm = std::min(per_sm, h->ctas_per_sm);
+  long long gmax = (long long)per_sm * h->num_sm;
+  *grid = (int)std::max(1LL, std::min(gmax, work_items));
+  return 0;
+}
+
+// launchers (one translation unit each, so nvcc runs in parallel)
+int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred);
+int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
+int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
+                  bool train, bool ordered, float *pred);
+int launch_delta(svdgpu *h, int mode, float scale);
+}  // namespace svdk

@@ -1,147 +1,16 @@
-// svdgpu_kernels.cuh -- the __global__ kernels built on svdgpu_device.cuh.
+// svdgpu_ordered.cu -- the kernels that are not the Hogwild stream:
 //
-//   k_stream  : Hogwild training / prediction over a CSR batch.  Persistent CTAs;
-//               a producer warp stages each tile's row_ptr/label and index/value
-//               slices into shared memory with 1-D bulk async copies (TMA,
-//               mbarrier-tracked, double buffered); 8 consumer warps run one lane
-//               group per instance.
 //   k_exact   : ordered data-flow training.  One instance per warp, fetched in
 //               input order; each feature waits until its row's version counter
 //               reaches the feature's ticket, so the result equals the reference's
-//               sequential loop while independent instances run in parallel.
-//   k_ugroup  : user-grouped (SVD++) blocks, one lane group (Hogwild) or one warp
-//               (exact) per user unit: feedback gather, the unit's rows in order,
+//               sequential loop (base.h:456-462) while independent instances overlap.
+//   k_ugroup  : user-grouped (SVD++) input, one lane group (Hogwild) or one warp
+//               (ordered) per user unit: feedback gather, the unit's rows in order,
 //               feedback scatter (base.h:523-582).
-//   k_delta_* : replicated-slab delta pack/apply for the multi-GPU exchange.
-#pragma once
-#include "svdgpu_device.cuh"
+//   k_delta   : replicated-slab snapshot / delta / apply for the multi-GPU exchange.
+#include "svdgpu_internal.h"
 
 namespace svdk {
-
-// ---------------------------------------------------------------------------
-// k_stream
-// ---------------------------------------------------------------------------
-constexpr int HW_TILE = 128;           // instances per tile
-constexpr int HW_STAGES = 2;           // tiles in flight per CTA
-constexpr int HW_CAP = 8 * HW_TILE;    // staged index/value entries per tile
-constexpr int HW_CWARPS = 8;           // consumer warps per CTA
-constexpr int HW_THREADS = (HW_CWARPS + 1) * 32;
-
-struct __align__(16) HwStage {
-  int rp[3 * HW_TILE + 8];
-  float label[HW_TILE + 4];
-  unsigned idx[HW_CAP + 8];
-  float val[HW_CAP + 8];
-};
-struct HwMeta {
-  int a_off;    // rp[a_off] is row_ptr[3*r0]
-  int l_off;    // label[l_off] is label[r0]
-  int sm_base;  // absolute feature position held by idx[0]/val[0]
-  int staged;   // 0: the tile's features did not fit, read them from global
-  int nrow;
-  int r0;
-};
-
-template <int LANES, int VEC>
-struct HwSmem {
-  HwStage st[HW_STAGES];
-  uint64_t barA[HW_STAGES], full[HW_STAGES], empty[HW_STAGES];
-  HwMeta meta[HW_STAGES];
-  float dot[HW_CWARPS][(32 / LANES) * Group<LANES, VEC>::DOT_FLOATS];
-};
-
-template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN>
-__global__ void __launch_bounds__(HW_THREADS)
-k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user,
-         int scatter_item, float *pred_out, int *err_flag) {
-  __shared__ HwSmem<LANES, VEC> sm;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntile = (row_end - row_begin + HW_TILE - 1) / HW_TILE;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < HW_STAGES; ++s) {
-      mbar_init(&sm.barA[s], 1);
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], HW_CWARPS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == HW_CWARPS) {
-    // ===== producer: one lane drives the bulk copies =====
-    if (lane == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < ntile; t += gridDim.x, ++it) {
-        const int s = it % HW_STAGES;
-        const unsigned ph = (it / HW_STAGES) & 1;
-        mbar_wait(&sm.empty[s], ph ^ 1);
-        HwStage &st = sm.st[s];
-        const int r0 = row_begin + t * HW_TILE;
-        const int nrow = min(HW_TILE, row_end - r0);
-        // phase A: row_ptr[3*r0 .. 3*(r0+nrow)] and label[r0 .. r0+nrow), 16-byte aligned windows
-        const int a_off = (3 * r0) & 3, l_off = r0 & 3;
-        const unsigned bytesA = (unsigned)((a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
-        const unsigned bytesL = (unsigned)((l_off + nrow + 3) & ~3) * 4u;
-        mbar_arrive_expect_tx(&sm.barA[s], bytesA + bytesL);
-        bulk_g2s(st.rp, csr.row_ptr + (3 * r0 - a_off), bytesA, &sm.barA[s]);
-        bulk_g2s(st.label, csr.label + (r0 - l_off), bytesL, &sm.barA[s]);
-        mbar_wait(&sm.barA[s], ph);
-        // phase B: the tile's feature slice
-        const int v0 = st.rp[a_off] - csr.val_base;
-        const int v1 = st.rp[a_off + 3 * nrow] - csr.val_base;
-        const int v_off = v0 & 3;
-        const int nel = (v_off + (v1 - v0) + 3) & ~3;
-        HwMeta mt;
-        mt.a_off = a_off; mt.l_off = l_off; mt.nrow = nrow; mt.r0 = r0;
-        mt.sm_base = v0 - v_off + csr.val_base;
-        mt.staged = (nel <= HW_CAP + 8) ? 1 : 0;
-        sm.meta[s] = mt;
-        if (mt.staged && nel > 0) {
-          mbar_arrive_expect_tx(&sm.full[s], 2u * (unsigned)nel * 4u);
-          bulk_g2s(st.idx, csr.index + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
-          bulk_g2s(st.val, csr.value + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
-        } else {
-          mbar_arrive(&sm.full[s]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumers =====
-  constexpr int GPW = 32 / LANES;  // groups per warp
-  Group<LANES, VEC> g;
-  g.gl = lane % LANES;
-  const int gw = lane / LANES;
-  g.gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (gw * LANES));
-  g.dot_s = &sm.dot[warp][gw * Group<LANES, VEC>::DOT_FLOATS];
-  const int gid = warp * GPW + gw;
-  constexpr int NGROUP = HW_CWARPS * GPW;
-
-  int it = 0;
-  for (int t = blockIdx.x; t < ntile; t += gridDim.x, ++it) {
-    const int s = it % HW_STAGES;
-    const unsigned ph = (it / HW_STAGES) & 1;
-    mbar_wait(&sm.barA[s], ph);
-    mbar_wait(&sm.full[s], ph);
-    const HwMeta mt = sm.meta[s];
-    const HwStage &st = sm.st[s];
-    const int *rp = st.rp + mt.a_off;
-    const float *lab = st.label + mt.l_off;
-    const unsigned *idx = mt.staged ? (st.idx - mt.sm_base) : (csr.index - csr.val_base);
-    const float *val = mt.staged ? (st.val - mt.sm_base) : (csr.value - csr.val_base);
-    for (int q = gid; q < mt.nrow; q += NGROUP) {
-      const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
-      const float p = process_instance<LANES, VEC, EXACT_DOT, TRAIN, false>(
-          g, m, hp, rp0, rp1, rp2, rp3, lab[q], idx, val, scatter_user, scatter_item, nullptr,
-          err_flag);
-      if (!TRAIN && g.gl == 0) pred_out[mt.r0 + q - row_begin] = p;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[s]);
-  }
-}
 
 // ---------------------------------------------------------------------------
 // k_exact
@@ -216,20 +85,6 @@ k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *
 // ---------------------------------------------------------------------------
 // k_ugroup
 // ---------------------------------------------------------------------------
-// A "unit" is one user's consecutive blocks: a DEFAULT block, or START..END
-// (apex_svd_data.h:353-371).  unit_off[u]..unit_off[u+1] are its blocks.
-struct DevUgroup {
-  const int *unit_off;     // [num_unit+1] block ranges
-  const int *blk_row_off;  // [num_block+1]
-  const int *blk_fb_off;   // [num_block+1]
-  const unsigned *fb_index;
-  const float *fb_value;
-  const unsigned *fb_ticket;  // exact mode
-  const int *order;           // hogwild: unit processing order (longest first), may be null
-  int row_base;               // blk_row_off values are absolute rows; csr arrays start at row_base
-  int fb_base;                // blk_fb_off values are absolute; fb arrays start at fb_base
-};
-
 template <int LANES, int VEC>
 __device__ __forceinline__ bool strictly_increasing(const Group<LANES, VEC> &g, const unsigned *idx,
                                                     int n) {
@@ -413,16 +268,6 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
 // ---------------------------------------------------------------------------
 // replicated-slab delta exchange (multi-GPU)
 // ---------------------------------------------------------------------------
-struct DeltaSeg {
-  float *cur;       // live slab segment
-  long long n;      // floats
-  long long off;    // offset in the packed buffers
-};
-struct DeltaPlan {
-  DeltaSeg seg[5];
-  int nseg;
-  long long total;
-};
 // mode 0: snap = cur ; 1: delta = cur - snap ; 2: cur = snap + scale*delta, snap = cur
 __global__ void k_delta(DeltaPlan plan, float *snap, float *delta, int mode, float scale) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -439,6 +284,84 @@ __global__ void k_delta(DeltaPlan plan, float *snap, float *delta, int mode, flo
       }
     }
   }
+}
+
+
+template <int L, int V>
+static int exact_geo(svdgpu *h, const DevCsr &csr, int r0, int r1) {
+  auto k = k_exact<L, V>;
+  int grid = 1;
+  if (grid_for(h, k, EX_WARPS * 32, ((long long)(r1 - r0) + EX_WARPS - 1) / EX_WARPS, &grid)) return 1;
+  CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
+  CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
+  CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
+  k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->d_counter, h->d_err);
+  CU(h, cudaGetLastError());
+  h->n_launch++;
+  return 0;
+}
+
+template <int L, int V>
+static int ugroup_geo(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0, int u1, bool train,
+                      bool ordered, float *pred) {
+  int grid = 1;
+  CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
+#define GO(ED, ORD, TR)                                                                         \
+  {                                                                                             \
+    auto k = k_ugroup<L, V, ED, ORD, TR>;                                                       \
+    const int gpw = ORD ? 1 : 32 / L;                                                           \
+    if (grid_for(h, k, EX_WARPS * 32, ((long long)(u1 - u0) + EX_WARPS * gpw - 1) / (EX_WARPS * gpw), &grid)) \
+      return 1;                                                                                 \
+    /* Hogwild across users is only SGD-like while the users in flight are a small   */        \
+    /* fraction of the launch: cap them at 1/32 of the units (no effect at C3 scale). */        \
+    if (!ORD && TR) grid = std::max(1, std::min(grid, (u1 - u0) / (32 * EX_WARPS * gpw)));      \
+    k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, ug, u0, u1, h->scatter_user,   \
+                                             h->scatter_item, h->d_counter, pred, h->d_err);    \
+  }
+  if (!train) {
+    GO(true, false, false)
+  } else if (ordered) {
+    CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
+    CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
+    GO(true, true, true)
+  } else {
+    if (h->exact_dot) GO(true, false, true) else GO(false, false, true)
+  }
+#undef GO
+  CU(h, cudaGetLastError());
+  h->n_launch++;
+  return 0;
+}
+
+// the ordered / user-group kernels are instantiated for the automatic geometries only
+#ifdef SVDGPU_TUNE_BUILD
+#define ORDERED_GEOS(X) X(4, 1) X(8, 2)
+#else
+#define ORDERED_GEOS(X) X(4, 1) X(4, 2) X(8, 2) X(16, 2) X(32, 2) X(32, 4) X(16, 1) X(32, 1)
+#endif
+
+int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1) {
+#define GEO(L, V) \
+  if (g.lanes == L && g.vec == V) return exact_geo<L, V>(h, csr, r0, r1);
+  ORDERED_GEOS(GEO)
+#undef GEO
+  return fail(h, "ordered mode: no kernel for lanes=%d vec=%d (unset option lanes)", g.lanes, g.vec);
+}
+
+int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
+                  bool train, bool ordered, float *pred) {
+#define GEO(L, V) \
+  if (g.lanes == L && g.vec == V) return ugroup_geo<L, V>(h, csr, ug, u0, u1, train, ordered, pred);
+  ORDERED_GEOS(GEO)
+#undef GEO
+  return fail(h, "user-group input: no kernel for lanes=%d vec=%d (unset option lanes)", g.lanes, g.vec);
+}
+
+int launch_delta(svdgpu *h, int mode, float scale) {
+  k_delta<<<h->num_sm * 4, 256, 0, h->stream>>>(h->plan, h->d_snap, h->d_delta, mode, scale);
+  CU(h, cudaGetLastError());
+  h->n_launch++;
+  return 0;
 }
 
 }  // namespace svdk

@@ -71,10 +71,10 @@ def test_reference_loads_gpu_model_and_predicts_the_same(native, tmp_path):
 def test_hogwild_through_trainer(native, tmp_path):
     from svdfeature_b200 import synth
 
-    nu, ni = 20000, 2000
+    nu, ni = 200000, 5000  # users in flight / users comparable to configs[1]
     params = dict(num_user=nu, num_item=ni, num_factor=64, learning_rate=0.005, wd_user=0.004, wd_item=0.004,
                   base_score=3.6)
-    data = synth.basic_mf(300000, nu, ni, seed=41)
+    data = synth.basic_mf(1000000, nu, ni, seed=41)
     g = native.GpuTrainer(0, 0, 0, dict(params, **{"gpu:mode": "hogwild"}))
     o = COracle(0, 0, 0, params)
     _, po = _train(o, data, "csr", tmp_path)
