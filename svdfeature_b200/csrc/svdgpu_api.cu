@@ -363,6 +363,7 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->dm.ver_g);
   cudaFree(h->d_err);
   cudaFree(h->d_counter);
+  cudaFree(h->d_tile_flag);
   cudaFree(h->d_snap);
   cudaFree(h->d_delta);
   for (int i = 0; i < 2; ++i) {
@@ -472,6 +473,7 @@ int svdgpu_sync(svdgpu_t *h) {
       case ERR_USER_INDEX: return fail(h, "user feature index exceed bound");
       case ERR_ITEM_INDEX: return fail(h, "item feature index exceed bound");
       case ERR_FB_INDEX: return fail(h, "ufeedback id exceed bound");
+      case ERR_ROW_PTR: return fail(h, "row_ptr must be non-decreasing and inside the batch");
       default: return fail(h, "device error %d", e);
     }
   }
@@ -526,14 +528,17 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
   if (num_row == 0) return 0;
   if (!row_ptr || !label || (row_ptr[3LL * num_row] > row_ptr[0] && (!index || !value)))
     return fail(h, "null input array");
-  if (validate_csr(h, num_row, row_ptr)) return 1;
   Geometry geo;
   if (pick_geometry(h, geo)) return 1;
   const bool exact = train && h->mode == SVDGPU_MODE_EXACT;
+  // the ordered mode walks every row on the host anyway (tickets); Hogwild leaves the
+  // row_ptr checks to the kernels so that the host never touches the batch
+  if (exact && validate_csr(h, num_row, row_ptr)) return 1;
   for (int r0 = 0; r0 < num_row; r0 += h->chunk_rows) {
     const int r1 = (int)std::min<long long>(num_row, (long long)r0 + h->chunk_rows);
     const int n = r1 - r0;
     const int v0 = row_ptr[3LL * r0], v1 = row_ptr[3LL * r1];
+    if (v0 < 0 || v1 < v0) return fail(h, "row_ptr must be non-decreasing");
     const size_t nv = (size_t)(v1 - v0);
     Slot &s = next_slot(h);
     if (h2d(h, s.d_rp, s.h_rp, row_ptr + 3LL * r0, (3 * (size_t)n + 1) * 4)) return 1;
@@ -547,6 +552,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     csr.value = (const float *)s.d_value.p;
     csr.ticket = nullptr;
     csr.val_base = v0;
+    csr.val_end = v1;
     if (exact) {
       if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
       reset_ticket_counters(h);
@@ -678,6 +684,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     csr.value = (const float *)s.d_value.p;
     csr.ticket = nullptr;
     csr.val_base = v0;
+    csr.val_end = v1;
     DevUgroup ug;
     const int *dmi = (const int *)s.d_misc.p;
     ug.unit_off = dmi;
@@ -825,6 +832,7 @@ static DevCsr batch_csr(const svdgpu_batch *b) {
   c.value = (const float *)b->d_value.p;
   c.ticket = b->has_ticket ? (const unsigned *)b->d_ticket.p : nullptr;
   c.val_base = 0;
+  c.val_end = (int)b->num_val;
   return c;
 }
 static DevUgroup batch_ug(const svdgpu_batch *b) {

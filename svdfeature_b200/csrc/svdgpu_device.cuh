@@ -59,10 +59,17 @@ struct DevCsr {
   const float *value;
   const unsigned *ticket;  // exact mode: row version each feature waits for
   int val_base;
+  int val_end;  // one past the last feature position the arrays hold (absolute)
 };
 
 enum { SCATTER_STORE = 0, SCATTER_RED = 1 };
-enum { ERR_NONE = 0, ERR_GLOBAL_INDEX = 1, ERR_USER_INDEX = 2, ERR_ITEM_INDEX = 3, ERR_FB_INDEX = 4 };
+enum { ERR_NONE = 0, ERR_GLOBAL_INDEX = 1, ERR_USER_INDEX = 2, ERR_ITEM_INDEX = 3, ERR_FB_INDEX = 4, ERR_ROW_PTR = 5 };
+
+// a row's four segment bounds must be ordered and inside the batch (checked on the
+// device so that the host never walks row_ptr)
+__device__ __forceinline__ bool row_ok(int rp0, int rp1, int rp2, int rp3, int lo, int hi) {
+  return rp0 >= lo && rp0 <= rp1 && rp1 <= rp2 && rp2 <= rp3 && rp3 <= hi;
+}
 
 // ---------------------------------------------------------------------------
 // small PTX helpers
@@ -119,6 +126,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
+      : "memory");
+}
+// same, with a suspend-time hint: the (single) producer lane mostly waits for consumers
+// to free a stage; a long hardware sleep keeps it out of the issue slots
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITS_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONES_%=;\n"
+      "bra WAITS_%=;\n"
+      "DONES_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 // 1-D bulk asynchronous copy global -> shared (TMA unit, SASS UBLKCP), completion

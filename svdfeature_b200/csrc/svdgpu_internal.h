@@ -73,6 +73,8 @@ struct svdgpu {
   size_t rows = 0;
   int *d_err = nullptr;
   unsigned *d_counter = nullptr;
+  int *d_tile_flag = nullptr;  // k_stream: tiles that need the generic pass
+  size_t tile_flag_cap = 0;
   Slot slot[2];
   int cur_slot = 0;
   // multi-GPU exchange

@@ -74,6 +74,7 @@ k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *
     if (r >= row_end) break;
     const int rp0 = csr.row_ptr[3 * r], rp1 = csr.row_ptr[3 * r + 1];
     const int rp2 = csr.row_ptr[3 * r + 2], rp3 = csr.row_ptr[3 * r + 3];
+    // (row_ptr was validated on the host together with the tickets)
     wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
     process_instance<LANES, VEC, true, true, false>(g, m, hp, rp0, rp1, rp2, rp3, csr.label[r], idx,
                                                     val, SCATTER_STORE, SCATTER_STORE, nullptr,
@@ -243,6 +244,10 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
       for (int r = ug.blk_row_off[b0]; r < ug.blk_row_off[b1]; ++r) {
         const int rp0 = row_ptr[3 * (long long)r], rp1 = row_ptr[3 * (long long)r + 1];
         const int rp2 = row_ptr[3 * (long long)r + 2], rp3 = row_ptr[3 * (long long)r + 3];
+        if (!ORDERED && !row_ok(rp0, rp1, rp2, rp3, csr.val_base, csr.val_end)) {
+          if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
+          continue;
+        }
         if (ORDERED && TRAIN) wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
         const float p = process_instance<LANES, VEC, EXACT_DOT, TRAIN, true>(
             g, m, hp, rp0, rp1, rp2, rp3, label[r], idx, val, scatter_user, scatter_item, &s,

@@ -1,23 +1,29 @@
 // svdgpu_stream.cu -- k_stream: Hogwild training / prediction over a CSR batch.
 //
-// Persistent CTAs.  A producer warp stages each tile's row_ptr/label window and
-// its index/value window into shared memory with 1-D bulk asynchronous copies
-// (cp.async.bulk = TMA unit, SASS UBLKCP; completion on mbarriers; two tiles in
-// flight), so the consumers never chase row_ptr -> index -> row through DRAM.
-// Eight consumer warps run one lane GROUP per instance (svdgpu_device.cuh).
+// Persistent CTAs (256 threads, 2 per SM).  A producer warp stages each
+// 128-instance tile into shared memory with 1-D bulk asynchronous copies
+// (cp.async.bulk = TMA unit, SASS UBLKCP; completion on mbarriers): phase A brings
+// the tile's row_ptr/label window, phase B -- once A has landed and the feature
+// range is known -- its index/value window.  Four tiles are in flight and the two
+// phases of consecutive tiles overlap, so consumers never chase
+// row_ptr -> index -> row through DRAM.  Seven consumer warps run one lane GROUP
+// per instance (svdgpu_device.cuh).
 //
-// Rows of the common shape -- no global feature, one user feature, one item
-// feature (configs[0..1]: basicMF) -- take a straight-line path whose gathers for
-// the NEXT instance are issued before the current instance is computed (register
-// double buffering), which doubles the bytes each warp keeps in flight.  Every
-// other row shape goes through the generic process_instance().  Both paths
-// perform bit-identical arithmetic.
+// Two passes over a batch (Hogwild has no order to keep):
+//   pass 1 (SIMPLE)  rows of the basic-MF shape -- no global feature, one user
+//           feature, one item feature (configs[0..1]) -- take a straight-line path
+//           whose gathers for the NEXT instance are issued before the current
+//           instance is computed (register double buffering).  A tile that holds
+//           any other row shape (or did not fit the staging window) is flagged.
+//   pass 2 (GENERIC) visits flagged tiles only and runs the remaining rows through
+//           the generic process_instance().  For configs[1] it finds nothing.
+// Both paths perform bit-identical arithmetic.
 #include "svdgpu_internal.h"
 
 namespace svdk {
 
-constexpr int HW_TILE = 256;           // instances per tile
-constexpr int HW_STAGES = 2;           // tiles in flight per CTA
+constexpr int HW_TILE = 128;           // instances per tile
+constexpr int HW_STAGES = 4;           // tiles in flight per CTA
 constexpr int HW_CAP = 4 * HW_TILE;    // staged index/value entries per tile
 constexpr int HW_CWARPS = 7;           // consumer warps per CTA (+1 producer = 256 threads)
 constexpr int HW_THREADS = (HW_CWARPS + 1) * 32;
@@ -35,6 +41,9 @@ struct HwMeta {
   int staged;   // 0: the tile's features did not fit, read them from global
   int nrow;
   int r0;
+  int tile;
+  int skip;     // GENERIC pass: tile not flagged, nothing to do
+  int v_hi;     // one past the last staged feature position (absolute)
 };
 
 template <int LANES, int VEC, bool EXACT_DOT>
@@ -51,29 +60,22 @@ struct Pre {
   float4 wu[VEC], wi[VEC];
   float ub, ib, uval, ival, label;
   unsigned uid, iid;
-  int q;
-  int kind;  // 0 none, 1 simple (0|1|1 features), 2 generic, 3 index out of bound
+  int q;      // row inside the tile, -1: nothing loaded
 };
-enum { PRE_NONE = 0, PRE_SIMPLE = 1, PRE_GENERIC = 2, PRE_BAD = 3 };
 
-// the generic row path, kept out of line so that it does not inflate the register
-// budget of the straight-line path
-template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN>
-__device__ __noinline__ float generic_instance(const Group<LANES, VEC> &g, const DevModel &m, const DevHP &hp,
-                                               int rp0, int rp1, int rp2, int rp3, float label,
-                                               const unsigned *idx, const float *val, int scatter_user,
-                                               int scatter_item, int *err_flag) {
-  return process_instance<LANES, VEC, EXACT_DOT, TRAIN, false>(g, m, hp, rp0, rp1, rp2, rp3, label, idx, val,
-                                                               scatter_user, scatter_item, nullptr, err_flag);
+__device__ __forceinline__ bool is_simple(const int *rp, int q) {
+  const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
+  return rp1 == rp0 && rp2 == rp1 + 1 && rp3 == rp2 + 1;
 }
 
-template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN>
+template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, bool GENERIC>
 __global__ void __launch_bounds__(HW_THREADS, 2)
 k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user,
-         int scatter_item, float *pred_out, int *err_flag) {
+         int scatter_item, float *pred_out, int *tile_flag, int *err_flag) {
   __shared__ HwSmem<LANES, VEC, EXACT_DOT> sm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile = (row_end - row_begin + HW_TILE - 1) / HW_TILE;
+  const int nlocal = ntile > (int)blockIdx.x ? (ntile - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < HW_STAGES; ++s) {
@@ -86,40 +88,59 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
   __syncthreads();
 
   if (warp == HW_CWARPS) {
-    // ===== producer: one lane drives the bulk copies =====
+    // ===== producer: one lane drives the bulk copies; phase A of tile i overlaps
+    // phase B of tile i-1 =====
     if (lane == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < ntile; t += gridDim.x, ++it) {
-        const int s = it % HW_STAGES;
-        const unsigned ph = (it / HW_STAGES) & 1;
-        mbar_wait(&sm.empty[s], ph ^ 1);
-        HwStage &st = sm.st[s];
-        const int r0 = row_begin + t * HW_TILE;
-        const int nrow = min(HW_TILE, row_end - r0);
-        // phase A: row_ptr[3*r0 .. 3*(r0+nrow)] and label[r0 .. r0+nrow), 16-byte aligned windows
-        const int a_off = (3 * r0) & 3, l_off = r0 & 3;
-        const unsigned bytesA = (unsigned)((a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
-        const unsigned bytesL = (unsigned)((l_off + nrow + 3) & ~3) * 4u;
-        mbar_arrive_expect_tx(&sm.barA[s], bytesA + bytesL);
-        bulk_g2s(st.rp, csr.row_ptr + (3 * r0 - a_off), bytesA, &sm.barA[s]);
-        bulk_g2s(st.label, csr.label + (r0 - l_off), bytesL, &sm.barA[s]);
-        mbar_wait(&sm.barA[s], ph);
-        // phase B: the tile's feature window
-        const int v0 = st.rp[a_off] - csr.val_base;
-        const int v1 = st.rp[a_off + 3 * nrow] - csr.val_base;
-        const int v_off = v0 & 3;
-        const int nel = (v_off + (v1 - v0) + 3) & ~3;
-        HwMeta mt;
-        mt.a_off = a_off; mt.l_off = l_off; mt.nrow = nrow; mt.r0 = r0;
-        mt.sm_base = v0 - v_off + csr.val_base;
-        mt.staged = (nel <= HW_CAP + 8) ? 1 : 0;
-        sm.meta[s] = mt;
-        if (mt.staged && nel > 0) {
-          mbar_arrive_expect_tx(&sm.full[s], 2u * (unsigned)nel * 4u);
-          bulk_g2s(st.idx, csr.index + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
-          bulk_g2s(st.val, csr.value + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
-        } else {
-          mbar_arrive(&sm.full[s]);
+      for (int it = 0; it <= nlocal; ++it) {
+        if (it < nlocal) {  // phase A of local tile `it`
+          const int s = it % HW_STAGES;
+          const unsigned ph = (it / HW_STAGES) & 1;
+          mbar_wait_sleepy(&sm.empty[s], ph ^ 1);
+          HwStage &st = sm.st[s];
+          const int t = blockIdx.x + it * gridDim.x;
+          const int r0 = row_begin + t * HW_TILE;
+          const int nrow = min(HW_TILE, row_end - r0);
+          HwMeta mt;
+          mt.tile = t; mt.r0 = r0; mt.nrow = nrow;
+          mt.a_off = (3 * r0) & 3; mt.l_off = r0 & 3;
+          mt.sm_base = 0; mt.staged = 0; mt.v_hi = 0;
+          mt.skip = (GENERIC && tile_flag[t] == 0) ? 1 : 0;
+          sm.meta[s] = mt;
+          if (mt.skip) {
+            mbar_arrive(&sm.barA[s]);
+          } else {
+            const unsigned bytesA = (unsigned)((mt.a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
+            const unsigned bytesL = (unsigned)((mt.l_off + nrow + 3) & ~3) * 4u;
+            mbar_arrive_expect_tx(&sm.barA[s], bytesA + bytesL);
+            bulk_g2s(st.rp, csr.row_ptr + (3 * r0 - mt.a_off), bytesA, &sm.barA[s]);
+            bulk_g2s(st.label, csr.label + (r0 - mt.l_off), bytesL, &sm.barA[s]);
+          }
+        }
+        const int j = it - 1;  // phase B of local tile `j`
+        if (j >= 0) {
+          const int s = j % HW_STAGES;
+          const unsigned ph = (j / HW_STAGES) & 1;
+          mbar_wait_sleepy(&sm.barA[s], ph);
+          HwStage &st = sm.st[s];
+          HwMeta &mt = sm.meta[s];
+          if (mt.skip) {
+            mbar_arrive(&sm.full[s]);
+          } else {
+            const int v0 = st.rp[mt.a_off] - csr.val_base;
+            const int v1 = st.rp[mt.a_off + 3 * mt.nrow] - csr.val_base;
+            const int v_off = v0 & 3;
+            const int nel = (v_off + (v1 - v0) + 3) & ~3;
+            mt.sm_base = v0 - v_off + csr.val_base;
+            mt.v_hi = v1 + csr.val_base;
+            mt.staged = (v0 >= 0 && v1 >= v0 && v1 + csr.val_base <= csr.val_end && nel <= HW_CAP + 8) ? 1 : 0;
+            if (mt.staged && nel > 0) {
+              mbar_arrive_expect_tx(&sm.full[s], 2u * (unsigned)nel * 4u);
+              bulk_g2s(st.idx, csr.index + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
+              bulk_g2s(st.val, csr.value + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
+            } else {
+              mbar_arrive(&sm.full[s]);
+            }
+          }
         }
       }
     }
@@ -136,49 +157,67 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
   const int gid = warp * GPW + gw;
   constexpr int NGROUP = HW_CWARPS * GPW;
 
-  int it = 0;
-  for (int t = blockIdx.x; t < ntile; t += gridDim.x, ++it) {
+  for (int it = 0; it < nlocal; ++it) {
     const int s = it % HW_STAGES;
     const unsigned ph = (it / HW_STAGES) & 1;
-    mbar_wait(&sm.barA[s], ph);
-    mbar_wait(&sm.full[s], ph);
+    mbar_wait(&sm.full[s], ph);  // the producer arrives on `full` only after phase A has landed
     const HwMeta mt = sm.meta[s];
     const HwStage &st = sm.st[s];
     const int *rp = st.rp + mt.a_off;
     const float *lab = st.label + mt.l_off;
-    const bool staged = mt.staged != 0;
-    const int gbase = csr.val_base;
 
-    auto IDX = [&](int f) -> unsigned { return staged ? st.idx[f - mt.sm_base] : csr.index[f - gbase]; };
-    auto VAL = [&](int f) -> float { return staged ? st.val[f - mt.sm_base] : csr.value[f - gbase]; };
+    if (GENERIC) {
+      // ---- pass 2: whatever pass 1 left in this (flagged) tile ----
+      if (!mt.skip) {
+        const unsigned *idx = mt.staged ? (st.idx - mt.sm_base) : (csr.index - csr.val_base);
+        const float *val = mt.staged ? (st.val - mt.sm_base) : (csr.value - csr.val_base);
+        for (int q = gid; q < mt.nrow; q += NGROUP) {
+          if (mt.staged && is_simple(rp, q) && rp[3 * q] >= mt.sm_base && rp[3 * q + 3] <= mt.v_hi) continue;  // done by pass 1
+          if (!row_ok(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], csr.val_base, csr.val_end)) {
+            if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
+            continue;
+          }
+          const float pr = process_instance<LANES, VEC, EXACT_DOT, TRAIN, false>(
+              g, m, hp, rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], lab[q], idx, val,
+              scatter_user, scatter_item, nullptr, err_flag);
+          if (!TRAIN && g.gl == 0) pred_out[mt.r0 + q - row_begin] = pr;
+        }
+      }
+    } else if (!mt.staged) {
+      // window did not fit: the whole tile goes to pass 2
+      if (threadIdx.x == 0) tile_flag[mt.tile] = 1;
+    } else {
+      // ---- pass 1: straight-line basic-MF rows, gathers one instance ahead ----
+      const unsigned *sidx = st.idx - mt.sm_base;
+      const float *sval = st.val - mt.sm_base;
+      bool other = false;  // this group met a row of another shape
 
-    // ---- issue the gathers of instance q ----
-    auto pre_load = [&](Pre<VEC> &p, int q) {
-      p.q = q;
-      const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
-      if (rp1 == rp0 && rp2 == rp1 + 1 && rp3 == rp2 + 1) {
-        p.uid = IDX(rp1);
-        p.iid = IDX(rp2);
-        p.uval = VAL(rp1);
-        p.ival = VAL(rp2);
-        p.label = lab[q];
-        if (p.uid >= (unsigned)m.num_user || p.iid >= (unsigned)m.num_item) {
-          p.kind = PRE_BAD;
+      auto pre_load = [&](Pre<VEC> &p, int q) {
+        p.q = -1;
+        if (q >= mt.nrow) return;
+        const int f = rp[3 * q + 1];
+        if (!is_simple(rp, q) || f < mt.sm_base || f + 2 > mt.v_hi) {
+          other = true;
           return;
         }
-        p.kind = PRE_SIMPLE;
+        p.uid = sidx[f];
+        p.iid = sidx[f + 1];
+        if (p.uid >= (unsigned)m.num_user || p.iid >= (unsigned)m.num_item) {
+          if (g.gl == 0) atomicCAS(err_flag, 0, p.uid >= (unsigned)m.num_user ? ERR_USER_INDEX : ERR_ITEM_INDEX);
+          return;
+        }
+        p.q = q;
+        p.uval = sval[f];
+        p.ival = sval[f + 1];
+        p.label = lab[q];
         g.load_row(m, (size_t)m.user_off + p.uid, p.wu);
         g.load_row(m, (size_t)m.item_off + p.iid, p.wi);
         p.ub = m.no_user_bias ? 0.0f : __ldcg(m.bias + m.user_off + p.uid);
         p.ib = __ldcg(m.bias + m.item_off + p.iid);
-      } else {
-        p.kind = PRE_GENERIC;
-      }
-    };
+      };
 
-    // ---- compute instance p (gathers already in registers when simple) ----
-    auto compute = [&](const Pre<VEC> &p) {
-      if (p.kind == PRE_SIMPLE) {
+      auto compute = [&](const Pre<VEC> &p) {
+        if (p.q < 0) return;
         // prepare_tmp (base.h:354-381): tmp = 0 + w*val
         float4 tu[VEC], ti[VEC];
         const bool one_u = scalar_is_one(p.uval), one_i = scalar_is_one(p.ival);
@@ -231,36 +270,21 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
           if (scatter_item == SCATTER_RED) red1(bp, __fsub_rn(nb, p.ib));
           else __stcg(bp, nb);
         }
-      } else if (p.kind == PRE_GENERIC) {
-        const int q = p.q;
-        const unsigned *idx = staged ? (st.idx - mt.sm_base) : (csr.index - gbase);
-        const float *val = staged ? (st.val - mt.sm_base) : (csr.value - gbase);
-        const float pr = generic_instance<LANES, VEC, EXACT_DOT, TRAIN>(
-            g, m, hp, rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], lab[q], idx, val,
-            scatter_user, scatter_item, err_flag);
-        if (!TRAIN && g.gl == 0) pred_out[mt.r0 + q - row_begin] = pr;
-      } else if (p.kind == PRE_BAD) {
-        if (g.gl == 0)
-          atomicCAS(err_flag, 0, p.uid >= (unsigned)m.num_user ? ERR_USER_INDEX : ERR_ITEM_INDEX);
-      }
-    };
+      };
 
-    Pre<VEC> A, B;
-    int q = gid;
-    A.kind = PRE_NONE;
-    if (q < mt.nrow) pre_load(A, q);
-    while (q < mt.nrow) {
-      int qn = q + NGROUP;
-      B.kind = PRE_NONE;
-      if (qn < mt.nrow) pre_load(B, qn);
-      compute(A);
-      q = qn;
-      if (q >= mt.nrow) break;
-      qn = q + NGROUP;
-      A.kind = PRE_NONE;
-      if (qn < mt.nrow) pre_load(A, qn);
-      compute(B);
-      q = qn;
+      Pre<VEC> A, B;
+      int q = gid;
+      pre_load(A, q);
+      while (q < mt.nrow) {
+        pre_load(B, q + NGROUP);
+        compute(A);
+        q += NGROUP;
+        if (q >= mt.nrow) break;
+        pre_load(A, q + NGROUP);
+        compute(B);
+        q += NGROUP;
+      }
+      if (__any_sync(g.gmask, other) && g.gl == 0) tile_flag[mt.tile] = 1;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);
@@ -270,22 +294,33 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
 template <int L, int V>
 static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
   const long long ntile = ((long long)(r1 - r0) + HW_TILE - 1) / HW_TILE;
+  // per-tile flags: which tiles pass 2 must visit
+  if ((size_t)ntile * sizeof(int) > h->tile_flag_cap) {
+    if (h->d_tile_flag) CU(h, cudaFree(h->d_tile_flag));
+    h->d_tile_flag = nullptr;
+    h->tile_flag_cap = 0;
+    const size_t cap = (size_t)ntile * sizeof(int) * 2;
+    CU(h, cudaMalloc(&h->d_tile_flag, cap));
+    h->tile_flag_cap = cap;
+  }
+  CU(h, cudaMemsetAsync(h->d_tile_flag, 0, (size_t)ntile * sizeof(int), h->stream));
   int grid = 1;
-#define GO(ED, TR)                                                                           \
-  {                                                                                          \
-    auto k = k_stream<L, V, ED, TR>;                                                         \
-    if (grid_for(h, k, HW_THREADS, ntile, &grid)) return 1;                                  \
-    k<<<grid, HW_THREADS, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,       \
-                                          h->scatter_item, pred, h->d_err);                  \
+#define GO(ED, TR, GEN)                                                                          \
+  {                                                                                              \
+    auto k = k_stream<L, V, ED, TR, GEN>;                                                        \
+    if (grid_for(h, k, HW_THREADS, ntile, &grid)) return 1;                                      \
+    k<<<grid, HW_THREADS, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,           \
+                                          h->scatter_item, pred, h->d_tile_flag, h->d_err);      \
+    h->n_launch++;                                                                               \
   }
   if (train) {
-    if (h->exact_dot) GO(true, true) else GO(false, true)
+    if (h->exact_dot) { GO(true, true, false) GO(true, true, true) }
+    else { GO(false, true, false) GO(false, true, true) }
   } else {
-    GO(true, false)
+    GO(true, false, false) GO(true, false, true)
   }
 #undef GO
   CU(h, cudaGetLastError());
-  h->n_launch++;
   return 0;
 }
 

@@ -311,3 +311,19 @@ def test_large_batch_properties(native):
     uu, ii = data[2][0::2][s].astype(np.int64), data[2][1::2][s].astype(np.int64)
     ref = 3.6 + ub[uu] + ub[nu + ii] + np.einsum("nk,nk->n", W[uu].astype(np.float64), W[nu + ii].astype(np.float64))
     assert np.abs(ref - p1[s]).max() <= 1e-5
+
+
+def test_bad_row_ptr_is_an_error(native):
+    """row_ptr is checked on the device in Hogwild mode (the host never walks the batch)."""
+    o, g, data, kind = _pair(native, "general_k40", native.MODE_HOGWILD)
+    rp = data[0].copy()
+    rp[301] = rp[300] - 2  # a decreasing segment bound
+    with pytest.raises(native.SvdGpuError, match="row_ptr"):
+        g.update_csr((rp, data[1], data[2], data[3]))
+        g.sync()
+    o2, g2, data, kind = _pair(native, "basic_k64", native.MODE_HOGWILD)
+    rp = data[0].copy()
+    rp[3 * 77 + 1] += 10 ** 6  # points far outside the batch
+    with pytest.raises(native.SvdGpuError, match="row_ptr"):
+        g2.update_csr((rp, data[1], data[2], data[3]))
+        g2.sync()
