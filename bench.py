@@ -301,18 +301,17 @@ def main():
     log("[rank %d] setup %.1fs: %d rows in %d chunks" % (rank, time.perf_counter() - t_setup, total, nchunk))
 
     use_allreduce = world > 1
+    xchg = [None]
 
     def exchange():
-        if not use_allreduce:
-            return
-        p, n = g.items_pack_delta()
-        t = _as_tensor(p, n, dev)
-        dist.all_reduce(t)
-        g.items_apply_delta(1.0)
+        if use_allreduce:
+            xchg[0].sync()  # pack item-side deltas, ONE NCCL all-reduce, apply (svdfeature_b200/parallel.py)
 
     with torch.cuda.stream(stream):
         if use_allreduce:
-            g.items_snapshot()
+            from svdfeature_b200 import parallel
+
+            xchg[0] = parallel.ItemExchange(g, dist, dev, scale=1.0)
         for s in range(args.warmup):
             step(s)
             if (s + 1) % args.allreduce_every == 0:
@@ -430,17 +429,6 @@ def main():
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
-
-
-class _DevArray:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-
-
-def _as_tensor(ptr, n, dev):
-    import torch
-
-    return torch.as_tensor(_DevArray(ptr, n), device=dev)
 
 
 if __name__ == "__main__":

@@ -327,3 +327,42 @@ def test_bad_row_ptr_is_an_error(native):
     with pytest.raises(native.SvdGpuError, match="row_ptr"):
         g2.update_csr((rp, data[1], data[2], data[3]))
         g2.sync()
+
+
+def test_items_delta_protocol(native):
+    """svdgpu_items_snapshot / pack_delta / apply_delta: two replicas that train on different
+    shards and exchange item-side deltas end with identical item rows = snapshot + sum of deltas."""
+    import torch
+
+    fmt, act, params, data, kind = CASES["basic_k64"]
+    o = COracle(fmt, act, 0, params)
+    o.init(10)
+    init = [a.copy() for a in o.arrays()]
+    from svdfeature_b200 import parallel
+
+    reps = []
+    for r in range(2):
+        g = native.SvdGpu(**_cases.shape_of(params, fmt, act))
+        g.set_hparams(**_cases.hparams_of(params, o.base_score))
+        g.set_mode(native.MODE_EXACT)
+        g.upload(*init)
+        g.items_snapshot()
+        g.update_csr(parallel.shard_rows(data, r, 2)[0])
+        reps.append(g)
+    deltas = []
+    for g in reps:
+        p, n = g.items_pack_delta()
+        g.sync()
+        deltas.append(parallel.device_tensor(p, n, torch.device("cuda", 0)).clone())
+    total = deltas[0] + deltas[1]
+    for g in reps:
+        p, n = g.items_pack_delta()
+        parallel.device_tensor(p, n, torch.device("cuda", 0)).copy_(total)
+        torch.cuda.synchronize()
+        g.items_apply_delta(1.0)
+    nu, ni, k = params["num_user"], params["num_item"], params["num_factor"]
+    a, b = reps[0].download(), reps[1].download()
+    assert np.array_equal(a[1][nu:], b[1][nu:]) and np.array_equal(a[0][nu:], b[0][nu:])
+    expect = init[1][nu:, :k] + total[:ni * k].cpu().numpy().reshape(ni, k)
+    assert np.allclose(a[1][nu:, :k], expect, atol=1e-7)
+    assert not np.array_equal(a[1][:nu], b[1][:nu])  # user rows stay private
