@@ -16,7 +16,8 @@
 //   apex_svd::SVDPlusBlock                apex_svd_data.h:376-466
 //   apex_svd::svd_type / SVDTypeParam     apex_svd_model.h:50-57, 242-287
 //   apex_svd::ISVDTrainer                 apex_svd.h:33-107
-//   apex_svd::create_svd_trainer          apex_svd.h:212
+//   apex_svd::ISVDRanker                  apex_svd.h:160-197
+//   apex_svd::create_svd_trainer/_ranker  apex_svd.h:212,222
 //   apex_utils::error / assert_true       apex-utils/apex_utils.h:47-58
 //
 // Nothing here computes; the arithmetic lives in svdgpu_kernels.cu.
@@ -161,7 +162,28 @@ class ISVDTrainer {
   virtual ~ISVDTrainer() {}
 };
 
+// Ranking utility interface (apex_svd.h:160-197); declared so that the factory pair the
+// reference's drivers link against is complete.  The GPU build provides no ranker.
+class ISVDRanker {
+ public:
+  virtual void load_model(FILE *fi) = 0;
+  virtual void init_ranker(int num_item_set) = 0;
+  virtual void set_param(const char *name, const char *val) = 0;
+
+ public:
+  virtual void process(std::vector<int> &result, const SVDFeatureCSR::Elem &feature) {
+    apex_utils::error("not implemented");
+  }
+  virtual void process(std::vector<int> &result, const SVDPlusBlock &data) {
+    apex_utils::error("not implemented");
+  }
+
+ public:
+  virtual ~ISVDRanker() {}
+};
+
 ISVDTrainer *create_svd_trainer(SVDTypeParam mtype);
+ISVDRanker *create_svd_ranker(SVDTypeParam mtype);
 
 }  // namespace apex_svd
 

@@ -467,6 +467,13 @@ ISVDTrainer *create_svd_trainer(SVDTypeParam mtype) {
   return new GpuSVDFeature(mtype);
 }
 
+// apex_svd.cpp:44-46.  SVDFeatureRanker (base.h:597-813) is inference-side dense scoring,
+// outside the SGD hot path: svd_feature_infer links, and says so if a ranker is requested.
+ISVDRanker *create_svd_ranker(SVDTypeParam mtype) {
+  apex_utils::error("GPU build: SVDFeatureRanker is not provided (use the reference's svd_feature_infer for ranking)");
+  return NULL;
+}
+
 }  // namespace apex_svd
 
 // ---- bulk C entry points (GPU trainer only; same handle as trainer_cabi.cpp) ----
