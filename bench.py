@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json configs[1]): Netflix-shaped basicMF, 480k users x 18k items,
 k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch of
---rows-per-step ratings (default 5M, i.e. 20 steps = one epoch).  Prints ONE JSON line.
+--rows-per-step ratings (default: all 100M, i.e. one step = one epoch).  Prints ONE JSON line.
 
   value      whole-job instances/s with the batches resident in HBM (device-timed, CUDA
              events on the launch stream, max over ranks)
@@ -108,7 +108,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="hogwild", choices=["hogwild", "exact"])
-    ap.add_argument("--rows-per-step", type=int, default=5_000_000)
+    ap.add_argument("--rows-per-step", type=int, default=TOTAL_ROWS)
     ap.add_argument("--ref-rows-per-step", type=int, default=2_000_000)
     ap.add_argument("--cpu-rows", type=int, default=20_000_000, help="rows of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,6 +239,17 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to
+    # stdout) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
 
     import torch
     from svdfeature_b200 import api
@@ -323,6 +334,7 @@ def main():
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
+            time.sleep(0.2)  # let nvidia-smi attach before the timed region
         l0 = g.counter("kernel_launches")
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
@@ -426,7 +438,7 @@ def main():
     if world > 1:
         line["config"]["parallelism"] = "user-hash shards x%d, item-side delta allreduce (NCCL) every %d step(s)" % (
             world, args.allreduce_every)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
