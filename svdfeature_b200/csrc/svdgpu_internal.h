@@ -97,9 +97,9 @@ int fail(svdgpu *h, const char *fmt, ...);
   } while (0)
 
 template <typename K>
-int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid) {
+int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid, size_t dyn_smem = 0) {
   int per_sm = 0;
-  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
   if (per_sm < 1) per_sm = 1;
   if (h->ctas_per_sm > 0) per_sm = std::min(per_sm, h->ctas_per_sm);
   long long gmax = (long long)per_sm * h->num_sm;

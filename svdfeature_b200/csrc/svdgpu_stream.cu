@@ -1,13 +1,18 @@
 // svdgpu_stream.cu -- k_stream: Hogwild training / prediction over a CSR batch.
 //
-// Persistent CTAs (256 threads, 2 per SM).  A producer warp stages each
-// 128-instance tile into shared memory with 1-D bulk asynchronous copies
-// (cp.async.bulk = TMA unit, SASS UBLKCP; completion on mbarriers): phase A brings
-// the tile's row_ptr/label window, phase B -- once A has landed and the feature
-// range is known -- its index/value window.  Four tiles are in flight and the two
-// phases of consecutive tiles overlap, so consumers never chase
-// row_ptr -> index -> row through DRAM.  Seven consumer warps run one lane GROUP
-// per instance (svdgpu_device.cuh).
+// Persistent CTAs (256 threads = 8 warps, 2 CTAs per SM).  EVERY warp owns a private
+// staging pipeline: it takes whole 64-instance tiles (tile w, w+W, w+2W, ... for warp slot w
+// of W), and its lane 0 stages them into the warp's slice of shared memory with 1-D bulk
+// asynchronous copies (cp.async.bulk = TMA unit, SASS UBLKCP; completion on the warp's own
+// mbarriers): phase A brings the tile's row_ptr/label window, phase B -- once A has landed
+// and the feature range is known -- its index/value window.  Four tiles per warp are in
+// flight (A of tile j+3 and B of tile j+2 are issued before tile j is computed; tile j+1 has
+// landed and its user rows are being pulled into L2 with prefetch.global.L2), so nobody
+// chases row_ptr -> index -> row through DRAM and no warp ever waits for another warp
+// (the first version shared tiles between warps through a producer warp; ncu showed the
+// consumers stalling on the shared tile barriers).
+//
+// Inside a warp one lane GROUP (svdgpu_device.cuh) runs one instance.
 //
 // Two passes over a batch (Hogwild has no order to keep):
 //   pass 1 (SIMPLE)  rows of the basic-MF shape -- no global feature, one user
@@ -22,11 +27,11 @@
 
 namespace svdk {
 
-constexpr int HW_TILE = 128;           // instances per tile
-constexpr int HW_STAGES = 4;           // tiles in flight per CTA
+constexpr int HW_TILE = 64;            // instances per tile (one tile belongs to ONE warp)
+constexpr int HW_STAGES = 4;           // tiles in flight per warp
 constexpr int HW_CAP = 4 * HW_TILE;    // staged index/value entries per tile
-constexpr int HW_CWARPS = 7;           // consumer warps per CTA (+1 producer = 256 threads)
-constexpr int HW_THREADS = (HW_CWARPS + 1) * 32;
+constexpr int HW_WARPS = 8;            // warps per CTA, every one a consumer with its own pipeline
+constexpr int HW_THREADS = HW_WARPS * 32;
 
 struct __align__(16) HwStage {
   int rp[3 * HW_TILE + 8];
@@ -34,33 +39,23 @@ struct __align__(16) HwStage {
   unsigned idx[HW_CAP + 8];
   float val[HW_CAP + 8];
 };
-struct HwMeta {
-  int a_off;    // rp[a_off] is row_ptr[3*r0]
-  int l_off;    // label[l_off] is label[r0]
-  int sm_base;  // absolute feature position held by idx[0]/val[0]
-  int staged;   // 0: the tile's features did not fit, read them from global
-  int nrow;
-  int r0;
-  int tile;
-  int skip;     // GENERIC pass: tile not flagged, nothing to do
-  int v_hi;     // one past the last staged feature position (absolute)
+struct __align__(16) HwWarp {
+  HwStage st[HW_STAGES];
+  uint64_t barA[HW_STAGES], barB[HW_STAGES];
 };
 
 template <int LANES, int VEC, bool EXACT_DOT>
-struct HwSmem {
-  HwStage st[HW_STAGES];
-  uint64_t barA[HW_STAGES], full[HW_STAGES], empty[HW_STAGES];
-  HwMeta meta[HW_STAGES];
-  float dot[EXACT_DOT ? HW_CWARPS * (32 / LANES) * Group<LANES, VEC>::DOT_FLOATS : 4];
-};
+constexpr size_t hw_smem_bytes() {
+  return sizeof(HwWarp) * HW_WARPS +
+         (EXACT_DOT ? sizeof(float) * HW_WARPS * (32 / LANES) * Group<LANES, VEC>::DOT_FLOATS : 0);
+}
 
 // gathers of one instance, issued ahead of its compute
 template <int VEC>
 struct Pre {
   float4 wu[VEC], wi[VEC];
-  float ub, ib, uval, ival, label;
-  unsigned uid, iid;
-  int q;      // row inside the tile, -1: nothing loaded
+  float ub, ib;
+  int q;  // row inside the tile, -1: nothing loaded
 };
 
 __device__ __forceinline__ bool is_simple(const int *rp, int q) {
@@ -72,176 +67,215 @@ template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, bool GENERIC>
 __global__ void __launch_bounds__(HW_THREADS, 2)
 k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user,
          int scatter_item, float *pred_out, int *tile_flag, int *err_flag) {
-  __shared__ HwSmem<LANES, VEC, EXACT_DOT> sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntile = (row_end - row_begin + HW_TILE - 1) / HW_TILE;
-  const int nlocal = ntile > (int)blockIdx.x ? (ntile - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  HwWarp &sw = reinterpret_cast<HwWarp *>(smem_raw)[warp];
+  float *dot_base = reinterpret_cast<float *>(smem_raw + sizeof(HwWarp) * HW_WARPS);
 
-  if (threadIdx.x == 0) {
+  const int ntile = (row_end - row_begin + HW_TILE - 1) / HW_TILE;
+  const int wslot = blockIdx.x * HW_WARPS + warp;  // this warp's first tile
+  const int wstride = gridDim.x * HW_WARPS;
+  const int nlocal = ntile > wslot ? (ntile - wslot + wstride - 1) / wstride : 0;
+
+  if (lane == 0) {
     for (int s = 0; s < HW_STAGES; ++s) {
-      mbar_init(&sm.barA[s], 1);
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], HW_CWARPS);
+      mbar_init(&sw.barA[s], 1);
+      mbar_init(&sw.barB[s], 1);
     }
     mbar_fence_init();
   }
-  __syncthreads();
+  __syncwarp();
 
-  if (warp == HW_CWARPS) {
-    // ===== producer: one lane drives the bulk copies; phase A of tile i overlaps
-    // phase B of tile i-1 =====
-    if (lane == 0) {
-      for (int it = 0; it <= nlocal; ++it) {
-        if (it < nlocal) {  // phase A of local tile `it`
-          const int s = it % HW_STAGES;
-          const unsigned ph = (it / HW_STAGES) & 1;
-          mbar_wait_sleepy(&sm.empty[s], ph ^ 1);
-          HwStage &st = sm.st[s];
-          const int t = blockIdx.x + it * gridDim.x;
-          const int r0 = row_begin + t * HW_TILE;
-          const int nrow = min(HW_TILE, row_end - r0);
-          HwMeta mt;
-          mt.tile = t; mt.r0 = r0; mt.nrow = nrow;
-          mt.a_off = (3 * r0) & 3; mt.l_off = r0 & 3;
-          mt.sm_base = 0; mt.staged = 0; mt.v_hi = 0;
-          mt.skip = (GENERIC && tile_flag[t] == 0) ? 1 : 0;
-          sm.meta[s] = mt;
-          if (mt.skip) {
-            mbar_arrive(&sm.barA[s]);
-          } else {
-            const unsigned bytesA = (unsigned)((mt.a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
-            const unsigned bytesL = (unsigned)((mt.l_off + nrow + 3) & ~3) * 4u;
-            mbar_arrive_expect_tx(&sm.barA[s], bytesA + bytesL);
-            bulk_g2s(st.rp, csr.row_ptr + (3 * r0 - mt.a_off), bytesA, &sm.barA[s]);
-            bulk_g2s(st.label, csr.label + (r0 - mt.l_off), bytesL, &sm.barA[s]);
-          }
-        }
-        const int j = it - 1;  // phase B of local tile `j`
-        if (j >= 0) {
-          const int s = j % HW_STAGES;
-          const unsigned ph = (j / HW_STAGES) & 1;
-          mbar_wait_sleepy(&sm.barA[s], ph);
-          HwStage &st = sm.st[s];
-          HwMeta &mt = sm.meta[s];
-          if (mt.skip) {
-            mbar_arrive(&sm.full[s]);
-          } else {
-            const int v0 = st.rp[mt.a_off] - csr.val_base;
-            const int v1 = st.rp[mt.a_off + 3 * mt.nrow] - csr.val_base;
-            const int v_off = v0 & 3;
-            const int nel = (v_off + (v1 - v0) + 3) & ~3;
-            mt.sm_base = v0 - v_off + csr.val_base;
-            mt.v_hi = v1 + csr.val_base;
-            mt.staged = (v0 >= 0 && v1 >= v0 && v1 + csr.val_base <= csr.val_end && nel <= HW_CAP + 8) ? 1 : 0;
-            if (mt.staged && nel > 0) {
-              mbar_arrive_expect_tx(&sm.full[s], 2u * (unsigned)nel * 4u);
-              bulk_g2s(st.idx, csr.index + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
-              bulk_g2s(st.val, csr.value + (v0 - v_off), (unsigned)nel * 4u, &sm.full[s]);
-            } else {
-              mbar_arrive(&sm.full[s]);
-            }
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumers =====
   constexpr int GPW = 32 / LANES;  // groups per warp
   Group<LANES, VEC> g;
   g.gl = lane % LANES;
   const int gw = lane / LANES;
   g.gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (gw * LANES));
-  g.dot_s = EXACT_DOT ? &sm.dot[(warp * GPW + gw) * Group<LANES, VEC>::DOT_FLOATS] : nullptr;
-  const int gid = warp * GPW + gw;
-  constexpr int NGROUP = HW_CWARPS * GPW;
+  g.dot_s = EXACT_DOT ? dot_base + (warp * GPW + gw) * Group<LANES, VEC>::DOT_FLOATS : nullptr;
 
-  for (int it = 0; it < nlocal; ++it) {
-    const int s = it % HW_STAGES;
-    const unsigned ph = (it / HW_STAGES) & 1;
-    mbar_wait(&sm.full[s], ph);  // the producer arrives on `full` only after phase A has landed
-    const HwMeta mt = sm.meta[s];
-    const HwStage &st = sm.st[s];
-    const int *rp = st.rp + mt.a_off;
-    const float *lab = st.label + mt.l_off;
+  // ---- the warp's private staging pipeline ---------------------------------
+  // phase parity of every stage barrier (bit s = stage s); a barrier is armed once per
+  // non-skipped tile and awaited exactly once, so the bits follow the barrier phases
+  unsigned ph_a = 0, ph_b = 0;
+  auto tile_of = [&](int j) { return wslot + j * wstride; };
+  auto skip_tile = [&](int j) -> bool { return GENERIC && tile_flag[tile_of(j)] == 0; };
+  // phase A: row_ptr[3*r0 .. 3*(r0+nrow)] and label[r0 .. r0+nrow), 16-byte aligned windows
+  auto issue_a = [&](int j) {
+    if (j >= nlocal || skip_tile(j)) return;
+    __syncwarp();  // every lane is done reading the stage being refilled
+    if (lane == 0) {
+      HwStage &st = sw.st[j % HW_STAGES];
+      const int r0 = row_begin + tile_of(j) * HW_TILE;
+      const int nrow = min(HW_TILE, row_end - r0);
+      const int a_off = (3 * r0) & 3, l_off = r0 & 3;
+      const unsigned bytesA = (unsigned)((a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
+      const unsigned bytesL = (unsigned)((l_off + nrow + 3) & ~3) * 4u;
+      mbar_arrive_expect_tx(&sw.barA[j % HW_STAGES], bytesA + bytesL);
+      bulk_g2s(st.rp, csr.row_ptr + (3 * r0 - a_off), bytesA, &sw.barA[j % HW_STAGES]);
+      bulk_g2s(st.label, csr.label + (r0 - l_off), bytesL, &sw.barA[j % HW_STAGES]);
+    }
+  };
+  // the tile's feature window [v0, v1) (positions relative to csr.val_base), known once A landed
+  struct Win {
+    int v0, v1, v_off, nel, staged;
+  };
+  auto window = [&](int j) -> Win {
+    const HwStage &st = sw.st[j % HW_STAGES];
+    const int r0 = row_begin + tile_of(j) * HW_TILE;
+    const int nrow = min(HW_TILE, row_end - r0);
+    const int a_off = (3 * r0) & 3;
+    Win w;
+    w.v0 = st.rp[a_off] - csr.val_base;
+    w.v1 = st.rp[a_off + 3 * nrow] - csr.val_base;
+    w.v_off = w.v0 & 3;
+    w.nel = (w.v_off + (w.v1 - w.v0) + 3) & ~3;
+    w.staged = (w.v0 >= 0 && w.v1 >= w.v0 && w.v1 + csr.val_base <= csr.val_end && w.nel <= HW_CAP + 8) ? 1 : 0;
+    return w;
+  };
+  // phase B: the tile's index/value window
+  auto issue_b = [&](int j) {
+    if (j >= nlocal || skip_tile(j)) return;
+    mbar_wait(&sw.barA[j % HW_STAGES], (ph_a >> (j % HW_STAGES)) & 1u);
+    ph_a ^= 1u << (j % HW_STAGES);
+    const Win w = window(j);
+    if (lane == 0 && w.staged && w.nel > 0) {
+      HwStage &st = sw.st[j % HW_STAGES];
+      mbar_arrive_expect_tx(&sw.barB[j % HW_STAGES], 2u * (unsigned)w.nel * 4u);
+      bulk_g2s(st.idx, csr.index + (w.v0 - w.v_off), (unsigned)w.nel * 4u, &sw.barB[j % HW_STAGES]);
+      bulk_g2s(st.val, csr.value + (w.v0 - w.v_off), (unsigned)w.nel * 4u, &sw.barB[j % HW_STAGES]);
+    }
+  };
+
+  // wait for phase B of tile j (once per tile) ...
+  auto wait_b = [&](int j) {
+    if (j >= nlocal || skip_tile(j)) return;
+    const Win w = window(j);
+    if (w.staged && w.nel > 0) {
+      mbar_wait(&sw.barB[j % HW_STAGES], (ph_b >> (j % HW_STAGES)) & 1u);
+      ph_b ^= 1u << (j % HW_STAGES);
+    }
+  };
+  // ... and pull the user rows (and user biases) of that tile into L2 a whole tile ahead of
+  // their use: ~1/3 of the user-row gathers of configs[1] miss L2, and a DRAM miss is longer
+  // than the one-instance register prefetch covers.  Item rows are L2-resident already.
+  auto l2_prefetch_tile = [&](int j) {
+    if (GENERIC || j >= nlocal) return;
+    const Win w = window(j);
+    if (!w.staged) return;
+    const HwStage &st = sw.st[j % HW_STAGES];
+    const int r0 = row_begin + tile_of(j) * HW_TILE;
+    const int nrow = min(HW_TILE, row_end - r0);
+    const int *rp = st.rp + ((3 * r0) & 3);
+    const int sm_base = w.v0 - w.v_off + csr.val_base, v_hi = w.v1 + csr.val_base;
+    const int row_bytes = m.pitch * 4;
+    for (int q = lane; q < nrow; q += 32) {
+      const int f = rp[3 * q + 1];
+      if (f < sm_base || f >= v_hi) continue;
+      const unsigned uid = st.idx[f - sm_base];
+      if (uid >= (unsigned)m.num_user) continue;
+      const char *row = reinterpret_cast<const char *>(m.W + ((size_t)m.user_off + uid) * (size_t)m.pitch);
+      for (int b = 0; b < row_bytes; b += 128) prefetch_l2(row + b);
+      if (!m.no_user_bias) prefetch_l2(m.bias + m.user_off + uid);
+    }
+  };
+
+  issue_a(0);
+  issue_a(1);
+  issue_a(2);
+  issue_b(0);
+  issue_b(1);
+  wait_b(0);
+  l2_prefetch_tile(0);
+  for (int j = 0; j < nlocal; ++j) {
+    issue_a(j + 3);
+    issue_b(j + 2);
+    wait_b(j + 1);
+    l2_prefetch_tile(j + 1);
+    if (skip_tile(j)) continue;
+    const HwStage &st = sw.st[j % HW_STAGES];
+    const int t = tile_of(j);
+    const int r0 = row_begin + t * HW_TILE;
+    const int nrow = min(HW_TILE, row_end - r0);
+    const int *rp = st.rp + ((3 * r0) & 3);
+    const float *lab = st.label + (r0 & 3);
+    const Win w = window(j);  // A(j) and B(j) were awaited one tile ago
+    const int sm_base = w.v0 - w.v_off + csr.val_base;  // absolute feature position held by idx[0]
+    const int v_hi = w.v1 + csr.val_base;
 
     if (GENERIC) {
       // ---- pass 2: whatever pass 1 left in this (flagged) tile ----
-      if (!mt.skip) {
-        const unsigned *idx = mt.staged ? (st.idx - mt.sm_base) : (csr.index - csr.val_base);
-        const float *val = mt.staged ? (st.val - mt.sm_base) : (csr.value - csr.val_base);
-        for (int q = gid; q < mt.nrow; q += NGROUP) {
-          if (mt.staged && is_simple(rp, q) && rp[3 * q] >= mt.sm_base && rp[3 * q + 3] <= mt.v_hi) continue;  // done by pass 1
-          if (!row_ok(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], csr.val_base, csr.val_end)) {
-            if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
-            continue;
-          }
-          const float pr = process_instance<LANES, VEC, EXACT_DOT, TRAIN, false>(
-              g, m, hp, rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], lab[q], idx, val,
-              scatter_user, scatter_item, nullptr, err_flag);
-          if (!TRAIN && g.gl == 0) pred_out[mt.r0 + q - row_begin] = pr;
+      const unsigned *idx = w.staged ? (st.idx - sm_base) : (csr.index - csr.val_base);
+      const float *val = w.staged ? (st.val - sm_base) : (csr.value - csr.val_base);
+      for (int q = gw; q < nrow; q += GPW) {
+        if (w.staged && is_simple(rp, q) && rp[3 * q] >= sm_base && rp[3 * q + 3] <= v_hi) continue;  // done by pass 1
+        if (!row_ok(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], csr.val_base, csr.val_end)) {
+          if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
+          continue;
         }
+        const float pr = process_instance<LANES, VEC, EXACT_DOT, TRAIN, false>(
+            g, m, hp, rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], lab[q], idx, val,
+            scatter_user, scatter_item, nullptr, err_flag);
+        if (!TRAIN && g.gl == 0) pred_out[r0 + q - row_begin] = pr;
       }
-    } else if (!mt.staged) {
-      // window did not fit: the whole tile goes to pass 2
-      if (threadIdx.x == 0) tile_flag[mt.tile] = 1;
+    } else if (!w.staged) {
+      // window did not fit (or is malformed): the whole tile goes to pass 2
+      if (lane == 0) tile_flag[t] = 1;
     } else {
       // ---- pass 1: straight-line basic-MF rows, gathers one instance ahead ----
-      const unsigned *sidx = st.idx - mt.sm_base;
-      const float *sval = st.val - mt.sm_base;
+      const unsigned *sidx = st.idx - sm_base;
+      const float *sval = st.val - sm_base;
       bool other = false;  // this group met a row of another shape
 
       auto pre_load = [&](Pre<VEC> &p, int q) {
         p.q = -1;
-        if (q >= mt.nrow) return;
+        if (q >= nrow) return;
         const int f = rp[3 * q + 1];
-        if (!is_simple(rp, q) || f < mt.sm_base || f + 2 > mt.v_hi) {
+        if (!is_simple(rp, q) || f < sm_base || f + 2 > v_hi) {
           other = true;
           return;
         }
-        p.uid = sidx[f];
-        p.iid = sidx[f + 1];
-        if (p.uid >= (unsigned)m.num_user || p.iid >= (unsigned)m.num_item) {
-          if (g.gl == 0) atomicCAS(err_flag, 0, p.uid >= (unsigned)m.num_user ? ERR_USER_INDEX : ERR_ITEM_INDEX);
+        const unsigned uid = sidx[f], iid = sidx[f + 1];
+        if (uid >= (unsigned)m.num_user || iid >= (unsigned)m.num_item) {
+          if (g.gl == 0) atomicCAS(err_flag, 0, uid >= (unsigned)m.num_user ? ERR_USER_INDEX : ERR_ITEM_INDEX);
           return;
         }
         p.q = q;
-        p.uval = sval[f];
-        p.ival = sval[f + 1];
-        p.label = lab[q];
-        g.load_row(m, (size_t)m.user_off + p.uid, p.wu);
-        g.load_row(m, (size_t)m.item_off + p.iid, p.wi);
-        p.ub = m.no_user_bias ? 0.0f : __ldcg(m.bias + m.user_off + p.uid);
-        p.ib = __ldcg(m.bias + m.item_off + p.iid);
+        g.load_row(m, (size_t)m.user_off + uid, p.wu);
+        g.load_row(m, (size_t)m.item_off + iid, p.wi);
+        p.ub = m.no_user_bias ? 0.0f : __ldcg(m.bias + m.user_off + uid);
+        p.ib = __ldcg(m.bias + m.item_off + iid);
       };
 
       auto compute = [&](const Pre<VEC> &p) {
         if (p.q < 0) return;
+        // the row's scalars come back from the staged tile (cheaper than carrying them)
+        const int f = rp[3 * p.q + 1];
+        const unsigned uid = sidx[f], iid = sidx[f + 1];
+        const float uval = sval[f], ival = sval[f + 1];
         // prepare_tmp (base.h:354-381): tmp = 0 + w*val
         float4 tu[VEC], ti[VEC];
-        const bool one_u = scalar_is_one(p.uval), one_i = scalar_is_one(p.ival);
+        const bool one_u = scalar_is_one(uval), one_i = scalar_is_one(ival);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          tu[v] = f4_add_scaled(f4_zero(), p.wu[v], p.uval, one_u);
-          ti[v] = f4_add_scaled(f4_zero(), p.wi[v], p.ival, one_i);
+          tu[v] = f4_add_scaled(f4_zero(), p.wu[v], uval, one_u);
+          ti[v] = f4_add_scaled(f4_zero(), p.wi[v], ival, one_i);
         }
         // calc_bias (base.h:313-353) + pred (base.h:445-454)
         double bsum = 0.0;
-        if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(p.uval, p.ub));
-        bsum = __dadd_rn(bsum, (double)__fmul_rn(p.ival, p.ib));
+        if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, p.ub));
+        bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, p.ib));
         const float d = g.template dot<EXACT_DOT>(m, tu, ti);
         double sum = __dadd_rn((double)hp.base_score, bsum);
         sum = __dadd_rn(sum, (double)d);
         const float pred = map_active((float)sum, m.active_type);
         if (!TRAIN) {
-          if (g.gl == 0) pred_out[mt.r0 + p.q - row_begin] = pred;
+          if (g.gl == 0) pred_out[r0 + p.q - row_begin] = pred;
           return;
         }
         // update_no_decay + regularize(after), fused (base.h:383-427, 211-283)
-        const float err = cal_grad(p.label, pred, m.active_type);
+        const float err = cal_grad(lab[p.q], pred, m.active_type);
         const float lrerr = __fmul_rn(hp.lr, err);
-        const float su = __fmul_rn(lrerr, p.uval), si = __fmul_rn(lrerr, p.ival);
+        const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);
         const bool one_su = scalar_is_one(su), one_si = scalar_is_one(si);
         float4 nw[VEC];
 #pragma unroll
@@ -249,23 +283,23 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
           nw[v] = f4_add_scaled(p.wu[v], ti[v], su, one_su);
           if (!hp.du_skip) nw[v] = f4_scale(nw[v], hp.du);
         }
-        if (scatter_user == SCATTER_RED) g.red_row(m, (size_t)m.user_off + p.uid, nw, p.wu);
-        else g.store_row(m, (size_t)m.user_off + p.uid, nw);
+        if (scatter_user == SCATTER_RED) g.red_row(m, (size_t)m.user_off + uid, nw, p.wu);
+        else g.store_row(m, (size_t)m.user_off + uid, nw);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           nw[v] = f4_add_scaled(p.wi[v], tu[v], si, one_si);
           if (!hp.di_skip) nw[v] = f4_scale(nw[v], hp.di);
         }
-        if (scatter_item == SCATTER_RED) g.red_row(m, (size_t)m.item_off + p.iid, nw, p.wi);
-        else g.store_row(m, (size_t)m.item_off + p.iid, nw);
+        if (scatter_item == SCATTER_RED) g.red_row(m, (size_t)m.item_off + iid, nw, p.wi);
+        else g.store_row(m, (size_t)m.item_off + iid, nw);
         if (g.gl == 0 && !m.no_user_bias) {
-          float *bp = m.bias + m.user_off + p.uid;
+          float *bp = m.bias + m.user_off + uid;
           const float nb = __fmul_rn(__fadd_rn(p.ub, su), hp.dub);
           if (scatter_user == SCATTER_RED) red1(bp, __fsub_rn(nb, p.ub));
           else __stcg(bp, nb);
         }
         if (g.gl == 1) {
-          float *bp = m.bias + m.item_off + p.iid;
+          float *bp = m.bias + m.item_off + iid;
           const float nb = __fmul_rn(__fadd_rn(p.ib, si), hp.dib);
           if (scatter_item == SCATTER_RED) red1(bp, __fsub_rn(nb, p.ib));
           else __stcg(bp, nb);
@@ -273,21 +307,19 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
       };
 
       Pre<VEC> A, B;
-      int q = gid;
+      int q = gw;
       pre_load(A, q);
-      while (q < mt.nrow) {
-        pre_load(B, q + NGROUP);
+      while (q < nrow) {
+        pre_load(B, q + GPW);
         compute(A);
-        q += NGROUP;
-        if (q >= mt.nrow) break;
-        pre_load(A, q + NGROUP);
+        q += GPW;
+        if (q >= nrow) break;
+        pre_load(A, q + GPW);
         compute(B);
-        q += NGROUP;
+        q += GPW;
       }
-      if (__any_sync(g.gmask, other) && g.gl == 0) tile_flag[mt.tile] = 1;
+      if (__any_sync(0xffffffffu, other) && lane == 0) tile_flag[t] = 1;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[s]);
   }
 }
 
@@ -308,9 +340,11 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
 #define GO(ED, TR, GEN)                                                                          \
   {                                                                                              \
     auto k = k_stream<L, V, ED, TR, GEN>;                                                        \
-    if (grid_for(h, k, HW_THREADS, ntile, &grid)) return 1;                                      \
-    k<<<grid, HW_THREADS, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,           \
-                                          h->scatter_item, pred, h->d_tile_flag, h->d_err);      \
+    const size_t smem = hw_smem_bytes<L, V, ED>();                                               \
+    CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    if (grid_for(h, k, HW_THREADS, (ntile + HW_WARPS - 1) / HW_WARPS, &grid, smem)) return 1;    \
+    k<<<grid, HW_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
+                                             h->scatter_item, pred, h->d_tile_flag, h->d_err);   \
     h->n_launch++;                                                                               \
   }
   if (train) {

@@ -121,7 +121,8 @@ def test_hogwild_fast_dot_close(native):
 def test_hogwild_statistical_parity(native):
     """Conflicting input (Zipf items): Hogwild differs from the sequential order only
     through races.  After 3 epochs the predictions stay close and the held-out RMSE matches."""
-    nu, ni, n = 20000, 2000, 400000
+    # users in flight / users comparable to configs[1] (a B200 keeps ~19k instances in flight)
+    nu, ni, n = 200000, 5000, 2000000
     params = dict(num_user=nu, num_item=ni, num_factor=64, learning_rate=0.005, wd_user=0.004, wd_item=0.004,
                   base_score=3.6)
     train = synth.basic_mf(n, nu, ni, seed=21)

@@ -221,7 +221,7 @@ def c3(scale):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if a in ("c2", "c3", "c4", "c5")]
     scale = 1.0
     if "--scale" in sys.argv:
         scale = float(sys.argv[sys.argv.index("--scale") + 1])
