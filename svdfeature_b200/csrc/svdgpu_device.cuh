@@ -416,16 +416,8 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
     }
   }
 
-  // ---- calc_bias (base.h:313-353) ------------------------------------------
-  double bsum = 0.0;
-  bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
-  if (!m.no_user_bias) {
-    bsum = g.bias_sum(bsum, m.bias, m.user_off, idx, val, rp1, rp2);
-    if (SVDPP) bsum = __dadd_rn(bsum, (double)fbs->fb_bias);  // get_bias_svdpp, base.h:509-511
-  }
-  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, rp2, rp3);
-
   // ---- prepare_tmp (base.h:354-381) ----------------------------------------
+  // (issued before calc_bias so that the row gathers and the bias gathers are in flight together)
   float4 tu[VEC], ti[VEC], wu0[VEC], wi0[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -456,6 +448,15 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       if (f == rp2) wi0[v] = w[v];
     }
   }
+
+  // ---- calc_bias (base.h:313-353) ------------------------------------------
+  double bsum = 0.0;
+  bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
+  if (!m.no_user_bias) {
+    bsum = g.bias_sum(bsum, m.bias, m.user_off, idx, val, rp1, rp2);
+    if (SVDPP) bsum = __dadd_rn(bsum, (double)fbs->fb_bias);  // get_bias_svdpp, base.h:509-511
+  }
+  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, rp2, rp3);
 
   // ---- pred (base.h:445-454) ------------------------------------------------
   const float d = g.template dot<EXACT_DOT>(m, tu, ti);
