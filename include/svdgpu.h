@@ -50,11 +50,15 @@ typedef struct {
   float wd_user, wd_item;
   float wd_user_bias, wd_item_bias;
   float wd_global;
-  int reg_method;  /* base.h:211-283: 0 L2 decay (supported), 1/3 L1, 2 projection */
-  int reg_global;  /* base.h:188-210: 0 L2 decay (supported), 1 L1                  */
+  int reg_method;  /* base.h:211-283: 0 L2 decay, 1 L1 soft threshold, 2 projection onto
+                      |w|^2 <= wd, 3 L1 on user rows + L2 decay on item rows.  The lazy
+                      variants 4/5 are rejected (broken in the reference: base.h:195,226) */
+  int reg_global;  /* base.h:188-210: 0 L2 decay, 1 L1 (4/5 rejected)              */
   unsigned num_regfree_global;
   float scale_lr_ufeedback, wd_ufeedback, wd_ufeedback_bias; /* base.h:512-520 */
   float base_score;
+  int user_nonnegative; /* SVDModelParam::user_nonnegative: clamp user rows at 0 after
+                           every update (base.h:242-245)                            */
 } svdgpu_hparams;
 
 /* How instances of one call are ordered against each other. */

@@ -38,7 +38,7 @@ class HParams(C.Structure):
         ("wd_user_bias", C.c_float), ("wd_item_bias", C.c_float), ("wd_global", C.c_float),
         ("reg_method", C.c_int), ("reg_global", C.c_int), ("num_regfree_global", C.c_uint),
         ("scale_lr_ufeedback", C.c_float), ("wd_ufeedback", C.c_float),
-        ("wd_ufeedback_bias", C.c_float), ("base_score", C.c_float)]
+        ("wd_ufeedback_bias", C.c_float), ("base_score", C.c_float), ("user_nonnegative", C.c_int)]
 
 
 # every symbol include/svdgpu.h declares: (restype, argtypes)

@@ -227,12 +227,18 @@ class GpuSVDFeature : public ISVDTrainer {
       float *base = &W_[(size_t)ustart_ * pitch_];
       for (int y = 0; y < ny; ++y)
         for (int x = 0; x < k; ++x) base[(size_t)y * pitch_ + x] = (float)sample_normal() * mp_.u_init_sigma;
+      if (mp_.user_nonnegative)  // model.h:678-683 (all num_user rows)
+        for (int y = 0; y < mp_.num_user; ++y)
+          for (int x = 0; x < k; ++x) base[(size_t)y * pitch_ + x] = fabsf(base[(size_t)y * pitch_ + x]);
     }
     {
       const int ny = mp_.num_randinit_ifactor != 0 ? mp_.num_randinit_ifactor : mp_.num_item;
       float *base = &W_[(size_t)(ustart_ + mp_.num_user) * pitch_];
       for (int y = 0; y < ny; ++y)
         for (int x = 0; x < k; ++x) base[(size_t)y * pitch_ + x] = (float)sample_normal() * mp_.i_init_sigma;
+      if (mp_.item_nonnegative)  // model.h:695-700 (the randomly initialised rows)
+        for (int y = 0; y < ny; ++y)
+          for (int x = 0; x < k; ++x) base[(size_t)y * pitch_ + x] = fabsf(base[(size_t)y * pitch_ + x]);
     }
     if (mtype_.format_type == svd_type::USER_GROUP_FORMAT) {
       for (int y = 0; y < mp_.num_ufeedback; ++y)
@@ -341,8 +347,6 @@ class GpuSVDFeature : public ISVDTrainer {
   void alloc_host() {  // model.h:511-556 (separate index spaces only)
     if (mp_.common_latent_space != 0 || mp_.common_feedback_space != 0)
       apex_utils::error("common_latent_space / common_feedback_space are not supported by the GPU trainer");
-    if (mp_.user_nonnegative != 0 || mp_.item_nonnegative != 0)
-      apex_utils::error("user_nonnegative / item_nonnegative are not supported by the GPU trainer");
     ustart_ = (mtype_.format_type == svd_type::USER_GROUP_FORMAT) ? mp_.num_ufeedback : 0;
     rows_total_ = (size_t)ustart_ + (size_t)mp_.num_user + (size_t)mp_.num_item;
     pitch_ = ((mp_.num_factor + 3) >> 2) << 2;
@@ -375,6 +379,7 @@ class GpuSVDFeature : public ISVDTrainer {
   }
   void push_hparams() {
     hp_.base_score = mp_.base_score;
+    hp_.user_nonnegative = mp_.user_nonnegative;
     check(h_, svdgpu_set_hparams(h_, &hp_));
   }
   void upload() { check(h_, svdgpu_upload_model(h_, ui_bias_.data(), W_.data(), (size_t)pitch_, g_bias_.data())); }

@@ -102,7 +102,14 @@ int h2d(svdgpu *h, DevBuf &d, HostBuf &stage, const void *src, size_t bytes) {
     memcpy(stage.p, src, bytes);
     from = stage.p;
   }
-  CU(h, cudaMemcpyAsync(d.p, from, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(d.p, from, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  h->n_h2d += (long long)bytes;
+  return 0;
+}
+// H2D of library-owned pinned memory into a slot buffer (tickets, block tables)
+int h2d_pinned(svdgpu *h, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return 0;
+  CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
   h->n_h2d += (long long)bytes;
   return 0;
 }
@@ -135,6 +142,17 @@ void refresh_hp(svdgpu *h) {
   d.dfb_skip = is_one_host(d.dfb);
   volatile float lfb = lrfb * p.wd_ufeedback_bias;  // base.h:518
   d.dfbb = 1.0f - lfb;
+  // reg_method 3: L1 on user rows, plain decay on item rows (base.h:217,256)
+  d.reg_user = p.reg_method == 3 ? 1 : p.reg_method;
+  d.reg_item = p.reg_method == 3 ? 0 : p.reg_method;
+  d.reg_global = p.reg_global;
+  d.l1_u = lu;
+  d.l1_i = li;
+  d.pb_u = p.wd_user;
+  d.pb_i = p.wd_item;
+  d.l1_g = lg;
+  d.user_nonneg = p.user_nonnegative != 0;
+  d.plain = (d.reg_user == 0 && d.reg_item == 0 && d.reg_global == 0 && !d.user_nonneg) ? 1 : 0;
 }
 
 // ---- lane geometry -----------------------------------------------------------
@@ -207,22 +225,38 @@ void reset_ticket_counters(svdgpu *h) {
 int check_ready(svdgpu *h) {
   if (!h) return 1;
   if (!h->hp_set) return fail(h, "svdgpu_set_hparams has not been called");
-  if (h->hp.reg_method != 0)
-    return fail(h, "reg_method=%d is not supported on the GPU path (only 0: L2 decay)", h->hp.reg_method);
-  if (h->hp.reg_global != 0)
-    return fail(h, "reg_global=%d is not supported on the GPU path (only 0: L2 decay)", h->hp.reg_global);
+  if (h->hp.reg_method < 0 || h->hp.reg_method > 3)
+    return fail(h, "reg_method=%d is not supported on the GPU path (0 L2 decay, 1 L1, 2 projection, 3 L1 user/L2 item)",
+                h->hp.reg_method);
+  if (h->hp.reg_global != 0 && h->hp.reg_global != 1)
+    return fail(h, "reg_global=%d is not supported on the GPU path (0 L2 decay, 1 L1)", h->hp.reg_global);
   return 0;
 }
 
+// Staging pipeline of the host-pointer calls: the H2D copies of a chunk go to the copy
+// stream into one of NSLOT slots, the kernels of that chunk wait for them on the launch
+// stream (slot_copied), and the slot is reused once its kernels are done (next_slot), so
+// the copy of chunk c+1 overlaps the kernels of chunk c.
 Slot &next_slot(svdgpu *h) {
   Slot &s = h->slot[h->cur_slot];
-  h->cur_slot ^= 1;
+  h->cur_slot = (h->cur_slot + 1) % svdgpu::NSLOT;
   if (s.used) cudaEventSynchronize(s.done);
   return s;
+}
+int slot_copied(svdgpu *h, Slot &s) {
+  CU(h, cudaEventRecord(s.copied, h->copy_stream));
+  CU(h, cudaStreamWaitEvent(h->stream, s.copied, 0));
+  return 0;
 }
 int slot_done(svdgpu *h, Slot &s) {
   CU(h, cudaEventRecord(s.done, h->stream));
   s.used = true;
+  return 0;
+}
+// host arrays are borrowed for the call only: wait until the copies have read them
+int copies_drained(svdgpu *h) {
+  CU(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+  CU(h, cudaEventSynchronize(h->ev_copy));
   return 0;
 }
 
@@ -314,7 +348,11 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
   CUC(cudaEventCreate(&h->ev0));
   CUC(cudaEventCreate(&h->ev1));
   CUC(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-  for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming));
+  CUC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < svdgpu::NSLOT; ++i) {
+    CUC(cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->slot[i].copied, cudaEventDisableTiming));
+  }
 
   DevModel &m = h->dm;
   memset(&m, 0, sizeof(m));
@@ -355,6 +393,7 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
 void svdgpu_destroy(svdgpu_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->dm.W);
   cudaFree(h->dm.bias);
@@ -366,17 +405,19 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->d_tile_flag);
   cudaFree(h->d_snap);
   cudaFree(h->d_delta);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < svdgpu::NSLOT; ++i) {
     Slot &s = h->slot[i];
     HostBuf *hb[] = {&s.h_rp, &s.h_label, &s.h_index, &s.h_value, &s.h_ticket, &s.h_misc, &s.h_fbi, &s.h_fbv, &s.h_fbt};
     for (HostBuf *b : hb) host_free(*b);
     DevBuf *db[] = {&s.d_rp, &s.d_label, &s.d_index, &s.d_value, &s.d_ticket, &s.d_misc, &s.d_fbi, &s.d_fbv, &s.d_fbt, &s.d_pred};
     for (DevBuf *b : db) dev_free(*b);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.copied) cudaEventDestroy(s.copied);
   }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -558,9 +599,9 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
       reset_ticket_counters(h);
       if (make_tickets(h, r0, r1, row_ptr, index, (unsigned *)s.h_ticket.p)) return 1;
       if (dev_reserve(h, s.d_ticket, nv * 4)) return 1;
-      if (nv) CU(h, cudaMemcpyAsync(s.d_ticket.p, s.h_ticket.p, nv * 4, cudaMemcpyHostToDevice, h->stream));
-      h->n_h2d += (long long)nv * 4;
+      if (h2d_pinned(h, s.d_ticket.p, s.h_ticket.p, nv * 4)) return 1;
       csr.ticket = (const unsigned *)s.d_ticket.p;
+      if (slot_copied(h, s)) return 1;
       // row_ptr on the device is the slice [3*r0, 3*r1]: rows are 0..n there
       if (launch_exact(h, geo, csr, 0, n)) return 1;
     } else {
@@ -569,6 +610,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
         if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
         pred = (float *)s.d_pred.p;
       }
+      if (slot_copied(h, s)) return 1;
       if (launch_stream(h, geo, csr, 0, n, train, pred)) return 1;
       if (!train) {
         CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -578,10 +620,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     if (slot_done(h, s)) return 1;
     h->n_inst += n;
   }
-  // host arrays are borrowed for the call only: wait until the copies have read them
-  CU(h, cudaEventRecord(h->ev_copy, h->stream));
-  CU(h, cudaEventSynchronize(h->ev_copy));
-  return 0;
+  return copies_drained(h);
 }
 
 int svdgpu_update_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
@@ -674,8 +713,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     }
     unit_order(nu, [&](int u) { return (long long)(m_row[m_unit[u + 1]] - m_row[m_unit[u]]); }, m_order);
     if (dev_reserve(h, s.d_misc, misc_ints * 4)) return 1;
-    CU(h, cudaMemcpyAsync(s.d_misc.p, mi, misc_ints * 4, cudaMemcpyHostToDevice, h->stream));
-    h->n_h2d += (long long)misc_ints * 4;
+    if (h2d_pinned(h, s.d_misc.p, mi, misc_ints * 4)) return 1;
 
     DevCsr csr;
     csr.row_ptr = (const int *)s.d_rp.p;
@@ -705,9 +743,8 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
         return 1;
       if (dev_reserve(h, s.d_ticket, nv * 4)) return 1;
       if (dev_reserve(h, s.d_fbt, nfb * 4)) return 1;
-      if (nv) CU(h, cudaMemcpyAsync(s.d_ticket.p, s.h_ticket.p, nv * 4, cudaMemcpyHostToDevice, h->stream));
-      if (nfb) CU(h, cudaMemcpyAsync(s.d_fbt.p, s.h_fbt.p, nfb * 4, cudaMemcpyHostToDevice, h->stream));
-      h->n_h2d += (long long)(nv + nfb) * 4;
+      if (h2d_pinned(h, s.d_ticket.p, s.h_ticket.p, nv * 4)) return 1;
+      if (h2d_pinned(h, s.d_fbt.p, s.h_fbt.p, nfb * 4)) return 1;
       csr.ticket = (const unsigned *)s.d_ticket.p;
       ug.fb_ticket = (const unsigned *)s.d_fbt.p;
     }
@@ -716,6 +753,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
       if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
       pred = (float *)s.d_pred.p;
     }
+    if (slot_copied(h, s)) return 1;
     if (launch_ugroup(h, geo, csr, ug, 0, nu, train, exact, pred)) return 1;
     if (!train && n) {
       CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -725,9 +763,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     h->n_inst += n;
     u0 = u1;
   }
-  CU(h, cudaEventRecord(h->ev_copy, h->stream));
-  CU(h, cudaEventSynchronize(h->ev_copy));
-  return 0;
+  return copies_drained(h);
 }
 
 int svdgpu_update_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,

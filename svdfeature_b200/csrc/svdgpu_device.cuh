@@ -48,6 +48,15 @@ struct DevHP {
   float dfb;          // 1 - lr_fb*wd_ufeedback                      (base.h:515)
   int dfb_skip;
   float dfbb;         // 1 - lr_fb*wd_ufeedback_bias                 (base.h:518)
+  // regularisers other than L2 decay (base.h:188-283)
+  int reg_user;       // row regulariser of user rows: 0 L2 decay, 1 L1 soft threshold, 2 projection
+  int reg_item;       //   ... of item rows (reg_method 3 = L1 on users, L2 decay on items)
+  int reg_global;     // 0 L2 decay, 1 L1                            (base.h:192-193)
+  float l1_u, l1_i;   // lr*wd_user, lr*wd_item: the L1 thresholds   (base.h:214,254)
+  float pb_u, pb_i;   // wd_user, wd_item: the projection bounds B   (base.h:181-186,226,266)
+  float l1_g;         // lr*wd_global                                (base.h:189)
+  int user_nonneg;    // model.param.user_nonnegative                (base.h:242-245)
+  int plain;          // reg_user == reg_item == reg_global == 0 and !user_nonneg
 };
 
 // A CSR batch in HBM.  index/value/ticket hold the elements [val_base, ...) of
@@ -215,6 +224,20 @@ __device__ __forceinline__ float4 f4_scale(float4 t, float s) {
   t.z = __fmul_rn(t.z, s); t.w = __fmul_rn(t.w, s);
   return t;
 }
+// base.h:175-180 / apex_tensor_cpu_inline_common.h:168-175: L1 soft threshold
+__device__ __forceinline__ float reg_l1(float w, float eps) {
+  if (w > eps) return __fsub_rn(w, eps);
+  if (w < -eps) return __fadd_rn(w, eps);
+  return 0.0f;
+}
+__device__ __forceinline__ float4 f4_reg_l1(float4 t, float eps) {
+  return make_float4(reg_l1(t.x, eps), reg_l1(t.y, eps), reg_l1(t.z, eps), reg_l1(t.w, eps));
+}
+// tensor::smaller_then_fill(w, 0): w <= 0 -> 0 (base.h:242-245)
+__device__ __forceinline__ float4 f4_nonneg(float4 t) {
+  return make_float4(t.x <= 0.0f ? 0.0f : t.x, t.y <= 0.0f ? 0.0f : t.y, t.z <= 0.0f ? 0.0f : t.z,
+                     t.w <= 0.0f ? 0.0f : t.w);
+}
 __device__ __forceinline__ float4 f4_sub(float4 a, float4 b) {
   return make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z),
                      __fsub_rn(a.w, b.w));
@@ -318,6 +341,37 @@ struct Group {
     }
   }
 
+  // ---- row regulariser (the factor part of reg_user / reg_item, base.h:211-283) ----
+  // method 0: w *= d unless d is "one"; 1: L1 soft threshold eps; 2: projection onto
+  // |w|^2 <= B (base.h:181-186: sum = dot(w,w); if sum > B, w *= sqrtf(B/sum)).
+  // Pad floats beyond k are zero and stay zero under all three.
+  template <bool EXACT>
+  __device__ __forceinline__ void reg_row(const DevModel &m, float4 (&w)[VEC], int method, float d,
+                                          int d_skip, float eps, float B, bool nonneg) const {
+    if (method == 0) {
+      if (!d_skip) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v] = f4_scale(w[v], d);
+      }
+    } else if (method == 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = f4_reg_l1(w[v], eps);
+    } else {
+      const float sum = dot<EXACT>(m, w, w);
+      if (sum > B) {
+        const float sc = __fsqrt_rn(__fdiv_rn(B, sum));
+        if (!scalar_is_one(sc)) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) w[v] = f4_scale(w[v], sc);
+        }
+      }
+    }
+    if (nonneg) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = f4_nonneg(w[v]);
+    }
+  }
+
   // ---- ordered fp64 sum of val[f]*table[off+idx[f]] over f in [beg,end) -----
   // base.h:318-322,325-334,340-350: each product is fp32, the running sum fp64,
   // added in feature order.  Lanes fetch LANES features at a time; the adds are
@@ -354,14 +408,15 @@ struct Group {
   __device__ __forceinline__ void scalar_seg(float *table, int off, const unsigned *idx,
                                              const float *val, int beg, int end, float lrerr,
                                              float decay, bool upd, bool dec, unsigned regfree,
-                                             bool parallel, int scatter) const {
+                                             bool parallel, int scatter, bool l1 = false) const {
+    // l1: the decay step is reg_L1(x, decay) instead of x *= decay (reg_global 1, base.h:193)
     if (parallel) {
       for (int f = beg + gl; f < end; f += LANES) {
         float *p = table + off + idx[f];
         const float x0 = __ldcg(p);
         float x = x0;
         if (upd) x = __fadd_rn(x, __fmul_rn(lrerr, val[f]));
-        if (dec && idx[f] >= regfree) x = __fmul_rn(x, decay);
+        if (dec && idx[f] >= regfree) x = l1 ? reg_l1(x, decay) : __fmul_rn(x, decay);
         if (scatter == SCATTER_RED) red1(p, __fsub_rn(x, x0));
         else __stcg(p, x);
       }
@@ -371,7 +426,7 @@ struct Group {
           float *p = table + off + idx[f];
           float x = __ldcg(p);
           if (upd) x = __fadd_rn(x, __fmul_rn(lrerr, val[f]));
-          if (dec && idx[f] >= regfree) x = __fmul_rn(x, decay);
+          if (dec && idx[f] >= regfree) x = l1 ? reg_l1(x, decay) : __fmul_rn(x, decay);
           __stcg(p, x);
         }
       }
@@ -475,9 +530,11 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
   const bool fused = !(dup_u || dup_i);
 
   // globals: g_bias[gid] += lr*err*gval ; later g_bias[gid] *= 1-lr*wd_global
+  const bool g_l1 = hp.reg_global == 1;
+  const float g_dec = g_l1 ? hp.l1_g : hp.dg;
   if (rp1 > rp0)
-    g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, lrerr, hp.dg, true, !dup_g, hp.regfree, !dup_g,
-                 dup_g ? SCATTER_STORE : scatter_item);
+    g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, lrerr, g_dec, true, !dup_g, hp.regfree, !dup_g,
+                 dup_g ? SCATTER_STORE : scatter_item, g_l1);
 
   if (fused) {
     // every touched row appears once: update and decay in one register pass
@@ -495,8 +552,10 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         nw[v] = f4_add_scaled(w[v], ti[v], sc, one);
-        if (!hp.du_skip) nw[v] = f4_scale(nw[v], hp.du);
+        if (hp.plain && !hp.du_skip) nw[v] = f4_scale(nw[v], hp.du);
       }
+      if (!hp.plain)
+        g.template reg_row<EXACT_DOT>(m, nw, hp.reg_user, hp.du, hp.du_skip, hp.l1_u, hp.pb_u, hp.user_nonneg != 0);
       if (scatter_user == SCATTER_RED) g.red_row(m, row, nw, w);
       else g.store_row(m, row, nw);
     }
@@ -517,8 +576,10 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         nw[v] = f4_add_scaled(w[v], tu[v], sc, one);
-        if (!hp.di_skip) nw[v] = f4_scale(nw[v], hp.di);
+        if (hp.plain && !hp.di_skip) nw[v] = f4_scale(nw[v], hp.di);
       }
+      if (!hp.plain)
+        g.template reg_row<EXACT_DOT>(m, nw, hp.reg_item, hp.di, hp.di_skip, hp.l1_i, hp.pb_i, false);
       if (scatter_item == SCATTER_RED) g.red_row(m, row, nw, w);
       else g.store_row(m, row, nw);
     }
@@ -570,16 +631,15 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
   }
 
   // ---- regularize(after) for the unfused cases --------------------------------
-  if (dup_g) g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, 0.f, hp.dg, false, true, hp.regfree, false,
-                          SCATTER_STORE);
+  if (dup_g) g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, 0.f, g_dec, false, true, hp.regfree, false,
+                          SCATTER_STORE, g_l1);
   if (!fused) {
     for (int f = rp1; f < rp2; ++f) {
       const size_t row = (size_t)m.user_off + idx[f];
-      if (!hp.du_skip) {
+      if (!hp.plain || !hp.du_skip) {
         float4 w[VEC];
         g.load_row(m, row, w);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) w[v] = f4_scale(w[v], hp.du);
+        g.template reg_row<EXACT_DOT>(m, w, hp.reg_user, hp.du, hp.du_skip, hp.l1_u, hp.pb_u, hp.user_nonneg != 0);
         g.store_row(m, row, w);
       }
       if (!m.no_user_bias)
@@ -588,11 +648,10 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
     }
     for (int f = rp2; f < rp3; ++f) {
       const size_t row = (size_t)m.item_off + idx[f];
-      if (!hp.di_skip) {
+      if (!hp.plain || !hp.di_skip) {
         float4 w[VEC];
         g.load_row(m, row, w);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) w[v] = f4_scale(w[v], hp.di);
+        g.template reg_row<EXACT_DOT>(m, w, hp.reg_item, hp.di, hp.di_skip, hp.l1_i, hp.pb_i, false);
         g.store_row(m, row, w);
       }
       g.scalar_seg(m.bias, m.item_off, idx, val, f, f + 1, 0.f, hp.dib, false, true, 0u, false,

@@ -21,7 +21,8 @@ struct HostBuf {
 struct Slot {
   HostBuf h_rp, h_label, h_index, h_value, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
   DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
-  cudaEvent_t done = nullptr;  // last kernel that read this slot
+  cudaEvent_t done = nullptr;    // last kernel that read this slot
+  cudaEvent_t copied = nullptr;  // the slot's H2D copies have landed (recorded on the copy stream)
   bool used = false;
 };
 
@@ -67,6 +68,8 @@ struct svdgpu {
   int chunk_rows = 1 << 20;
   int ctas_per_sm = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // host-pointer calls stage chunk c+1 on this stream while the kernels of chunk c run on `stream`
+  cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
   svdk::DevModel dm;
   svdk::DevHP dhp;
@@ -75,7 +78,8 @@ struct svdgpu {
   unsigned *d_counter = nullptr;
   int *d_tile_flag = nullptr;  // k_stream: tiles that need the generic pass
   size_t tile_flag_cap = 0;
-  Slot slot[2];
+  static constexpr int NSLOT = 3;
+  Slot slot[NSLOT];
   int cur_slot = 0;
   // multi-GPU exchange
   svdk::DeltaPlan plan;

@@ -207,7 +207,8 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
       const unsigned *idx = w.staged ? (st.idx - sm_base) : (csr.index - csr.val_base);
       const float *val = w.staged ? (st.val - sm_base) : (csr.value - csr.val_base);
       for (int q = gw; q < nrow; q += GPW) {
-        if (w.staged && is_simple(rp, q) && rp[3 * q] >= sm_base && rp[3 * q + 3] <= v_hi) continue;  // done by pass 1
+        // done by pass 1 (which runs only for the plain L2-decay regulariser)
+        if (hp.plain && w.staged && is_simple(rp, q) && rp[3 * q] >= sm_base && rp[3 * q + 3] <= v_hi) continue;
         if (!row_ok(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], csr.val_base, csr.val_end)) {
           if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
           continue;
@@ -335,7 +336,10 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
     CU(h, cudaMalloc(&h->d_tile_flag, cap));
     h->tile_flag_cap = cap;
   }
-  CU(h, cudaMemsetAsync(h->d_tile_flag, 0, (size_t)ntile * sizeof(int), h->stream));
+  // the straight-line pass implements the plain L2-decay regulariser only: any other
+  // reg_method / reg_global / user_nonnegative sends every tile to the generic pass
+  const bool pass1 = h->dhp.plain != 0;
+  CU(h, cudaMemsetAsync(h->d_tile_flag, pass1 ? 0 : 1, (size_t)ntile * sizeof(int), h->stream));
   int grid = 1;
 #define GO(ED, TR, GEN)                                                                          \
   {                                                                                              \
@@ -348,10 +352,10 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
     h->n_launch++;                                                                               \
   }
   if (train) {
-    if (h->exact_dot) { GO(true, true, false) GO(true, true, true) }
-    else { GO(false, true, false) GO(false, true, true) }
+    if (h->exact_dot) { if (pass1) GO(true, true, false) GO(true, true, true) }
+    else { if (pass1) GO(false, true, false) GO(false, true, true) }
   } else {
-    GO(true, false, false) GO(true, false, true)
+    if (pass1) GO(true, false, false) GO(true, false, true)
   }
 #undef GO
   CU(h, cudaGetLastError());

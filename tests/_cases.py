@@ -77,6 +77,20 @@ def cases():
                              split_tags(synth.user_grouped(3000, NU, NI, avg_fb=40, seed=10)), "ug")
     out["svdpp_no_user_bias"] = (1, 0, dict(pp, no_user_bias=1), synth.user_grouped(2000, NU, NI, avg_fb=10, seed=14), "ug")
     out["lr_decay"] = (0, 0, dict(BASE, decay_learning_rate=1, decay_rate=0.9), synth.basic_mf(3000, NU, NI, seed=15), "csr")
+    # regularisers other than L2 decay (base.h:188-283): L1 soft threshold, projection, L1-user/L2-item,
+    # L1 on the global bias, non-negative user factors
+    out["reg_l1"] = (0, 0, dict(gen, reg_method=1, reg_global=1, wd_user=0.02, wd_item=0.03, wd_global=0.05),
+                     synth.random_general(2500, NU, NI, NG, seed=16, allow_dup=True), "csr")
+    out["reg_project"] = (0, 0, dict(gen, num_factor=24, reg_method=2, wd_user=0.0015, wd_item=0.002),
+                          synth.random_general(2500, NU, NI, NG, seed=17), "csr")
+    out["reg_l1_user_only"] = (0, 0, dict(gen, num_factor=20, reg_method=3, wd_user=0.02),
+                               synth.random_general(2500, NU, NI, NG, seed=18, allow_dup=True), "csr")
+    out["reg_project_basic_k64"] = (0, 0, dict(BASE, num_factor=64, reg_method=2, wd_user=0.005, wd_item=0.006),
+                                    synth.basic_mf(4000, NU, NI, seed=19), "csr")
+    out["user_nonnegative"] = (0, 0, dict(gen, num_factor=16, user_nonnegative=1, item_nonnegative=1),
+                               synth.random_general(2500, NU, NI, NG, seed=20), "csr")
+    out["svdpp_reg_l1"] = (1, 0, dict(pp, reg_method=1, wd_user=0.02, wd_item=0.02),
+                           synth.user_grouped(2500, NU, NI, avg_fb=12, seed=21), "ug")
     return out
 
 
@@ -86,7 +100,8 @@ SIGMOID_CASES = {"active_1", "active_2", "active_3", "active_7", "pairwise_csr",
 
 def hparams_of(params, base_score):
     keys = ("learning_rate", "wd_user", "wd_item", "wd_user_bias", "wd_item_bias", "wd_global", "reg_method",
-            "reg_global", "num_regfree_global", "scale_lr_ufeedback", "wd_ufeedback", "wd_ufeedback_bias")
+            "reg_global", "num_regfree_global", "scale_lr_ufeedback", "wd_ufeedback", "wd_ufeedback_bias",
+            "user_nonnegative")
     hp = {k: params[k] for k in keys if k in params}
     hp["base_score"] = base_score
     return hp

@@ -110,6 +110,29 @@ def test_hogwild_conflict_free_is_exact(native, k, scatter):
     assert diff == 0.0 if scatter == 0 else diff <= 1e-6, diff
 
 
+@pytest.mark.parametrize("name", ["reg_l1", "reg_project_basic_k64", "user_nonnegative"])
+def test_hogwild_other_regularisers_conflict_free(native, name):
+    """reg_method 1/2, reg_global 1 and user_nonnegative in Hogwild mode (every tile takes the
+    generic pass): on conflict-free input the result equals the sequential oracle."""
+    fmt, act, params, _, kind = CASES[name]
+    params = dict(params, num_user=3000, num_item=2500)
+    o = COracle(fmt, act, 0, params)
+    o.init(4)
+    g = native.SvdGpu(**_cases.shape_of(params, fmt, act))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_mode(native.MODE_HOGWILD)
+    g.set_option("scatter_user", 0)
+    g.set_option("scatter_item", 0)
+    g.set_option("exact_dot", 1)
+    g.upload(*[a.copy() for a in o.arrays()])
+    for r in range(3):
+        data = _conflict_free(3000, 2500, 2000, 200 + r)
+        o.update_csr(data)
+        g.update_csr(data)
+    g.sync()
+    assert _maxdiff(o, g) == 0.0
+
+
 def test_hogwild_fast_dot_close(native):
     o, g, data, kind = _pair(native, "basic_k64", native.MODE_HOGWILD, {"exact_dot": 0, "scatter_item": 0})
     data = _conflict_free(200, 100, 100, 5)
@@ -263,8 +286,11 @@ def test_index_out_of_bound_is_an_error(native):
 
 def test_unsupported_settings_fail_loudly(native):
     o, g, data, kind = _pair(native, "basic_k16", native.MODE_EXACT)
-    g.set_hparams(learning_rate=0.01, reg_method=1)
+    g.set_hparams(learning_rate=0.01, reg_method=4)  # lazy decay: broken in the reference, rejected here
     with pytest.raises(native.SvdGpuError, match="reg_method"):
+        g.update_csr(data)
+    g.set_hparams(learning_rate=0.01, reg_global=5)
+    with pytest.raises(native.SvdGpuError, match="reg_global"):
         g.update_csr(data)
     with pytest.raises(native.SvdGpuError):
         native.SvdGpu(10, 10, 8, active_type=4)
