@@ -11,8 +11,9 @@ k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch
              events on the launch stream, max over ranks)
   e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D of every
              step's batch and a D2H read of a probe prediction inside the timed region
-  roofline   dominant kernel (k_stream): algorithmic bytes (1072 B/instance)
-             / measured launch time vs the measured HBM copy peak
+  roofline   dominant kernel (k_mf, the basic-MF fast pass): algorithmic bytes (1072 B/instance,
+             SURVEY 8d) / measured launch time vs the measured HBM copy peak; `traffic` = DRAM
+             bytes per launch from the committed ncu capture (profiles/)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref) timed on the host, 1 thread,
              on a bounded prefix of the same workload
 
@@ -38,6 +39,9 @@ NUM_USER, NUM_ITEM, K = 480000, 18000, 64
 TOTAL_ROWS = 100_000_000
 HP = dict(learning_rate=0.005, wd_user=0.004, wd_item=0.004, base_score=3.6)
 BYTES_PER_INSTANCE = 8 * K * 2 + 8 * 2 + 16 + 8 * 2  # = 1072, SURVEY.md section 8(d)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_mf launch over 100M ratings, from
+# `ncu --set full` (profiles/r1_kmf_v5_100M_ncu_full_summary.txt): 7.549 GB + 8.126 GB
+NCU_DRAM_BYTES_PER_INSTANCE = (7.548526e9 + 8.126198e9) / 100e6
 
 
 def log(*a):
@@ -417,7 +421,10 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = rows * BYTES_PER_INSTANCE / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_stream" if args.mode == "hogwild" else "k_exact",
+                "traffic": rows * NCU_DRAM_BYTES_PER_INSTANCE if args.mode == "hogwild" else None,
+                "traffic_source": "ncu --set full, profiles/r1_kmf_v5_100M_ncu_full_summary.txt (156.7 B/instance: the "
+                                  "128 MB model is L2-resident, so DRAM moves less than the algorithmic bytes)",
+                "kernel": "k_mf" if args.mode == "hogwild" else "k_exact",
                 "algorithmic_bytes_per_instance": BYTES_PER_INSTANCE, "launch_ms": kms, "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0}
 

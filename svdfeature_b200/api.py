@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_GPU = os.path.join(HERE, "libsvdgpu.so")
+LIB_GPU = os.environ.get("SVDGPU_LIB") or os.path.join(HERE, "libsvdgpu.so")  # (override: kernel A/B experiments)
 LIB_TRAINER = os.path.join(HERE, "libsvdf_gpu.so")
 
 MODE_EXACT, MODE_HOGWILD = 0, 1

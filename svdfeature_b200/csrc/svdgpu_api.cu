@@ -370,8 +370,9 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
   const size_t wbytes = std::max<size_t>(h->rows, 1) * m.pitch * sizeof(float);
   CUC(cudaMalloc(&m.W, wbytes));
   CUC(cudaMemset(m.W, 0, wbytes));
-  CUC(cudaMalloc(&m.bias, std::max<size_t>(h->rows, 1) * sizeof(float)));
-  CUC(cudaMemset(m.bias, 0, std::max<size_t>(h->rows, 1) * sizeof(float)));
+  // (+4 floats: the fast pass fetches biases as aligned 16-byte windows)
+  CUC(cudaMalloc(&m.bias, (std::max<size_t>(h->rows, 1) + 4) * sizeof(float)));
+  CUC(cudaMemset(m.bias, 0, (std::max<size_t>(h->rows, 1) + 4) * sizeof(float)));
   CUC(cudaMalloc(&m.g_bias, (size_t)std::max(shape->num_global, 1) * sizeof(float)));
   CUC(cudaMemset(m.g_bias, 0, (size_t)std::max(shape->num_global, 1) * sizeof(float)));
   CUC(cudaMalloc(&m.ver_ui, std::max<size_t>(h->rows, 1) * sizeof(unsigned)));
@@ -402,7 +403,7 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->dm.ver_g);
   cudaFree(h->d_err);
   cudaFree(h->d_counter);
-  cudaFree(h->d_tile_flag);
+  cudaFree(h->d_row_mask);
   cudaFree(h->d_snap);
   cudaFree(h->d_delta);
   for (int i = 0; i < svdgpu::NSLOT; ++i) {
@@ -454,6 +455,9 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
     if (v < 1) return fail(h, "chunk_rows must be >= 1");
     h->chunk_rows = (int)std::min<long long>(v, 1LL << 28);
   } else if (!strcmp(name, "ctas_per_sm")) h->ctas_per_sm = (int)v;
+  else if (!strcmp(name, "pass1")) h->pass1 = v ? 1 : 0;
+  else if (!strcmp(name, "ring_depth")) h->ring_depth = (int)v;
+  else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else return fail(h, "unknown option '%s'", name);
   return 0;
 }

@@ -76,8 +76,12 @@ struct svdgpu {
   size_t rows = 0;
   int *d_err = nullptr;
   unsigned *d_counter = nullptr;
-  int *d_tile_flag = nullptr;  // k_stream: tiles that need the generic pass
-  size_t tile_flag_cap = 0;
+  unsigned *d_row_mask = nullptr;  // Hogwild: rows the fast pass left to the generic pass (1 bit per row)
+  size_t row_mask_cap = 0;
+  size_t any_left_at = 0;  // index of the "pass 1 left something" word inside d_row_mask
+  int pass1 = 1;  // option "pass1": 0 sends every row through the generic pass
+  int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
+  int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
   static constexpr int NSLOT = 3;
   Slot slot[NSLOT];
   int cur_slot = 0;
@@ -113,6 +117,7 @@ int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid, 
 
 // launchers (one translation unit each, so nvcc runs in parallel)
 int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred);
+int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred);
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
 int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
                   bool train, bool ordered, float *pred);

@@ -1,0 +1,427 @@
+// svdgpu_mf.cu -- k_mf: the Hogwild fast pass over rows of the basic-MF shape.
+//
+// A row of this shape has no global feature, one user feature and one item feature
+// (BASELINE configs[0..1]; SVDFeature::update_inner with ng=0, nu=1, ni=1, base.h:456-462).
+// Rows of any other shape, rows whose tile did not fit the staging window and rows with an
+// out-of-range index are left to the generic pass (k_stream): the fast pass records them in
+// a per-tile bit mask, one bit per row.
+//
+// Persistent CTAs, every warp works alone (no block-wide barrier in the loop):
+//   * CSR staging: the warp takes whole 32-row tiles (tile w, w+W, ...) and its lane 0 stages
+//     them with 1-D bulk copies (cp.async.bulk = TMA unit, SASS UBLKCP; completion on the
+//     warp's own mbarriers): phase A = the row_ptr/label window, phase B = the index/value
+//     window once A has landed; four tiles in flight.
+//   * row gathers: a ring of DEPTH iterations per warp in shared memory.  One iteration =
+//     one instance per lane group; its user row, item row and the two 16-byte windows
+//     holding its biases are fetched with cp.async.cg (SASS LDGSTS, L2-coherent, no register
+//     destination) DEPTH iterations before they are used, so every warp keeps
+//     DEPTH x (32/LANES) x 2 rows in flight without holding them in registers.  (The first
+//     version held ONE prefetched instance in registers: ncu showed the warps waiting for
+//     L2 -- long_scoreboard -- with DRAM 11 % busy.)
+//   * compute: rows come back from shared memory (LDS.128), the update is formed in
+//     registers and leaves as red.global.add.v4.f32 of (new - old) (or plain stores).
+//
+// Arithmetic is that of process_instance() (svdgpu_device.cuh), specialised: with
+// EXACT_DOT the result is bit-identical to the generic routine; without it the dot uses the
+// shuffle-tree order and the "0 +" of prepare_tmp (base.h:357,372) is dropped (it can only
+// change the sign of a zero).
+#include "svdgpu_internal.h"
+
+namespace svdk {
+
+constexpr int MF_TILE = 32;            // rows per tile = bits of one row mask
+constexpr int MF_STAGES = 2;           // staged tiles per warp (a decoded tile lives in registers)
+constexpr int MF_CAP = 2 * MF_TILE;    // staged index/value entries per tile (2 per row)
+#ifndef MF_WARPS_PER_CTA
+#define MF_WARPS_PER_CTA 8
+#endif
+constexpr int MF_WARPS = MF_WARPS_PER_CTA;
+constexpr int MF_THREADS = MF_WARPS * 32;
+
+struct __align__(16) MfStage {
+  int rp[3 * MF_TILE + 8];
+  float label[MF_TILE + 4];
+  unsigned idx[MF_CAP + 8];
+  float val[MF_CAP + 8];
+};
+struct __align__(16) MfWarp {
+  MfStage st[MF_STAGES];
+  uint64_t barA[MF_STAGES], barB[MF_STAGES];
+};
+
+template <int LANES, int VEC, int DEPTH>
+struct MfRing {
+  static constexpr int GPW = 32 / LANES;
+  static constexpr int NCH = LANES * VEC;
+  // per (iteration slot, group): user row | item row | user-bias window | item-bias window
+  static constexpr int SLOT_F4 = 2 * NCH + 2;
+  static constexpr size_t BYTES = (size_t)DEPTH * GPW * SLOT_F4 * sizeof(float4);
+};
+
+template <int LANES, int VEC, bool EXACT_DOT, int DEPTH>
+constexpr size_t mf_smem_bytes() {
+  return (sizeof(MfWarp) + MfRing<LANES, VEC, DEPTH>::BYTES) * MF_WARPS +
+         (EXACT_DOT ? sizeof(float) * MF_WARPS * (32 / LANES) * Group<LANES, VEC>::DOT_FLOATS : 0);
+}
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// One decoded tile: lane q of the warp holds row q (a tile is 32 rows).  Decoding once per
+// tile and handing the fields to the lane groups with shuffles keeps the per-instance loop
+// free of row_ptr / index loads and shape checks.
+struct MfDec {
+  unsigned urow, irow;  // slab rows of the user / item feature (valid if the row is taken)
+  float uval, ival, lab;
+  unsigned take;        // warp-uniform: bit q = the fast pass takes row q
+  unsigned left;        // warp-uniform: bit q = row q exists and is left to the generic pass
+  bool all_one;         // warp-uniform: every taken row has uval = ival = "one"
+  int r0;               // first row of the tile (absolute)
+};
+
+template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB>
+__global__ void __launch_bounds__(MF_THREADS, MINB)
+k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user, int scatter_item,
+     float *pred_out, unsigned *row_mask, unsigned *any_left) {
+  using Ring = MfRing<LANES, VEC, DEPTH>;
+  constexpr int GPW = Ring::GPW, NCH = Ring::NCH;
+  constexpr int ITER = MF_TILE / GPW;  // iterations per tile
+  static_assert(ITER % DEPTH == 0 && DEPTH <= ITER, "ring depth must divide the iterations of a tile");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MfWarp &sw = reinterpret_cast<MfWarp *>(smem_raw)[warp];
+  float4 *ring = reinterpret_cast<float4 *>(smem_raw + sizeof(MfWarp) * MF_WARPS + Ring::BYTES * warp);
+  float *dot_base = reinterpret_cast<float *>(smem_raw + (sizeof(MfWarp) + Ring::BYTES) * MF_WARPS);
+
+  const int ntile = (row_end - row_begin + MF_TILE - 1) / MF_TILE;
+  const int wslot = blockIdx.x * MF_WARPS + warp;
+  const int wstride = gridDim.x * MF_WARPS;
+  const int nlocal = ntile > wslot ? (ntile - wslot + wstride - 1) / wstride : 0;
+
+  if (lane == 0) {
+    for (int s = 0; s < MF_STAGES; ++s) {
+      mbar_init(&sw.barA[s], 1);
+      mbar_init(&sw.barB[s], 1);
+    }
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  Group<LANES, VEC> g;
+  g.gl = lane % LANES;
+  const int gw = lane / LANES;
+  g.gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (gw * LANES));
+  g.dot_s = EXACT_DOT ? dot_base + (warp * GPW + gw) * Group<LANES, VEC>::DOT_FLOATS : nullptr;
+
+  // ---- CSR staging (same scheme as k_stream, 32-row tiles) -------------------------------
+  unsigned ph_a = 0, ph_b = 0;
+  auto tile_of = [&](int j) { return wslot + j * wstride; };
+  auto issue_a = [&](int j) {
+    if (j >= nlocal) return;
+    __syncwarp();  // every lane is done reading the stage being refilled
+    if (lane == 0) {
+      MfStage &st = sw.st[j % MF_STAGES];
+      const int r0 = row_begin + tile_of(j) * MF_TILE;
+      const int nrow = min(MF_TILE, row_end - r0);
+      const int a_off = (3 * r0) & 3, l_off = r0 & 3;
+      const unsigned bytesA = (unsigned)((a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
+      const unsigned bytesL = (unsigned)((l_off + nrow + 3) & ~3) * 4u;
+      mbar_arrive_expect_tx(&sw.barA[j % MF_STAGES], bytesA + bytesL);
+      bulk_g2s(st.rp, csr.row_ptr + (3 * r0 - a_off), bytesA, &sw.barA[j % MF_STAGES]);
+      bulk_g2s(st.label, csr.label + (r0 - l_off), bytesL, &sw.barA[j % MF_STAGES]);
+    }
+  };
+  struct Win {
+    int v0, v1, v_off, nel, staged;
+  };
+  auto window = [&](int j) -> Win {
+    const MfStage &st = sw.st[j % MF_STAGES];
+    const int r0 = row_begin + tile_of(j) * MF_TILE;
+    const int nrow = min(MF_TILE, row_end - r0);
+    const int a_off = (3 * r0) & 3;
+    Win w;
+    w.v0 = st.rp[a_off] - csr.val_base;
+    w.v1 = st.rp[a_off + 3 * nrow] - csr.val_base;
+    w.v_off = w.v0 & 3;
+    w.nel = (w.v_off + (w.v1 - w.v0) + 3) & ~3;
+    w.staged = (w.v0 >= 0 && w.v1 >= w.v0 && w.v1 + csr.val_base <= csr.val_end && w.nel <= MF_CAP + 8) ? 1 : 0;
+    return w;
+  };
+  auto issue_b = [&](int j) {
+    if (j >= nlocal) return;
+    mbar_wait(&sw.barA[j % MF_STAGES], (ph_a >> (j % MF_STAGES)) & 1u);
+    ph_a ^= 1u << (j % MF_STAGES);
+    const Win w = window(j);
+    if (lane == 0 && w.staged && w.nel > 0) {
+      MfStage &st = sw.st[j % MF_STAGES];
+      mbar_arrive_expect_tx(&sw.barB[j % MF_STAGES], 2u * (unsigned)w.nel * 4u);
+      bulk_g2s(st.idx, csr.index + (w.v0 - w.v_off), (unsigned)w.nel * 4u, &sw.barB[j % MF_STAGES]);
+      bulk_g2s(st.val, csr.value + (w.v0 - w.v_off), (unsigned)w.nel * 4u, &sw.barB[j % MF_STAGES]);
+    }
+  };
+  auto wait_b = [&](int j) {
+    if (j >= nlocal) return;
+    const Win w = window(j);
+    if (w.staged && w.nel > 0) {
+      mbar_wait(&sw.barB[j % MF_STAGES], (ph_b >> (j % MF_STAGES)) & 1u);
+      ph_b ^= 1u << (j % MF_STAGES);
+    }
+  };
+  // decode tile j (its A and B phases have landed): lane q looks at row q
+  auto decode = [&](int j) -> MfDec {
+    MfDec d;
+    d.urow = d.irow = 0u;
+    d.uval = d.ival = d.lab = 0.0f;
+    d.take = d.left = 0u;
+    d.all_one = true;
+    d.r0 = 0;
+    if (j >= nlocal) return d;
+    const MfStage &st = sw.st[j % MF_STAGES];
+    d.r0 = row_begin + tile_of(j) * MF_TILE;
+    const int nrow = min(MF_TILE, row_end - d.r0);
+    const Win w = window(j);
+    const int sm_base = w.v0 - w.v_off + csr.val_base;  // absolute feature position held by idx[0]
+    const int v_hi = w.v1 + csr.val_base;
+    const int *rp = st.rp + ((3 * d.r0) & 3) + 3 * lane;
+    bool ok = w.staged && lane < nrow;
+    bool one = true;
+    if (ok) {
+      const int rp0 = rp[0], rp1 = rp[1], rp2 = rp[2], rp3 = rp[3];
+      // the basic-MF shape (0 | 1 | 1 features), inside the staged window
+      ok = rp1 == rp0 && rp2 == rp1 + 1 && rp3 == rp2 + 1 && rp1 >= sm_base && rp3 <= v_hi;
+      if (ok) {
+        const int f = rp1 - sm_base;
+        const unsigned uid = st.idx[f], iid = st.idx[f + 1];
+        ok = uid < (unsigned)m.num_user && iid < (unsigned)m.num_item;  // else: generic pass reports it
+        d.urow = (unsigned)m.user_off + uid;
+        d.irow = (unsigned)m.item_off + iid;
+        d.uval = st.val[f];
+        d.ival = st.val[f + 1];
+        d.lab = st.label[(d.r0 & 3) + lane];
+        one = scalar_is_one(d.uval) && scalar_is_one(d.ival);
+      }
+    }
+    d.take = __ballot_sync(0xffffffffu, ok);
+    d.left = ~d.take & (nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u));
+    d.all_one = __all_sync(0xffffffffu, !ok || one);
+    return d;
+  };
+
+  // ---- the row ring -------------------------------------------------------------------------
+  const int row_f4 = m.pitch >> 2;  // float4 chunks a row really has (<= NCH)
+  float4 *const my_ring = ring + (size_t)gw * Ring::SLOT_F4;  // this group's part of slot 0
+  constexpr int SLOT_STRIDE = GPW * Ring::SLOT_F4;             // float4 between consecutive slots
+  // issue the gathers of iteration i of tile d into ring slot `slot` (always one commit group)
+  auto prefetch = [&](const MfDec &d, int i, int slot) {
+    const int src = i * GPW + gw;
+    const unsigned urow = __shfl_sync(0xffffffffu, d.urow, src);
+    const unsigned irow = __shfl_sync(0xffffffffu, d.irow, src);
+    if ((d.take >> src) & 1u) {
+      float4 *dst = my_ring + slot * SLOT_STRIDE;
+      const float *pu = m.W + (size_t)urow * (size_t)m.pitch, *pi = m.W + (size_t)irow * (size_t)m.pitch;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int ch = g.gl + v * LANES;
+        if (ch < row_f4) {
+          cp_async16(dst + ch, pu + 4 * ch);
+          cp_async16(dst + NCH + ch, pi + 4 * ch);
+        }
+      }
+      // biases: the aligned 16-byte window that holds the element (cp.async.cg moves 16 bytes)
+      if (g.gl == 0 && !m.no_user_bias) cp_async16(dst + 2 * NCH, m.bias + (urow & ~3u));
+      if (g.gl == LANES - 1) cp_async16(dst + 2 * NCH + 1, m.bias + (irow & ~3u));
+    }
+    cp_async_commit();
+  };
+
+    // one instance per lane group: rows from ring slot `slot`, scalars from the decoded tile.
+  // Groups whose row is not taken run the arithmetic on whatever the slot holds and skip the
+  // memory operations (no divergent control flow in the common path).
+  struct Rows {
+    float4 wu[VEC], wi[VEC];
+    float ub, ib;
+    unsigned urow, irow;
+  };
+  auto load_slot = [&](const MfDec &d, int i, int slot, Rows &r) {
+    const int src = i * GPW + gw;
+    r.urow = __shfl_sync(0xffffffffu, d.urow, src);
+    r.irow = __shfl_sync(0xffffffffu, d.irow, src);
+    const float4 *rs = my_ring + slot * SLOT_STRIDE;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int ch = g.gl + v * LANES;
+      r.wu[v] = rs[ch];
+      r.wi[v] = rs[NCH + ch];
+      if (ch >= row_f4) r.wu[v] = r.wi[v] = f4_zero();  // chunks the row does not have
+    }
+    const float *bw = reinterpret_cast<const float *>(rs + 2 * NCH);
+    r.ub = m.no_user_bias ? 0.0f : bw[r.urow & 3u];
+    r.ib = bw[4 + (r.irow & 3u)];
+  };
+  auto compute = [&](const MfDec &d, int i, const Rows &r) {
+    const int src = i * GPW + gw;
+    const bool take = (d.take >> src) & 1u;
+    const unsigned urow = r.urow, irow = r.irow;
+    const float4(&wu)[VEC] = r.wu;
+    const float4(&wi)[VEC] = r.wi;
+    const float ub = r.ub, ib = r.ib;
+
+    // prepare_tmp (base.h:354-381): tmp = 0 + w*val
+    float4 tu[VEC], ti[VEC];
+    float uval = 1.0f, ival = 1.0f;
+    if (d.all_one && !EXACT_DOT) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        tu[v] = wu[v];
+        ti[v] = wi[v];
+      }
+    } else {
+      uval = __shfl_sync(0xffffffffu, d.uval, src);
+      ival = __shfl_sync(0xffffffffu, d.ival, src);
+      // w*1.0f is w exactly, so the "scalar is one" shortcut needs no second code path
+      const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        tu[v] = f4_add_scaled(f4_zero(), wu[v], um, false);
+        ti[v] = f4_add_scaled(f4_zero(), wi[v], im, false);
+      }
+    }
+    // calc_bias (base.h:313-353) + pred (base.h:445-454)
+    double bsum = 0.0;
+    if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, ub));
+    bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+    // (measured: an out-of-line sigmoid path or full-mask shuffles here cost 4 % each)
+    const float dt = g.template dot<EXACT_DOT>(m, tu, ti);
+    double sum = __dadd_rn((double)hp.base_score, bsum);
+    sum = __dadd_rn(sum, (double)dt);
+    const float lab = TRAIN ? __shfl_sync(0xffffffffu, d.lab, src) : 0.0f;
+    const float pred = map_active((float)sum, m.active_type);
+    const float err = cal_grad(lab, pred, m.active_type);
+    if (!TRAIN) {
+      if (take && g.gl == 0) pred_out[d.r0 + src - row_begin] = pred;
+      return;
+    }
+    // update_no_decay + regularize(after), fused (base.h:383-427, 211-283)
+    const float lrerr = __fmul_rn(hp.lr, err);
+    const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);
+    const float su_m = scalar_is_one(su) ? 1.0f : su, si_m = scalar_is_one(si) ? 1.0f : si;
+    float4 nu[VEC], ni[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      nu[v] = f4_add_scaled(wu[v], ti[v], su_m, false);
+      ni[v] = f4_add_scaled(wi[v], tu[v], si_m, false);
+      if (!hp.du_skip) nu[v] = f4_scale(nu[v], hp.du);
+      if (!hp.di_skip) ni[v] = f4_scale(ni[v], hp.di);
+    }
+    const float nub = __fmul_rn(__fadd_rn(ub, su), hp.dub), nib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
+    if (take) {
+      if (scatter_user == SCATTER_RED) g.red_row(m, urow, nu, wu);
+      else g.store_row(m, urow, nu);
+      if (scatter_item == SCATTER_RED) g.red_row(m, irow, ni, wi);
+      else g.store_row(m, irow, ni);
+      if (g.gl == 0 && !m.no_user_bias) {
+        if (scatter_user == SCATTER_RED) red1(m.bias + urow, __fsub_rn(nub, ub));
+        else __stcg(m.bias + urow, nub);
+      }
+      if (g.gl == LANES - 1) {
+        if (scatter_item == SCATTER_RED) red1(m.bias + irow, __fsub_rn(nib, ib));
+        else __stcg(m.bias + irow, nib);
+      }
+    }
+  };
+
+  // ---- main loop ------------------------------------------------------------------------------
+  // Staging schedule (two stages; tile t uses stage t % 2): a tile's stage is free again as soon
+  // as the tile is decoded into registers, so while tile j is computed, tile j+1 is decoded,
+  // B(j+2) is in flight in the stage tile j left and A(j+3) in the stage tile j+1 left.
+  issue_a(0);
+  issue_a(1);
+  issue_b(0);
+  wait_b(0);
+  MfDec cur = decode(0);
+  issue_a(2);
+  issue_b(1);
+#pragma unroll
+  for (int i = 0; i < DEPTH; ++i) prefetch(cur, i, i);  // fill the ring: DEPTH groups pending
+  for (int j = 0; j < nlocal; ++j) {
+    wait_b(j + 1);
+    const MfDec nxt = decode(j + 1);
+    issue_a(j + 3);
+    issue_b(j + 2);
+    if (cur.left != 0u && lane == 0) {
+      row_mask[tile_of(j)] = cur.left;
+      *any_left = 1u;  // the generic pass has something to do
+    }
+#pragma unroll 1
+    for (int i = 0; i < ITER; ++i) {  // iteration i lives in ring slot i % DEPTH (one copy of the code:
+      const int slot = i % DEPTH;     // the unrolled loop did not fit the instruction cache)
+      cp_async_wait<DEPTH - 1>();     // its gathers have landed (this thread's part)
+      __syncwarp();                   // ... and every lane's part
+      Rows r;
+      load_slot(cur, i, slot, r);
+      __syncwarp();                   // the slot has been read by every lane: refill it
+      if (i + DEPTH < ITER) prefetch(cur, i + DEPTH, slot);
+      else prefetch(nxt, i + DEPTH - ITER, slot);
+      compute(cur, i, r);
+    }
+    cur = nxt;
+  }
+  cp_async_wait<0>();
+}
+
+template <int L, int V, int DEPTH, int MINB>
+static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
+  const long long ntile = ((long long)(r1 - r0) + MF_TILE - 1) / MF_TILE;
+  int grid = 1;
+#define GO(ED, TR)                                                                               \
+  {                                                                                              \
+    auto k = k_mf<L, V, ED, TR, DEPTH, MINB>;                                                    \
+    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH>();                                        \
+    CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    if (grid_for(h, k, MF_THREADS, (ntile + MF_WARPS - 1) / MF_WARPS, &grid, smem)) return 1;    \
+    k<<<grid, MF_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
+                                             h->scatter_item, pred, h->d_row_mask,               \
+                                             h->d_row_mask + h->any_left_at);                    \
+    h->n_launch++;                                                                               \
+  }
+  if (train) {
+    if (h->exact_dot) GO(true, true) else GO(false, true)
+  } else {
+    GO(true, false)
+  }
+#undef GO
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+// the fast pass over rows [r0, r1); h->d_row_mask (one word per 32-row tile, zeroed by the
+// caller) receives the rows left for the generic pass
+int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
+  // tuning knobs (options "ring_depth", "mf_ctas"): ring depth 2 or 4, 2 or 3 CTAs per SM
+  const int depth = h->ring_depth == 2 ? 2 : 4;
+  const int minb = h->mf_ctas == 3 ? 3 : 2;
+#define GEO(L, V)                                                                                      \
+  if (g.lanes == L && g.vec == V) {                                                                    \
+    if (depth == 2 && minb == 3) return launch_mf_geo<L, V, 2, 3>(h, csr, r0, r1, train, pred);        \
+    if (depth == 2) return launch_mf_geo<L, V, 2, 2>(h, csr, r0, r1, train, pred);                     \
+    if (minb == 3) return launch_mf_geo<L, V, 4, 3>(h, csr, r0, r1, train, pred);                      \
+    return launch_mf_geo<L, V, 4, 2>(h, csr, r0, r1, train, pred);                                     \
+  }
+#ifdef SVDGPU_TUNE_BUILD
+  GEO(4, 4) GEO(8, 2)
+#else
+  GEO(4, 1) GEO(4, 2) GEO(4, 4) GEO(8, 1) GEO(8, 2) GEO(8, 4) GEO(16, 1) GEO(16, 2) GEO(16, 4)
+  GEO(32, 1) GEO(32, 2) GEO(32, 4)
+#endif
+#undef GEO
+  return fail(h, "k_mf: no kernel instantiated for lanes=%d vec=%d", g.lanes, g.vec);
+}
+
+}  // namespace svdk

@@ -133,6 +133,56 @@ def test_hogwild_other_regularisers_conflict_free(native, name):
     assert _maxdiff(o, g) == 0.0
 
 
+@pytest.mark.parametrize("chunk_rows", [1 << 20, 37, 1000])
+@pytest.mark.parametrize("k", [64, 16, 256])
+def test_hogwild_mixed_shapes_conflict_free(native, k, chunk_rows):
+    """Fast pass (k_mf) and generic pass (k_stream) share a batch: rows of the basic-MF shape
+    interleaved with rows carrying global features, two user features, several item features,
+    no features at all, and non-unit values.  Every model row is touched at most once, so the
+    result must equal the sequential oracle whatever pass takes which row."""
+    nu, ni, ng, n = 6000, 9000, 40, 2500
+    rng = np.random.default_rng(7 + k)
+    users = rng.permutation(nu)
+    items = rng.permutation(ni)
+    globs = rng.permutation(ng)
+    rows, up, ip, gp = [], 0, 0, 0
+    for r in range(n):
+        lab = float(rng.integers(1, 6))
+        shape = rng.integers(0, 10)
+        if shape < 6:  # basic-MF shape (the fast pass)
+            rows.append((lab, [], [(users[up], 1.0)], [(items[ip], 1.0)])); up += 1; ip += 1
+        elif shape == 6:  # basic-MF shape with non-unit values (still the fast pass)
+            rows.append((lab, [], [(users[up], 0.5)], [(items[ip], -1.25)])); up += 1; ip += 1
+        elif shape == 7 and gp < ng:  # a global feature
+            rows.append((lab, [(globs[gp], 0.7)], [(users[up], 1.0)], [(items[ip], 1.0)])); up += 1; ip += 1; gp += 1
+        elif shape == 8:  # two user features, three item features
+            rows.append((lab, [], [(users[up], 1.0), (users[up + 1], 0.3)],
+                         [(items[ip], 1.0), (items[ip + 1], -1.0), (items[ip + 2], 0.25)])); up += 2; ip += 3
+        else:  # nothing at all / item only
+            rows.append((lab, [], [], [(items[ip], 1.0)] if r % 2 else [])); ip += r % 2
+    data = synth.ragged_csr(rows)
+    params = dict(num_user=nu, num_item=ni, num_global=ng, num_factor=k, learning_rate=0.01, wd_user=0.004,
+                  wd_item=0.003, wd_user_bias=0.001, wd_item_bias=0.002, wd_global=0.001, base_score=3.6)
+    o = COracle(0, 0, 0, params)
+    o.init(5)
+    g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_mode(native.MODE_HOGWILD)
+    g.set_option("scatter_user", 0)
+    g.set_option("scatter_item", 0)
+    g.set_option("exact_dot", 1)
+    g.set_option("chunk_rows", chunk_rows)
+    g.upload(*[a.copy() for a in o.arrays()])
+    o.update_csr(data)
+    g.update_csr(data)
+    g.sync()
+    assert _maxdiff(o, g) == 0.0
+    assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
+    # the same rows with every row forced through the generic pass
+    g.set_option("pass1", 0)
+    assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
+
+
 def test_hogwild_fast_dot_close(native):
     o, g, data, kind = _pair(native, "basic_k64", native.MODE_HOGWILD, {"exact_dot": 0, "scatter_item": 0})
     data = _conflict_free(200, 100, 100, 5)

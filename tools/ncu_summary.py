@@ -1,34 +1,37 @@
-"""Print the metrics we care about from an .ncu-rep (run here, no GPU needed)."""
+"""One-screen summary of an .ncu-rep (raw page): time, DRAM traffic, L2/L1 use, issue rate, stalls.
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/<name>_summary.txt]"""
 import csv
 import subprocess
 import sys
 
-WANT = [
+KEYS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+    "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
     "lts__t_sectors_srcunit_tex_op_write.sum", "lts__t_sectors_srcunit_tex.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_ldgsts.sum",
 ]
-STALL = "smsp__average_warps_issue_stalled_"
-
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, data = rows[0], rows[1], rows[2:]
-kn = hdr.index("Kernel Name")
-for r in data:
-    print("kernel:", r[kn][:110])
-    for w in WANT:
-        if w in hdr:
-            i = hdr.index(w)
-            print("  %-62s %s %s" % (w, r[i], units[i]))
-    st = [(float(r[i]), hdr[i][len(STALL):].replace("_per_issue_active.ratio", "")) for i in range(len(hdr))
-          if hdr[i].startswith(STALL) and hdr[i].endswith("_per_issue_active.ratio") and r[i]]
-    for v, n in sorted(st, reverse=True)[:8]:
-        print("  stall %-28s %.3f" % (n, v))
-    break
+hdr, units = rows[0], rows[1]
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    print("kernel:", d["Kernel Name"])
+    for k in KEYS:
+        if k in d:
+            print("  %-62s %s %s" % (k, d[k], units[hdr.index(k)]))
+    stalls = []
+    for k in hdr:
+        if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((float(d[k]), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+            except ValueError:
+                pass
+    for v, k in sorted(stalls, reverse=True)[:9]:
+        print("  stall %-28s %.3f" % (k, v))
