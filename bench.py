@@ -332,13 +332,13 @@ def main():
             if (s + 1) % args.allreduce_every == 0:
                 exchange()
         g.sync()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
             time.sleep(0.2)  # let nvidia-smi attach before the timed region
+        if dist:
+            dist.barrier()  # (after rank 0's sleep: every rank enters the timed region together)
+        torch.cuda.synchronize()
         l0 = g.counter("kernel_launches")
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
@@ -363,6 +363,17 @@ def main():
             kev[s][1].record(stream)
         g.sync()
         kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+        if use_allreduce:  # per-rank diagnostics (stderr): the exchange alone, back to back
+            xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            xe0.record(stream)
+            for _ in range(5):
+                exchange()
+            xe1.record(stream)
+            g.sync()
+            torch.cuda.synchronize()
+            log("[rank %d] kernel-only %.3f ms/step, exchange-only %.3f ms, timed loop %.3f ms/step"
+                % (rank, kms, xe0.elapsed_time(xe1) / 5, ms / args.steps))
 
     if dist:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)

@@ -1,9 +1,7 @@
-set -x
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 ) > gpurun_out/pytest_gpu.log 2>&1
-tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
-cat gpurun_out/bench_1gpu.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mf -s 3 -c 1 -o gpurun_out/kmf_v5_100M python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b_ncu2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mf -s 3 -c 1 -o gpurun_out/kmf_v5_5M python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --rows-per-step 5000000 > gpurun_out/b_ncu3.log 2>&1
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
+grep -E "rank|value" gpurun_out/bench_2gpu.err | tail; python -c "
+import json; l=json.load(open('gpurun_out/bench_2gpu.json')); print(l['value']/1e9, l['ms_per_step'], l['roofline']['launch_ms'])"
+NCCL_DEBUG=INFO timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --rows-per-step 5000000 > gpurun_out/bench_2gpu_5M.json 2> gpurun_out/bench_2gpu_5M.err
+grep -E "rank [01]\]|NVLS|P2P|SHM|via" gpurun_out/bench_2gpu_5M.err | tail -12
