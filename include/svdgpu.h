@@ -86,7 +86,9 @@ int svdgpu_set_hparams(svdgpu_t *h, const svdgpu_hparams *hp);
 int svdgpu_set_mode(svdgpu_t *h, int mode);
 /* Tunables, by name:
  *   "scatter_user", "scatter_item" : 0 plain store, 1 red.global.add of the delta (hogwild)
- *   "exact_dot"   : 1 keep the reference's 4-lane dot order in hogwild mode (default 1)
+ *   "exact_dot"   : 1 keep the reference's 4-lane dot order in hogwild mode (default 0)
+ *   "pass1"       : 0 sends every row through the generic pass (default 1: basic-MF rows take the fast pass)
+ *   "ring_depth", "mf_ctas" : fast-pass tuning (gather ring depth 2|4, CTAs per SM 2|3)
  *   "lanes"       : lanes per instance in hogwild mode (0 = auto = pitch/4, max 32)
  *   "chunk_rows"  : rows per launch for host-pointer calls
  *   "ctas_per_sm" : persistent CTAs per SM (0 = auto) */
@@ -129,6 +131,31 @@ int svdgpu_predict_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off,
                           const float *fb_value, const int *row_ptr, const float *label,
                           const unsigned *index, const float *value, float *out);
 
+/* ---- evaluation on the device ------------------------------------------- */
+/* Predict and accumulate the squared error on the device; only two doubles come back.
+ * *sum_sq = sum over rows of ((pred - label) * scale)^2, *count = rows.
+ * replaces: the predict + RMSEEvaluator::add_eval loop of svd_feature_infer.cpp:38-56,243-277
+ * (the caller prints sqrt(sum_sq / count)). */
+int svdgpu_eval_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
+                    const unsigned *index, const float *value, float scale, double *sum_sq,
+                    long long *count);
+int svdgpu_eval_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                       const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                       const int *row_ptr, const float *label, const unsigned *index,
+                       const float *value, float scale, double *sum_sq, long long *count);
+
+/* ---- bulk ingest of the reference's binary buffer files ------------------ */
+/* One pass over a buffer file written by tools/make_feature_buffer (format_type 0) or
+ * tools/make_ugroup_buffer (format_type 1): batches are read into pinned memory, concatenated
+ * into chunks of "chunk_rows" rows and handed to the hot path.
+ * replaces: SVDFeatureCSRFactory / SVDPlusBlockFactory::load_next (apex_svd_data.cpp:218-248,
+ * 556-640; apex_svd_data.h:220-230,437-450) + the per-row loop svd_feature.cpp:231-247. */
+int svdgpu_update_buffer_file(svdgpu_t *h, const char *path, long long *num_row);
+int svdgpu_predict_buffer_file(svdgpu_t *h, const char *path, float *out, long long out_cap,
+                               long long *num_row);
+int svdgpu_eval_buffer_file(svdgpu_t *h, const char *path, float scale, double *sum_sq,
+                            long long *num_row);
+
 /* ---- the hot path, batches resident in HBM ----------------------------- */
 /* Copy a CSR batch to the device once and train on it every round (the
  * reference re-reads its buffer file each round, svd_feature.cpp:245-246). */
@@ -142,6 +169,9 @@ int svdgpu_batch_set_ugroup(svdgpu_t *h, svdgpu_batch_t *b, int num_block, const
 int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end);
 /* out_host may be NULL (predictions stay on the device; see svdgpu_batch_pred_ptr) */
 int svdgpu_batch_predict(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float *out_host);
+/* squared error of rows [begin,end) of a resident batch (see svdgpu_eval_csr) */
+int svdgpu_batch_eval(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float scale, double *sum_sq,
+                      long long *count);
 void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b);
 
 /* ---- synchronisation, timing, introspection ---------------------------- */
@@ -151,7 +181,8 @@ int svdgpu_sync(svdgpu_t *h);
 /* CUDA-event stopwatch on the launch stream */
 int svdgpu_timer_start(svdgpu_t *h);
 int svdgpu_timer_stop(svdgpu_t *h, float *elapsed_ms);
-/* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm" */
+/* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm", "lanes",
+ * "ingest_read_us", "ingest_call_us" (bulk ingest: time reading the file / inside the hot-path calls) */
 long long svdgpu_get_counter(const svdgpu_t *h, const char *name);
 /* device pointers of the model slabs (for peer / collective plumbing): 0 ui_bias,
  * 1 W_uiset, 2 g_bias; *pitch_floats receives the device row stride */

@@ -56,6 +56,12 @@ SVDGPU_SYMBOLS = {
     "svdgpu_predict_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "svdgpu_update_ugroup": (C.c_int, [_vp, C.c_int] + [_vp] * 9),
     "svdgpu_predict_ugroup": (C.c_int, [_vp, C.c_int] + [_vp] * 10),
+    "svdgpu_eval_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "svdgpu_eval_ugroup": (C.c_int, [_vp, C.c_int] + [_vp] * 9 + [C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "svdgpu_update_buffer_file": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_longlong)]),
+    "svdgpu_predict_buffer_file": (C.c_int, [_vp, C.c_char_p, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
+    "svdgpu_eval_buffer_file": (C.c_int, [_vp, C.c_char_p, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "svdgpu_batch_eval": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "svdgpu_batch_create": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp, _vp]),
     "svdgpu_batch_set_ugroup": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 5),
     "svdgpu_batch_update": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -210,6 +216,46 @@ class SvdGpu:
                                                 _ptr(fi), _ptr(fv), _ptr(rp), _ptr(lb), _ptr(ix),
                                                 _ptr(vl), _ptr(out)))
         return out
+
+    # evaluation on the device: (sum of squared errors, rows)
+    def eval_csr(self, csr, scale=1.0):
+        rp, lb, ix, vl = csr
+        s, n = C.c_double(), C.c_longlong()
+        self._ck(self.lib.svdgpu_eval_csr(self.h, len(lb), _ptr(rp), _ptr(lb), _ptr(ix), _ptr(vl), scale,
+                                          C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def eval_ugroup(self, ug, scale=1.0):
+        bro, bfo, tag, fi, fv, rp, lb, ix, vl = ug
+        s, n = C.c_double(), C.c_longlong()
+        self._ck(self.lib.svdgpu_eval_ugroup(self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag), _ptr(fi),
+                                             _ptr(fv), _ptr(rp), _ptr(lb), _ptr(ix), _ptr(vl), scale,
+                                             C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    # bulk ingest of the reference's binary buffer files
+    def update_buffer_file(self, path):
+        n = C.c_longlong()
+        self._ck(self.lib.svdgpu_update_buffer_file(self.h, str(path).encode(), C.byref(n)))
+        return n.value
+
+    def predict_buffer_file(self, path, max_rows):
+        out = np.empty(max_rows, np.float32)
+        n = C.c_longlong()
+        self._ck(self.lib.svdgpu_predict_buffer_file(self.h, str(path).encode(), _ptr(out), max_rows, C.byref(n)))
+        return out[:n.value]
+
+    def eval_buffer_file(self, path, scale=1.0):
+        s, n = C.c_double(), C.c_longlong()
+        self._ck(self.lib.svdgpu_eval_buffer_file(self.h, str(path).encode(), scale, C.byref(s), C.byref(n)))
+        return s.value, n.value
+
+    def batch_eval(self, batch, begin=0, end=None, scale=1.0):
+        if end is None:
+            end = batch.num_unit if batch.num_unit is not None else batch.num_row
+        s, n = C.c_double(), C.c_longlong()
+        self._ck(self.lib.svdgpu_batch_eval(self.h, batch.h, begin, end, scale, C.byref(s), C.byref(n)))
+        return s.value, n.value
 
     # hot path, resident batches
     def batch_create(self, csr, ugroup=None):

@@ -48,7 +48,31 @@ int fail(svdgpu *h, const char *fmt, ...) {
 }
 }  // namespace svdk
 
+// RMSEEvaluator::add_eval (svd_feature_infer.cpp:45-49): diff = (pred - label) * scale in fp32,
+// diff*diff accumulated in (long) double.  acc[0] += sum of squares, acc[1] += count.
+__global__ void k_sse(const float *__restrict__ pred, const float *__restrict__ label, int n, float scale,
+                      double *acc) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = (double)__fmul_rn(__fsub_rn(pred[i], label[i]), scale);
+    s += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(acc, s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(acc + 1, (double)n);
+}
+
 namespace {
+
+// squared-error accumulation of one predicted chunk (only while an svdgpu_eval_* call is active)
+int eval_chunk(svdgpu *h, const float *pred, const float *label, int n) {
+  if (!h->eval_on || n <= 0) return 0;
+  const int grid = std::min(h->num_sm * 8, (n + 255) / 256);
+  k_sse<<<grid, 256, 0, h->stream>>>(pred, label, n, h->eval_scale, h->d_eval);
+  CU(h, cudaGetLastError());
+  h->n_launch++;
+  return 0;
+}
 
 int dev_reserve(svdgpu *h, DevBuf &b, size_t bytes) {
   bytes += 64;  // bulk copies read 16-byte windows past the last element
@@ -380,6 +404,7 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
   CUC(cudaMalloc(&h->d_err, sizeof(int)));
   CUC(cudaMemset(h->d_err, 0, sizeof(int)));
   CUC(cudaMalloc(&h->d_counter, sizeof(unsigned)));
+  CUC(cudaMalloc(&h->d_eval, 2 * sizeof(double)));
 #undef CUC
   Geometry g;
   if (pick_geometry(h, g)) {
@@ -403,9 +428,14 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->dm.ver_g);
   cudaFree(h->d_err);
   cudaFree(h->d_counter);
+  cudaFree(h->d_eval);
   cudaFree(h->d_row_mask);
   cudaFree(h->d_snap);
   cudaFree(h->d_delta);
+  {
+    HostBuf *ib[] = {&h->ing_rp, &h->ing_label, &h->ing_index, &h->ing_value};
+    for (HostBuf *b : ib) host_free(*b);
+  }
   for (int i = 0; i < svdgpu::NSLOT; ++i) {
     Slot &s = h->slot[i];
     HostBuf *hb[] = {&s.h_rp, &s.h_label, &s.h_index, &s.h_value, &s.h_ticket, &s.h_misc, &s.h_fbi, &s.h_fbv, &s.h_fbt};
@@ -545,6 +575,8 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
   if (!strcmp(name, "h2d_bytes")) return h->n_h2d;
   if (!strcmp(name, "d2h_bytes")) return h->n_d2h;
   if (!strcmp(name, "num_sm")) return h->num_sm;
+  if (!strcmp(name, "ingest_read_us")) return (long long)(h->ingest_read_s * 1e6);  // file -> pinned chunk
+  if (!strcmp(name, "ingest_call_us")) return (long long)(h->ingest_call_s * 1e6);  // hot-path calls
   if (!strcmp(name, "lanes")) {
     Geometry g;
     return pick_geometry(const_cast<svdgpu *>(h), g) ? -1 : g.lanes;
@@ -616,7 +648,8 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
       }
       if (slot_copied(h, s)) return 1;
       if (launch_stream(h, geo, csr, 0, n, train, pred)) return 1;
-      if (!train) {
+      if (!train && eval_chunk(h, pred, csr.label, n)) return 1;
+      if (!train && out) {
         CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
         h->n_d2h += (long long)n * 4;
       }
@@ -759,7 +792,8 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     }
     if (slot_copied(h, s)) return 1;
     if (launch_ugroup(h, geo, csr, ug, 0, nu, train, exact, pred)) return 1;
-    if (!train && n) {
+    if (!train && eval_chunk(h, pred, csr.label, n)) return 1;
+    if (!train && n && out) {
       CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
       h->n_d2h += (long long)n * 4;
     }
@@ -786,6 +820,47 @@ int svdgpu_predict_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, co
                       label, index, value, out, false))
     return 1;
   return svdgpu_sync(h);
+}
+
+// ---------------------------------------------------------------------------
+// evaluation on the device (svd_feature_infer.cpp:38-56, 243-277: task_eval)
+// ---------------------------------------------------------------------------
+static int eval_begin(svdgpu *h, float scale) {
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemsetAsync(h->d_eval, 0, 2 * sizeof(double), h->stream));
+  h->eval_on = true;
+  h->eval_scale = scale;
+  return 0;
+}
+static int eval_end(svdgpu *h, int rc, double *sum_sq, long long *count) {
+  h->eval_on = false;
+  if (rc) return rc;
+  double acc[2] = {0.0, 0.0};
+  if (svdgpu_sync(h)) return 1;
+  CU(h, cudaMemcpy(acc, h->d_eval, sizeof(acc), cudaMemcpyDeviceToHost));
+  h->n_d2h += (long long)sizeof(acc);
+  if (sum_sq) *sum_sq = acc[0];
+  if (count) *count = (long long)(acc[1] + 0.5);
+  return 0;
+}
+
+int svdgpu_eval_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label, const unsigned *index,
+                    const float *value, float scale, double *sum_sq, long long *count) {
+  if (!h) return 1;
+  if (eval_begin(h, scale)) return 1;
+  return eval_end(h, run_csr_host(h, num_row, row_ptr, label, index, value, nullptr, false), sum_sq, count);
+}
+
+int svdgpu_eval_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                       const int *blk_tag, const unsigned *fb_index, const float *fb_value, const int *row_ptr,
+                       const float *label, const unsigned *index, const float *value, float scale,
+                       double *sum_sq, long long *count) {
+  if (!h) return 1;
+  if (eval_begin(h, scale)) return 1;
+  return eval_end(h,
+                  run_ugroup_host(h, num_block, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value, row_ptr,
+                                  label, index, value, nullptr, false),
+                  sum_sq, count);
 }
 
 // ---------------------------------------------------------------------------
@@ -944,12 +1019,20 @@ int svdgpu_batch_predict(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, flo
     if (begin == end) return 0;
     if (launch_stream(h, geo, batch_csr(b), begin, end, false, pred + begin)) return 1;
   }
+  if (eval_chunk(h, pred + r0, (const float *)b->d_label.p + r0, r1 - r0)) return 1;
   if (out_host) {
     CU(h, cudaMemcpyAsync(out_host, pred + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, h->stream));
     h->n_d2h += (long long)(r1 - r0) * 4;
     return svdgpu_sync(h);
   }
   return 0;
+}
+
+int svdgpu_batch_eval(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float scale, double *sum_sq,
+                      long long *count) {
+  if (!h) return 1;
+  if (eval_begin(h, scale)) return 1;
+  return eval_end(h, svdgpu_batch_predict(h, b, begin, end, nullptr), sum_sq, count);
 }
 
 void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b) {

@@ -76,6 +76,9 @@ struct svdgpu {
   size_t rows = 0;
   int *d_err = nullptr;
   unsigned *d_counter = nullptr;
+  double *d_eval = nullptr;  // {sum of squared errors, count} of an svdgpu_eval_* call
+  bool eval_on = false;
+  float eval_scale = 1.0f;
   unsigned *d_row_mask = nullptr;  // Hogwild: rows the fast pass left to the generic pass (1 bit per row)
   size_t row_mask_cap = 0;
   size_t any_left_at = 0;  // index of the "pass 1 left something" word inside d_row_mask
@@ -85,6 +88,9 @@ struct svdgpu {
   static constexpr int NSLOT = 3;
   Slot slot[NSLOT];
   int cur_slot = 0;
+  // bulk ingest: pinned chunk buffers (kept across calls) and where the time went
+  HostBuf ing_rp, ing_label, ing_index, ing_value;
+  double ingest_read_s = 0.0, ingest_call_s = 0.0;
   // multi-GPU exchange
   svdk::DeltaPlan plan;
   float *d_snap = nullptr, *d_delta = nullptr;
