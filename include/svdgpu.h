@@ -96,6 +96,15 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
 int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);
 
+/* Side features (the reference's feature_user / feature_item files, SparseFeatureArray<float>,
+ * apex-utils/apex_utils.h:141-196): feature index r of the user (which = 0) or item (which = 1)
+ * space expands to the extra pairs (index[j], value[j]), j in [row_ptr[r], row_ptr[r+1]);
+ * indices >= num_row have none.  num_row = 0 clears.  Every later update/predict call applies
+ * the expansion exactly as base.h:298-308,330-349,365-379,399-422 do (on the host, per chunk).
+ * replaces: SparseFeatureArray::load + the "extra feature" loops of SVDFeature. */
+int svdgpu_set_side_features(svdgpu_t *h, int which, int num_row, const unsigned *row_ptr,
+                             const unsigned *index, const float *value);
+
 /* ---- model transfer ---------------------------------------------------- */
 /* Layout = SVDModel's slabs (model.h:481-556): ui_bias[rows], W_uiset[rows][pitch],
  * g_bias[num_global] with rows = ustart + num_user + num_item, ustart =

@@ -68,6 +68,9 @@ struct svdo {
   int init_end, round_counter;
   unsigned sample_counter;
   unsigned *ref_user, *ref_item, *ref_global;
+  /* side features (base.h:98-99; apex-utils/apex_utils.h:141-196 SparseFeatureArray<float>) */
+  char name_feat_user[256], name_feat_item[256];
+  struct { unsigned num_row; unsigned *row_ptr; unsigned *index; float *value; } feat_user, feat_item;
   float *tmp_ufactor, *tmp_ifactor, *tmp_ufeedback, *old_ufeedback;
   float norm_ufeedback, tmp_ufeedback_bias, old_ufeedback_bias;
   int is_svdpp; /* apex_svd.cpp:32-45: extend_type==1 or USER_GROUP -> SVDPPFeature */
@@ -277,6 +280,8 @@ svdo_t *svdo_create(int format_type, int active_type, int extend_type) {
   range_wd_init(&m->u_param, "up:", "uip:");
   range_wd_init(&m->i_param, "ip:", "uip:");
   range_wd_init(&m->g_param, "gp:", "gp:");
+  strcpy(m->name_feat_user, "NULL"); /* base.h:105-106 */
+  strcpy(m->name_feat_item, "NULL");
   return m;
 }
 
@@ -297,13 +302,14 @@ void svdo_destroy(svdo_t *m) {
   free(m->ref_user);
   free(m->ref_item);
   free(m->ref_global);
+  free(m->feat_user.row_ptr); free(m->feat_user.index); free(m->feat_user.value);
+  free(m->feat_item.row_ptr); free(m->feat_item.index); free(m->feat_item.value);
   free(m);
 }
 
 void svdo_set_param(svdo_t *m, const char *name, const char *val) { /* base.h:126-136 */
-  if (!strcmp(name, "feature_user") || !strcmp(name, "feature_item")) {
-    if (strcmp(val, "NULL")) die("oracle: feature_user/feature_item side features are out of scope");
-  }
+  if (!strcmp(name, "feature_user")) strncpy(m->name_feat_user, val, 255); /* base.h:127-128 */
+  if (!strcmp(name, "feature_item")) strncpy(m->name_feat_item, val, 255);
   /* model.h:350-368 SVDTrainParam::set_param */
   if (!strcmp("learning_rate", name)) m->learning_rate = (float)atof(val);
   if (!strcmp("wd_user", name)) m->wd_user = (float)atof(val);
@@ -391,8 +397,44 @@ void svdo_init_model(svdo_t *m) { /* base.h:146-149; model.h:665-705 rand_init *
     sample_gaussian_rows(m->W_ufeedback, m->pitch, m->num_ufeedback, m->num_factor, m->ufeedback_init_sigma);
 }
 
+/* SparseFeatureArray<float>::load (apex-utils/apex_utils.h:176-195): per line "n idx:val x n" */
+static void sparse_load(const char *fname, unsigned *num_row, unsigned **row_ptr, unsigned **index, float **value) {
+  FILE *fi = fopen(fname, "r");
+  size_t cap_r = 16, cap_e = 64, ne = 0;
+  int n;
+  if (!fi) die("can not open file");
+  *num_row = 0;
+  *row_ptr = (unsigned *)malloc(cap_r * sizeof(unsigned));
+  *index = (unsigned *)malloc(cap_e * sizeof(unsigned));
+  *value = (float *)malloc(cap_e * sizeof(float));
+  (*row_ptr)[0] = 0;
+  while (fscanf(fi, "%d", &n) == 1) {
+    int i;
+    if (*num_row + 2 > cap_r) *row_ptr = (unsigned *)realloc(*row_ptr, (cap_r *= 2) * sizeof(unsigned));
+    (*row_ptr)[*num_row + 1] = (*row_ptr)[*num_row] + (unsigned)n;
+    (*num_row)++;
+    for (i = 0; i < n; ++i) {
+      if (ne + 1 > cap_e) {
+        cap_e *= 2;
+        *index = (unsigned *)realloc(*index, cap_e * sizeof(unsigned));
+        *value = (float *)realloc(*value, cap_e * sizeof(float));
+      }
+      if (fscanf(fi, "%u:%f", &(*index)[ne], &(*value)[ne]) != 2) die("load sparse feature");
+      ne++;
+    }
+  }
+  fclose(fi);
+}
+/* SparseFeatureArray::operator[] (apex_utils.h:163-172): rows beyond the file are empty */
+#define SIDE_BEGIN(f, id) ((id) < (f).num_row ? (f).row_ptr[(id)] : 0u)
+#define SIDE_END(f, id) ((id) < (f).num_row ? (f).row_ptr[(id) + 1] : 0u)
+
 void svdo_init_trainer(svdo_t *m) { /* base.h:151-173, 499-503 */
   size_t n = (size_t)(m->pitch > 0 ? m->pitch : 1);
+  if (strcmp(m->name_feat_user, "NULL"))
+    sparse_load(m->name_feat_user, &m->feat_user.num_row, &m->feat_user.row_ptr, &m->feat_user.index, &m->feat_user.value);
+  if (strcmp(m->name_feat_item, "NULL"))
+    sparse_load(m->name_feat_item, &m->feat_item.num_row, &m->feat_item.row_ptr, &m->feat_item.index, &m->feat_item.value);
   m->tmp_ufactor = (float *)calloc(n, sizeof(float));
   m->tmp_ifactor = (float *)calloc(n, sizeof(float));
   m->tmp_ufeedback = (float *)calloc(n, sizeof(float));
@@ -642,8 +684,15 @@ static void regularize(svdo_t *m, const elem_t *e, int is_after) { /* base.h:286
   if ((is_after && m->reg_global < 4) || (!is_after && m->reg_global >= 4))
     for (i = 0; i < e->ng; ++i) reg_global(m, e->gi[i]);
   if ((is_after && m->reg_method < 4) || (!is_after && m->reg_method >= 4)) {
-    for (i = 0; i < e->nu; ++i) reg_user(m, e->ui[i]);
-    for (i = 0; i < e->ni; ++i) reg_item(m, e->ii[i]);
+    unsigned j;
+    for (i = 0; i < e->nu; ++i) { /* base.h:298-303 */
+      reg_user(m, e->ui[i]);
+      for (j = SIDE_BEGIN(m->feat_user, e->ui[i]); j < SIDE_END(m->feat_user, e->ui[i]); ++j) reg_user(m, m->feat_user.index[j]);
+    }
+    for (i = 0; i < e->ni; ++i) { /* base.h:304-309 */
+      reg_item(m, e->ii[i]);
+      for (j = SIDE_BEGIN(m->feat_item, e->ii[i]); j < SIDE_END(m->feat_item, e->ii[i]); ++j) reg_item(m, m->feat_item.index[j]);
+    }
   }
 }
 
@@ -664,6 +713,13 @@ static double calc_bias(svdo_t *m, const elem_t *e) { /* base.h:313-353 */
       if (!(uid < (unsigned)m->num_user)) die("user feature index exceed bound");
       p = e->uv[i] * m->u_bias[uid];
       sum += p;
+      { /* extra feature, base.h:329-333 */
+        unsigned j;
+        for (j = SIDE_BEGIN(m->feat_user, uid); j < SIDE_END(m->feat_user, uid); ++j) {
+          float q = m->u_bias[m->feat_user.index[j]] * m->feat_user.value[j];
+          sum += q;
+        }
+      }
     }
     sum += (m->is_svdpp ? m->tmp_ufeedback_bias : 0.0f); /* base.h:433-435, 509-511 */
   }
@@ -674,6 +730,14 @@ static double calc_bias(svdo_t *m, const elem_t *e) { /* base.h:313-353 */
     if (!(iid < (unsigned)m->num_item)) die("item feature index exceed bound");
     p = e->iv[i] * m->i_bias[iid];
     sum += p;
+    { /* extra feature, base.h:345-349: (i_bias * value) * ival, left to right in float */
+      unsigned j;
+      for (j = SIDE_BEGIN(m->feat_item, iid); j < SIDE_END(m->feat_item, iid); ++j) {
+        float q = m->i_bias[m->feat_item.index[j]] * m->feat_item.value[j];
+        q = q * e->iv[i];
+        sum += q;
+      }
+    }
   }
   return sum;
 }
@@ -688,11 +752,24 @@ static void prepare_tmp(svdo_t *m, const elem_t *e) { /* base.h:354-381 */
     unsigned uid = e->ui[i];
     if (!(uid < (unsigned)m->num_user)) die("user feature index exceed bound");
     row_add_scaled(m->tmp_ufactor, m->W_user + (size_t)uid * m->pitch, e->uv[i], k);
+    { /* extra feature, base.h:364-368 */
+      unsigned j;
+      for (j = SIDE_BEGIN(m->feat_user, uid); j < SIDE_END(m->feat_user, uid); ++j)
+        row_add_scaled(m->tmp_ufactor, m->W_user + (size_t)m->feat_user.index[j] * m->pitch, m->feat_user.value[j], k);
+    }
   }
   for (i = 0; i < e->ni; ++i) {
     unsigned iid = e->ii[i];
     if (!(iid < (unsigned)m->num_item)) die("item feature index exceed bound");
     row_add_scaled(m->tmp_ifactor, m->W_item + (size_t)iid * m->pitch, e->iv[i], k);
+    { /* extra feature, base.h:375-379: W * value * ival -- the two scalars are folded in double by
+         operator*(ScalarMapExp, double) (apex_exp_template.h:500-503) and cast to float once */
+      unsigned j;
+      for (j = SIDE_BEGIN(m->feat_item, iid); j < SIDE_END(m->feat_item, iid); ++j) {
+        float sc = (float)((double)m->feat_item.value[j] * (double)e->iv[i]);
+        row_add_scaled(m->tmp_ifactor, m->W_item + (size_t)m->feat_item.index[j] * m->pitch, sc, k);
+      }
+    }
   }
 }
 
@@ -723,12 +800,28 @@ static void update_no_decay(svdo_t *m, float err, const elem_t *e) { /* base.h:3
     float scale = m->learning_rate * err * e->uv[i];
     row_add_scaled(m->W_user + (size_t)uid * m->pitch, m->tmp_ifactor, scale, k);
     if (m->no_user_bias == 0) m->u_bias[uid] += scale;
+    { /* extra feature, base.h:399-407 */
+      unsigned j;
+      for (j = SIDE_BEGIN(m->feat_user, uid); j < SIDE_END(m->feat_user, uid); ++j) {
+        float sc = m->learning_rate * err * m->feat_user.value[j];
+        row_add_scaled(m->W_user + (size_t)m->feat_user.index[j] * m->pitch, m->tmp_ifactor, sc, k);
+        if (m->no_user_bias == 0) m->u_bias[m->feat_user.index[j]] += sc;
+      }
+    }
   }
   for (i = 0; i < e->ni; ++i) {
     unsigned iid = e->ii[i];
     float scale = m->learning_rate * err * e->iv[i];
     row_add_scaled(m->W_item + (size_t)iid * m->pitch, m->tmp_ufactor, scale, k);
     m->i_bias[iid] += scale;
+    { /* extra feature, base.h:417-422 */
+      unsigned j;
+      for (j = SIDE_BEGIN(m->feat_item, iid); j < SIDE_END(m->feat_item, iid); ++j) {
+        float sc = m->learning_rate * err * m->feat_item.value[j] * e->iv[i];
+        m->i_bias[m->feat_item.index[j]] += sc;
+        row_add_scaled(m->W_item + (size_t)m->feat_item.index[j] * m->pitch, m->tmp_ufactor, sc, k);
+      }
+    }
   }
   if (m->is_svdpp) update_svdpp(m, err);
 }

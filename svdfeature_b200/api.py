@@ -50,6 +50,7 @@ SVDGPU_SYMBOLS = {
     "svdgpu_set_mode": (C.c_int, [_vp, C.c_int]),
     "svdgpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "svdgpu_set_stream": (C.c_int, [_vp, _vp]),
+    "svdgpu_set_side_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "svdgpu_upload_model": (C.c_int, [_vp, _f32p, _f32p, C.c_size_t, _f32p]),
     "svdgpu_download_model": (C.c_int, [_vp, _f32p, _f32p, C.c_size_t, _f32p]),
     "svdgpu_update_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
@@ -173,6 +174,14 @@ class SvdGpu:
 
     def set_stream(self, cuda_stream):
         self._ck(self.lib.svdgpu_set_stream(self.h, cuda_stream))
+
+    def set_side_features(self, which, side):
+        """side: list of (index array, value array) per feature index (see svdgpu_set_side_features)."""
+        rp = np.zeros(len(side) + 1, np.uint32)
+        rp[1:] = np.cumsum([len(i) for i, _ in side])
+        idx = np.concatenate([i for i, _ in side]).astype(np.uint32) if side else np.zeros(0, np.uint32)
+        val = np.concatenate([v for _, v in side]).astype(np.float32) if side else np.zeros(0, np.float32)
+        self._ck(self.lib.svdgpu_set_side_features(self.h, which, len(side), _ptr(rp), _ptr(idx), _ptr(val)))
 
     # model
     def upload(self, ui_bias, W, g_bias):

@@ -121,10 +121,8 @@ class GpuSVDFeature : public ISVDTrainer {
 
   // ---- model related interface (base.h:126-173) ---------------------------
   virtual void set_param(const char *name, const char *val) {
-    if (!strcmp(name, "feature_user") || !strcmp(name, "feature_item")) {
-      if (strcmp(val, "NULL"))
-        apex_utils::error("feature_user/feature_item side features are not supported by the GPU trainer");
-    }
+    if (!strcmp(name, "feature_user")) name_feat_user_ = val;  // base.h:127-128
+    if (!strcmp(name, "feature_item")) name_feat_item_ = val;
     if (!strncmp(name, "up:", 3) || !strncmp(name, "ip:", 3) || !strncmp(name, "uip:", 4) || !strncmp(name, "gp:", 3))
       apex_utils::error("ranged weight decay (up:/ip:/uip:/gp:) is not supported by the GPU trainer");
     // SVDTrainParam::set_param, model.h:350-368
@@ -250,6 +248,8 @@ class GpuSVDFeature : public ISVDTrainer {
   virtual void init_trainer(void) {  // base.h:151-173
     apex_utils::assert_true(space_allocated_ != 0, "init_trainer: no model (call init_model or load_model first)");
     ensure_handle();
+    load_side_features(0, name_feat_user_);  // base.h:152-153
+    load_side_features(1, name_feat_item_);
     upload();
     init_end_ = 1;
   }
@@ -377,6 +377,30 @@ class GpuSVDFeature : public ISVDTrainer {
       check(h_, svdgpu_set_option(h_, options_[i].first.c_str(), options_[i].second));
     push_hparams();
   }
+  // SparseFeatureArray<float>::load (apex-utils/apex_utils.h:176-195): per line "n idx:val x n"
+  void load_side_features(int which, const std::string &fname) {
+    if (fname == "NULL") return;
+    FILE *fi = fopen(fname.c_str(), "r");
+    if (!fi) {
+      fprintf(stderr, "can not open file \"%s\"\n", fname.c_str());
+      exit(-1);
+    }
+    std::vector<unsigned> rp(1, 0u), idx;
+    std::vector<float> val;
+    int n;
+    while (fscanf(fi, "%d", &n) == 1) {
+      rp.push_back(rp.back() + (unsigned)n);
+      for (int i = 0; i < n; ++i) {
+        unsigned id;
+        float v;
+        apex_utils::assert_true(fscanf(fi, "%u:%f", &id, &v) == 2, "load sparse feature");
+        idx.push_back(id);
+        val.push_back(v);
+      }
+    }
+    fclose(fi);
+    check(h_, svdgpu_set_side_features(h_, which, (int)rp.size() - 1, rp.data(), idx.data(), val.data()));
+  }
   void push_hparams() {
     hp_.base_score = mp_.base_score;
     hp_.user_nonnegative = mp_.user_nonnegative;
@@ -453,6 +477,7 @@ class GpuSVDFeature : public ISVDTrainer {
   int device_ = 0, mode_ = SVDGPU_MODE_EXACT;
   int batch_rows_ = 1 << 20;
   std::vector<std::pair<std::string, long long> > options_;
+  std::string name_feat_user_ = "NULL", name_feat_item_ = "NULL";
   svdgpu_t *h_ = NULL;
   // host mirror of the model (init, load/save)
   int ustart_ = 0, pitch_ = 0;

@@ -22,8 +22,8 @@ thread_local std::string g_create_error;
 struct svdgpu_batch {
   int num_row = 0;
   long long num_val = 0;
-  DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_pred;
-  bool has_ticket = false;
+  DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_pred;
+  bool has_ticket = false, has_value2 = false;
   // user-group structure
   bool ugroup = false;
   int num_block = 0, num_unit = 0;
@@ -246,6 +246,54 @@ void reset_ticket_counters(svdgpu *h) {
   h->cnt_g.assign((size_t)std::max(h->shape.num_global, 1), 0u);
 }
 
+// ---- side-feature expansion (feature_user / feature_item) ---------------------------------
+// The reference walks, after every user feature uid, the extra pairs feat_user[uid] (value used
+// as is), and after every item feature (iid, ival) the pairs feat_item[iid] whose value enters
+// as value*ival (base.h:298-308,330-349,365-379,399-422).  A chunk is rewritten on the host into
+// a plain CSR with those extra entries in the reference's order; item entries carry the second
+// factor in val2 (1 for the base entry, ival for its extras) so that the device reproduces the
+// reference's products exactly.  Host work is O(nnz): this path is for completeness, not speed.
+struct Expanded {
+  std::vector<int> rp;
+  std::vector<unsigned> idx;
+  std::vector<float> val, val2;
+};
+bool sides_on(const svdgpu *h) { return h->side_u.on() || h->side_i.on(); }
+int expand_rows(svdgpu *h, int r0, int r1, const int *row_ptr, const unsigned *index, const float *value,
+                Expanded &e) {
+  e.rp.assign(1, 0);
+  e.idx.clear();
+  e.val.clear();
+  e.val2.clear();
+  auto push = [&](unsigned i, float v, float v2) {
+    e.idx.push_back(i);
+    e.val.push_back(v);
+    e.val2.push_back(v2);
+  };
+  for (int r = r0; r < r1; ++r) {
+    const int *p = row_ptr + 3LL * r;
+    if (p[0] < 0 || p[1] < p[0] || p[2] < p[1] || p[3] < p[2]) return fail(h, "row_ptr must be non-decreasing");
+    for (int f = p[0]; f < p[1]; ++f) push(index[f], value[f], 1.0f);
+    e.rp.push_back((int)e.idx.size());
+    for (int f = p[1]; f < p[2]; ++f) {
+      push(index[f], value[f], 1.0f);
+      const svdgpu::Side &sd = h->side_u;
+      if (sd.on() && index[f] + 1 < sd.rp.size())
+        for (unsigned j = sd.rp[index[f]]; j < sd.rp[index[f] + 1]; ++j) push(sd.idx[j], sd.val[j], 1.0f);
+    }
+    e.rp.push_back((int)e.idx.size());
+    for (int f = p[2]; f < p[3]; ++f) {
+      push(index[f], value[f], 1.0f);
+      const svdgpu::Side &sd = h->side_i;
+      if (sd.on() && index[f] + 1 < sd.rp.size())
+        for (unsigned j = sd.rp[index[f]]; j < sd.rp[index[f] + 1]; ++j) push(sd.idx[j], sd.val[j], value[f]);
+    }
+    e.rp.push_back((int)e.idx.size());
+    if (e.idx.size() > 0x7fffffffULL) return fail(h, "expanded batch exceeds 2^31 feature entries: lower chunk_rows");
+  }
+  return 0;
+}
+
 int check_ready(svdgpu *h) {
   if (!h) return 1;
   if (!h->hp_set) return fail(h, "svdgpu_set_hparams has not been called");
@@ -438,9 +486,9 @@ void svdgpu_destroy(svdgpu_t *h) {
   }
   for (int i = 0; i < svdgpu::NSLOT; ++i) {
     Slot &s = h->slot[i];
-    HostBuf *hb[] = {&s.h_rp, &s.h_label, &s.h_index, &s.h_value, &s.h_ticket, &s.h_misc, &s.h_fbi, &s.h_fbv, &s.h_fbt};
+    HostBuf *hb[] = {&s.h_rp, &s.h_label, &s.h_index, &s.h_value, &s.h_value2, &s.h_ticket, &s.h_misc, &s.h_fbi, &s.h_fbv, &s.h_fbt};
     for (HostBuf *b : hb) host_free(*b);
-    DevBuf *db[] = {&s.d_rp, &s.d_label, &s.d_index, &s.d_value, &s.d_ticket, &s.d_misc, &s.d_fbi, &s.d_fbv, &s.d_fbt, &s.d_pred};
+    DevBuf *db[] = {&s.d_rp, &s.d_label, &s.d_index, &s.d_value, &s.d_value2, &s.d_ticket, &s.d_misc, &s.d_fbi, &s.d_fbv, &s.d_fbt, &s.d_pred};
     for (DevBuf *b : db) dev_free(*b);
     if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
@@ -487,6 +535,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   } else if (!strcmp(name, "ctas_per_sm")) h->ctas_per_sm = (int)v;
   else if (!strcmp(name, "pass1")) h->pass1 = v ? 1 : 0;
   else if (!strcmp(name, "ring_depth")) h->ring_depth = (int)v;
+  else if (!strcmp(name, "l2_ahead")) h->l2_ahead = (int)v;
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else return fail(h, "unknown option '%s'", name);
   return 0;
@@ -497,6 +546,27 @@ int svdgpu_set_stream(svdgpu_t *h, void *s) {
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaStreamSynchronize(h->stream));
   h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return 0;
+}
+
+int svdgpu_set_side_features(svdgpu_t *h, int which, int num_row, const unsigned *row_ptr, const unsigned *index,
+                             const float *value) {
+  if (!h) return 1;
+  if (which != 0 && which != 1) return fail(h, "set_side_features: which must be 0 (user) or 1 (item)");
+  svdgpu::Side &sd = which == 0 ? h->side_u : h->side_i;
+  sd.rp.clear();
+  sd.idx.clear();
+  sd.val.clear();
+  if (num_row <= 0) return 0;
+  if (!row_ptr || (row_ptr[num_row] > 0 && (!index || !value))) return fail(h, "set_side_features: null array");
+  const unsigned bound = (unsigned)(which == 0 ? h->shape.num_user : h->shape.num_item);
+  for (int r = 0; r < num_row; ++r)
+    if (row_ptr[r + 1] < row_ptr[r]) return fail(h, "set_side_features: row_ptr must be non-decreasing");
+  for (unsigned j = 0; j < row_ptr[num_row]; ++j)
+    if (index[j] >= bound) return fail(h, which == 0 ? "user feature index exceed bound" : "item feature index exceed bound");
+  sd.rp.assign(row_ptr, row_ptr + num_row + 1);
+  sd.idx.assign(index, index + row_ptr[num_row]);
+  sd.val.assign(value, value + row_ptr[num_row]);
   return 0;
 }
 
@@ -614,26 +684,37 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
   for (int r0 = 0; r0 < num_row; r0 += h->chunk_rows) {
     const int r1 = (int)std::min<long long>(num_row, (long long)r0 + h->chunk_rows);
     const int n = r1 - r0;
-    const int v0 = row_ptr[3LL * r0], v1 = row_ptr[3LL * r1];
+    // the chunk's arrays: the caller's, or their side-feature expansion (0-based)
+    Expanded ex;
+    const bool side = sides_on(h);
+    if (side && expand_rows(h, r0, r1, row_ptr, index, value, ex)) return 1;
+    const int *c_rp = side ? ex.rp.data() : row_ptr + 3LL * r0;
+    const int v0 = c_rp[0], v1 = c_rp[3LL * n];
     if (v0 < 0 || v1 < v0) return fail(h, "row_ptr must be non-decreasing");
     const size_t nv = (size_t)(v1 - v0);
+    const unsigned *c_idx = side ? ex.idx.data() : index + v0;
+    const float *c_val = side ? ex.val.data() : value + v0;
     Slot &s = next_slot(h);
-    if (h2d(h, s.d_rp, s.h_rp, row_ptr + 3LL * r0, (3 * (size_t)n + 1) * 4)) return 1;
+    if (h2d(h, s.d_rp, s.h_rp, c_rp, (3 * (size_t)n + 1) * 4)) return 1;
     if (h2d(h, s.d_label, s.h_label, label + r0, (size_t)n * 4)) return 1;
-    if (h2d(h, s.d_index, s.h_index, index + v0, nv * 4)) return 1;
-    if (h2d(h, s.d_value, s.h_value, value + v0, nv * 4)) return 1;
+    if (h2d(h, s.d_index, s.h_index, c_idx, nv * 4)) return 1;
+    if (h2d(h, s.d_value, s.h_value, c_val, nv * 4)) return 1;
+    if (side && h2d(h, s.d_value2, s.h_value2, ex.val2.data(), nv * 4)) return 1;
     DevCsr csr;
     csr.row_ptr = (const int *)s.d_rp.p;
     csr.label = (const float *)s.d_label.p;
     csr.index = (const unsigned *)s.d_index.p;
     csr.value = (const float *)s.d_value.p;
+    csr.value2 = side ? (const float *)s.d_value2.p : nullptr;
     csr.ticket = nullptr;
     csr.val_base = v0;
     csr.val_end = v1;
     if (exact) {
       if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
       reset_ticket_counters(h);
-      if (make_tickets(h, r0, r1, row_ptr, index, (unsigned *)s.h_ticket.p)) return 1;
+      if (side ? make_tickets(h, 0, n, ex.rp.data(), ex.idx.data(), (unsigned *)s.h_ticket.p)
+               : make_tickets(h, r0, r1, row_ptr, index, (unsigned *)s.h_ticket.p))
+        return 1;
       if (dev_reserve(h, s.d_ticket, nv * 4)) return 1;
       if (h2d_pinned(h, s.d_ticket.p, s.h_ticket.p, nv * 4)) return 1;
       csr.ticket = (const unsigned *)s.d_ticket.p;
@@ -678,7 +759,7 @@ int svdgpu_predict_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float
 static int fb_tickets(svdgpu *h, const std::vector<int> &unit_off, int u0, int u1, const int *blk_row_off,
                       const int *blk_fb_off, const unsigned *fb_index, const int *row_ptr,
                       const unsigned *index, unsigned *fb_ticket, int fb_base, unsigned *ticket,
-                      int row0) {
+                      int row0, int row_shift = 0 /* row_ptr/index hold rows (absolute - row_shift) */) {
   // sequential order: unit gather (holds its feedback rows) -> rows -> scatter
   unsigned *cf = h->cnt_ui.data();  // feedback rows are rows [0,num_ufeedback) of the slab
   for (int u = u0; u < u1; ++u) {
@@ -688,8 +769,8 @@ static int fb_tickets(svdgpu *h, const std::vector<int> &unit_off, int u0, int u
       if (fb_index[f] >= (unsigned)h->dm.num_ufeedback) return fail(h, "ufeedback id exceed bound");
       fb_ticket[f - fb_base] = cf[fb_index[f]];
     }
-    if (make_tickets(h, blk_row_off[b0], blk_row_off[b1], row_ptr, index,
-                     ticket + (row_ptr[3LL * blk_row_off[b0]] - row_ptr[3LL * row0])))
+    if (make_tickets(h, blk_row_off[b0] - row_shift, blk_row_off[b1] - row_shift, row_ptr, index,
+                     ticket + (row_ptr[3LL * (blk_row_off[b0] - row_shift)] - row_ptr[3LL * row0])))
       return 1;
     for (int f = f0; f < f1; ++f) cf[fb_index[f]]++;
   }
@@ -726,15 +807,20 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     const int b0 = unit_off[u0], b1 = unit_off[u1];
     const int r0 = blk_row_off[b0], r1 = blk_row_off[b1];
     const int n = r1 - r0;
-    const int v0 = row_ptr[3LL * r0], v1 = row_ptr[3LL * r1];
+    Expanded ex;
+    const bool side = sides_on(h);
+    if (side && expand_rows(h, r0, r1, row_ptr, index, value, ex)) return 1;
+    const int *c_rp = side ? ex.rp.data() : row_ptr + 3LL * r0;
+    const int v0 = c_rp[0], v1 = c_rp[3LL * n];
     const size_t nv = (size_t)(v1 - v0);
     const int fb0 = blk_fb_off[b0], fb1 = blk_fb_off[b1];
     const size_t nfb = (size_t)(fb1 - fb0);
     Slot &s = next_slot(h);
-    if (h2d(h, s.d_rp, s.h_rp, row_ptr + 3LL * r0, (3 * (size_t)n + 1) * 4)) return 1;
+    if (h2d(h, s.d_rp, s.h_rp, c_rp, (3 * (size_t)n + 1) * 4)) return 1;
     if (h2d(h, s.d_label, s.h_label, label + r0, (size_t)n * 4)) return 1;
-    if (h2d(h, s.d_index, s.h_index, index + v0, nv * 4)) return 1;
-    if (h2d(h, s.d_value, s.h_value, value + v0, nv * 4)) return 1;
+    if (h2d(h, s.d_index, s.h_index, side ? ex.idx.data() : index + v0, nv * 4)) return 1;
+    if (h2d(h, s.d_value, s.h_value, side ? ex.val.data() : value + v0, nv * 4)) return 1;
+    if (side && h2d(h, s.d_value2, s.h_value2, ex.val2.data(), nv * 4)) return 1;
     if (h2d(h, s.d_fbi, s.h_fbi, fb_index + fb0, nfb * 4)) return 1;
     if (h2d(h, s.d_fbv, s.h_fbv, fb_value + fb0, nfb * 4)) return 1;
     // misc = unit_off (relative blocks) | blk_row_off | blk_fb_off | order
@@ -757,6 +843,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     csr.label = (const float *)s.d_label.p;
     csr.index = (const unsigned *)s.d_index.p;
     csr.value = (const float *)s.d_value.p;
+    csr.value2 = side ? (const float *)s.d_value2.p : nullptr;
     csr.ticket = nullptr;
     csr.val_base = v0;
     csr.val_end = v1;
@@ -775,8 +862,9 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
       if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
       if (host_reserve(h, s.h_fbt, nfb * 4 + 4)) return 1;
       reset_ticket_counters(h);
-      if (fb_tickets(h, unit_off, u0, u1, blk_row_off, blk_fb_off, fb_index, row_ptr, index,
-                     (unsigned *)s.h_fbt.p, fb0, (unsigned *)s.h_ticket.p, r0))
+      if (fb_tickets(h, unit_off, u0, u1, blk_row_off, blk_fb_off, fb_index, side ? ex.rp.data() : row_ptr,
+                     side ? ex.idx.data() : index, (unsigned *)s.h_fbt.p, fb0, (unsigned *)s.h_ticket.p,
+                     side ? 0 : r0, side ? r0 : 0))
         return 1;
       if (dev_reserve(h, s.d_ticket, nv * 4)) return 1;
       if (dev_reserve(h, s.d_fbt, nfb * 4)) return 1;
@@ -883,6 +971,14 @@ int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const in
   if (num_row < 0 || !row_ptr || (num_row > 0 && !label)) return fail(h, "batch_create: bad arguments");
   if (validate_csr(h, num_row, row_ptr)) return 1;
   if (row_ptr[0] != 0) return fail(h, "batch_create: row_ptr[0] must be 0");
+  Expanded ex;  // side features: the resident batch holds the expanded rows
+  const bool side = sides_on(h);
+  if (side) {
+    if (expand_rows(h, 0, num_row, row_ptr, index, value, ex)) return 1;
+    row_ptr = ex.rp.data();
+    index = ex.idx.data();
+    value = ex.val.data();
+  }
   svdgpu_batch *b = new svdgpu_batch();
   b->num_row = num_row;
   b->num_val = row_ptr[3LL * num_row];
@@ -892,6 +988,8 @@ int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const in
   rc |= upload_plain(h, b->d_label, label, (size_t)num_row * 4);
   rc |= upload_plain(h, b->d_index, index, nv * 4);
   rc |= upload_plain(h, b->d_value, value, nv * 4);
+  if (side) rc |= upload_plain(h, b->d_value2, ex.val2.data(), nv * 4);
+  b->has_value2 = side;
   if (!rc && h->mode == SVDGPU_MODE_EXACT && h->shape.format_type == 0) {
     std::vector<unsigned> tk(nv + 1);
     reset_ticket_counters(h);
@@ -945,6 +1043,7 @@ static DevCsr batch_csr(const svdgpu_batch *b) {
   c.label = (const float *)b->d_label.p;
   c.index = (const unsigned *)b->d_index.p;
   c.value = (const float *)b->d_value.p;
+  c.value2 = b->has_value2 ? (const float *)b->d_value2.p : nullptr;
   c.ticket = b->has_ticket ? (const unsigned *)b->d_ticket.p : nullptr;
   c.val_base = 0;
   c.val_end = (int)b->num_val;
@@ -1041,7 +1140,7 @@ void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
   }
-  DevBuf *db[] = {&b->d_rp, &b->d_label, &b->d_index, &b->d_value, &b->d_ticket, &b->d_pred,
+  DevBuf *db[] = {&b->d_rp, &b->d_label, &b->d_index, &b->d_value, &b->d_value2, &b->d_ticket, &b->d_pred,
                   &b->d_unit_off, &b->d_blk_row_off, &b->d_blk_fb_off, &b->d_fbi, &b->d_fbv, &b->d_fbt, &b->d_order};
   for (DevBuf *d : db) dev_free(*d);
   delete b;

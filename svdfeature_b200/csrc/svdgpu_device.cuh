@@ -66,6 +66,7 @@ struct DevCsr {
   const float *label;
   const unsigned *index;
   const float *value;
+  const float *value2;     // side-feature expansion only: second factor of an item entry's value, else null
   const unsigned *ticket;  // exact mode: row version each feature waits for
   int val_base;
   int val_end;  // one past the last feature position the arrays hold (absolute)
@@ -378,11 +379,14 @@ struct Group {
   // replayed in order through shuffles so every lane ends with the same sum.
   __device__ __forceinline__ double bias_sum(double sum, const float *table, int off,
                                             const unsigned *idx, const float *val, int beg,
-                                            int end) const {
+                                            int end, const float *val2 = nullptr) const {
     for (int base = beg; base < end; base += LANES) {
       const int f = base + gl;
       float p = 0.0f;
-      if (f < end) p = __fmul_rn(val[f], __ldcg(table + off + idx[f]));
+      if (f < end) {
+        p = __fmul_rn(val[f], __ldcg(table + off + idx[f]));
+        if (val2) p = __fmul_rn(p, val2[f]);  // side feature of an item: (i_bias*value)*ival, base.h:348
+      }
       const int cnt = min(LANES, end - base);
       for (int j = 0; j < cnt; ++j) sum = __dadd_rn(sum, (double)bcast(p, j));
     }
@@ -408,14 +412,15 @@ struct Group {
   __device__ __forceinline__ void scalar_seg(float *table, int off, const unsigned *idx,
                                              const float *val, int beg, int end, float lrerr,
                                              float decay, bool upd, bool dec, unsigned regfree,
-                                             bool parallel, int scatter, bool l1 = false) const {
+                                             bool parallel, int scatter, bool l1 = false,
+                                             const float *val2 = nullptr) const {
     // l1: the decay step is reg_L1(x, decay) instead of x *= decay (reg_global 1, base.h:193)
     if (parallel) {
       for (int f = beg + gl; f < end; f += LANES) {
         float *p = table + off + idx[f];
         const float x0 = __ldcg(p);
         float x = x0;
-        if (upd) x = __fadd_rn(x, __fmul_rn(lrerr, val[f]));
+        if (upd) x = __fadd_rn(x, val2 ? __fmul_rn(__fmul_rn(lrerr, val[f]), val2[f]) : __fmul_rn(lrerr, val[f]));
         if (dec && idx[f] >= regfree) x = l1 ? reg_l1(x, decay) : __fmul_rn(x, decay);
         if (scatter == SCATTER_RED) red1(p, __fsub_rn(x, x0));
         else __stcg(p, x);
@@ -425,7 +430,7 @@ struct Group {
         for (int f = beg; f < end; ++f) {
           float *p = table + off + idx[f];
           float x = __ldcg(p);
-          if (upd) x = __fadd_rn(x, __fmul_rn(lrerr, val[f]));
+          if (upd) x = __fadd_rn(x, val2 ? __fmul_rn(__fmul_rn(lrerr, val[f]), val2[f]) : __fmul_rn(lrerr, val[f]));
           if (dec && idx[f] >= regfree) x = l1 ? reg_l1(x, decay) : __fmul_rn(x, decay);
           __stcg(p, x);
         }
@@ -455,7 +460,9 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
                                                   int rp3, float label, const unsigned *idx,
                                                   const float *val, int scatter_user,
                                                   int scatter_item, FbState<VEC> *fbs,
-                                                  int *err_flag) {
+                                                  int *err_flag, const float *val2 = nullptr) {
+  // val2 (side-feature expansion, base.h:375-379,417-422): an item entry's value is the pair
+  // (val, val2) -- prepare_tmp uses val*val2, the update (lr*err*val)*val2 like the reference
   // ---- index bounds (base.h:320,327,343: assert_true -> error) -------------
   {
     int bad = 0;
@@ -495,7 +502,7 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
   for (int f = rp2; f < rp3; ++f) {
     float4 w[VEC];
     g.load_row(m, (size_t)m.item_off + idx[f], w);
-    const float s = val[f];
+    const float s = val2 ? __fmul_rn(val[f], val2[f]) : val[f];
     const bool one = scalar_is_one(s);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -511,7 +518,7 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
     bsum = g.bias_sum(bsum, m.bias, m.user_off, idx, val, rp1, rp2);
     if (SVDPP) bsum = __dadd_rn(bsum, (double)fbs->fb_bias);  // get_bias_svdpp, base.h:509-511
   }
-  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, rp2, rp3);
+  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, rp2, rp3, val2);
 
   // ---- pred (base.h:445-454) ------------------------------------------------
   const float d = g.template dot<EXACT_DOT>(m, tu, ti);
@@ -571,7 +578,7 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       } else {
         g.load_row(m, row, w);
       }
-      const float sc = __fmul_rn(lrerr, val[f]);
+      const float sc = val2 ? __fmul_rn(__fmul_rn(lrerr, val[f]), val2[f]) : __fmul_rn(lrerr, val[f]);
       const bool one = scalar_is_one(sc);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
@@ -584,7 +591,7 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       else g.store_row(m, row, nw);
     }
     g.scalar_seg(m.bias, m.item_off, idx, val, rp2, rp3, lrerr, hp.dib, true, true, 0u, true,
-                 scatter_item);
+                 scatter_item, false, val2);
   } else {
     // a row index repeats inside this instance: replay the reference's passes
     // through memory in its order (all updates, then all decays).
@@ -605,14 +612,14 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       const size_t row = (size_t)m.item_off + idx[f];
       float4 w[VEC];
       g.load_row(m, row, w);
-      const float sc = __fmul_rn(lrerr, val[f]);
+      const float sc = val2 ? __fmul_rn(__fmul_rn(lrerr, val[f]), val2[f]) : __fmul_rn(lrerr, val[f]);
       const bool one = scalar_is_one(sc);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) w[v] = f4_add_scaled(w[v], tu[v], sc, one);
       g.store_row(m, row, w);
     }
     g.scalar_seg(m.bias, m.item_off, idx, val, rp2, rp3, lrerr, 0.f, true, false, 0u, false,
-                 SCATTER_STORE);
+                 SCATTER_STORE, false, val2);
   }
 
   // ---- update_svdpp (base.h:512-520) -----------------------------------------

@@ -19,8 +19,8 @@ struct HostBuf {
 };
 // One staging slot for host-pointer calls: pinned mirrors + device arrays.
 struct Slot {
-  HostBuf h_rp, h_label, h_index, h_value, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
-  DevBuf d_rp, d_label, d_index, d_value, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
+  HostBuf h_rp, h_label, h_index, h_value, h_value2, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
+  DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
   cudaEvent_t done = nullptr;    // last kernel that read this slot
   cudaEvent_t copied = nullptr;  // the slot's H2D copies have landed (recorded on the copy stream)
   bool used = false;
@@ -83,6 +83,7 @@ struct svdgpu {
   size_t row_mask_cap = 0;
   size_t any_left_at = 0;  // index of the "pass 1 left something" word inside d_row_mask
   int pass1 = 1;  // option "pass1": 0 sends every row through the generic pass
+  int l2_ahead = -1;   // option "l2_ahead": generic pass prefetches the next tile's rows into L2 (-1 auto)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
   static constexpr int NSLOT = 3;
@@ -91,6 +92,12 @@ struct svdgpu {
   // bulk ingest: pinned chunk buffers (kept across calls) and where the time went
   HostBuf ing_rp, ing_label, ing_index, ing_value;
   double ingest_read_s = 0.0, ingest_call_s = 0.0;
+  // side features (feature_user / feature_item, base.h:98-99): index -> extra (index, value) pairs
+  struct Side {
+    std::vector<unsigned> rp, idx;
+    std::vector<float> val;
+    bool on() const { return rp.size() > 1; }
+  } side_u, side_i;
   // multi-GPU exchange
   svdk::DeltaPlan plan;
   float *d_snap = nullptr, *d_delta = nullptr;

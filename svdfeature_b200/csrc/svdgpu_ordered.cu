@@ -65,6 +65,7 @@ k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *
   g.dot_s = dot_s[warp];
   const unsigned *idx = csr.index - csr.val_base;
   const float *val = csr.value - csr.val_base;
+  const float *val2 = csr.value2 ? csr.value2 - csr.val_base : nullptr;
   const unsigned *tk = csr.ticket - csr.val_base;
   for (;;) {
     unsigned n = 0;
@@ -78,7 +79,7 @@ k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *
     wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
     process_instance<LANES, VEC, true, true, false>(g, m, hp, rp0, rp1, rp2, rp3, csr.label[r], idx,
                                                     val, SCATTER_STORE, SCATTER_STORE, nullptr,
-                                                    err_flag);
+                                                    err_flag, val2);
     release_tickets(g, m, rp0, rp1, rp2, rp3, idx);
   }
 }
@@ -203,6 +204,7 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
   g.dot_s = &dot_s[warp][gw * Group<LANES, VEC>::DOT_FLOATS];
   const unsigned *idx = csr.index - csr.val_base;
   const float *val = csr.value - csr.val_base;
+  const float *val2 = csr.value2 ? csr.value2 - csr.val_base : nullptr;
   const unsigned *tk = ORDERED ? csr.ticket - csr.val_base : nullptr;
   const int *row_ptr = csr.row_ptr - 3 * (long long)ug.row_base;
   const float *label = csr.label - ug.row_base;
@@ -251,7 +253,7 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
         if (ORDERED && TRAIN) wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
         const float p = process_instance<LANES, VEC, EXACT_DOT, TRAIN, true>(
             g, m, hp, rp0, rp1, rp2, rp3, label[r], idx, val, scatter_user, scatter_item, &s,
-            err_flag);
+            err_flag, val2);
         if (!TRAIN && g.gl == 0) pred_out[r - ug.row_base] = p;
         if (ORDERED && TRAIN) release_tickets(g, m, rp0, rp1, rp2, rp3, idx);
       }

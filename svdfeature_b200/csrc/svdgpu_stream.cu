@@ -49,7 +49,7 @@ template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN>
 __global__ void __launch_bounds__(HW_THREADS, 2)
 k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user,
          int scatter_item, float *pred_out, const unsigned *row_mask, const unsigned *any_left,
-         int *err_flag) {
+         int *err_flag, int l2_ahead) {
   if (*any_left == 0u) return;  // pass 1 took every row
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,16 +143,52 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
       ph_b ^= 1u << (j % HW_STAGES);
     }
   };
+  // Pull every model row (and bias) the marked rows of tile j touch into L2, one tile before
+  // they are used.  For models far larger than the 126 MB L2 (configs[3..4]: 0.7-11 GB) each
+  // gather of the generic routine is otherwise a DRAM round trip on the instance's critical path.
+  auto l2_prefetch_tile = [&](int j) {
+    if (!l2_ahead || j >= nlocal || skip_tile(j)) return;
+    const Win w = window(j);
+    if (!w.staged) return;
+    const HwStage &st = sw.st[j % HW_STAGES];
+    const int r0 = row_begin + tile_of(j) * HW_TILE;
+    const int nrow = min(HW_TILE, row_end - r0);
+    const int *rp = st.rp + ((3 * r0) & 3);
+    const int sm_base = w.v0 - w.v_off + csr.val_base, v_hi = w.v1 + csr.val_base;
+    const uint2 mk = *reinterpret_cast<const uint2 *>(row_mask + 2 * tile_of(j));
+    const int row_bytes = m.pitch * 4;
+    for (int q = lane; q < nrow; q += 32) {
+      if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) continue;
+      const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
+      if (!(rp0 >= sm_base && rp0 <= rp1 && rp1 <= rp2 && rp2 <= rp3 && rp3 <= v_hi)) continue;
+      for (int f = rp0; f < min(rp3, rp0 + 24); ++f) {  // (bounded: very wide rows prefetch their head)
+        const unsigned id = st.idx[f - sm_base];
+        if (f < rp1) {
+          if (id < (unsigned)m.num_global) prefetch_l2(m.g_bias + id);
+          continue;
+        }
+        const bool is_user = f < rp2;
+        if (id >= (unsigned)(is_user ? m.num_user : m.num_item)) continue;
+        const size_t row = (size_t)(is_user ? m.user_off : m.item_off) + id;
+        const char *p = reinterpret_cast<const char *>(m.W + row * (size_t)m.pitch);
+        for (int b = 0; b < row_bytes; b += 128) prefetch_l2(p + b);
+        prefetch_l2(m.bias + row);
+      }
+    }
+  };
+
   issue_a(0);
   issue_a(1);
   issue_a(2);
   issue_b(0);
   issue_b(1);
   wait_b(0);
+  l2_prefetch_tile(0);
   for (int j = 0; j < nlocal; ++j) {
     issue_a(j + 3);
     issue_b(j + 2);
     wait_b(j + 1);
+    l2_prefetch_tile(j + 1);
     if (skip_tile(j)) continue;
     const HwStage &st = sw.st[j % HW_STAGES];
     const int t = tile_of(j);
@@ -167,6 +203,7 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
     const uint2 mk = *reinterpret_cast<const uint2 *>(row_mask + 2 * t);
     const unsigned *idx = w.staged ? (st.idx - sm_base) : (csr.index - csr.val_base);
     const float *val = w.staged ? (st.val - sm_base) : (csr.value - csr.val_base);
+    const float *val2 = csr.value2 ? csr.value2 - csr.val_base : nullptr;  // (not staged: side features only)
     (void)v_hi;
     for (int q = gw; q < nrow; q += GPW) {
       if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) continue;  // done by pass 1
@@ -177,7 +214,7 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
       // a staged window holds the whole tile or nothing, so every row of it is addressable
       const float pr = process_instance<LANES, VEC, EXACT_DOT, TRAIN, false>(
           g, m, hp, rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], lab[q], idx, val,
-          scatter_user, scatter_item, nullptr, err_flag);
+          scatter_user, scatter_item, nullptr, err_flag, val2);
       if (!TRAIN && g.gl == 0) pred_out[r0 + q - row_begin] = pr;
     }
   }
@@ -187,6 +224,9 @@ template <int L, int V>
 static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
   const long long ntile = ((long long)(r1 - r0) + HW_TILE - 1) / HW_TILE;
   int grid = 1;
+  // tile-ahead L2 prefetch of the gathered rows when the model cannot live in L2 (option "l2_ahead")
+  const size_t model_bytes = h->rows * (size_t)h->dm.pitch * sizeof(float);
+  const int l2_ahead = h->l2_ahead >= 0 ? h->l2_ahead : (model_bytes > (size_t)(96u << 20) ? 1 : 0);
 #define GO(ED, TR)                                                                               \
   {                                                                                              \
     auto k = k_stream<L, V, ED, TR>;                                                             \
@@ -195,7 +235,8 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
     if (grid_for(h, k, HW_THREADS, (ntile + HW_WARPS - 1) / HW_WARPS, &grid, smem)) return 1;    \
     k<<<grid, HW_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
                                              h->scatter_item, pred, h->d_row_mask,               \
-                                             h->d_row_mask + h->any_left_at, h->d_err);          \
+                                             h->d_row_mask + h->any_left_at, h->d_err,           \
+                                             l2_ahead);                                          \
     h->n_launch++;                                                                               \
   }
   if (train) {

@@ -94,6 +94,22 @@ def cases():
     return out
 
 
+def write_side_features(path, num_row, num_target, seed, max_extra=3, covered=0.7):
+    """A feature_user / feature_item file (apex-utils/apex_utils.h:176-195): line r lists the extra
+    (index:value) pairs feature index r expands to; rows beyond the file have none."""
+    rng = np.random.default_rng(seed)
+    rows = int(num_row * covered)
+    side = []
+    with open(path, "w") as f:
+        for r in range(rows):
+            n = int(rng.integers(0, max_extra + 1))
+            idx = rng.integers(0, num_target, n)
+            val = np.round(rng.uniform(-1.0, 1.0, n), 3)
+            side.append((idx.astype(np.uint32), val.astype(np.float32)))
+            f.write("%d %s\n" % (n, " ".join("%d:%g" % (i, v) for i, v in zip(idx, val))))
+    return side
+
+
 # cases whose arithmetic calls expf: the GPU is allowed 1 ulp of expf (see svdgpu.h)
 SIGMOID_CASES = {"active_1", "active_2", "active_3", "active_7", "pairwise_csr", "pairwise_ugroup"}
 

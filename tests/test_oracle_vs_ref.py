@@ -42,6 +42,24 @@ def test_oracle_other_regularisers(reg_method, reg_global, tmp_path):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["general_k13_dups", "general_k40", "basic_k16", "active_2", "svdpp_k16", "reg_l1"])
+def test_oracle_side_features(name, tmp_path):
+    """feature_user / feature_item expansion (base.h:298-308,330-349,365-379,399-422) against the
+    compiled reference: same model bytes and predictions."""
+    fmt, act, params, data, kind = CASES[name]
+    fu, fi = str(tmp_path / "user.side"), str(tmp_path / "item.side")
+    _cases.write_side_features(fu, params["num_user"], params["num_user"], seed=1)
+    _cases.write_side_features(fi, params["num_item"], params["num_item"], seed=2)
+    params = dict(params, feature_user=fu, feature_item=fi)
+    mo, po = _train(COracle, fmt, act, params, data, kind, tmp_path)
+    mr, pr = _train(RefTrainer, fmt, act, params, data, kind, tmp_path)
+    assert mo == mr and np.array_equal(po, pr)
+    # and the side features do change the result
+    m0, p0 = _train(COracle, fmt, act, CASES[name][2], data, kind, tmp_path)
+    assert not np.array_equal(p0, po)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 def test_oracle_loads_reference_model_file(tmp_path):
     fmt, act, params, data, kind = CASES["svdpp_k16"]
     r = RefTrainer(fmt, act, 0, params)

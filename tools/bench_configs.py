@@ -76,7 +76,19 @@ def init_model(g, rows, k, sigma=0.01, seed=10):
     g.upload(np.zeros(rows, np.float32), W, np.zeros(max(g.shape.num_global, 1), np.float32))
 
 
+def apply_opts(g):
+    """--opt name=value (repeatable) -> svdgpu_set_option"""
+    opts = {}
+    for i, a in enumerate(sys.argv):
+        if a == "--opt":
+            k, v = sys.argv[i + 1].split("=")
+            g.set_option(k, int(v))
+            opts[k] = int(v)
+    return opts
+
+
 def run_steps(g, batch, nstep, rows_per_step, bytes_per_row, name, units=None, extra=None):
+    extra = dict(extra or {}, opts=apply_opts(g))
     def step(s):
         if units is None:
             g.batch_update(batch, s * rows_per_step, (s + 1) * rows_per_step)
