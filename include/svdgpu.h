@@ -183,6 +183,32 @@ int svdgpu_batch_eval(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float 
                       long long *count);
 void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b);
 
+/* ---- pairwise-rank sample generation on the device ----------------------- */
+/* PairwiseRankGenerator's parameters (apex_svd_data.cpp:967-989), same names and defaults. */
+typedef struct {
+  int rank_sample_method;    /* 0: positives vs negatives, label 1; 10: same, label = p.label - n.label.
+                                Method 1 (label-gap pairs) is not provided on the device.       */
+  int rank_sample_num;       /* pairs per block; <= 0: one per negative row (reference: -1)     */
+  int rank_sample_max;       /* cap on pairs per block; <= 0: none (reference: INT_MAX)         */
+  int rank_sample_pointwise; /* emit (p, label 1) and (n, label 0) instead of the merged pair   */
+  float pos_sample_lowerb;   /* reference default 0.8  */
+  float neg_sample_upperb;   /* reference default 1e-6 */
+  unsigned long long seed;   /* change it every round: the reference reshuffles on every pass   */
+} svdgpu_pair_params;
+/* From a resident user-grouped batch of rated rows make the resident batch of pair rows the
+ * reference's host sampler would feed the trainer (same blocks and feedback lists, rows replaced).
+ * Train on it with svdgpu_batch_update; free it with svdgpu_batch_destroy.
+ * replaces: PairwiseRankGenerator::next -> sample_posneg / genpair / merge
+ * (apex_svd_data.cpp:828-915, 946-965, 1001-1018); the rand()-driven shuffles become keyed
+ * permutations, so parity with the host sampler is structural, not bit-level. */
+int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const svdgpu_pair_params *params,
+                              svdgpu_batch_t **out);
+/* Copy a resident batch back to the host (any output may be NULL): row_ptr[3*num_row+1],
+ * label[num_row], index/value[num_val], blk_row_off[num_block+1]. */
+int svdgpu_batch_download(svdgpu_t *h, svdgpu_batch_t *b, int *num_row, long long *num_val,
+                          int *row_ptr, float *label, unsigned *index, float *value,
+                          int *blk_row_off);
+
 /* ---- synchronisation, timing, introspection ---------------------------- */
 /* wait for all queued work; reports device-side input errors (index out of
  * bound -- the reference's assert_true at base.h:320,327,343) */

@@ -41,6 +41,12 @@ class HParams(C.Structure):
         ("wd_ufeedback_bias", C.c_float), ("base_score", C.c_float), ("user_nonnegative", C.c_int)]
 
 
+class PairParams(C.Structure):
+    _fields_ = [("rank_sample_method", C.c_int), ("rank_sample_num", C.c_int), ("rank_sample_max", C.c_int),
+                ("rank_sample_pointwise", C.c_int), ("pos_sample_lowerb", C.c_float),
+                ("neg_sample_upperb", C.c_float), ("seed", C.c_ulonglong)]
+
+
 # every symbol include/svdgpu.h declares: (restype, argtypes)
 SVDGPU_SYMBOLS = {
     "svdgpu_create": (C.c_int, [C.POINTER(_vp), C.POINTER(Shape), C.c_int]),
@@ -63,6 +69,8 @@ SVDGPU_SYMBOLS = {
     "svdgpu_predict_buffer_file": (C.c_int, [_vp, C.c_char_p, _vp, C.c_longlong, C.POINTER(C.c_longlong)]),
     "svdgpu_eval_buffer_file": (C.c_int, [_vp, C.c_char_p, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "svdgpu_batch_eval": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "svdgpu_batch_sample_pairs": (C.c_int, [_vp, _vp, C.POINTER(PairParams), C.POINTER(_vp)]),
+    "svdgpu_batch_download": (C.c_int, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)] + [_vp] * 5),
     "svdgpu_batch_create": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp, _vp]),
     "svdgpu_batch_set_ugroup": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 5),
     "svdgpu_batch_update": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -292,6 +300,32 @@ class SvdGpu:
         out = np.empty(n, np.float32) if fetch else None
         self._ck(self.lib.svdgpu_batch_predict(self.h, batch.h, begin, end, _ptr(out)))
         return out
+
+    # pairwise-rank samples on the device
+    def batch_sample_pairs(self, batch, seed=0, method=0, num=-1, maxn=-1, pointwise=0, pos_lowerb=0.8,
+                           neg_upperb=1e-6):
+        pp = PairParams(method, num, maxn, pointwise, pos_lowerb, neg_upperb, seed)
+        out = _vp()
+        self._ck(self.lib.svdgpu_batch_sample_pairs(self.h, batch.h, C.byref(pp), C.byref(out)))
+        n, nv = C.c_int(), C.c_longlong()
+        self._ck(self.lib.svdgpu_batch_download(self.h, out, C.byref(n), C.byref(nv), None, None, None, None, None))
+        b = Batch(self, out, n.value)
+        b.num_unit = batch.num_unit
+        b.num_val = nv.value
+        return b
+
+    def batch_download(self, batch):
+        """(blk_row_off or None, row_ptr, label, index, value) of a resident batch."""
+        n, nv = C.c_int(), C.c_longlong()
+        self._ck(self.lib.svdgpu_batch_download(self.h, batch.h, C.byref(n), C.byref(nv), None, None, None, None, None))
+        rp = np.zeros(3 * n.value + 1, np.int32)
+        lab = np.zeros(n.value, np.float32)
+        idx = np.zeros(nv.value, np.uint32)
+        val = np.zeros(nv.value, np.float32)
+        bro = np.zeros(batch.num_unit + 1, np.int32) if batch.num_unit is not None else None
+        self._ck(self.lib.svdgpu_batch_download(self.h, batch.h, None, None, _ptr(rp), _ptr(lab), _ptr(idx), _ptr(val),
+                                                _ptr(bro)))
+        return bro, rp, lab, idx, val
 
     # sync / timing / introspection
     def sync(self):

@@ -19,17 +19,6 @@ namespace {
 thread_local std::string g_create_error;
 }  // namespace
 
-struct svdgpu_batch {
-  int num_row = 0;
-  long long num_val = 0;
-  DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_pred;
-  bool has_ticket = false, has_value2 = false;
-  // user-group structure
-  bool ugroup = false;
-  int num_block = 0, num_unit = 0;
-  DevBuf d_unit_off, d_blk_row_off, d_blk_fb_off, d_fbi, d_fbv, d_fbt, d_order;
-  std::vector<int> unit_off;  // host copy: block range of each unit
-};
 
 namespace {
 

@@ -143,52 +143,16 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
       ph_b ^= 1u << (j % HW_STAGES);
     }
   };
-  // Pull every model row (and bias) the marked rows of tile j touch into L2, one tile before
-  // they are used.  For models far larger than the 126 MB L2 (configs[3..4]: 0.7-11 GB) each
-  // gather of the generic routine is otherwise a DRAM round trip on the instance's critical path.
-  auto l2_prefetch_tile = [&](int j) {
-    if (!l2_ahead || j >= nlocal || skip_tile(j)) return;
-    const Win w = window(j);
-    if (!w.staged) return;
-    const HwStage &st = sw.st[j % HW_STAGES];
-    const int r0 = row_begin + tile_of(j) * HW_TILE;
-    const int nrow = min(HW_TILE, row_end - r0);
-    const int *rp = st.rp + ((3 * r0) & 3);
-    const int sm_base = w.v0 - w.v_off + csr.val_base, v_hi = w.v1 + csr.val_base;
-    const uint2 mk = *reinterpret_cast<const uint2 *>(row_mask + 2 * tile_of(j));
-    const int row_bytes = m.pitch * 4;
-    for (int q = lane; q < nrow; q += 32) {
-      if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) continue;
-      const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
-      if (!(rp0 >= sm_base && rp0 <= rp1 && rp1 <= rp2 && rp2 <= rp3 && rp3 <= v_hi)) continue;
-      for (int f = rp0; f < min(rp3, rp0 + 24); ++f) {  // (bounded: very wide rows prefetch their head)
-        const unsigned id = st.idx[f - sm_base];
-        if (f < rp1) {
-          if (id < (unsigned)m.num_global) prefetch_l2(m.g_bias + id);
-          continue;
-        }
-        const bool is_user = f < rp2;
-        if (id >= (unsigned)(is_user ? m.num_user : m.num_item)) continue;
-        const size_t row = (size_t)(is_user ? m.user_off : m.item_off) + id;
-        const char *p = reinterpret_cast<const char *>(m.W + row * (size_t)m.pitch);
-        for (int b = 0; b < row_bytes; b += 128) prefetch_l2(p + b);
-        prefetch_l2(m.bias + row);
-      }
-    }
-  };
-
   issue_a(0);
   issue_a(1);
   issue_a(2);
   issue_b(0);
   issue_b(1);
   wait_b(0);
-  l2_prefetch_tile(0);
   for (int j = 0; j < nlocal; ++j) {
     issue_a(j + 3);
     issue_b(j + 2);
     wait_b(j + 1);
-    l2_prefetch_tile(j + 1);
     if (skip_tile(j)) continue;
     const HwStage &st = sw.st[j % HW_STAGES];
     const int t = tile_of(j);
@@ -204,8 +168,34 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
     const unsigned *idx = w.staged ? (st.idx - sm_base) : (csr.index - csr.val_base);
     const float *val = w.staged ? (st.val - sm_base) : (csr.value - csr.val_base);
     const float *val2 = csr.value2 ? csr.value2 - csr.val_base : nullptr;  // (not staged: side features only)
-    (void)v_hi;
+    // Pull the model rows (and biases) of the instance this group runs L2_AHEAD turns from now into
+    // L2.  For models far larger than the 126 MB L2 (configs[3..4]: 0.7-11 GB) every gather of the
+    // generic routine is otherwise a DRAM round trip on the instance's critical path.  (A whole
+    // tile ahead is too far: 16 warps x 64 rows x 1.5 KB per SM do not survive in L2.)
+    constexpr int L2_AHEAD = 2;
+    auto l2_prefetch_row = [&](int q) {
+      if (!l2_ahead || q >= nrow || !w.staged) return;
+      if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) return;
+      const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
+      if (!(rp0 >= sm_base && rp0 <= rp1 && rp1 <= rp2 && rp2 <= rp3 && rp3 <= v_hi)) return;
+      const int row_bytes = m.pitch * 4;
+      for (int f = rp0 + g.gl; f < rp3; f += LANES) {
+        const unsigned id = st.idx[f - sm_base];
+        if (f < rp1) {
+          if (id < (unsigned)m.num_global) prefetch_l2(m.g_bias + id);
+          continue;
+        }
+        const bool is_user = f < rp2;
+        if (id >= (unsigned)(is_user ? m.num_user : m.num_item)) continue;
+        const size_t row = (size_t)(is_user ? m.user_off : m.item_off) + id;
+        const char *p = reinterpret_cast<const char *>(m.W + row * (size_t)m.pitch);
+        for (int b = 0; b < row_bytes; b += 128) prefetch_l2(p + b);
+        prefetch_l2(m.bias + row);
+      }
+    };
+    for (int a = 0; a < L2_AHEAD; ++a) l2_prefetch_row(gw + a * GPW);
     for (int q = gw; q < nrow; q += GPW) {
+      l2_prefetch_row(q + L2_AHEAD * GPW);
       if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) continue;  // done by pass 1
       if (!row_ok(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], csr.val_base, csr.val_end)) {
         if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
