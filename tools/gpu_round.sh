@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests/test_gpu_pairs.py tests/test_abi.py -x -q 2>&1 | tail -40 ) > gpurun_out/pytest_gpu.log 2>&1
-tail -30 gpurun_out/pytest_gpu.log
+timeout 900 python tools/hogwild_parity.py 2>&1 | tail -1 | tee gpurun_out/hogwild_parity.json
+timeout 900 python tools/hogwild_parity.py 480000 10000000 2>&1 | tail -1 | tee gpurun_out/hogwild_parity_480k.json
