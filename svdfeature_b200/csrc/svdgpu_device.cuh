@@ -478,47 +478,78 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
     }
   }
 
+  // ---- gathers of the common small shapes, all issued before anything is consumed ----------
+  // (first user row, first two item rows, their biases: one memory round trip instead of one
+  // per feature; the generic routine used to load a row, use it, load the next)
+  const int nu_ = rp2 - rp1, ni_ = rp3 - rp2;
+  float4 tu[VEC], ti[VEC], wu0[VEC], wi0[VEC], wi1[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) wu0[v] = wi0[v] = wi1[v] = f4_zero();
+  if (nu_ > 0) g.load_row(m, (size_t)m.user_off + idx[rp1], wu0);
+  if (ni_ > 0) g.load_row(m, (size_t)m.item_off + idx[rp2], wi0);
+  if (ni_ > 1) g.load_row(m, (size_t)m.item_off + idx[rp2 + 1], wi1);
+  float pre_ub = 0.0f, pre_ib0 = 0.0f, pre_ib1 = 0.0f;
+  if (nu_ > 0 && !m.no_user_bias) pre_ub = __ldcg(m.bias + m.user_off + idx[rp1]);
+  if (ni_ > 0) pre_ib0 = __ldcg(m.bias + m.item_off + idx[rp2]);
+  if (ni_ > 1) pre_ib1 = __ldcg(m.bias + m.item_off + idx[rp2 + 1]);
+
+  // ---- calc_bias, global part (base.h:318-322): its gathers overlap the row gathers --------
+  double bsum = 0.0;
+  bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
+
   // ---- prepare_tmp (base.h:354-381) ----------------------------------------
-  // (issued before calc_bias so that the row gathers and the bias gathers are in flight together)
-  float4 tu[VEC], ti[VEC], wu0[VEC], wi0[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     tu[v] = SVDPP ? fbs->fb[v] : f4_zero();  // prepare_svdpp, base.h:430-432 / 506-508
     ti[v] = f4_zero();
-    wu0[v] = f4_zero();
-    wi0[v] = f4_zero();
   }
   for (int f = rp1; f < rp2; ++f) {
     float4 w[VEC];
-    g.load_row(m, (size_t)m.user_off + idx[f], w);
+    if (f == rp1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = wu0[v];
+    } else {
+      g.load_row(m, (size_t)m.user_off + idx[f], w);
+    }
     const float s = val[f];
     const bool one = scalar_is_one(s);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      tu[v] = f4_add_scaled(tu[v], w[v], s, one);
-      if (f == rp1) wu0[v] = w[v];
-    }
+    for (int v = 0; v < VEC; ++v) tu[v] = f4_add_scaled(tu[v], w[v], s, one);
   }
   for (int f = rp2; f < rp3; ++f) {
     float4 w[VEC];
-    g.load_row(m, (size_t)m.item_off + idx[f], w);
+    if (f == rp2) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = wi0[v];
+    } else if (f == rp2 + 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) w[v] = wi1[v];
+    } else {
+      g.load_row(m, (size_t)m.item_off + idx[f], w);
+    }
     const float s = val2 ? __fmul_rn(val[f], val2[f]) : val[f];
     const bool one = scalar_is_one(s);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      ti[v] = f4_add_scaled(ti[v], w[v], s, one);
-      if (f == rp2) wi0[v] = w[v];
-    }
+    for (int v = 0; v < VEC; ++v) ti[v] = f4_add_scaled(ti[v], w[v], s, one);
   }
 
-  // ---- calc_bias (base.h:313-353) ------------------------------------------
-  double bsum = 0.0;
-  bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
+  // ---- calc_bias, user and item part (base.h:324-350), first entries from the early gathers --
   if (!m.no_user_bias) {
-    bsum = g.bias_sum(bsum, m.bias, m.user_off, idx, val, rp1, rp2);
+    if (nu_ > 0) bsum = __dadd_rn(bsum, (double)__fmul_rn(val[rp1], pre_ub));
+    bsum = g.bias_sum(bsum, m.bias, m.user_off, idx, val, min(rp1 + 1, rp2), rp2);
     if (SVDPP) bsum = __dadd_rn(bsum, (double)fbs->fb_bias);  // get_bias_svdpp, base.h:509-511
   }
-  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, rp2, rp3, val2);
+  if (ni_ > 0) {
+    float p = __fmul_rn(val[rp2], pre_ib0);
+    if (val2) p = __fmul_rn(p, val2[rp2]);
+    bsum = __dadd_rn(bsum, (double)p);
+  }
+  if (ni_ > 1) {
+    float p = __fmul_rn(val[rp2 + 1], pre_ib1);
+    if (val2) p = __fmul_rn(p, val2[rp2 + 1]);
+    bsum = __dadd_rn(bsum, (double)p);
+  }
+  bsum = g.bias_sum(bsum, m.bias, m.item_off, idx, val, min(rp2 + 2, rp3), rp3, val2);
 
   // ---- pred (base.h:445-454) ------------------------------------------------
   const float d = g.template dot<EXACT_DOT>(m, tu, ti);
@@ -543,6 +574,15 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
     g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, lrerr, g_dec, true, !dup_g, hp.regfree, !dup_g,
                  dup_g ? SCATTER_STORE : scatter_item, g_l1);
 
+  // bias read-modify-write of one feature whose old value was gathered early (lane `who` does it)
+  auto bias_rmw = [&](float *p, float x0, float v, float v2, bool has2, float decay, int who, int scatter) {
+    if (g.gl != who) return;
+    float add = __fmul_rn(lrerr, v);
+    if (has2) add = __fmul_rn(add, v2);
+    const float x = __fmul_rn(__fadd_rn(x0, add), decay);
+    if (scatter == SCATTER_RED) red1(p, __fsub_rn(x, x0));
+    else __stcg(p, x);
+  };
   if (fused) {
     // every touched row appears once: update and decay in one register pass
     for (int f = rp1; f < rp2; ++f) {
@@ -566,15 +606,20 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       if (scatter_user == SCATTER_RED) g.red_row(m, row, nw, w);
       else g.store_row(m, row, nw);
     }
-    if (!m.no_user_bias)
-      g.scalar_seg(m.bias, m.user_off, idx, val, rp1, rp2, lrerr, hp.dub, true, true, 0u, true,
+    if (!m.no_user_bias) {
+      if (nu_ > 0) bias_rmw(m.bias + m.user_off + idx[rp1], pre_ub, val[rp1], 1.0f, false, hp.dub, 0, scatter_user);
+      g.scalar_seg(m.bias, m.user_off, idx, val, min(rp1 + 1, rp2), rp2, lrerr, hp.dub, true, true, 0u, true,
                    scatter_user);
+    }
     for (int f = rp2; f < rp3; ++f) {
       const size_t row = (size_t)m.item_off + idx[f];
       float4 w[VEC], nw[VEC];
       if (f == rp2) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) w[v] = wi0[v];
+      } else if (f == rp2 + 1) {  // (fused path: no row repeats, so the early gather is still current)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[v] = wi1[v];
       } else {
         g.load_row(m, row, w);
       }
@@ -590,7 +635,13 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       if (scatter_item == SCATTER_RED) g.red_row(m, row, nw, w);
       else g.store_row(m, row, nw);
     }
-    g.scalar_seg(m.bias, m.item_off, idx, val, rp2, rp3, lrerr, hp.dib, true, true, 0u, true,
+    if (ni_ > 0)
+      bias_rmw(m.bias + m.item_off + idx[rp2], pre_ib0, val[rp2], val2 ? val2[rp2] : 1.0f, val2 != nullptr, hp.dib,
+               LANES - 1, scatter_item);
+    if (ni_ > 1)
+      bias_rmw(m.bias + m.item_off + idx[rp2 + 1], pre_ib1, val[rp2 + 1], val2 ? val2[rp2 + 1] : 1.0f,
+               val2 != nullptr, hp.dib, LANES - 2, scatter_item);
+    g.scalar_seg(m.bias, m.item_off, idx, val, min(rp2 + 2, rp3), rp3, lrerr, hp.dib, true, true, 0u, true,
                  scatter_item, false, val2);
   } else {
     // a row index repeats inside this instance: replay the reference's passes

@@ -110,15 +110,17 @@ __device__ __forceinline__ bool prepare_ufeedback(const Group<LANES, VEC> &g, co
   s.fb_bias = 0.0f;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) s.fb[v] = f4_zero();
+  {
 #pragma unroll 4
-  for (int i = 0; i < nfb; ++i) {
-    float4 w[VEC];
-    g.load_row(m, (size_t)fi[i], w);
-    const float x = fv[i];
-    const bool one = scalar_is_one(x);
+    for (int i = 0; i < nfb; ++i) {
+      float4 w[VEC];
+      g.load_row(m, (size_t)fi[i], w);
+      const float x = fv[i];
+      const bool one = scalar_is_one(x);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) s.fb[v] = f4_add_scaled(s.fb[v], w[v], x, one);
-    s.norm = __fadd_rn(s.norm, __fmul_rn(x, x));
+      for (int v = 0; v < VEC; ++v) s.fb[v] = f4_add_scaled(s.fb[v], w[v], x, one);
+      s.norm = __fadd_rn(s.norm, __fmul_rn(x, x));
+    }
   }
   if (!m.no_user_bias) {
     for (int base = 0; base < nfb; base += LANES) {
@@ -210,17 +212,46 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
   const float *label = csr.label - ug.row_base;
   if (ORDERED) scatter_user = scatter_item = SCATTER_STORE;  // ordered results must not depend on atomics
 
-  for (;;) {
+  // ---- per-unit state of this group ------------------------------------------------------
+  FbState<VEC> s;
+  float4 old[VEC];
+  float old_bias = 0.0f;
+  s.norm = s.fb_bias = 0.0f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s.fb[v] = old[v] = f4_zero();
+  int f0 = 0, nf0 = 0, f1 = 0, nf1 = 0, r_cur = 0, r_end = 0;
+  // Hogwild fast path: a unit is one user, so the user row (and bias) of consecutive
+  // basic-MF-shaped rows is the same -- it stays in registers from the first row that needs
+  // it to the last and is written back once (the reference reads and writes it per row,
+  // base.h:354-427; nobody else touches it meanwhile, so the result is the same).
+  unsigned c_uid = 0xffffffffu;
+  float4 c_wu[VEC];
+  float c_ub = 0.0f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) c_wu[v] = f4_zero();
+  auto flush_user = [&]() {
+    if (c_uid != 0xffffffffu && TRAIN) {
+      g.store_row(m, (size_t)m.user_off + c_uid, c_wu);
+      if (!m.no_user_bias && g.gl == 0) __stcg(m.bias + m.user_off + c_uid, c_ub);
+    }
+    c_uid = 0xffffffffu;
+  };
+  // take the next unit: false when none is left.  `ok` = its feedback list is usable.
+  auto next_unit = [&](bool &ok) -> bool {
     unsigned n = 0;
     if (g.gl == 0) n = atomicAdd(counter, 1u);
     n = g.bcast(n, 0);
-    if ((long long)unit_begin + n >= unit_end) break;
+    if ((long long)unit_begin + n >= unit_end) return false;
     int u = unit_begin + (int)n;
     if (!ORDERED && ug.order) u = ug.order[u];
     const int b0 = ug.unit_off[u], b1 = ug.unit_off[u + 1];
     // feedback list of the first block feeds the gather, of the last block the scatter
-    const int f0 = ug.blk_fb_off[b0] - ug.fb_base, nf0 = ug.blk_fb_off[b0 + 1] - ug.blk_fb_off[b0];
-    const int f1 = ug.blk_fb_off[b1 - 1] - ug.fb_base, nf1 = ug.blk_fb_off[b1] - ug.blk_fb_off[b1 - 1];
+    f0 = ug.blk_fb_off[b0] - ug.fb_base;
+    nf0 = ug.blk_fb_off[b0 + 1] - ug.blk_fb_off[b0];
+    f1 = ug.blk_fb_off[b1 - 1] - ug.fb_base;
+    nf1 = ug.blk_fb_off[b1] - ug.blk_fb_off[b1 - 1];
+    r_cur = ug.blk_row_off[b0];
+    r_end = ug.blk_row_off[b1];
     if (ORDERED) {
       // hold the feedback rows of this unit from gather to scatter
       for (int i = g.gl; i < nf0; i += LANES) {
@@ -236,31 +267,102 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
       }
       g.gsync();
     }
-    FbState<VEC> s;
-    float4 old[VEC];
-    const bool ok = prepare_ufeedback(g, m, ug.fb_index + f0, ug.fb_value + f0, nf0, s, err_flag);
-    const float old_bias = s.fb_bias;
+    ok = prepare_ufeedback(g, m, ug.fb_index + f0, ug.fb_value + f0, nf0, s, err_flag);
+    old_bias = s.fb_bias;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) old[v] = s.fb[v];
-    if (ok) {
-      for (int r = ug.blk_row_off[b0]; r < ug.blk_row_off[b1]; ++r) {
-        const int rp0 = row_ptr[3 * (long long)r], rp1 = row_ptr[3 * (long long)r + 1];
-        const int rp2 = row_ptr[3 * (long long)r + 2], rp3 = row_ptr[3 * (long long)r + 3];
-        if (!ORDERED && !row_ok(rp0, rp1, rp2, rp3, csr.val_base, csr.val_end)) {
-          if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
-          continue;
-        }
-        if (ORDERED && TRAIN) wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
-        const float p = process_instance<LANES, VEC, EXACT_DOT, TRAIN, true>(
-            g, m, hp, rp0, rp1, rp2, rp3, label[r], idx, val, scatter_user, scatter_item, &s,
-            err_flag, val2);
-        if (!TRAIN && g.gl == 0) pred_out[r - ug.row_base] = p;
-        if (ORDERED && TRAIN) release_tickets(g, m, rp0, rp1, rp2, rp3, idx);
-      }
-      if (TRAIN)
-        update_ufeedback(g, m, ug.fb_index + f1, ug.fb_value + f1, nf1, s, old, old_bias,
-                         scatter_item);
+    return true;
+  };
+  auto do_row = [&](int r) {
+    const int rp0 = row_ptr[3 * (long long)r], rp1 = row_ptr[3 * (long long)r + 1];
+    const int rp2 = row_ptr[3 * (long long)r + 2], rp3 = row_ptr[3 * (long long)r + 3];
+    if (!ORDERED && !row_ok(rp0, rp1, rp2, rp3, csr.val_base, csr.val_end)) {
+      if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
+      return;
     }
+    if (!ORDERED && hp.plain && !val2 && rp1 == rp0 && rp2 == rp1 + 1 && rp3 == rp2 + 1 &&
+        idx[rp1] < (unsigned)m.num_user && idx[rp2] < (unsigned)m.num_item) {
+      const unsigned uid = idx[rp1], iid = idx[rp2];
+      const size_t irow = (size_t)m.item_off + iid;
+      float4 wi[VEC];
+      g.load_row(m, irow, wi);
+      const float ib = __ldcg(m.bias + irow);
+      if (uid != c_uid) {
+        flush_user();
+        c_uid = uid;
+        g.load_row(m, (size_t)m.user_off + uid, c_wu);
+        c_ub = m.no_user_bias ? 0.0f : __ldcg(m.bias + m.user_off + uid);
+      }
+      const float uval = val[rp1], ival = val[rp2];
+      const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
+      // prepare_tmp (base.h:354-381) on top of tmp_ufeedback (prepare_svdpp, :506-508)
+      float4 tu[VEC], ti[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        tu[v] = f4_add_scaled(s.fb[v], c_wu[v], um, false);
+        ti[v] = f4_add_scaled(f4_zero(), wi[v], im, false);
+      }
+      // calc_bias (base.h:313-353) with get_bias_svdpp (:509-511), pred (:445-454)
+      double bsum = 0.0;
+      if (!m.no_user_bias) {
+        bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, c_ub));
+        bsum = __dadd_rn(bsum, (double)s.fb_bias);
+      }
+      bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+      const float d = g.template dot<EXACT_DOT>(m, tu, ti);
+      double sum = __dadd_rn((double)hp.base_score, bsum);
+      sum = __dadd_rn(sum, (double)d);
+      const float p = map_active((float)sum, m.active_type);
+      if (!TRAIN) {
+        if (g.gl == 0) pred_out[r - ug.row_base] = p;
+        return;
+      }
+      // update_no_decay + regularize(after) (base.h:383-427, 211-283)
+      const float err = cal_grad(label[r], p, m.active_type);
+      const float lrerr = __fmul_rn(hp.lr, err);
+      const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);
+      const float su_m = scalar_is_one(su) ? 1.0f : su, si_m = scalar_is_one(si) ? 1.0f : si;
+      float4 ni[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        c_wu[v] = f4_add_scaled(c_wu[v], ti[v], su_m, false);
+        ni[v] = f4_add_scaled(wi[v], tu[v], si_m, false);
+        if (!hp.du_skip) c_wu[v] = f4_scale(c_wu[v], hp.du);
+        if (!hp.di_skip) ni[v] = f4_scale(ni[v], hp.di);
+      }
+      if (!m.no_user_bias) c_ub = __fmul_rn(__fadd_rn(c_ub, su), hp.dub);
+      if (scatter_item == SCATTER_RED) g.red_row(m, irow, ni, wi);
+      else g.store_row(m, irow, ni);
+      if (g.gl == LANES - 1) {
+        const float nib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
+        if (scatter_item == SCATTER_RED) red1(m.bias + irow, __fsub_rn(nib, ib));
+        else __stcg(m.bias + irow, nib);
+      }
+      // update_svdpp (base.h:512-520)
+      const float sf = __fmul_rn(__fmul_rn(hp.lr_fb, err), s.norm);
+      const float sf_m = scalar_is_one(sf) ? 1.0f : sf;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        s.fb[v] = f4_add_scaled(s.fb[v], ti[v], sf_m, false);
+        if (!hp.dfb_skip) s.fb[v] = f4_scale(s.fb[v], hp.dfb);
+      }
+      if (!m.no_user_bias) {
+        s.fb_bias = __fadd_rn(s.fb_bias, sf);
+        s.fb_bias = __fmul_rn(s.fb_bias, hp.dfbb);
+      }
+      return;
+    }
+    flush_user();  // the generic routine reads the user row from memory
+    if (ORDERED && TRAIN) wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
+    const float p = process_instance<LANES, VEC, EXACT_DOT, TRAIN, true>(
+        g, m, hp, rp0, rp1, rp2, rp3, label[r], idx, val, scatter_user, scatter_item, &s,
+        err_flag, val2);
+    if (!TRAIN && g.gl == 0) pred_out[r - ug.row_base] = p;
+    if (ORDERED && TRAIN) release_tickets(g, m, rp0, rp1, rp2, rp3, idx);
+  };
+  auto finish_unit = [&](bool ok) {
+    flush_user();
+    if (ok && TRAIN) update_ufeedback(g, m, ug.fb_index + f1, ug.fb_value + f1, nf1, s, old, old_bias, scatter_item);
     if (ORDERED && TRAIN) {
       __threadfence();
       g.gsync();
@@ -269,6 +371,42 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
         if (id < (unsigned)m.num_ufeedback) red_release_add_u32(m.ver_ui + id, 1u);
       }
     }
+  };
+
+  if (ORDERED) {  // one unit per warp, units in input order
+    for (;;) {
+      bool ok = false;
+      if (!next_unit(ok)) break;
+      if (ok)
+        for (; r_cur < r_end; ++r_cur) do_row(r_cur);
+      finish_unit(ok);
+    }
+    return;
+  }
+  // Hogwild: one unit per lane group.  The groups of a warp are brought back together before
+  // every row (ncu of the free-running version: 11 of 32 lanes active on average, ~600
+  // warp-instructions per row): the row step -- the bulk of the work -- then runs as one SIMD
+  // instruction stream for all groups that have a row, and only the per-unit gather / scatter
+  // of the feedback rows runs divergent.
+  bool have = false, done = false, ok = false;
+  for (;;) {
+    if (!have && !done) {
+      have = next_unit(ok);
+      done = !have;
+      if (have && !ok) r_cur = r_end;  // unusable feedback list (error flagged): skip the unit's rows
+    }
+    if (__all_sync(0xffffffffu, !have)) break;
+    if (have) {
+      if (r_cur < r_end) {
+        do_row(r_cur);
+        ++r_cur;
+      }
+      if (r_cur >= r_end) {
+        finish_unit(ok);
+        have = false;
+      }
+    }
+    __syncwarp();
   }
 }
 
