@@ -525,6 +525,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "pass1")) h->pass1 = v ? 1 : 0;
   else if (!strcmp(name, "ring_depth")) h->ring_depth = (int)v;
   else if (!strcmp(name, "l2_ahead")) h->l2_ahead = (int)v;
+  else if (!strcmp(name, "ugroup_units")) h->ugroup_units = (int)v;
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else return fail(h, "unknown option '%s'", name);
   return 0;
@@ -847,6 +848,7 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
     ug.fb_ticket = nullptr;
     ug.row_base = r0;
     ug.fb_base = fb0;
+    ug.has_fb = nfb > 0;
     if (exact) {
       if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
       if (host_reserve(h, s.h_fbt, nfb * 4 + 4)) return 1;
@@ -1017,6 +1019,7 @@ int svdgpu_batch_set_ugroup(svdgpu_t *h, svdgpu_batch_t *b, int num_block, const
   rc |= upload_plain(h, b->d_unit_off, b->unit_off.data(), b->unit_off.size() * 4);
   rc |= upload_plain(h, b->d_blk_row_off, blk_row_off, ((size_t)num_block + 1) * 4);
   rc |= upload_plain(h, b->d_blk_fb_off, blk_fb_off, ((size_t)num_block + 1) * 4);
+  b->has_fb = nfb > 0;
   rc |= upload_plain(h, b->d_fbi, fb_index, nfb * 4);
   rc |= upload_plain(h, b->d_fbv, fb_value, nfb * 4);
   rc |= upload_plain(h, b->d_order, order.data(), order.size() * 4);
@@ -1049,6 +1052,7 @@ static DevUgroup batch_ug(const svdgpu_batch *b) {
   u.order = (const int *)b->d_order.p;
   u.row_base = 0;
   u.fb_base = 0;
+  u.has_fb = b->has_fb;
   return u;
 }
 

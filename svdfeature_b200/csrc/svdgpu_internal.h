@@ -49,6 +49,7 @@ struct DevUgroup {
   const int *order;           // hogwild: unit processing order (longest first), may be null
   int row_base;               // blk_row_off values are absolute rows; csr arrays start at row_base
   int fb_base;                // blk_fb_off values are absolute; fb arrays start at fb_base
+  int has_fb;                 // any feedback entry in the launch (SVD++): bounds the Hogwild concurrency
 };
 struct Geometry {
   int lanes, vec;
@@ -83,6 +84,8 @@ struct svdgpu {
   size_t row_mask_cap = 0;
   size_t any_left_at = 0;  // index of the "pass 1 left something" word inside d_row_mask
   int pass1 = 1;  // option "pass1": 0 sends every row through the generic pass
+  int ugroup_units = 0;  // option "ugroup_units": user units in flight in Hogwild user-group training (0 = auto: 64 with
+                         // feedback lists -- more diverges, tools/hogwild_parity.py --svdpp -- else the occupancy limit)
   int l2_ahead = -1;   // option "l2_ahead": generic pass prefetches the next tile's rows into L2 (-1 auto)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
@@ -114,7 +117,7 @@ struct svdgpu_batch {
   DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_pred;
   bool has_ticket = false, has_value2 = false;
   // user-group structure
-  bool ugroup = false;
+  bool ugroup = false, has_fb = false;
   int num_block = 0, num_unit = 0;
   DevBuf d_unit_off, d_blk_row_off, d_blk_fb_off, d_fbi, d_fbv, d_fbt, d_order;
   std::vector<int> unit_off;  // host copy: block range of each unit

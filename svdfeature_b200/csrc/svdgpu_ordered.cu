@@ -189,6 +189,139 @@ __device__ __forceinline__ void update_ufeedback(const Group<LANES, VEC> &g, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// Whole-warp versions of the feedback gather / scatter (Hogwild).  A unit's feedback list is
+// as long as its rating rows (configs[2]: ~200 each) and one lane group alone handles it at a
+// quarter of the warp's width, so the warp does it together for one group at a time: lane l owns
+// the CPL = pitch/32 components [l*CPL, (l+1)*CPL) of every row.  Per component the arithmetic
+// and its order are those of prepare_ufeedback / update_ufeedback, so the result is bit-identical;
+// the owning group receives / provides the k-vector through `xch` (shared memory, pitch floats).
+// ---------------------------------------------------------------------------
+template <int CPL>
+__device__ __forceinline__ void ld_cpl(const float *p, float (&w)[CPL]) {
+  if (CPL == 4) {
+    const float4 q = __ldcg(reinterpret_cast<const float4 *>(p));
+    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3 % CPL] = q.w;
+  } else if (CPL == 2) {
+    const float2 q = __ldcg(reinterpret_cast<const float2 *>(p));
+    w[0] = q.x; w[1 % CPL] = q.y;
+  } else {
+    w[0] = __ldcg(p);
+  }
+}
+template <int CPL>
+__device__ __forceinline__ void st_cpl(float *p, const float (&w)[CPL]) {
+  if (CPL == 4) __stcg(reinterpret_cast<float4 *>(p), make_float4(w[0], w[1 % CPL], w[2 % CPL], w[3 % CPL]));
+  else if (CPL == 2) __stcg(reinterpret_cast<float2 *>(p), make_float2(w[0], w[1 % CPL]));
+  else __stcg(p, w[0]);
+}
+template <int CPL>
+__device__ __forceinline__ void red_cpl(float *p, const float (&w)[CPL]) {
+  if (CPL == 4) red4(p, make_float4(w[0], w[1 % CPL], w[2 % CPL], w[3 % CPL]));
+  else if (CPL == 2)
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(w[0]), "f"(w[1 % CPL]) : "memory");
+  else red1(p, w[0]);
+}
+
+// base.h:523-538, all 32 lanes.  Returns false (error flagged) on a bad feedback id.
+template <int CPL>
+__device__ __forceinline__ bool coop_prepare_ufeedback(const DevModel &m, const unsigned *fi, const float *fv,
+                                                       int nfb, int lane, float *xch, float &norm, float &fb_bias,
+                                                       int *err_flag) {
+  bool bad = false;
+  for (int i = lane; i < nfb; i += 32) bad |= fi[i] >= (unsigned)m.num_ufeedback;
+  if (__any_sync(0xffffffffu, bad)) {
+    if (bad) atomicCAS(err_flag, 0, ERR_FB_INDEX);
+    return false;
+  }
+  float acc[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) acc[c] = 0.0f;
+  norm = 0.0f;
+  fb_bias = 0.0f;
+  constexpr int B = 8;  // rows gathered before any is consumed
+  for (int i0 = 0; i0 < nfb; i0 += B) {
+    float w[B][CPL], x[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int i = min(i0 + j, nfb - 1);
+      x[j] = fv[i];
+      ld_cpl<CPL>(m.W + (size_t)fi[i] * (size_t)m.pitch + lane * CPL, w[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      if (i0 + j < nfb) {
+        const float xm = scalar_is_one(x[j]) ? 1.0f : x[j];  // w*1.0f is w: the "scalar is one" shortcut
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w[j][c], xm));
+        norm = __fadd_rn(norm, __fmul_rn(x[j], x[j]));
+      }
+    }
+  }
+  if (!m.no_user_bias) {
+    for (int base = 0; base < nfb; base += 32) {
+      const int i = base + lane;
+      float p = 0.0f;
+      if (i < nfb) p = __fmul_rn(__ldcg(m.bias + fi[i]), fv[i]);
+      const int cnt = min(32, nfb - base);
+      for (int j = 0; j < cnt; ++j) fb_bias = __fadd_rn(fb_bias, __shfl_sync(0xffffffffu, p, j));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) xch[lane * CPL + c] = acc[c];
+  __syncwarp();
+  return true;
+}
+
+// base.h:539-554, all 32 lanes; xch holds d = (tmp_ufeedback - old) / norm, dbias its bias part
+template <int CPL>
+__device__ __forceinline__ void coop_update_ufeedback(const DevModel &m, const unsigned *fi, const float *fv,
+                                                      int nfb, int lane, const float *xch, float dbias,
+                                                      int scatter) {
+  if (nfb == 0) return;
+  float d[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) d[c] = xch[lane * CPL + c];
+  bool bad = false;
+  for (int i = lane; i + 1 < nfb; i += 32) bad |= !(fi[i] < fi[i + 1]);
+  const bool unique = !__any_sync(0xffffffffu, bad);
+  const bool use_red = unique && scatter == SCATTER_RED;
+#pragma unroll 4
+  for (int i = 0; i < nfb; ++i) {
+    const float x = fv[i];
+    const float xm = scalar_is_one(x) ? 1.0f : x;
+    float *p = m.W + (size_t)fi[i] * (size_t)m.pitch + lane * CPL;
+    float v[CPL];
+    if (use_red) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) v[c] = __fmul_rn(d[c], xm);
+      red_cpl<CPL>(p, v);
+    } else {
+      ld_cpl<CPL>(p, v);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) v[c] = __fadd_rn(v[c], __fmul_rn(d[c], xm));
+      st_cpl<CPL>(p, v);
+    }
+  }
+  if (!m.no_user_bias) {
+    if (unique) {
+      for (int i = lane; i < nfb; i += 32) {
+        float *p = m.bias + fi[i];
+        const float add = __fmul_rn(dbias, fv[i]);
+        if (use_red) red1(p, add);
+        else __stcg(p, __fadd_rn(__ldcg(p), add));
+      }
+    } else {
+      if (lane == 0)
+        for (int i = 0; i < nfb; ++i) {
+          float *p = m.bias + fi[i];
+          __stcg(p, __fadd_rn(__ldcg(p), __fmul_rn(dbias, fv[i])));
+        }
+    }
+  }
+  __syncwarp();
+}
+
 // ORDERED: exact data-flow (one unit per warp, tickets); else Hogwild (one unit per group).
 // TRAIN=false: prediction (base.h:583-591), pred_out indexed by row - row_base.
 template <int LANES, int VEC, bool EXACT_DOT, bool ORDERED, bool TRAIN>
@@ -197,6 +330,8 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
          int scatter_user, int scatter_item, unsigned *counter, float *pred_out, int *err_flag) {
   constexpr int GPW = ORDERED ? 1 : 32 / LANES;
   __shared__ float dot_s[EX_WARPS][GPW * Group<LANES, VEC>::DOT_FLOATS];
+  // k-vector hand-off between a lane group and the whole warp (cooperative feedback phases)
+  __shared__ __align__(16) float xch_s[ORDERED ? 1 : EX_WARPS][ORDERED ? 4 : LANES * VEC * 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (ORDERED && lane >= LANES) return;
   Group<LANES, VEC> g;
@@ -236,6 +371,9 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
     }
     c_uid = 0xffffffffu;
   };
+  // cooperative feedback phases need the row to split evenly over 32 lanes
+  const int cpl = ORDERED ? 0 : ((m.pitch & 31) == 0 ? m.pitch >> 5 : 0);
+  const bool coop = !ORDERED && (cpl == 1 || cpl == 2 || cpl == 4);
   // take the next unit: false when none is left.  `ok` = its feedback list is usable.
   auto next_unit = [&](bool &ok) -> bool {
     unsigned n = 0;
@@ -267,6 +405,7 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
       }
       g.gsync();
     }
+    if (coop) return true;  // the warp gathers the feedback rows together (below)
     ok = prepare_ufeedback(g, m, ug.fb_index + f0, ug.fb_value + f0, nf0, s, err_flag);
     old_bias = s.fb_bias;
 #pragma unroll
@@ -362,6 +501,7 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
   };
   auto finish_unit = [&](bool ok) {
     flush_user();
+    if (coop) return;  // the warp scatters the feedback rows together (below)
     if (ok && TRAIN) update_ufeedback(g, m, ug.fb_index + f1, ug.fb_value + f1, nf1, s, old, old_bias, scatter_item);
     if (ORDERED && TRAIN) {
       __threadfence();
@@ -389,13 +529,46 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
   // instruction stream for all groups that have a row, and only the per-unit gather / scatter
   // of the feedback rows runs divergent.
   bool have = false, done = false, ok = false;
+  float *xch = xch_s[warp];
+  const unsigned my_group = g.gmask;
   for (;;) {
-    if (!have && !done) {
+    // ---- unit begin: every group without a unit takes one; the feedback gather of each is done
+    //      by the whole warp, one group after the other
+    const bool want = !have && !done;
+    if (want) {
       have = next_unit(ok);
       done = !have;
-      if (have && !ok) r_cur = r_end;  // unusable feedback list (error flagged): skip the unit's rows
+      if (have && !coop && !ok) r_cur = r_end;  // unusable feedback list (error flagged): skip the rows
+    }
+    if (coop) {
+      unsigned todo = __ballot_sync(0xffffffffu, want && have);
+      while (todo) {
+        const int src = __ffs(todo) - 1;  // first lane of the group served now
+        todo &= ~__shfl_sync(0xffffffffu, my_group, src);
+        const int cf0 = __shfl_sync(0xffffffffu, f0, src), cnf0 = __shfl_sync(0xffffffffu, nf0, src);
+        float norm = 0.0f, fbb = 0.0f;
+        bool good = false;
+        if (cpl == 4) good = coop_prepare_ufeedback<4>(m, ug.fb_index + cf0, ug.fb_value + cf0, cnf0, lane, xch, norm, fbb, err_flag);
+        else if (cpl == 2) good = coop_prepare_ufeedback<2>(m, ug.fb_index + cf0, ug.fb_value + cf0, cnf0, lane, xch, norm, fbb, err_flag);
+        else good = coop_prepare_ufeedback<1>(m, ug.fb_index + cf0, ug.fb_value + cf0, cnf0, lane, xch, norm, fbb, err_flag);
+        if (lane / LANES == src / LANES) {  // the owning group takes the result in its chunk layout
+          ok = good;
+          if (!good) r_cur = r_end;
+          s.norm = norm;
+          s.fb_bias = old_bias = fbb;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const int ch = g.gl + v * LANES;
+            s.fb[v] = (good && 4 * ch < m.pitch) ? *reinterpret_cast<const float4 *>(xch + 4 * ch) : f4_zero();
+            old[v] = s.fb[v];
+          }
+        }
+        __syncwarp();
+      }
     }
     if (__all_sync(0xffffffffu, !have)) break;
+    // ---- one rating row per group, all groups in step
+    bool fin = false;
     if (have) {
       if (r_cur < r_end) {
         do_row(r_cur);
@@ -404,9 +577,37 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
       if (r_cur >= r_end) {
         finish_unit(ok);
         have = false;
+        fin = true;
       }
     }
     __syncwarp();
+    // ---- unit end: the feedback scatter of each finished group, again by the whole warp
+    if (coop) {
+      unsigned todo = __ballot_sync(0xffffffffu, fin && ok && TRAIN);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= ~__shfl_sync(0xffffffffu, my_group, src);
+        const int cf1 = __shfl_sync(0xffffffffu, f1, src), cnf1 = __shfl_sync(0xffffffffu, nf1, src);
+        float dbias = 0.0f;
+        if (lane / LANES == src / LANES && cnf1 > 0) {  // d = (tmp_ufeedback - old) / norm, base.h:541-546
+          const float inv = __fdiv_rn(1.0f, s.norm);
+          const bool inv_one = scalar_is_one(inv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            float4 d = f4_sub(s.fb[v], old[v]);
+            if (!inv_one) d = f4_scale(d, inv);
+            const int ch = g.gl + v * LANES;
+            if (4 * ch < m.pitch) *reinterpret_cast<float4 *>(xch + 4 * ch) = d;
+          }
+          dbias = __fmul_rn(__fsub_rn(s.fb_bias, old_bias), inv);
+        }
+        dbias = __shfl_sync(0xffffffffu, dbias, src);
+        __syncwarp();
+        if (cpl == 4) coop_update_ufeedback<4>(m, ug.fb_index + cf1, ug.fb_value + cf1, cnf1, lane, xch, dbias, scatter_item);
+        else if (cpl == 2) coop_update_ufeedback<2>(m, ug.fb_index + cf1, ug.fb_value + cf1, cnf1, lane, xch, dbias, scatter_item);
+        else coop_update_ufeedback<1>(m, ug.fb_index + cf1, ug.fb_value + cf1, cnf1, lane, xch, dbias, scatter_item);
+      }
+    }
   }
 }
 
@@ -458,8 +659,16 @@ static int ugroup_geo(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0,
     if (grid_for(h, k, EX_WARPS * 32, ((long long)(u1 - u0) + EX_WARPS * gpw - 1) / (EX_WARPS * gpw), &grid)) \
       return 1;                                                                                 \
     /* Hogwild across users is only SGD-like while the users in flight are a small   */        \
-    /* fraction of the launch: cap them at 1/32 of the units (no effect at C3 scale). */        \
+    /* fraction of the launch: cap them at 1/32 of the units.                          */        \
     if (!ORD && TR) grid = std::max(1, std::min(grid, (u1 - u0) / (32 * EX_WARPS * gpw)));      \
+    /* With feedback lists (SVD++) the W_ufeedback rows of popular items are shared by a   */   \
+    /* large share of all users: measured (tools/hogwild_parity.py --svdpp, 120k users,    */   \
+    /* 100 feedback entries each) 32..64 users in flight track the sequential order to     */   \
+    /* 1e-2, 128 wobble, 256 drift away and >= 600 end in NaN.  Default 64.                */   \
+    {                                                                                           \
+      const int units = h->ugroup_units > 0 ? h->ugroup_units : (ug.has_fb ? 64 : 0);           \
+      if (!ORD && TR && units > 0) grid = std::max(1, std::min(grid, units / (EX_WARPS * gpw))); \
+    }                                                                                           \
     k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, ug, u0, u1, h->scatter_user,   \
                                              h->scatter_item, h->d_counter, pred, h->d_err);    \
   }

@@ -311,6 +311,7 @@ extern "C" int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const
     // the pair batch keeps the source's blocks and feedback lists (PairwiseRankGenerator::next
     // replaces e.data only, :1001-1018)
     b->ugroup = true;
+    b->has_fb = src->has_fb;
     b->num_block = nb;
     b->num_unit = nb;
     b->unit_off = src->unit_off;
