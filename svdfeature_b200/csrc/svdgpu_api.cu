@@ -467,6 +467,7 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->d_counter);
   cudaFree(h->d_eval);
   cudaFree(h->d_row_mask);
+  cudaFree(h->d_unit_kind);
   cudaFree(h->d_snap);
   cudaFree(h->d_delta);
   {
@@ -526,6 +527,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "ring_depth")) h->ring_depth = (int)v;
   else if (!strcmp(name, "l2_ahead")) h->l2_ahead = (int)v;
   else if (!strcmp(name, "ugroup_units")) h->ugroup_units = (int)v;
+  else if (!strcmp(name, "svdpp_fast")) h->svdpp_fast = v ? 1 : 0;
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else return fail(h, "unknown option '%s'", name);
   return 0;

@@ -84,6 +84,9 @@ struct svdgpu {
   size_t row_mask_cap = 0;
   size_t any_left_at = 0;  // index of the "pass 1 left something" word inside d_row_mask
   int pass1 = 1;  // option "pass1": 0 sends every row through the generic pass
+  int svdpp_fast = 1;    // option "svdpp_fast": 0 keeps every user unit in k_ugroup
+  unsigned char *d_unit_kind = nullptr;  // per unit of a launch: 1 = taken by k_svdpp
+  size_t unit_kind_cap = 0;
   int ugroup_units = 0;  // option "ugroup_units": user units in flight in Hogwild user-group training (0 = auto: 64 with
                          // feedback lists -- more diverges, tools/hogwild_parity.py --svdpp -- else the occupancy limit)
   int l2_ahead = -1;   // option "l2_ahead": generic pass prefetches the next tile's rows into L2 (-1 auto)
@@ -151,4 +154,6 @@ int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1
 int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
                   bool train, bool ordered, float *pred);
 int launch_delta(svdgpu *h, int mode, float scale);
+int launch_svdpp(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0, int u1, int warps,
+                 const unsigned char **kind_out);
 }  // namespace svdk

@@ -9,6 +9,7 @@
 //               feedback scatter (base.h:523-582).
 //   k_delta   : replicated-slab snapshot / delta / apply for the multi-GPU exchange.
 #include "svdgpu_internal.h"
+#include "svdgpu_fb.cuh"
 
 namespace svdk {
 
@@ -189,145 +190,13 @@ __device__ __forceinline__ void update_ufeedback(const Group<LANES, VEC> &g, con
   }
 }
 
-// ---------------------------------------------------------------------------
-// Whole-warp versions of the feedback gather / scatter (Hogwild).  A unit's feedback list is
-// as long as its rating rows (configs[2]: ~200 each) and one lane group alone handles it at a
-// quarter of the warp's width, so the warp does it together for one group at a time: lane l owns
-// the CPL = pitch/32 components [l*CPL, (l+1)*CPL) of every row.  Per component the arithmetic
-// and its order are those of prepare_ufeedback / update_ufeedback, so the result is bit-identical;
-// the owning group receives / provides the k-vector through `xch` (shared memory, pitch floats).
-// ---------------------------------------------------------------------------
-template <int CPL>
-__device__ __forceinline__ void ld_cpl(const float *p, float (&w)[CPL]) {
-  if (CPL == 4) {
-    const float4 q = __ldcg(reinterpret_cast<const float4 *>(p));
-    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3 % CPL] = q.w;
-  } else if (CPL == 2) {
-    const float2 q = __ldcg(reinterpret_cast<const float2 *>(p));
-    w[0] = q.x; w[1 % CPL] = q.y;
-  } else {
-    w[0] = __ldcg(p);
-  }
-}
-template <int CPL>
-__device__ __forceinline__ void st_cpl(float *p, const float (&w)[CPL]) {
-  if (CPL == 4) __stcg(reinterpret_cast<float4 *>(p), make_float4(w[0], w[1 % CPL], w[2 % CPL], w[3 % CPL]));
-  else if (CPL == 2) __stcg(reinterpret_cast<float2 *>(p), make_float2(w[0], w[1 % CPL]));
-  else __stcg(p, w[0]);
-}
-template <int CPL>
-__device__ __forceinline__ void red_cpl(float *p, const float (&w)[CPL]) {
-  if (CPL == 4) red4(p, make_float4(w[0], w[1 % CPL], w[2 % CPL], w[3 % CPL]));
-  else if (CPL == 2)
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(w[0]), "f"(w[1 % CPL]) : "memory");
-  else red1(p, w[0]);
-}
-
-// base.h:523-538, all 32 lanes.  Returns false (error flagged) on a bad feedback id.
-template <int CPL>
-__device__ __forceinline__ bool coop_prepare_ufeedback(const DevModel &m, const unsigned *fi, const float *fv,
-                                                       int nfb, int lane, float *xch, float &norm, float &fb_bias,
-                                                       int *err_flag) {
-  bool bad = false;
-  for (int i = lane; i < nfb; i += 32) bad |= fi[i] >= (unsigned)m.num_ufeedback;
-  if (__any_sync(0xffffffffu, bad)) {
-    if (bad) atomicCAS(err_flag, 0, ERR_FB_INDEX);
-    return false;
-  }
-  float acc[CPL];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) acc[c] = 0.0f;
-  norm = 0.0f;
-  fb_bias = 0.0f;
-  constexpr int B = 8;  // rows gathered before any is consumed
-  for (int i0 = 0; i0 < nfb; i0 += B) {
-    float w[B][CPL], x[B];
-#pragma unroll
-    for (int j = 0; j < B; ++j) {
-      const int i = min(i0 + j, nfb - 1);
-      x[j] = fv[i];
-      ld_cpl<CPL>(m.W + (size_t)fi[i] * (size_t)m.pitch + lane * CPL, w[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < B; ++j) {
-      if (i0 + j < nfb) {
-        const float xm = scalar_is_one(x[j]) ? 1.0f : x[j];  // w*1.0f is w: the "scalar is one" shortcut
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w[j][c], xm));
-        norm = __fadd_rn(norm, __fmul_rn(x[j], x[j]));
-      }
-    }
-  }
-  if (!m.no_user_bias) {
-    for (int base = 0; base < nfb; base += 32) {
-      const int i = base + lane;
-      float p = 0.0f;
-      if (i < nfb) p = __fmul_rn(__ldcg(m.bias + fi[i]), fv[i]);
-      const int cnt = min(32, nfb - base);
-      for (int j = 0; j < cnt; ++j) fb_bias = __fadd_rn(fb_bias, __shfl_sync(0xffffffffu, p, j));
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) xch[lane * CPL + c] = acc[c];
-  __syncwarp();
-  return true;
-}
-
-// base.h:539-554, all 32 lanes; xch holds d = (tmp_ufeedback - old) / norm, dbias its bias part
-template <int CPL>
-__device__ __forceinline__ void coop_update_ufeedback(const DevModel &m, const unsigned *fi, const float *fv,
-                                                      int nfb, int lane, const float *xch, float dbias,
-                                                      int scatter) {
-  if (nfb == 0) return;
-  float d[CPL];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) d[c] = xch[lane * CPL + c];
-  bool bad = false;
-  for (int i = lane; i + 1 < nfb; i += 32) bad |= !(fi[i] < fi[i + 1]);
-  const bool unique = !__any_sync(0xffffffffu, bad);
-  const bool use_red = unique && scatter == SCATTER_RED;
-#pragma unroll 4
-  for (int i = 0; i < nfb; ++i) {
-    const float x = fv[i];
-    const float xm = scalar_is_one(x) ? 1.0f : x;
-    float *p = m.W + (size_t)fi[i] * (size_t)m.pitch + lane * CPL;
-    float v[CPL];
-    if (use_red) {
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) v[c] = __fmul_rn(d[c], xm);
-      red_cpl<CPL>(p, v);
-    } else {
-      ld_cpl<CPL>(p, v);
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) v[c] = __fadd_rn(v[c], __fmul_rn(d[c], xm));
-      st_cpl<CPL>(p, v);
-    }
-  }
-  if (!m.no_user_bias) {
-    if (unique) {
-      for (int i = lane; i < nfb; i += 32) {
-        float *p = m.bias + fi[i];
-        const float add = __fmul_rn(dbias, fv[i]);
-        if (use_red) red1(p, add);
-        else __stcg(p, __fadd_rn(__ldcg(p), add));
-      }
-    } else {
-      if (lane == 0)
-        for (int i = 0; i < nfb; ++i) {
-          float *p = m.bias + fi[i];
-          __stcg(p, __fadd_rn(__ldcg(p), __fmul_rn(dbias, fv[i])));
-        }
-    }
-  }
-  __syncwarp();
-}
-
 // ORDERED: exact data-flow (one unit per warp, tickets); else Hogwild (one unit per group).
 // TRAIN=false: prediction (base.h:583-591), pred_out indexed by row - row_base.
 template <int LANES, int VEC, bool EXACT_DOT, bool ORDERED, bool TRAIN>
 __global__ void __launch_bounds__(EX_WARPS * 32)
 k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int unit_end,
-         int scatter_user, int scatter_item, unsigned *counter, float *pred_out, int *err_flag) {
+         int scatter_user, int scatter_item, unsigned *counter, float *pred_out, int *err_flag,
+         const unsigned char *skip_kind /* units k_svdpp has done (kind 1), or null */) {
   constexpr int GPW = ORDERED ? 1 : 32 / LANES;
   __shared__ float dot_s[EX_WARPS][GPW * Group<LANES, VEC>::DOT_FLOATS];
   // k-vector hand-off between a lane group and the whole warp (cooperative feedback phases)
@@ -376,12 +245,16 @@ k_ugroup(DevModel m, DevHP hp, DevCsr csr, DevUgroup ug, int unit_begin, int uni
   const bool coop = !ORDERED && (cpl == 1 || cpl == 2 || cpl == 4);
   // take the next unit: false when none is left.  `ok` = its feedback list is usable.
   auto next_unit = [&](bool &ok) -> bool {
-    unsigned n = 0;
-    if (g.gl == 0) n = atomicAdd(counter, 1u);
-    n = g.bcast(n, 0);
-    if ((long long)unit_begin + n >= unit_end) return false;
-    int u = unit_begin + (int)n;
-    if (!ORDERED && ug.order) u = ug.order[u];
+    int u;
+    for (;;) {
+      unsigned n = 0;
+      if (g.gl == 0) n = atomicAdd(counter, 1u);
+      n = g.bcast(n, 0);
+      if ((long long)unit_begin + n >= unit_end) return false;
+      u = unit_begin + (int)n;
+      if (!ORDERED && ug.order) u = ug.order[u];
+      if (!(skip_kind && skip_kind[u - unit_begin])) break;
+    }
     const int b0 = ug.unit_off[u], b1 = ug.unit_off[u + 1];
     // feedback list of the first block feeds the gather, of the last block the scatter
     f0 = ug.blk_fb_off[b0] - ug.fb_base;
@@ -651,6 +524,13 @@ template <int L, int V>
 static int ugroup_geo(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0, int u1, bool train,
                       bool ordered, float *pred) {
   int grid = 1;
+  // Hogwild training with the default dot order: units made of basic-MF rows of one user go to
+  // k_svdpp (one warp per unit, svdgpu_svdpp.cu); k_ugroup then skips them
+  const unsigned char *kind = nullptr;
+  if (train && !ordered && !h->exact_dot && h->dhp.plain && !csr.value2 && h->svdpp_fast) {
+    const int units = h->ugroup_units > 0 ? h->ugroup_units : (ug.has_fb ? 64 : h->num_sm * 16);
+    if (launch_svdpp(h, csr, ug, u0, u1, std::min(units, std::max(1, (u1 - u0) / 32)), &kind)) return 1;
+  }
   CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
 #define GO(ED, ORD, TR)                                                                         \
   {                                                                                             \
@@ -670,7 +550,8 @@ static int ugroup_geo(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0,
       if (!ORD && TR && units > 0) grid = std::max(1, std::min(grid, units / (EX_WARPS * gpw))); \
     }                                                                                           \
     k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, ug, u0, u1, h->scatter_user,   \
-                                             h->scatter_item, h->d_counter, pred, h->d_err);    \
+                                             h->scatter_item, h->d_counter, pred, h->d_err,     \
+                                             (!ORD && TR) ? kind : nullptr);                    \
   }
   if (!train) {
     GO(true, false, false)

@@ -262,6 +262,37 @@ def test_hogwild_ugroup_conflict_free_is_exact(native, k, scatter):
     assert diff == 0.0 if scatter == 0 else diff <= 1e-6, diff
 
 
+@pytest.mark.parametrize("k,scatter", [(64, 1), (64, 0), (32, 1), (128, 0), (96, 1)])
+def test_hogwild_svdpp_warp_per_user_conflict_free(native, k, scatter):
+    """k_svdpp (one warp per user, default dot order): on conflict-free input the result equals the
+    sequential oracle up to the dot product's summation order, and equals k_ugroup's."""
+    n_unit, rows_per, fb_per = 500, 37, 9
+    params = dict(num_user=n_unit, num_item=n_unit * rows_per, num_factor=k, learning_rate=0.01, wd_user=0.004,
+                  wd_item=0.004, base_score=3.6, num_ufeedback=n_unit * fb_per, wd_ufeedback=0.004,
+                  wd_ufeedback_bias=0.002, wd_user_bias=0.001, ufeedback_init_sigma=0.01)
+    o = COracle(1, 0, 0, params)
+    o.init(3)
+    gs = []
+    for fast in (1, 0):
+        g = native.SvdGpu(**_cases.shape_of(params, 1, 0))
+        g.set_hparams(**_cases.hparams_of(params, o.base_score))
+        g.set_mode(native.MODE_HOGWILD)
+        g.set_option("scatter_item", scatter)
+        g.set_option("svdpp_fast", fast)
+        g.upload(*[a.copy() for a in o.arrays()])
+        gs.append(g)
+    for r in range(2):
+        data = _conflict_free_ugroup(n_unit, rows_per, fb_per, 70 + r)
+        o.update_ugroup(data)
+        for g in gs:
+            g.update_ugroup(data)
+    for g in gs:
+        g.sync()
+        assert _maxdiff(o, g) <= 2e-6
+    if k % 32 == 0 and k // 32 in (1, 2, 4):  # k_svdpp splits a row evenly over the 32 lanes
+        assert gs[0].counter("kernel_launches") > gs[1].counter("kernel_launches")  # classification + k_svdpp ran
+
+
 def test_hogwild_ugroup_statistical_parity(native):
     """SVD++ blocks, Hogwild across users (rows of a user stay sequential)."""
     nu, ni, n = 20000, 2000, 300000
