@@ -31,7 +31,7 @@ namespace svdk {
 
 constexpr int MF_TILE = 32;            // rows per tile = bits of one row mask
 constexpr int MF_STAGES = 2;           // staged tiles per warp (a decoded tile lives in registers)
-constexpr int MF_CAP = 2 * MF_TILE;    // staged index/value entries per tile (2 per row)
+constexpr int MF_CAP = 3 * MF_TILE;    // staged index/value entries per tile (up to 3 per row)
 #ifndef MF_WARPS_PER_CTA
 #define MF_WARPS_PER_CTA 8
 #endif
@@ -49,18 +49,18 @@ struct __align__(16) MfWarp {
   uint64_t barA[MF_STAGES], barB[MF_STAGES];
 };
 
-template <int LANES, int VEC, int DEPTH>
+template <int LANES, int VEC, int DEPTH, int NI>
 struct MfRing {
   static constexpr int GPW = 32 / LANES;
   static constexpr int NCH = LANES * VEC;
-  // per (iteration slot, group): user row | item row | user-bias window | item-bias window
-  static constexpr int SLOT_F4 = 2 * NCH + 2;
+  // per (iteration slot, group): user row | NI item rows | user-bias window | NI item-bias windows
+  static constexpr int SLOT_F4 = (1 + NI) * NCH + (1 + NI);
   static constexpr size_t BYTES = (size_t)DEPTH * GPW * SLOT_F4 * sizeof(float4);
 };
 
-template <int LANES, int VEC, bool EXACT_DOT, int DEPTH>
+template <int LANES, int VEC, bool EXACT_DOT, int DEPTH, int NI>
 constexpr size_t mf_smem_bytes() {
-  return (sizeof(MfWarp) + MfRing<LANES, VEC, DEPTH>::BYTES) * MF_WARPS +
+  return (sizeof(MfWarp) + MfRing<LANES, VEC, DEPTH, NI>::BYTES) * MF_WARPS +
          (EXACT_DOT ? sizeof(float) * MF_WARPS * (32 / LANES) * Group<LANES, VEC>::DOT_FLOATS : 0);
 }
 
@@ -78,18 +78,23 @@ __device__ __forceinline__ void cp_async_wait() {
 // free of row_ptr / index loads and shape checks.
 struct MfDec {
   unsigned urow, irow;  // slab rows of the user / item feature (valid if the row is taken)
-  float uval, ival, lab;
+  unsigned irow2;       // NI = 2: slab row of the second item feature, 0xffffffff if the row has one
+  float uval, ival, ival2, lab;
   unsigned take;        // warp-uniform: bit q = the fast pass takes row q
   unsigned left;        // warp-uniform: bit q = row q exists and is left to the generic pass
   bool all_one;         // warp-uniform: every taken row has uval = ival = "one"
   int r0;               // first row of the tile (absolute)
 };
 
-template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB>
+// NI = 1: rows (0 | 1 | 1), every row is a candidate.  NI = 2 (the second fast pass): rows
+// (0 | 1 | 1..2) -- the pairwise-rank shape of configs[3], two distinct item features -- among the
+// rows the first pass left (`gate` = its "something left" flag: nothing left, nothing to do).
+template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB, int NI>
 __global__ void __launch_bounds__(MF_THREADS, MINB)
 k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user, int scatter_item,
-     float *pred_out, unsigned *row_mask, unsigned *any_left) {
-  using Ring = MfRing<LANES, VEC, DEPTH>;
+     float *pred_out, unsigned *row_mask, unsigned *any_left, const unsigned *gate) {
+  if (NI == 2 && *gate == 0u) return;
+  using Ring = MfRing<LANES, VEC, DEPTH, NI>;
   constexpr int GPW = Ring::GPW, NCH = Ring::NCH;
   constexpr int ITER = MF_TILE / GPW;  // iterations per tile
   static_assert(ITER % DEPTH == 0 && DEPTH <= ITER, "ring depth must divide the iterations of a tile");
@@ -178,7 +183,8 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
   auto decode = [&](int j) -> MfDec {
     MfDec d;
     d.urow = d.irow = 0u;
-    d.uval = d.ival = d.lab = 0.0f;
+    d.irow2 = 0xffffffffu;
+    d.uval = d.ival = d.ival2 = d.lab = 0.0f;
     d.take = d.left = 0u;
     d.all_one = true;
     d.r0 = 0;
@@ -190,12 +196,16 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     const int sm_base = w.v0 - w.v_off + csr.val_base;  // absolute feature position held by idx[0]
     const int v_hi = w.v1 + csr.val_base;
     const int *rp = st.rp + ((3 * d.r0) & 3) + 3 * lane;
-    bool ok = w.staged && lane < nrow;
+    // candidates: every row of the tile (first pass) / the rows the first pass left (second pass)
+    unsigned cand = nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u);
+    if (NI == 2) cand &= row_mask[tile_of(j)];
+    bool ok = w.staged && ((cand >> lane) & 1u);
     bool one = true;
     if (ok) {
       const int rp0 = rp[0], rp1 = rp[1], rp2 = rp[2], rp3 = rp[3];
-      // the basic-MF shape (0 | 1 | 1 features), inside the staged window
-      ok = rp1 == rp0 && rp2 == rp1 + 1 && rp3 == rp2 + 1 && rp1 >= sm_base && rp3 <= v_hi;
+      // the basic-MF shape (0 | 1 | 1 features; 0 | 1 | 2 too when NI = 2), inside the staged window
+      const bool two = NI == 2 && rp3 == rp2 + 2;
+      ok = rp1 == rp0 && rp2 == rp1 + 1 && (rp3 == rp2 + 1 || two) && rp1 >= sm_base && rp3 <= v_hi;
       if (ok) {
         const int f = rp1 - sm_base;
         const unsigned uid = st.idx[f], iid = st.idx[f + 1];
@@ -206,10 +216,17 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
         d.ival = st.val[f + 1];
         d.lab = st.label[(d.r0 & 3) + lane];
         one = scalar_is_one(d.uval) && scalar_is_one(d.ival);
+        if (two) {
+          const unsigned iid2 = st.idx[f + 2];
+          ok = ok && iid2 < (unsigned)m.num_item && iid2 != iid;  // a repeated index: the generic pass
+          d.irow2 = (unsigned)m.item_off + iid2;
+          d.ival2 = st.val[f + 2];
+          one = false;
+        }
       }
     }
     d.take = __ballot_sync(0xffffffffu, ok);
-    d.left = ~d.take & (nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u));
+    d.left = ~d.take & cand;
     d.all_one = __all_sync(0xffffffffu, !ok || one);
     return d;
   };
@@ -223,6 +240,7 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     const int src = i * GPW + gw;
     const unsigned urow = __shfl_sync(0xffffffffu, d.urow, src);
     const unsigned irow = __shfl_sync(0xffffffffu, d.irow, src);
+    const unsigned irow2 = NI == 2 ? __shfl_sync(0xffffffffu, d.irow2, src) : 0xffffffffu;
     if ((d.take >> src) & 1u) {
       float4 *dst = my_ring + slot * SLOT_STRIDE;
       const float *pu = m.W + (size_t)urow * (size_t)m.pitch, *pi = m.W + (size_t)irow * (size_t)m.pitch;
@@ -232,11 +250,14 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
         if (ch < row_f4) {
           cp_async16(dst + ch, pu + 4 * ch);
           cp_async16(dst + NCH + ch, pi + 4 * ch);
+          if (NI == 2 && irow2 != 0xffffffffu) cp_async16(dst + 2 * NCH + ch, m.W + (size_t)irow2 * (size_t)m.pitch + 4 * ch);
         }
       }
       // biases: the aligned 16-byte window that holds the element (cp.async.cg moves 16 bytes)
-      if (g.gl == 0 && !m.no_user_bias) cp_async16(dst + 2 * NCH, m.bias + (urow & ~3u));
-      if (g.gl == LANES - 1) cp_async16(dst + 2 * NCH + 1, m.bias + (irow & ~3u));
+      constexpr int WIN = (1 + NI) * NCH;
+      if (g.gl == 0 && !m.no_user_bias) cp_async16(dst + WIN, m.bias + (urow & ~3u));
+      if (g.gl == LANES - 1) cp_async16(dst + WIN + 1, m.bias + (irow & ~3u));
+      if (NI == 2 && g.gl == LANES - 2 && irow2 != 0xffffffffu) cp_async16(dst + WIN + 2, m.bias + (irow2 & ~3u));
     }
     cp_async_commit();
   };
@@ -245,9 +266,9 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
   // Groups whose row is not taken run the arithmetic on whatever the slot holds and skip the
   // memory operations (no divergent control flow in the common path).
   struct Rows {
-    float4 wu[VEC], wi[VEC];
-    float ub, ib;
-    unsigned urow, irow;
+    float4 wu[VEC], wi[VEC], wi2[VEC];
+    float ub, ib, ib2;
+    unsigned urow, irow, irow2;
   };
   auto load_slot = [&](const MfDec &d, int i, int slot, Rows &r) {
     const int src = i * GPW + gw;
@@ -261,9 +282,21 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
       r.wi[v] = rs[NCH + ch];
       if (ch >= row_f4) r.wu[v] = r.wi[v] = f4_zero();  // chunks the row does not have
     }
-    const float *bw = reinterpret_cast<const float *>(rs + 2 * NCH);
+    const float *bw = reinterpret_cast<const float *>(rs + (1 + NI) * NCH);
     r.ub = m.no_user_bias ? 0.0f : bw[r.urow & 3u];
     r.ib = bw[4 + (r.irow & 3u)];
+    r.irow2 = 0xffffffffu;
+    r.ib2 = 0.0f;
+    if (NI == 2) {
+      r.irow2 = __shfl_sync(0xffffffffu, d.irow2, src);
+      const bool two = r.irow2 != 0xffffffffu;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int ch = g.gl + v * LANES;
+        r.wi2[v] = (two && ch < row_f4) ? rs[2 * NCH + ch] : f4_zero();  // (never garbage: it enters tmp_ifactor)
+      }
+      r.ib2 = two ? bw[8 + (r.irow2 & 3u)] : 0.0f;
+    }
   };
   auto compute = [&](const MfDec &d, int i, const Rows &r) {
     const int src = i * GPW + gw;
@@ -293,10 +326,21 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
         ti[v] = f4_add_scaled(f4_zero(), wi[v], im, false);
       }
     }
+    // second item feature (NI = 2; a row without one contributes exact zeros)
+    const bool two = NI == 2 && r.irow2 != 0xffffffffu;
+    float ival2 = 0.0f;
+    if (NI == 2) {
+      const float iv2 = __shfl_sync(0xffffffffu, d.ival2, src);  // (every lane takes part in the shuffle)
+      ival2 = two ? iv2 : 0.0f;
+      const float im2 = scalar_is_one(ival2) ? 1.0f : ival2;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) ti[v] = f4_add_scaled(ti[v], r.wi2[v], im2, false);
+    }
     // calc_bias (base.h:313-353) + pred (base.h:445-454)
     double bsum = 0.0;
     if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, ub));
     bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+    if (NI == 2) bsum = __dadd_rn(bsum, two ? (double)__fmul_rn(ival2, r.ib2) : 0.0);
     // (measured: an out-of-line sigmoid path or full-mask shuffles here cost 4 % each)
     const float dt = g.template dot<EXACT_DOT>(m, tu, ti);
     double sum = __dadd_rn((double)hp.base_score, bsum);
@@ -335,6 +379,23 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
         else __stcg(m.bias + irow, nib);
       }
     }
+    if (NI == 2 && take && two) {  // second item feature: same update with its own value
+      const float si2 = __fmul_rn(lrerr, ival2);
+      const float si2_m = scalar_is_one(si2) ? 1.0f : si2;
+      float4 n2[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        n2[v] = f4_add_scaled(r.wi2[v], tu[v], si2_m, false);
+        if (!hp.di_skip) n2[v] = f4_scale(n2[v], hp.di);
+      }
+      if (scatter_item == SCATTER_RED) g.red_row(m, r.irow2, n2, r.wi2);
+      else g.store_row(m, r.irow2, n2);
+      if (g.gl == LANES - 2) {
+        const float nib2 = __fmul_rn(__fadd_rn(r.ib2, si2), hp.dib);
+        if (scatter_item == SCATTER_RED) red1(m.bias + r.irow2, __fsub_rn(nib2, r.ib2));
+        else __stcg(m.bias + r.irow2, nib2);
+      }
+    }
   };
 
   // ---- main loop ------------------------------------------------------------------------------
@@ -355,9 +416,9 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     const MfDec nxt = decode(j + 1);
     issue_a(j + 3);
     issue_b(j + 2);
-    if (cur.left != 0u && lane == 0) {
-      row_mask[tile_of(j)] = cur.left;
-      *any_left = 1u;  // the generic pass has something to do
+    if (lane == 0 && (cur.left != 0u || (NI == 2 && cur.take != 0u))) {
+      row_mask[tile_of(j)] = cur.left;   // (second pass: also clears the rows it takes)
+      if (cur.left != 0u) *any_left = 1u;  // the generic pass has something to do
     }
 #pragma unroll 1
     for (int i = 0; i < ITER; ++i) {  // iteration i lives in ring slot i % DEPTH (one copy of the code:
@@ -376,19 +437,21 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
   cp_async_wait<0>();
 }
 
-template <int L, int V, int DEPTH, int MINB>
+template <int L, int V, int DEPTH, int MINB, int NI>
 static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
   const long long ntile = ((long long)(r1 - r0) + MF_TILE - 1) / MF_TILE;
   int grid = 1;
+  // flags behind the masks: [any_left_at - 1] set by the first pass, [any_left_at] by the second
+  unsigned *flag_a = h->d_row_mask + h->any_left_at - 1, *flag_b = h->d_row_mask + h->any_left_at;
 #define GO(ED, TR)                                                                               \
   {                                                                                              \
-    auto k = k_mf<L, V, ED, TR, DEPTH, MINB>;                                                    \
-    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH>();                                        \
+    auto k = k_mf<L, V, ED, TR, DEPTH, MINB, NI>;                                                \
+    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH, NI>();                                    \
     CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     if (grid_for(h, k, MF_THREADS, (ntile + MF_WARPS - 1) / MF_WARPS, &grid, smem)) return 1;    \
     k<<<grid, MF_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
                                              h->scatter_item, pred, h->d_row_mask,               \
-                                             h->d_row_mask + h->any_left_at);                    \
+                                             NI == 2 ? flag_b : flag_a, flag_a);                 \
     h->n_launch++;                                                                               \
   }
   if (train) {
@@ -401,21 +464,24 @@ static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool trai
   return 0;
 }
 
-// the fast pass over rows [r0, r1); h->d_row_mask (one word per 32-row tile, zeroed by the
-// caller) receives the rows left for the generic pass
-int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
+// The fast passes over rows [r0, r1); h->d_row_mask (one word per 32-row tile, zeroed by the
+// caller) receives the rows left for the generic pass.  First pass: rows (0|1|1).  Second pass
+// (`second`): rows (0|1|1..2) among those the first pass left; exits at once if it left none.
+int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred,
+              bool second) {
   // tuning knobs (options "ring_depth", "mf_ctas"): ring depth 2 or 4, 2 or 3 CTAs per SM
   const int depth = h->ring_depth == 2 ? 2 : 4;
   const int minb = h->mf_ctas == 3 ? 3 : 2;
 #define GEO(L, V)                                                                                      \
   if (g.lanes == L && g.vec == V) {                                                                    \
-    if (depth == 2 && minb == 3) return launch_mf_geo<L, V, 2, 3>(h, csr, r0, r1, train, pred);        \
-    if (depth == 2) return launch_mf_geo<L, V, 2, 2>(h, csr, r0, r1, train, pred);                     \
-    if (minb == 3) return launch_mf_geo<L, V, 4, 3>(h, csr, r0, r1, train, pred);                      \
-    return launch_mf_geo<L, V, 4, 2>(h, csr, r0, r1, train, pred);                                     \
+    if (second) return launch_mf_geo<L, V, 2, 2, 2>(h, csr, r0, r1, train, pred);                      \
+    if (depth == 2 && minb == 3) return launch_mf_geo<L, V, 2, 3, 1>(h, csr, r0, r1, train, pred);     \
+    if (depth == 2) return launch_mf_geo<L, V, 2, 2, 1>(h, csr, r0, r1, train, pred);                  \
+    if (minb == 3) return launch_mf_geo<L, V, 4, 3, 1>(h, csr, r0, r1, train, pred);                   \
+    return launch_mf_geo<L, V, 4, 2, 1>(h, csr, r0, r1, train, pred);                                  \
   }
 #ifdef SVDGPU_TUNE_BUILD
-  GEO(4, 4) GEO(8, 2)
+  GEO(4, 4) GEO(8, 2) GEO(16, 2)
 #else
   GEO(4, 1) GEO(4, 2) GEO(4, 4) GEO(8, 1) GEO(8, 2) GEO(8, 4) GEO(16, 1) GEO(16, 2) GEO(16, 4)
   GEO(32, 1) GEO(32, 2) GEO(32, 4)

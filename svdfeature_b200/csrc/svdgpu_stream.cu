@@ -225,7 +225,7 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
     if (grid_for(h, k, HW_THREADS, (ntile + HW_WARPS - 1) / HW_WARPS, &grid, smem)) return 1;    \
     k<<<grid, HW_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
                                              h->scatter_item, pred, h->d_row_mask,               \
-                                             h->d_row_mask + h->any_left_at, h->d_err,           \
+                                             h->d_row_mask + h->flag_for_generic, h->d_err,      \
                                              l2_ahead);                                          \
     h->n_launch++;                                                                               \
   }
@@ -257,7 +257,11 @@ int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r
   // reg_method / reg_global / user_nonnegative sends every row to the generic pass
   const bool pass1 = h->dhp.plain != 0 && h->pass1 != 0;
   CU(h, cudaMemsetAsync(h->d_row_mask, pass1 ? 0 : 0xff, (size_t)nmask * sizeof(unsigned), h->stream));
-  if (pass1 && launch_mf(h, g, csr, r0, r1, train, pred)) return 1;
+  if (pass1 && launch_mf(h, g, csr, r0, r1, train, pred, false)) return 1;
+  // second fast pass: rows with two item features (pairwise-rank rows) among those left
+  const bool pass1b = pass1 && h->pass1 >= 2;
+  if (pass1b && launch_mf(h, g, csr, r0, r1, train, pred, true)) return 1;
+  h->flag_for_generic = pass1b ? h->any_left_at : h->any_left_at - 1;
 #define GEO(L, V) \
   if (g.lanes == L && g.vec == V) return launch_geo<L, V>(h, csr, r0, r1, train, pred);
 #ifdef SVDGPU_TUNE_BUILD

@@ -183,6 +183,45 @@ def test_hogwild_mixed_shapes_conflict_free(native, k, chunk_rows):
     assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
 
 
+@pytest.mark.parametrize("k", [128, 32, 64])
+def test_hogwild_pairwise_rows_second_fast_pass(native, k):
+    """Rows of the pairwise-rank shape (0 | 1 | 2, values +1 / -1, sigmoid-rank loss) take the
+    second fast pass (k_mf, NI = 2); on conflict-free input the result equals the sequential oracle
+    (1 ulp of expf) whichever pass runs them."""
+    nu, ni, n = 4000, 9000, 3000
+    rng = np.random.default_rng(k)
+    u = rng.permutation(nu)[:n].astype(np.uint32)
+    it = rng.permutation(ni)[:2 * n].astype(np.uint32).reshape(n, 2)
+    it.sort(axis=1)
+    sign = np.where(rng.random(n) < 0.5, 1.0, -1.0).astype(np.float32)
+    data = synth.fixed_csr(np.ones(n, np.float32), uidx=u, uval=np.ones(n, np.float32), iidx=it,
+                           ival=np.stack([sign, -sign], 1))
+    params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.01, wd_user=0.004, wd_item=0.004,
+                  no_user_bias=1, base_score=0.5)
+    o = COracle(0, 3, 0, params)
+    o.init(8)
+    res = []
+    for p1 in (2, 1, 0):
+        g = native.SvdGpu(**_cases.shape_of(params, 0, 3))
+        g.set_hparams(**_cases.hparams_of(params, o.base_score))
+        g.set_mode(native.MODE_HOGWILD)
+        g.set_option("scatter_user", 0)
+        g.set_option("scatter_item", 0)
+        g.set_option("exact_dot", 1)
+        g.set_option("pass1", p1)
+        g.upload(*[a.copy() for a in o.arrays()])
+        g.update_csr(data)
+        g.sync()
+        res.append(g)
+    o.update_csr(data)
+    for g in res:
+        assert _maxdiff(o, g) <= 2e-6
+        assert np.abs(o.predict_csr(data) - g.predict_csr(data)).max() <= 2e-6
+    ub0, W0, _ = res[0].download()
+    ub1, W1, _ = res[1].download()
+    assert np.array_equal(W0, W1)  # fast and generic pass: the same arithmetic, bit for bit
+
+
 def test_hogwild_fast_dot_close(native):
     o, g, data, kind = _pair(native, "basic_k64", native.MODE_HOGWILD, {"exact_dot": 0, "scatter_item": 0})
     data = _conflict_free(200, 100, 100, 5)
