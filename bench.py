@@ -19,7 +19,8 @@ k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch
 
 N>1 (torchrun): users are hash-partitioned (user mod N) so user rows are private to a
 rank; item rows/bias are replicated and their deltas are all-reduced over NCCL every
-step.  Weak scaling: every rank processes --rows-per-step rows per step.
+step.  Weak scaling: the global problem is 480k*N users x 18k items with 100M*N ratings;
+every rank owns 480k users (local indices) and processes --rows-per-step rows per step.
 """
 import argparse
 import json
@@ -62,8 +63,8 @@ def marginals(seed=10):
 
 
 def gen_rows_torch(n, seed, device, rank=0, world=1):
-    """(row_ptr, label, index, value) as torch tensors on `device`; users of rank r are
-    the ids congruent to r mod world (hash partition)."""
+    """(row_ptr, label, index, value) as torch tensors on `device`: the rows of rank `rank`'s user
+    shard (hash partition by user id mod world), user ids already local to the shard."""
     import torch
 
     ucdf, icdf, iperm = marginals()
@@ -72,10 +73,10 @@ def gen_rows_torch(n, seed, device, rank=0, world=1):
     ucdf_t = torch.from_numpy(ucdf).to(device)
     icdf_t = torch.from_numpy(icdf).to(device)
     iperm_t = torch.from_numpy(iperm.astype(np.int64)).to(device)
+    # weak scaling: the global population is NUM_USER * world users; rank r owns the users whose id
+    # is congruent to r mod world and stores them under the local index id // world, so every rank
+    # trains NUM_USER local users -- the same per-GPU problem as the single-GPU run
     u = torch.searchsorted(ucdf_t, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=NUM_USER - 1)
-    if world > 1:
-        u = (u // world) * world + rank
-        u = torch.where(u >= NUM_USER, u - world, u)
     it = iperm_t[torch.searchsorted(icdf_t, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=NUM_ITEM - 1)]
     lab = torch.clamp(torch.round(3.6 + 1.1 * torch.randn(n, generator=g, device=device)), 1, 5).float()
     index = torch.stack([u, it], 1).reshape(-1).to(torch.int32)  # ids < 2^31: same bits as uint32
@@ -454,8 +455,9 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu,
     }
     if world > 1:
-        line["config"]["parallelism"] = "user-hash shards x%d, item-side delta allreduce (NCCL) every %d step(s)" % (
-            world, args.allreduce_every)
+        line["config"]["parallelism"] = ("user-hash shards x%d (global problem %d users x %d items, %d ratings per step; "
+                                         "each rank owns %d users), item-side delta allreduce (NCCL) every %d step(s)"
+                                         % (world, NUM_USER * world, NUM_ITEM, rows * world, NUM_USER, args.allreduce_every))
     emit(line)
     if dist:
         dist.destroy_process_group()

@@ -872,7 +872,14 @@ static int run_ugroup_host(svdgpu_t *h, int num_block, const int *blk_row_off, c
       pred = (float *)s.d_pred.p;
     }
     if (slot_copied(h, s)) return 1;
-    if (launch_ugroup(h, geo, csr, ug, 0, nu, train, exact, pred)) return 1;
+    // Units without feedback entries (pairwise-rank blocks, apex_svd_data.cpp:1001-1018) are plain
+    // rows: tmp_ufeedback stays zero (base.h:506-520 with norm 0), so outside the ordered mode they
+    // take the stream kernels and their fast passes.
+    if (!exact && nfb == 0) {
+      if (launch_stream(h, geo, csr, 0, n, train, pred)) return 1;
+    } else if (launch_ugroup(h, geo, csr, ug, 0, nu, train, exact, pred)) {
+      return 1;
+    }
     if (!train && eval_chunk(h, pred, csr.label, n)) return 1;
     if (!train && n && out) {
       CU(h, cudaMemcpyAsync(out + r0, pred, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1072,7 +1079,12 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
     // the LPT order array covers the whole batch: partial ranges run in input order
     DevUgroup ug = batch_ug(b);
     if (begin != 0 || end != b->num_unit) ug.order = nullptr;
-    if (launch_ugroup(h, geo, batch_csr(b), ug, begin, end, true, false, (float *)nullptr)) return 1;
+    if (!b->has_fb && begin == 0 && end == b->num_unit) {
+      // no feedback entries anywhere: plain rows (see run_ugroup_host)
+      if (b->num_row > 0 && launch_stream(h, geo, batch_csr(b), 0, b->num_row, true, (float *)nullptr)) return 1;
+    } else if (launch_ugroup(h, geo, batch_csr(b), ug, begin, end, true, false, (float *)nullptr)) {
+      return 1;
+    }
     h->n_inst += b->num_row;
     return 0;
   }

@@ -31,7 +31,10 @@ namespace svdk {
 
 constexpr int MF_TILE = 32;            // rows per tile = bits of one row mask
 constexpr int MF_STAGES = 2;           // staged tiles per warp (a decoded tile lives in registers)
-constexpr int MF_CAP = 3 * MF_TILE;    // staged index/value entries per tile (up to 3 per row)
+#ifndef MF_CAP_PER_ROW
+#define MF_CAP_PER_ROW 3
+#endif
+constexpr int MF_CAP = MF_CAP_PER_ROW * MF_TILE;    // staged index/value entries per tile (up to 3 per row)
 #ifndef MF_WARPS_PER_CTA
 #define MF_WARPS_PER_CTA 8
 #endif

@@ -150,6 +150,47 @@ def c4(scale):
     g.close()
 
 
+def c4u(scale):
+    """configs[3] the way the reference runs it: rated user blocks -> pairwise-rank samples (on the
+    device, svdgpu_batch_sample_pairs) -> training on the pair blocks."""
+    nu_, ni_, k = 1_000_000, 300_000, 128
+    n = int(40_000_000 * scale)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(4)
+    u = torch.sort(lognormal_users(n, nu_, gen)).values
+    it = zipf_items(n, ni_, gen)
+    lab = (torch.rand(n, generator=gen, device=DEV) < 0.3).float()
+    ones = torch.ones(n, device=DEV)
+    csr = host(fixed_csr(lab, [u, it], [ones, ones], 0, 1, 1))
+    uu, cnt = torch.unique_consecutive(u, return_counts=True)
+    bro = np.concatenate([[0], np.cumsum(cnt.cpu().numpy())]).astype(np.int32)
+    nb = len(bro) - 1
+    ug = (bro, np.zeros(nb + 1, np.int32), None, np.zeros(0, np.uint32), np.zeros(0, np.float32))
+    g = api.SvdGpu(nu_, ni_, k, num_ufeedback=1, no_user_bias=1, active_type=3, format_type=1)
+    g.set_hparams(learning_rate=0.005, wd_user=0.004, wd_item=0.004, base_score=0.0)
+    g.set_mode(api.MODE_HOGWILD)
+    init_model(g, 1 + nu_ + ni_, k)
+    opts = apply_opts(g)
+    src = g.batch_create(csr, ugroup=ug)
+    g.sync()
+    t0 = time.perf_counter()
+    pairs = g.batch_sample_pairs(src, seed=1)
+    g.sync()
+    t_sample = time.perf_counter() - t0
+    for _ in range(2):
+        g.batch_update(pairs)
+    g.sync()
+    g.timer_start()
+    reps = 5
+    for _ in range(reps):
+        g.batch_update(pairs)
+    ms = g.timer_stop() / reps
+    emit(exp="config", config="c4u pairwise via user blocks + device sampler 1Mx300k k=128", rated_rows=n, blocks=nb,
+         pairs=pairs.num_row, sample_ms=1e3 * t_sample, sample_gpairs_s=pairs.num_row / t_sample / 1e9, train_ms=ms,
+         ginst_s=pairs.num_row / ms / 1e6, algorithmic_gbs=pairs.num_row * 3128 / ms / 1e6, bytes_per_row=3128, opts=opts)
+    g.close()
+
+
 def c5(scale):
     nu_, ni_, ngl, k, ng = 10_000_000, 1_000_000, 1_000_000, 256, 8
     n = int(20_000_000 * scale)
@@ -233,12 +274,12 @@ def c3(scale):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if a in ("c2", "c3", "c4", "c5")]
+    args = [a for a in sys.argv[1:] if a in ("c2", "c3", "c4", "c4u", "c5")]
     scale = 1.0
     if "--scale" in sys.argv:
         scale = float(sys.argv[sys.argv.index("--scale") + 1])
     for name in args or ["c2", "c4", "c5", "c3"]:
         t0 = time.perf_counter()
-        {"c2": c2, "c3": c3, "c4": c4, "c5": c5}[name](scale)
+        {"c2": c2, "c3": c3, "c4": c4, "c4u": c4u, "c5": c5}[name](scale)
         print("# %s done in %.1fs" % (name, time.perf_counter() - t0), file=sys.stderr, flush=True)
         torch.cuda.empty_cache()
