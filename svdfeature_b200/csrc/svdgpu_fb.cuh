@@ -40,8 +40,9 @@ __device__ __forceinline__ void red_cpl(float *p, const float (&w)[CPL]) {
 }
 
 // base.h:523-538, all 32 lanes.  Returns false (error flagged) on a bad feedback id.
-// register form: acc[] = this lane's CPL components of tmp_ufeedback
-template <int CPL>
+// register form: acc[] = this lane's CPL components of tmp_ufeedback; B = rows gathered before any
+// is consumed (measured: 32 instead of 8 changes nothing in k_svdpp)
+template <int CPL, int B = 8>
 __device__ __forceinline__ bool coop_prepare_ufeedback_regs(const DevModel &m, const unsigned *fi, const float *fv,
                                                             int nfb, int lane, float (&acc)[CPL], float &norm,
                                                             float &fb_bias, int *err_flag) {
@@ -55,7 +56,6 @@ __device__ __forceinline__ bool coop_prepare_ufeedback_regs(const DevModel &m, c
   for (int c = 0; c < CPL; ++c) acc[c] = 0.0f;
   norm = 0.0f;
   fb_bias = 0.0f;
-  constexpr int B = 8;  // rows gathered before any is consumed
   for (int i0 = 0; i0 < nfb; i0 += B) {
     float w[B][CPL], x[B];
 #pragma unroll
