@@ -494,8 +494,25 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
   if (ni_ > 1) pre_ib1 = __ldcg(m.bias + m.item_off + idx[rp2 + 1]);
 
   // ---- calc_bias, global part (base.h:318-322): its gathers overlap the row gathers --------
+  // Up to LANES global features (the neighbourhood rows of configs[4] carry 8): lane gl keeps the
+  // bias of feature rp0+gl for the update below, so g_bias is read once per instance.
+  const int ng_ = rp1 - rp0;
+  const bool g_small = ng_ > 0 && ng_ <= LANES;
+  float pre_gb = 0.0f, pre_gv = 0.0f;
+  unsigned pre_gid = 0u;
   double bsum = 0.0;
-  bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
+  if (g_small) {
+    float p = 0.0f;
+    if (g.gl < ng_) {
+      pre_gid = idx[rp0 + g.gl];
+      pre_gv = val[rp0 + g.gl];
+      pre_gb = __ldcg(m.g_bias + pre_gid);
+      p = __fmul_rn(pre_gv, pre_gb);
+    }
+    for (int j = 0; j < ng_; ++j) bsum = __dadd_rn(bsum, (double)g.bcast(p, j));
+  } else {
+    bsum = g.bias_sum(bsum, m.g_bias, 0, idx, val, rp0, rp1);
+  }
 
   // ---- prepare_tmp (base.h:354-381) ----------------------------------------
 #pragma unroll
@@ -570,9 +587,17 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
   // globals: g_bias[gid] += lr*err*gval ; later g_bias[gid] *= 1-lr*wd_global
   const bool g_l1 = hp.reg_global == 1;
   const float g_dec = g_l1 ? hp.l1_g : hp.dg;
-  if (rp1 > rp0)
+  if (g_small && !dup_g) {  // every global index once: update and decay from the value gathered above
+    if (g.gl < ng_) {
+      float x = __fadd_rn(pre_gb, __fmul_rn(lrerr, pre_gv));
+      if (pre_gid >= hp.regfree) x = g_l1 ? reg_l1(x, g_dec) : __fmul_rn(x, g_dec);
+      if (scatter_item == SCATTER_RED) red1(m.g_bias + pre_gid, __fsub_rn(x, pre_gb));
+      else __stcg(m.g_bias + pre_gid, x);
+    }
+  } else if (rp1 > rp0) {
     g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, lrerr, g_dec, true, !dup_g, hp.regfree, !dup_g,
                  dup_g ? SCATTER_STORE : scatter_item, g_l1);
+  }
 
   // bias read-modify-write of one feature whose old value was gathered early (lane `who` does it)
   auto bias_rmw = [&](float *p, float x0, float v, float v2, bool has2, float decay, int who, int scatter) {
