@@ -105,6 +105,16 @@ int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);
 int svdgpu_set_side_features(svdgpu_t *h, int which, int num_row, const unsigned *row_ptr,
                              const unsigned *index, const float *value);
 
+/* Ranged weight decay (the reference's "up:" / "ip:" / "uip:" / "gp:" keys, ParameterSet,
+ * base.h:33-75): indices of the user (which = 0), item (1) or global (2) space below bound[0]
+ * take wd[0], those in [bound[j-1], bound[j]) take wd[j] instead of wd_user / wd_item /
+ * wd_global; bound[] is what the configuration file gives ("up:bound = 100": EXCLUSIVE, strictly
+ * ascending, non-zero).  An index >= bound[n-1] met during training is the reference's
+ * "bound set err" (reported by svdgpu_sync).  n = 0 clears; n <= 8.
+ * replaces: ParameterSet::set_param / get_wd as used by reg_global / reg_user / reg_item
+ * (base.h:189,213,253). */
+int svdgpu_set_wd_ranges(svdgpu_t *h, int which, int n, const unsigned *bound, const float *wd);
+
 /* ---- model transfer ---------------------------------------------------- */
 /* Layout = SVDModel's slabs (model.h:481-556): ui_bias[rows], W_uiset[rows][pitch],
  * g_bias[num_global] with rows = ustart + num_user + num_item, ustart =

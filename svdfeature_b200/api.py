@@ -57,6 +57,7 @@ SVDGPU_SYMBOLS = {
     "svdgpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "svdgpu_set_stream": (C.c_int, [_vp, _vp]),
     "svdgpu_set_side_features": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "svdgpu_set_wd_ranges": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "svdgpu_upload_model": (C.c_int, [_vp, _f32p, _f32p, C.c_size_t, _f32p]),
     "svdgpu_download_model": (C.c_int, [_vp, _f32p, _f32p, C.c_size_t, _f32p]),
     "svdgpu_update_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
@@ -190,6 +191,25 @@ class SvdGpu:
         idx = np.concatenate([i for i, _ in side]).astype(np.uint32) if side else np.zeros(0, np.uint32)
         val = np.concatenate([v for _, v in side]).astype(np.float32) if side else np.zeros(0, np.float32)
         self._ck(self.lib.svdgpu_set_side_features(self.h, which, len(side), _ptr(rp), _ptr(idx), _ptr(val)))
+
+    def set_wd_ranges(self, which, bounds, wds):
+        """Ranged weight decay of the user (0) / item (1) / global (2) space: indices below bounds[0] take
+        wds[0], those in [bounds[j-1], bounds[j]) take wds[j] (the reference's up:/ip:/gp: keys)."""
+        b = np.asarray(bounds, np.uint32)
+        w = np.asarray(wds, np.float32)[: len(b)]
+        self._ck(self.lib.svdgpu_set_wd_ranges(self.h, which, len(b), _ptr(b), _ptr(w)))
+
+    def set_wd_range_params(self, pairs):
+        """pairs: the ordered (key, value) configuration pairs with the prefixes up: / ip: / uip: / gp:."""
+        sets = {0: ("up:", "uip:"), 1: ("ip:", "uip:"), 2: ("gp:", "gp:")}
+        for which, prefixes in sets.items():
+            bounds, wds = [], []
+            for k, v in pairs:
+                for pre in prefixes:
+                    if k.startswith(pre):
+                        (bounds if k[len(pre):] == "bound" else wds).append(v)
+                        break
+            self.set_wd_ranges(which, bounds, wds)
 
     # model
     def upload(self, ui_bias, W, g_bias):
@@ -415,6 +435,10 @@ class GpuTrainer:
 
     def set_params(self, params):
         for k, v in params.items():
+            if k == "wd_ranges":  # ordered (key, value) pairs: up:wd / up:bound / ip:... / gp:...
+                for kk, vv in v:
+                    self.lib.svdtr_set_param(self.h, str(kk).encode(), str(vv).encode())
+                continue
             self.lib.svdtr_set_param(self.h, str(k).encode(), str(v).encode())
 
     def init(self, seed=10):

@@ -98,6 +98,31 @@ struct CsrStage {
   }
 };
 
+// ParameterSet (base.h:33-75): "<prefix>wd" / "<prefix>bound" pairs given in order; the bounds are
+// kept as the configuration gives them (the C ABI takes them exclusive).
+struct RangedWd {
+  std::string prefix_a, prefix_b;
+  std::vector<float> wd;
+  std::vector<unsigned> bound;
+  RangedWd(const char *a, const char *b) : prefix_a(a), prefix_b(b) {}
+  void set_param(const char *name, const char *val) {
+    if (!strncmp(name, prefix_a.c_str(), prefix_a.size())) name += prefix_a.size();
+    else if (!strncmp(name, prefix_b.c_str(), prefix_b.size())) name += prefix_b.size();
+    else return;
+    if (!strcmp("bound", name)) {
+      const unsigned bd = (unsigned)atoi(val);
+      apex_utils::assert_true(bd > 0, "can't give 0 as bound");
+      apex_utils::assert_true(bound.empty() || bound.back() < bd, "bound must be given in order");
+      apex_utils::assert_true(bound.size() + 1 == wd.size(), "must specifiy wd in each range");
+      bound.push_back(bd);
+    }
+    if (!strcmp("wd", name)) {
+      apex_utils::assert_true(wd.size() == bound.size(), "setting must be exactly");
+      wd.push_back((float)atof(val));
+    }
+  }
+};
+
 }  // namespace
 
 namespace apex_svd {
@@ -123,8 +148,10 @@ class GpuSVDFeature : public ISVDTrainer {
   virtual void set_param(const char *name, const char *val) {
     if (!strcmp(name, "feature_user")) name_feat_user_ = val;  // base.h:127-128
     if (!strcmp(name, "feature_item")) name_feat_item_ = val;
-    if (!strncmp(name, "up:", 3) || !strncmp(name, "ip:", 3) || !strncmp(name, "uip:", 4) || !strncmp(name, "gp:", 3))
-      apex_utils::error("ranged weight decay (up:/ip:/uip:/gp:) is not supported by the GPU trainer");
+    // ranged weight decay (base.h:136-138): every key is offered to all three sets
+    u_param_.set_param(name, val);
+    i_param_.set_param(name, val);
+    g_param_.set_param(name, val);
     // SVDTrainParam::set_param, model.h:350-368
     if (!strcmp("learning_rate", name)) hp_.learning_rate = (float)atof(val);
     if (!strcmp("wd_user", name)) hp_.wd_user = (float)atof(val);
@@ -405,6 +432,9 @@ class GpuSVDFeature : public ISVDTrainer {
     hp_.base_score = mp_.base_score;
     hp_.user_nonnegative = mp_.user_nonnegative;
     check(h_, svdgpu_set_hparams(h_, &hp_));
+    const RangedWd *sets[3] = {&u_param_, &i_param_, &g_param_};
+    for (int w = 0; w < 3; ++w)  // get_wd consults the ranges only when a bound was given (base.h:70)
+      check(h_, svdgpu_set_wd_ranges(h_, w, (int)sets[w]->bound.size(), sets[w]->bound.data(), sets[w]->wd.data()));
   }
   void upload() { check(h_, svdgpu_upload_model(h_, ui_bias_.data(), W_.data(), (size_t)pitch_, g_bias_.data())); }
 
@@ -478,6 +508,7 @@ class GpuSVDFeature : public ISVDTrainer {
   int batch_rows_ = 1 << 20;
   std::vector<std::pair<std::string, long long> > options_;
   std::string name_feat_user_ = "NULL", name_feat_item_ = "NULL";
+  RangedWd u_param_{"up:", "uip:"}, i_param_{"ip:", "uip:"}, g_param_{"gp:", "gp:"};  // base.h:102-103
   svdgpu_t *h_ = NULL;
   // host mirror of the model (init, load/save)
   int ustart_ = 0, pitch_ = 0;

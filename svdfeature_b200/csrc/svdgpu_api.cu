@@ -165,7 +165,10 @@ void refresh_hp(svdgpu *h) {
   d.pb_i = p.wd_item;
   d.l1_g = lg;
   d.user_nonneg = p.user_nonnegative != 0;
-  d.plain = (d.reg_user == 0 && d.reg_item == 0 && d.reg_global == 0 && !d.user_nonneg) ? 1 : 0;
+  // ranged weight decay (d.ru / d.ri / d.rg, set by svdgpu_set_wd_ranges) is looked up per index
+  // by the generic routine only
+  d.plain = (d.reg_user == 0 && d.reg_item == 0 && d.reg_global == 0 && !d.user_nonneg && d.ru.n == 0 &&
+             d.ri.n == 0 && d.rg.n == 0) ? 1 : 0;
 }
 
 // ---- lane geometry -----------------------------------------------------------
@@ -562,6 +565,25 @@ int svdgpu_set_side_features(svdgpu_t *h, int which, int num_row, const unsigned
   return 0;
 }
 
+int svdgpu_set_wd_ranges(svdgpu_t *h, int which, int n, const unsigned *bound, const float *wd) {
+  if (!h) return 1;
+  if (which < 0 || which > 2) return fail(h, "set_wd_ranges: which must be 0 (user), 1 (item) or 2 (global)");
+  if (n < 0 || n > WD_MAX_RANGES) return fail(h, "set_wd_ranges: at most %d ranges", (int)WD_MAX_RANGES);
+  if (n > 0 && (!bound || !wd)) return fail(h, "set_wd_ranges: null array");
+  WdRanges r{};
+  for (int j = 0; j < n; ++j) {
+    // ParameterSet::set_param (base.h:56-58): "can't give 0 as bound", "bound must be given in order"
+    if (bound[j] == 0) return fail(h, "can't give 0 as bound");
+    if (j > 0 && !(bound[j - 1] < bound[j])) return fail(h, "bound must be given in order");
+    r.bound[j] = bound[j] - 1;  // inclusive last index of the range (base.h:59)
+    r.wd[j] = wd[j];
+  }
+  r.n = n;
+  (which == 0 ? h->dhp.ru : which == 1 ? h->dhp.ri : h->dhp.rg) = r;
+  if (h->hp_set) refresh_hp(h);
+  return 0;
+}
+
 int svdgpu_upload_model(svdgpu_t *h, const float *ui_bias, const float *W, size_t pitch_floats,
                         const float *g_bias) {
   if (!h) return 1;
@@ -611,6 +633,7 @@ int svdgpu_sync(svdgpu_t *h) {
       case ERR_ITEM_INDEX: return fail(h, "item feature index exceed bound");
       case ERR_FB_INDEX: return fail(h, "ufeedback id exceed bound");
       case ERR_ROW_PTR: return fail(h, "row_ptr must be non-decreasing and inside the batch");
+      case ERR_WD_BOUND: return fail(h, "bound set err");  // base.h:72
       default: return fail(h, "device error %d", e);
     }
   }

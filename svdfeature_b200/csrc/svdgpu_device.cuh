@@ -36,6 +36,15 @@ struct DevModel {
   int active_type;
 };
 
+// ParameterSet (base.h:33-75): per-index-range weight decay ("up:" / "ip:" / "uip:" / "gp:" keys).
+// bound[j] is the INCLUSIVE last index of range j (the reference stores bound-1, base.h:59).
+enum { WD_MAX_RANGES = 8 };
+struct WdRanges {
+  int n;  // 0: no ranges, the default weight decay applies to every index
+  unsigned bound[WD_MAX_RANGES];
+  float wd[WD_MAX_RANGES];
+};
+
 struct DevHP {
   float lr;
   float du, di;       // 1 - lr*wd_user, 1 - lr*wd_item              (base.h:216,257)
@@ -56,7 +65,8 @@ struct DevHP {
   float pb_u, pb_i;   // wd_user, wd_item: the projection bounds B   (base.h:181-186,226,266)
   float l1_g;         // lr*wd_global                                (base.h:189)
   int user_nonneg;    // model.param.user_nonnegative                (base.h:242-245)
-  int plain;          // reg_user == reg_item == reg_global == 0 and !user_nonneg
+  int plain;          // reg_user == reg_item == reg_global == 0 and !user_nonneg and no ranged weight decay
+  WdRanges ru, ri, rg;  // ranged weight decay of user rows / item rows / global biases (base.h:189,213,253)
 };
 
 // A CSR batch in HBM.  index/value/ticket hold the elements [val_base, ...) of
@@ -73,7 +83,8 @@ struct DevCsr {
 };
 
 enum { SCATTER_STORE = 0, SCATTER_RED = 1 };
-enum { ERR_NONE = 0, ERR_GLOBAL_INDEX = 1, ERR_USER_INDEX = 2, ERR_ITEM_INDEX = 3, ERR_FB_INDEX = 4, ERR_ROW_PTR = 5 };
+enum { ERR_NONE = 0, ERR_GLOBAL_INDEX = 1, ERR_USER_INDEX = 2, ERR_ITEM_INDEX = 3, ERR_FB_INDEX = 4, ERR_ROW_PTR = 5,
+       ERR_WD_BOUND = 6 };
 
 // a row's four segment bounds must be ordered and inside the batch (checked on the
 // device so that the host never walks row_ptr)
@@ -175,6 +186,54 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 __device__ __forceinline__ bool scalar_is_one(float s) {
   // fabs((double)(s-1.0f)) > 1e-6  <=>  fabsf(s-1.0f) > 1e-6f, because (float)1e-6 < 1e-6
   return !(fabsf(__fsub_rn(s, 1.0f)) > 1e-6f);
+}
+// ParameterSet::get_wd (base.h:69-74): lower_bound over the inclusive range ends; an index beyond
+// the last range is the reference's "bound set err".  Branch-free selects: hp lives in the
+// kernel parameter bank and must not be indexed dynamically.
+__device__ __forceinline__ bool wd_lookup(const WdRanges &r, unsigned id, float &wd) {
+  int k = 0;
+#pragma unroll
+  for (int j = 0; j < WD_MAX_RANGES; ++j) k += (j < r.n && r.bound[j] < id) ? 1 : 0;
+  float w = 0.0f;
+#pragma unroll
+  for (int j = 0; j < WD_MAX_RANGES; ++j) w = (j == k) ? r.wd[j] : w;
+  wd = w;
+  return k < r.n;
+}
+// the four constants reg_user / reg_item derive from one weight decay (base.h:213-226,253-266)
+struct RowReg {
+  float d;   // 1 - lr*wd
+  int skip;  // d is "one": no multiply
+  float l1;  // lr*wd
+  float pb;  // wd
+};
+__device__ __forceinline__ RowReg row_reg(const WdRanges &r, unsigned id, float lr, float d, int skip, float l1,
+                                          float pb, int *err_flag) {
+  RowReg o = {d, skip, l1, pb};
+  if (r.n) {
+    float wd;
+    if (!wd_lookup(r, id, wd)) {
+      atomicCAS(err_flag, 0, ERR_WD_BOUND);
+      return o;
+    }
+    o.pb = wd;
+    o.l1 = __fmul_rn(lr, wd);
+    o.d = __fsub_rn(1.0f, o.l1);
+    o.skip = !(fabsf(__fsub_rn(o.d, 1.0f)) > 1e-6f);
+  }
+  return o;
+}
+// decay constant of one global bias (base.h:189-193): 1 - lr*wd, or lr*wd for the L1 variant
+__device__ __forceinline__ float global_dec(const WdRanges &r, unsigned gid, float lr, bool l1, float dflt,
+                                            int *err_flag) {
+  if (!r.n) return dflt;
+  float wd;
+  if (!wd_lookup(r, gid, wd)) {
+    atomicCAS(err_flag, 0, ERR_WD_BOUND);
+    return dflt;
+  }
+  const float lambda = __fmul_rn(lr, wd);
+  return l1 ? lambda : __fsub_rn(1.0f, lambda);
 }
 // expf: the reference calls glibc expf (<= 0.502 ulp).  exp() in fp64 rounded to
 // fp32 is correctly rounded in all but ~1e-8 of cases, i.e. equal to glibc's in
@@ -413,7 +472,9 @@ struct Group {
                                              const float *val, int beg, int end, float lrerr,
                                              float decay, bool upd, bool dec, unsigned regfree,
                                              bool parallel, int scatter, bool l1 = false,
-                                             const float *val2 = nullptr) const {
+                                             const float *val2 = nullptr, const WdRanges *rng = nullptr,
+                                             float lr = 0.0f, int *err_flag = nullptr) const {
+    // rng (globals only): the decay constant comes from the index's weight-decay range
     // l1: the decay step is reg_L1(x, decay) instead of x *= decay (reg_global 1, base.h:193)
     if (parallel) {
       for (int f = beg + gl; f < end; f += LANES) {
@@ -421,6 +482,7 @@ struct Group {
         const float x0 = __ldcg(p);
         float x = x0;
         if (upd) x = __fadd_rn(x, val2 ? __fmul_rn(__fmul_rn(lrerr, val[f]), val2[f]) : __fmul_rn(lrerr, val[f]));
+        if (dec && rng) decay = global_dec(*rng, idx[f], lr, l1, decay, err_flag);
         if (dec && idx[f] >= regfree) x = l1 ? reg_l1(x, decay) : __fmul_rn(x, decay);
         if (scatter == SCATTER_RED) red1(p, __fsub_rn(x, x0));
         else __stcg(p, x);
@@ -431,6 +493,7 @@ struct Group {
           float *p = table + off + idx[f];
           float x = __ldcg(p);
           if (upd) x = __fadd_rn(x, val2 ? __fmul_rn(__fmul_rn(lrerr, val[f]), val2[f]) : __fmul_rn(lrerr, val[f]));
+          if (dec && rng) decay = global_dec(*rng, idx[f], lr, l1, decay, err_flag);
           if (dec && idx[f] >= regfree) x = l1 ? reg_l1(x, decay) : __fmul_rn(x, decay);
           __stcg(p, x);
         }
@@ -590,13 +653,14 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
   if (g_small && !dup_g) {  // every global index once: update and decay from the value gathered above
     if (g.gl < ng_) {
       float x = __fadd_rn(pre_gb, __fmul_rn(lrerr, pre_gv));
-      if (pre_gid >= hp.regfree) x = g_l1 ? reg_l1(x, g_dec) : __fmul_rn(x, g_dec);
+      const float dec = global_dec(hp.rg, pre_gid, hp.lr, g_l1, g_dec, err_flag);
+      if (pre_gid >= hp.regfree) x = g_l1 ? reg_l1(x, dec) : __fmul_rn(x, dec);
       if (scatter_item == SCATTER_RED) red1(m.g_bias + pre_gid, __fsub_rn(x, pre_gb));
       else __stcg(m.g_bias + pre_gid, x);
     }
   } else if (rp1 > rp0) {
     g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, lrerr, g_dec, true, !dup_g, hp.regfree, !dup_g,
-                 dup_g ? SCATTER_STORE : scatter_item, g_l1);
+                 dup_g ? SCATTER_STORE : scatter_item, g_l1, nullptr, &hp.rg, hp.lr, err_flag);
   }
 
   // bias read-modify-write of one feature whose old value was gathered early (lane `who` does it)
@@ -626,8 +690,10 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
         nw[v] = f4_add_scaled(w[v], ti[v], sc, one);
         if (hp.plain && !hp.du_skip) nw[v] = f4_scale(nw[v], hp.du);
       }
-      if (!hp.plain)
-        g.template reg_row<EXACT_DOT>(m, nw, hp.reg_user, hp.du, hp.du_skip, hp.l1_u, hp.pb_u, hp.user_nonneg != 0);
+      if (!hp.plain) {
+        const RowReg rr = row_reg(hp.ru, idx[f], hp.lr, hp.du, hp.du_skip, hp.l1_u, hp.pb_u, err_flag);
+        g.template reg_row<EXACT_DOT>(m, nw, hp.reg_user, rr.d, rr.skip, rr.l1, rr.pb, hp.user_nonneg != 0);
+      }
       if (scatter_user == SCATTER_RED) g.red_row(m, row, nw, w);
       else g.store_row(m, row, nw);
     }
@@ -655,8 +721,10 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
         nw[v] = f4_add_scaled(w[v], tu[v], sc, one);
         if (hp.plain && !hp.di_skip) nw[v] = f4_scale(nw[v], hp.di);
       }
-      if (!hp.plain)
-        g.template reg_row<EXACT_DOT>(m, nw, hp.reg_item, hp.di, hp.di_skip, hp.l1_i, hp.pb_i, false);
+      if (!hp.plain) {
+        const RowReg rr = row_reg(hp.ri, idx[f], hp.lr, hp.di, hp.di_skip, hp.l1_i, hp.pb_i, err_flag);
+        g.template reg_row<EXACT_DOT>(m, nw, hp.reg_item, rr.d, rr.skip, rr.l1, rr.pb, false);
+      }
       if (scatter_item == SCATTER_RED) g.red_row(m, row, nw, w);
       else g.store_row(m, row, nw);
     }
@@ -715,14 +783,15 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
 
   // ---- regularize(after) for the unfused cases --------------------------------
   if (dup_g) g.scalar_seg(m.g_bias, 0, idx, val, rp0, rp1, 0.f, g_dec, false, true, hp.regfree, false,
-                          SCATTER_STORE, g_l1);
+                          SCATTER_STORE, g_l1, nullptr, &hp.rg, hp.lr, err_flag);
   if (!fused) {
     for (int f = rp1; f < rp2; ++f) {
       const size_t row = (size_t)m.user_off + idx[f];
       if (!hp.plain || !hp.du_skip) {
         float4 w[VEC];
         g.load_row(m, row, w);
-        g.template reg_row<EXACT_DOT>(m, w, hp.reg_user, hp.du, hp.du_skip, hp.l1_u, hp.pb_u, hp.user_nonneg != 0);
+        const RowReg rr = row_reg(hp.ru, idx[f], hp.lr, hp.du, hp.du_skip, hp.l1_u, hp.pb_u, err_flag);
+        g.template reg_row<EXACT_DOT>(m, w, hp.reg_user, rr.d, rr.skip, rr.l1, rr.pb, hp.user_nonneg != 0);
         g.store_row(m, row, w);
       }
       if (!m.no_user_bias)
@@ -734,7 +803,8 @@ __device__ __forceinline__ float process_instance(const Group<LANES, VEC> &g, co
       if (!hp.plain || !hp.di_skip) {
         float4 w[VEC];
         g.load_row(m, row, w);
-        g.template reg_row<EXACT_DOT>(m, w, hp.reg_item, hp.di, hp.di_skip, hp.l1_i, hp.pb_i, false);
+        const RowReg rr = row_reg(hp.ri, idx[f], hp.lr, hp.di, hp.di_skip, hp.l1_i, hp.pb_i, err_flag);
+        g.template reg_row<EXACT_DOT>(m, w, hp.reg_item, rr.d, rr.skip, rr.l1, rr.pb, false);
         g.store_row(m, row, w);
       }
       g.scalar_seg(m.bias, m.item_off, idx, val, f, f + 1, 0.f, hp.dib, false, true, 0u, false,

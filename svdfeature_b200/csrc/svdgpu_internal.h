@@ -73,7 +73,7 @@ struct svdgpu {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
   svdk::DevModel dm;
-  svdk::DevHP dhp;
+  svdk::DevHP dhp{};
   size_t rows = 0;
   int *d_err = nullptr;
   unsigned *d_counter = nullptr;

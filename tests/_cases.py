@@ -91,6 +91,20 @@ def cases():
                                synth.random_general(2500, NU, NI, NG, seed=20), "csr")
     out["svdpp_reg_l1"] = (1, 0, dict(pp, reg_method=1, wd_user=0.02, wd_item=0.02),
                            synth.user_grouped(2500, NU, NI, avg_fb=12, seed=21), "ug")
+    # ranged weight decay (ParameterSet, base.h:33-75): user / item / global index ranges with their own wd
+    rng_pairs = [("up:wd", 0.02), ("up:bound", 50), ("up:wd", 0.0), ("up:bound", 120), ("up:wd", 0.008),
+                 ("up:bound", NU), ("ip:wd", 0.001), ("ip:bound", 10), ("ip:wd", 0.03), ("ip:bound", NI),
+                 ("gp:wd", 0.05), ("gp:bound", 12), ("gp:wd", 0.0005), ("gp:bound", NG)]
+    out["ranged_wd"] = (0, 0, dict(gen, num_factor=20, num_regfree_global=3, wd_ranges=rng_pairs),
+                        synth.random_general(3000, NU, NI, NG, seed=22, allow_dup=True), "csr")
+    out["ranged_wd_l1"] = (0, 0, dict(gen, reg_method=1, reg_global=1, wd_ranges=rng_pairs),
+                           synth.random_general(2500, NU, NI, NG, seed=23), "csr")
+    out["ranged_wd_project_uip"] = (0, 0, dict(BASE, num_factor=64, reg_method=2,
+                                               wd_ranges=[("uip:wd", 0.002), ("uip:bound", 60), ("uip:wd", 0.004),
+                                                          ("uip:bound", NU)]),
+                                    synth.basic_mf(4000, NU, NI, seed=24), "csr")
+    out["svdpp_ranged_wd"] = (1, 0, dict(pp, wd_ranges=rng_pairs[:10]),
+                              synth.user_grouped(2500, NU, NI, avg_fb=12, seed=25), "ug")
     return out
 
 

@@ -79,6 +79,10 @@ class _Base:
 
     def set_params(self, params):
         for k, v in params.items():
+            if k == "wd_ranges":  # ordered (key, value) pairs: up:wd / up:bound / ip:... / gp:...
+                for kk, vv in v:
+                    self._f("set_param")(self.h, str(kk).encode(), str(vv).encode())
+                continue
             self._f("set_param")(self.h, str(k).encode(), str(v).encode())
 
     def init(self, seed=10):

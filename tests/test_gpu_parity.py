@@ -27,6 +27,8 @@ def _pair(native, name, mode, options=None, seed=10):
     ub, W, gb = [a.copy() for a in o.arrays()]
     g = native.SvdGpu(**_cases.shape_of(params, fmt, act))
     g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    if "wd_ranges" in params:
+        g.set_wd_range_params(params["wd_ranges"])
     g.set_mode(mode)
     for k, v in (options or {}).items():
         g.set_option(k, v)
@@ -573,3 +575,60 @@ def test_side_features_through_the_trainer_seam(native, tmp_path):
     g.update_csr(data)
     assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
     assert o.model_bytes(tmp_path) == g.model_bytes(tmp_path)
+
+
+def test_ranged_wd_hogwild_conflict_free(native):
+    """Ranged weight decay (up:/ip: keys, base.h:33-75) in Hogwild mode: the fast passes stand down and
+    the generic pass looks the decay up per index; on conflict-free input the result is the oracle's."""
+    pairs = [("up:wd", 0.05), ("up:bound", 1000), ("up:wd", 0.0), ("up:bound", 2500), ("up:wd", 0.01),
+             ("up:bound", 5000), ("ip:wd", 0.02), ("ip:bound", 2000), ("ip:wd", 0.001), ("ip:bound", 4000)]
+    params = dict(num_user=5000, num_item=4000, num_factor=64, learning_rate=0.01, wd_user=0.004,
+                  wd_item=0.004, wd_user_bias=0.001, base_score=3.6, wd_ranges=pairs)
+    o = COracle(0, 0, 0, params)
+    o.init(3)
+    g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_wd_range_params(pairs)
+    g.set_mode(native.MODE_HOGWILD)
+    g.set_option("scatter_user", 0)
+    g.set_option("scatter_item", 0)
+    g.set_option("exact_dot", 1)
+    g.upload(*[a.copy() for a in o.arrays()])
+    for r in range(2):
+        data = _conflict_free(5000, 4000, 3500, 300 + r)
+        o.update_csr(data)
+        g.update_csr(data)
+    g.sync()
+    assert _maxdiff(o, g) == 0.0
+    # and the ranges matter: the same steps without them end elsewhere
+    o2 = COracle(0, 0, 0, {k: v for k, v in params.items() if k != "wd_ranges"})
+    o2.init(3)
+    for r in range(2):
+        o2.update_csr(_conflict_free(5000, 4000, 3500, 300 + r))
+    assert np.abs(o2.arrays()[1] - o.arrays()[1]).max() > 0.0
+
+
+def test_ranged_wd_errors(native):
+    """ParameterSet's checks (base.h:56-58,72): zero / unordered bounds are refused at set time, an index
+    beyond the last range is the reference's "bound set err", reported by the next sync."""
+    params = dict(num_user=100, num_item=80, num_factor=16, learning_rate=0.01, base_score=3.0)
+    o = COracle(0, 0, 0, params)
+    o.init(1)
+    g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    with pytest.raises(native.SvdGpuError, match="can't give 0 as bound"):
+        g.set_wd_ranges(0, [0], [0.1])
+    with pytest.raises(native.SvdGpuError, match="bound must be given in order"):
+        g.set_wd_ranges(0, [10, 10], [0.1, 0.2])
+    with pytest.raises(native.SvdGpuError, match="at most"):
+        g.set_wd_ranges(1, list(range(1, 11)), [0.1] * 10)
+    g.set_wd_ranges(0, [50], [0.1])  # users 50..99 have no range
+    g.upload(*[a.copy() for a in o.arrays()])
+    data = synth.fixed_csr(np.ones(1, np.float32), uidx=np.array([70], np.uint32), uval=np.ones(1, np.float32),
+                           iidx=np.array([3], np.uint32), ival=np.ones(1, np.float32))
+    with pytest.raises(native.SvdGpuError, match="bound set err"):
+        g.update_csr(data)
+        g.sync()
+    g.set_wd_ranges(0, [], [])  # cleared: the default wd_user applies again
+    g.update_csr(data)
+    g.sync()

@@ -9,7 +9,7 @@ from _oracle import COracle, RefTrainer, have_ref, parse_model
 pytestmark = pytest.mark.gpu
 CASES = _cases.cases()
 FILE_CASES = ["basic_k16", "basic_k64", "general_k13_dups", "neighborhood_k32", "svdpp_k16", "svdpp_k64_tags",
-              "pairwise_ugroup", "lr_decay", "active_5"]
+              "pairwise_ugroup", "lr_decay", "active_5", "ranged_wd", "svdpp_ranged_wd"]
 
 
 def _train(t, data, kind, tmp, rounds=2):
