@@ -74,6 +74,13 @@ struct svdo {
   float *tmp_ufactor, *tmp_ifactor, *tmp_ufeedback, *old_ufeedback;
   float norm_ufeedback, tmp_ufeedback_bias, old_ufeedback_bias;
   int is_svdpp; /* apex_svd.cpp:32-45: extend_type==1 or USER_GROUP -> SVDPPFeature */
+  /* SVDFeatureRanker state (base.h:605-631) */
+  struct {
+    int init_end, num_item_set, num_item_processed, top_k;
+    float *tmp_ifactors, *bias_ifactors; /* [num_item_set][pitch], [num_item_set] */
+    float *tmp_ufactor, *tmp_ifactor, *tmp_ufeedback, *item_score;
+    int *item_tag, *pos_item, num_pos, cap_pos;
+  } rk;
 };
 
 static void die(const char *msg) { /* apex-utils/apex_utils.h:47-50 */
@@ -304,6 +311,8 @@ void svdo_destroy(svdo_t *m) {
   free(m->ref_global);
   free(m->feat_user.row_ptr); free(m->feat_user.index); free(m->feat_user.value);
   free(m->feat_item.row_ptr); free(m->feat_item.index); free(m->feat_item.value);
+  free(m->rk.tmp_ifactors); free(m->rk.bias_ifactors); free(m->rk.tmp_ufactor); free(m->rk.tmp_ifactor);
+  free(m->rk.tmp_ufeedback); free(m->rk.item_score); free(m->rk.item_tag); free(m->rk.pos_item);
   free(m);
 }
 
@@ -328,6 +337,7 @@ void svdo_set_param(svdo_t *m, const char *name, const char *val) { /* base.h:12
   if (!strcmp("scale_lr_ufeedback", name)) m->scale_lr_ufeedback = (float)atof(val);
   if (!strcmp("wd_ufeedback", name)) m->wd_ufeedback = (float)atof(val);
   if (!strcmp("wd_ufeedback_bias", name)) m->wd_ufeedback_bias = (float)atof(val);
+  if (!strcmp(name, "top_k")) m->rk.top_k = atoi(val); /* SVDFeatureRanker::set_param, base.h:656-660 */
   range_wd_set(&m->u_param, name, val);
   range_wd_set(&m->i_param, name, val);
   range_wd_set(&m->g_param, name, val);
@@ -945,3 +955,207 @@ long svdo_info(svdo_t *m, int what) {
 }
 float svdo_base_score(svdo_t *m) { return m->base_score; }
 float svdo_learning_rate(svdo_t *m) { return m->learning_rate; }
+
+/* ======================================================================================
+ * SVDFeatureRanker (base.h:597-813): rank a fixed item set for a stream of user sections.
+ * The input is a tagged instance stream (svdranker_tag, apex_svd.h:115-152): the label field
+ * holds the tag, item indices of POS/BAN/SPEC rows sit in the user-feature field.
+ * ====================================================================================== */
+enum { RK_ITEM = 0, RK_POS = 1, RK_USER = 2, RK_SPEC = 3, RK_PROCESS = 4, RK_BAN = -1 };
+
+void svdo_init_ranker(svdo_t *m, int num_item_set) { /* base.h:668-688 */
+  size_t n = (size_t)(m->pitch > 0 ? m->pitch : 1), ns = (size_t)(num_item_set > 0 ? num_item_set : 1);
+  if (strcmp(m->name_feat_user, "NULL"))
+    sparse_load(m->name_feat_user, &m->feat_user.num_row, &m->feat_user.row_ptr, &m->feat_user.index, &m->feat_user.value);
+  if (strcmp(m->name_feat_item, "NULL"))
+    sparse_load(m->name_feat_item, &m->feat_item.num_row, &m->feat_item.row_ptr, &m->feat_item.index, &m->feat_item.value);
+  m->rk.num_item_processed = 0;
+  m->rk.num_item_set = num_item_set;
+  m->rk.tmp_ufactor = (float *)calloc(n, sizeof(float));
+  m->rk.tmp_ifactor = (float *)calloc(n, sizeof(float));
+  m->rk.tmp_ufeedback = (float *)calloc(n, sizeof(float));
+  m->rk.tmp_ifactors = (float *)calloc(n * ns, sizeof(float));
+  m->rk.bias_ifactors = (float *)calloc(ns, sizeof(float));
+  m->rk.item_score = (float *)calloc(ns, sizeof(float));
+  m->rk.item_tag = (int *)calloc(ns, sizeof(int));
+  m->rk.init_end = 1;
+}
+
+static void rk_prepare_ifactor(svdo_t *m, float *ifactor, float *bias_out, const elem_t *e) { /* base.h:690-716 */
+  const int k = m->num_factor;
+  float bias = 0.0f;
+  int i;
+  row_fill(ifactor, 0.0f, k);
+  for (i = 0; i < e->ni; ++i) {
+    const unsigned iid = e->ii[i];
+    const float ival = e->iv[i];
+    unsigned j;
+    if (!(iid < (unsigned)m->num_item)) die("item feature index exceed setting");
+    row_add_scaled(ifactor, m->W_item + (size_t)iid * m->pitch, ival, k);
+    {
+      float p = m->i_bias[iid] * ival;
+      bias = bias + p;
+    }
+    for (j = SIDE_BEGIN(m->feat_item, iid); j < SIDE_END(m->feat_item, iid); ++j) {
+      /* W * value * ival: the two scalars fold in double (apex_exp_template.h:500-503), see prepare_tmp */
+      float sc = (float)((double)m->feat_item.value[j] * (double)ival);
+      float p = m->i_bias[m->feat_item.index[j]] * m->feat_item.value[j];
+      row_add_scaled(ifactor, m->W_item + (size_t)m->feat_item.index[j] * m->pitch, sc, k);
+      p = p * ival;
+      bias = bias + p;
+    }
+  }
+  for (i = 0; i < e->ng; ++i) {
+    const unsigned gid = e->gi[i];
+    float p;
+    if (!(gid < (unsigned)m->num_global)) die("global feature index exceed setting");
+    p = e->gv[i] * m->g_bias[gid];
+    bias = bias + p;
+  }
+  *bias_out = bias;
+}
+
+static void rk_proc_item(svdo_t *m, const elem_t *e) { /* base.h:718-723 */
+  const int idx = m->rk.num_item_processed++;
+  if (!(m->rk.num_item_processed <= m->rk.num_item_set)) die("item instance exceed specified item set size");
+  rk_prepare_ifactor(m, m->rk.tmp_ifactors + (size_t)idx * m->pitch, &m->rk.bias_ifactors[idx], e);
+}
+
+static void rk_proc_user(svdo_t *m, const elem_t *e) { /* base.h:725-746 */
+  const int k = m->num_factor;
+  int i;
+  if (m->format_type == FMT_USER_GROUP) memcpy(m->rk.tmp_ufactor, m->rk.tmp_ufeedback, sizeof(float) * (size_t)k);
+  else row_fill(m->rk.tmp_ufactor, 0.0f, k);
+  for (i = 0; i < e->nu; ++i) {
+    const unsigned uid = e->ui[i];
+    unsigned j;
+    if (!(uid < (unsigned)m->num_user)) die("user feature index exceed bound");
+    row_add_scaled(m->rk.tmp_ufactor, m->W_user + (size_t)uid * m->pitch, e->uv[i], k);
+    for (j = SIDE_BEGIN(m->feat_user, uid); j < SIDE_END(m->feat_user, uid); ++j)
+      row_add_scaled(m->rk.tmp_ufactor, m->W_user + (size_t)m->feat_user.index[j] * m->pitch, m->feat_user.value[j], k);
+  }
+  m->rk.num_pos = 0;
+  for (i = 0; i < m->rk.num_item_set; ++i) m->rk.item_score[i] = 0.0f;
+  for (i = 0; i < m->rk.num_item_processed; ++i) m->rk.item_tag[i] = 0;
+}
+
+static void rk_proc_tag(svdo_t *m, const elem_t *e, int tag) { /* base.h:747-755 */
+  int i;
+  for (i = 0; i < e->nu; ++i) {
+    const int idx = (int)e->ui[i];
+    if (!(idx < m->rk.num_item_processed)) die("sample item index exceed bound");
+    if (!(m->rk.item_tag[idx] == 0)) die("each pos sample item can not occur in baned sample list");
+    m->rk.item_tag[idx] = tag;
+    if (tag == RK_POS) {
+      if (m->rk.num_pos == m->rk.cap_pos) {
+        m->rk.cap_pos = m->rk.cap_pos ? 2 * m->rk.cap_pos : 16;
+        m->rk.pos_item = (int *)realloc(m->rk.pos_item, sizeof(int) * (size_t)m->rk.cap_pos);
+      }
+      m->rk.pos_item[m->rk.num_pos++] = idx;
+    }
+  }
+}
+
+static void rk_proc_spec(svdo_t *m, const elem_t *e) { /* base.h:756-764 */
+  float bias, d;
+  int idx;
+  if (!(e->nu == 1)) die("must specify item index of sample in user feature field\n");
+  idx = (int)e->ui[0];
+  if (!(idx < m->rk.num_item_processed)) die("sample item index exceed bound");
+  rk_prepare_ifactor(m, m->rk.tmp_ifactor, &bias, e);
+  d = row_dot(m->rk.tmp_ufactor, m->rk.tmp_ifactor, m->num_factor);
+  m->rk.item_score[idx] = bias + d;
+}
+
+typedef struct { int iid; float score; } rk_entry;
+/* Entry::operator< (base.h:621): higher score first.  std::sort leaves the order of equal scores
+ * to the implementation; this restatement puts the lower item index first (stable). */
+static int rk_cmp(const void *a, const void *b) {
+  const rk_entry *x = (const rk_entry *)a, *y = (const rk_entry *)b;
+  if (x->score > y->score) return -1;
+  if (y->score > x->score) return 1;
+  return x->iid < y->iid ? -1 : (x->iid > y->iid ? 1 : 0);
+}
+
+static long rk_proc_rank(svdo_t *m, int *rst, long cap, long n_out) { /* base.h:765-789 */
+  const int n = m->rk.num_item_processed;
+  rk_entry *entry = (rk_entry *)malloc(sizeof(rk_entry) * (size_t)(n > 0 ? n : 1));
+  int ne = 0, i;
+  for (i = 0; i < n; ++i) {
+    float t;
+    if (m->rk.item_tag[i] == RK_BAN) continue;
+    t = row_dot(m->rk.tmp_ufactor, m->rk.tmp_ifactors + (size_t)i * m->pitch, m->num_factor);
+    t = m->rk.bias_ifactors[i] + t;
+    m->rk.item_score[i] = m->rk.item_score[i] + t;
+    entry[ne].iid = i;
+    entry[ne].score = m->rk.item_score[i];
+    ne++;
+  }
+  qsort(entry, (size_t)ne, sizeof(rk_entry), rk_cmp);
+  if (m->rk.top_k > 0) {
+    if (!(ne >= m->rk.top_k)) die("k can not exceed candidate size");
+    for (i = 0; i < m->rk.top_k; ++i) {
+      if (n_out < cap) rst[n_out] = entry[i].iid;
+      n_out++;
+    }
+  } else {
+    for (i = 0; i < ne; ++i) m->rk.item_tag[entry[i].iid] = i;
+    for (i = 0; i < m->rk.num_pos; ++i) {
+      if (n_out < cap) rst[n_out] = m->rk.item_tag[m->rk.pos_item[i]];
+      n_out++;
+    }
+  }
+  free(entry);
+  return n_out;
+}
+
+static long rk_proc(svdo_t *m, const elem_t *e, int *rst, long cap, long n_out) { /* base.h:790-800 */
+  const int tag = (int)e->label;
+  switch (tag) {
+    case RK_ITEM: rk_proc_item(m, e); break;
+    case RK_USER: rk_proc_user(m, e); break;
+    case RK_POS:
+    case RK_BAN: rk_proc_tag(m, e, tag); break;
+    case RK_SPEC: rk_proc_spec(m, e); break;
+    case RK_PROCESS: n_out = rk_proc_rank(m, rst, cap, n_out); break;
+    default: break;
+  }
+  return n_out;
+}
+
+/* for each row ISVDRanker::process(result, Elem) (base.h:802-804); returns the number of results
+ * (those beyond cap are counted but not stored) */
+long svdo_rank_csr(svdo_t *m, int num_row, const int *row_ptr, const float *label, const unsigned *index,
+                   const float *value, int *result, long cap) {
+  long n_out = 0;
+  int r;
+  for (r = 0; r < num_row; ++r) {
+    elem_t e = csr_row(r, row_ptr, label, index, value);
+    n_out = rk_proc(m, &e, result, cap, n_out);
+  }
+  return n_out;
+}
+
+/* for each block ISVDRanker::process(result, SVDPlusBlock) (base.h:805-819) */
+long svdo_rank_ugroup(svdo_t *m, int num_block, const int *blk_row_off, const int *blk_fb_off, const int *blk_tag,
+                      const unsigned *fb_index, const float *fb_value, const int *row_ptr, const float *label,
+                      const unsigned *index, const float *value, int *result, long cap) {
+  long n_out = 0;
+  int b, r, i;
+  for (b = 0; b < num_block; ++b) {
+    const int tag = blk_tag ? blk_tag[b] : TAG_DEFAULT;
+    if (tag == TAG_DEFAULT || tag == TAG_START) {
+      row_fill(m->rk.tmp_ufeedback, 0.0f, m->num_factor);
+      for (i = blk_fb_off[b]; i < blk_fb_off[b + 1]; ++i) {
+        const unsigned fid = fb_index[i];
+        if (!(fid < (unsigned)m->num_ufeedback)) die("ufeedback id exceed bound");
+        row_add_scaled(m->rk.tmp_ufeedback, m->W_ufeedback + (size_t)fid * m->pitch, fb_value[i], m->num_factor);
+      }
+    }
+    for (r = blk_row_off[b]; r < blk_row_off[b + 1]; ++r) {
+      elem_t e = csr_row(r, row_ptr, label, index, value);
+      n_out = rk_proc(m, &e, result, cap, n_out);
+    }
+  }
+  return n_out;
+}

@@ -39,6 +39,17 @@ void svdo_predict_ugroup(svdo_t *m, int num_block, const int *blk_row_off, const
                          const int *row_ptr, const float *label, const unsigned *index,
                          const float *value, float *out);
 
+/* SVDFeatureRanker (base.h:597-813): load_model, set_param("top_k" ...), init_ranker, then a tagged
+ * instance stream; results (item indices for top_k > 0, else rank positions of the POS items) are
+ * appended in stream order.  Return value: number of results (beyond cap: counted, not stored). */
+void svdo_init_ranker(svdo_t *m, int num_item_set);
+long svdo_rank_csr(svdo_t *m, int num_row, const int *row_ptr, const float *label, const unsigned *index,
+                   const float *value, int *result, long cap);
+long svdo_rank_ugroup(svdo_t *m, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                      const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                      const int *row_ptr, const float *label, const unsigned *index, const float *value,
+                      int *result, long cap);
+
 /* raw views for tests: which = 0 ui_bias, 1 W_uiset, 2 g_bias */
 float *svdo_data(svdo_t *m, int which);
 /* what = 0 rows of W_uiset, 1 pitch in floats, 2 ustart (feedback rows), 3 num_factor,

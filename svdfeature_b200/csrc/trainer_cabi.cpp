@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <vector>
 
+using apex_svd::ISVDRanker;
 using apex_svd::ISVDTrainer;
 using apex_svd::SVDFeatureCSR;
 using apex_svd::SVDPlusBlock;
@@ -32,6 +33,10 @@ namespace {
 struct Handle {
   SVDTypeParam mtype;
   ISVDTrainer *tr;
+};
+struct RankHandle {
+  SVDTypeParam mtype;
+  ISVDRanker *rk;
 };
 
 inline SVDFeatureCSR make_csr(int num_row, const int *row_ptr, const float *label,
@@ -160,6 +165,67 @@ void svdtr_predict_ugroup(void *hv, int num_block, const int *blk_row_off, const
     tr->predict(p, blk);
     for (size_t i = 0; i < p.size(); ++i) out[blk_row_off[b] + (int)i] = p[i];
   }
+}
+
+// ---- ISVDRanker (apex_svd.h:160-197), driven like svd_feature_infer.cpp:126-154,233-241,349-371 ----
+// The model file's 4-byte SVDTypeParam decides the ranker's type (svd_feature_infer.cpp:128-137).
+void *svdrk_create_from_model(const char *path) {
+  FILE *fi = std::fopen(path, "rb");
+  if (!fi) return NULL;
+  RankHandle *h = new RankHandle();
+  if (std::fread(&h->mtype, sizeof(SVDTypeParam), 1, fi) != 1) {
+    std::fclose(fi);
+    delete h;
+    return NULL;
+  }
+  h->rk = apex_svd::create_svd_ranker(h->mtype);
+  h->rk->load_model(fi);
+  std::fclose(fi);
+  return h;
+}
+void svdrk_destroy(void *hv) {
+  RankHandle *h = static_cast<RankHandle *>(hv);
+  if (!h) return;
+  delete h->rk;
+  delete h;
+}
+void svdrk_set_param(void *hv, const char *name, const char *val) {
+  static_cast<RankHandle *>(hv)->rk->set_param(name, val);
+}
+void svdrk_init_ranker(void *hv, int num_item_set) { static_cast<RankHandle *>(hv)->rk->init_ranker(num_item_set); }
+
+// for each row: process(result, Elem) -- the loop of svd_feature_infer.cpp:352-360; results are
+// appended in stream order; returns their number (those beyond cap are counted, not stored)
+long svdrk_rank_csr(void *hv, int num_row, const int *row_ptr, const float *label, const unsigned *index,
+                    const float *value, int *result, long cap) {
+  ISVDRanker *rk = static_cast<RankHandle *>(hv)->rk;
+  const SVDFeatureCSR c = make_csr(num_row, row_ptr, label, index, value);
+  long n = 0;
+  std::vector<int> p;
+  for (int r = 0; r < num_row; ++r) {
+    p.clear();
+    rk->process(p, c[r]);
+    for (size_t i = 0; i < p.size(); ++i, ++n)
+      if (n < cap) result[n] = p[i];
+  }
+  return n;
+}
+// for each block: process(result, SVDPlusBlock) -- svd_feature_infer.cpp:362-370
+long svdrk_rank_ugroup(void *hv, int num_block, const int *blk_row_off, const int *blk_fb_off, const int *blk_tag,
+                       const unsigned *fb_index, const float *fb_value, const int *row_ptr, const float *label,
+                       const unsigned *index, const float *value, int *result, long cap) {
+  ISVDRanker *rk = static_cast<RankHandle *>(hv)->rk;
+  long n = 0;
+  std::vector<int> p;
+  for (int b = 0; b < num_block; ++b) {
+    const SVDPlusBlock blk = make_block(b, blk_row_off, blk_fb_off, blk_tag, fb_index, fb_value, row_ptr, label,
+                                        index, value);
+    p.clear();
+    rk->process(p, blk);
+    for (size_t i = 0; i < p.size(); ++i, ++n)
+      if (n < cap) result[n] = p[i];
+  }
+  return n;
 }
 
 }  // extern "C"

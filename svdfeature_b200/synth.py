@@ -167,3 +167,70 @@ def random_general(n, num_user, num_item, num_global, seed=10, max_g=3, max_u=2,
         rows.append((float(rng.integers(1, 6)), pick(ng, max(num_global, 1)), pick(nu, num_user),
                      pick(ni, num_item)))
     return ragged_csr(rows)
+
+
+# svdranker_tag (apex_svd.h:115-152): the tag of a ranker input row sits in its label field
+RK_ITEM, RK_POS, RK_USER, RK_SPEC, RK_PROCESS, RK_BAN = 0, 1, 2, 3, 4, -1
+
+
+def rank_stream(num_item_set, num_sections, num_user, num_item, num_global=0, seed=10, max_pos=4, max_ban=3,
+                max_spec=2, ugroup=False, num_ufeedback=0, avg_fb=6, split_every=0):
+    """A tagged ranker input stream (SVDFeatureRanker, base.h:597-813): ``num_item_set`` ITEM rows (item
+    and global features of each candidate), then ``num_sections`` user sections USER / POS* / BAN* /
+    SPEC* / PROCESS.  Item indices of POS/BAN/SPEC rows are positions in the item set and sit in the
+    user-feature field.  Returns CSR arrays; with ``ugroup`` the SVDPlusBlock arrays in front (block 0
+    = the item set, then one block per section carrying that user's feedback list; every
+    ``split_every``-th section is cut into START / END blocks)."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    pick = lambda hi, n: [int(x) for x in rng.choice(hi, size=n, replace=False)]
+    fval = lambda: float(np.float32(rng.uniform(-1.0, 1.0)))
+    for _ in range(num_item_set):
+        ni = int(rng.integers(1, 4))
+        ng = int(rng.integers(0, 3)) if num_global else 0
+        rows.append((RK_ITEM, [(g, fval()) for g in pick(num_global, ng)] if ng else [], [],
+                     # (a lone item feature never has value 1: two such rows on one item would tie, and
+                     # the order of equal scores is std::sort's business, base.h:773)
+                     [(i, 1.0 if j == 0 and ni > 1 else fval()) for j, i in enumerate(pick(num_item, ni))]))
+    item_rows = len(rows)
+    sec_start, sec_cut = [], []
+    for s_ in range(num_sections):
+        sec_start.append(len(rows))
+        nu = int(rng.integers(1, 3))
+        rows.append((RK_USER, [], [(u, 1.0 if j == 0 else fval()) for j, u in enumerate(pick(num_user, nu))], []))
+        npos, nban = int(rng.integers(0, max_pos + 1)), int(rng.integers(0, max_ban + 1))
+        tagged = pick(num_item_set, min(npos + nban, num_item_set))
+        pos, ban = tagged[:npos], tagged[npos:]
+        if pos:
+            half = len(pos) // 2
+            for part in ([pos[:half], pos[half:]] if half else [pos]):  # several indices per row, several rows
+                rows.append((RK_POS, [], [(i, 1.0) for i in part], []))
+        sec_cut.append(len(rows))
+        if ban:
+            rows.append((RK_BAN, [], [(i, 1.0) for i in ban], []))
+        for _ in range(int(rng.integers(0, max_spec + 1))):
+            ng = int(rng.integers(0, 3)) if num_global else 0
+            ni = int(rng.integers(0, 3))
+            rows.append((RK_SPEC, [(g, fval()) for g in pick(num_global, ng)] if ng else [],
+                         [(int(rng.integers(0, num_item_set)), 1.0)], [(i, fval()) for i in pick(num_item, ni)]))
+        rows.append((RK_PROCESS, [], [], []))
+    csr = ragged_csr(rows)
+    if not ugroup:
+        return csr
+    bro, bfo, tag, fbi, fbv = [0, item_rows], [0, 0], [0], [], []
+    ends = sec_start[1:] + [len(rows)]
+    for s_ in range(num_sections):
+        nfb = int(rng.integers(0, 2 * avg_fb + 1)) if num_ufeedback else 0
+        fi = pick(num_ufeedback, min(nfb, num_ufeedback)) if nfb else []
+        fv = [float(np.float32(1.0 / np.sqrt(max(len(fi), 1))))] * len(fi)
+        pieces = [ends[s_]]
+        if split_every and s_ % split_every == 0 and sec_cut[s_] < ends[s_]:
+            pieces = [sec_cut[s_], ends[s_]]
+        for pi, end in enumerate(pieces):
+            bro.append(end)
+            fbi += fi
+            fbv += fv
+            bfo.append(len(fbi))
+            tag.append(0 if len(pieces) == 1 else (1 if pi == 0 else 2))
+    return (np.asarray(bro, np.int32), np.asarray(bfo, np.int32), np.asarray(tag, np.int32),
+            np.asarray(fbi, np.uint32), np.asarray(fbv, np.float32)) + csr

@@ -141,3 +141,36 @@ def shape_of(params, fmt, act):
     return dict(num_user=params["num_user"], num_item=params["num_item"], num_factor=params["num_factor"],
                 num_global=params.get("num_global", 0), num_ufeedback=params.get("num_ufeedback", 0),
                 no_user_bias=params.get("no_user_bias", 0), active_type=act, format_type=fmt)
+
+
+def rank_cases():
+    """name -> (format_type, model params, stream kwargs, ranker params) for SVDFeatureRanker parity.
+    The model is trained for one round on a small batch first so that no tensor is at its initial value."""
+    gen = dict(BASE, num_factor=20, num_global=NG, wd_global=0.001)
+    pp = dict(BASE, num_factor=16, num_ufeedback=NI, wd_ufeedback=0.004, ufeedback_init_sigma=0.05)
+    out = {}
+    out["rank_pos_k20"] = (0, gen, dict(num_item_set=70, num_sections=25, num_global=NG, seed=1), {})
+    out["rank_top5_k20"] = (0, gen, dict(num_item_set=70, num_sections=25, num_global=NG, seed=2), {"top_k": 5})
+    out["rank_top3_k64"] = (0, dict(BASE, num_factor=64), dict(num_item_set=300, num_sections=40, seed=3), {"top_k": 3})
+    out["rank_pos_k13"] = (0, dict(gen, num_factor=13), dict(num_item_set=129, num_sections=30, num_global=NG, seed=4,
+                                                             max_pos=9, max_ban=20), {})
+    out["rank_svdpp_pos"] = (1, pp, dict(num_item_set=60, num_sections=20, seed=5, ugroup=True, num_ufeedback=NI), {})
+    out["rank_svdpp_top4_split"] = (1, pp, dict(num_item_set=60, num_sections=20, seed=6, ugroup=True,
+                                                num_ufeedback=NI, split_every=2), {"top_k": 4})
+    return out
+
+
+def rank_model(fmt, params, tmpdir, cls=None):
+    """Train a model of the case's shape with the oracle and save it: the file every ranker loads."""
+    import os
+    from _oracle import COracle
+    o = COracle(fmt, 0, 0, params)
+    o.init(7)
+    nu, ni, ng = params["num_user"], params["num_item"], params.get("num_global", 0)
+    if fmt == 1:
+        o.update_ugroup(synth.user_grouped(1500, nu, ni, avg_fb=8, seed=31))
+    else:
+        o.update_csr(synth.random_general(1500, nu, ni, ng, seed=31) if ng else synth.basic_mf(1500, nu, ni, seed=31))
+    path = os.path.join(str(tmpdir), "rank.model")
+    o.save_model(path)
+    return path

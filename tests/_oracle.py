@@ -227,6 +227,89 @@ class RefTrainer(_Base):
 
 
 # ---------------------------------------------------------------------------
+# SVDFeatureRanker (base.h:597-813) behind the same two checkers
+# ---------------------------------------------------------------------------
+def _rank_call(fn, h, stream, kind, cap):
+    out = np.full(cap, -12345, np.int32)
+    if kind == "csr":
+        n = fn(h, *_csr_args(stream), _p(out, _i32p), cap)
+    else:
+        args, _ = _ug_args(stream)
+        n = fn(h, *args, _p(out, _i32p), cap)
+    assert 0 <= n <= cap, n
+    return out[:n].copy()
+
+
+_RANK_CSR = [C.c_void_p, C.c_int, _i32p, _f32p, _u32p, _f32p, _i32p, C.c_long]
+_RANK_UG = [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, _u32p, _f32p, _i32p, _f32p, _u32p, _f32p, _i32p, C.c_long]
+
+
+class COracleRanker:
+    """The restated ranker: load_model -> set_param -> init_ranker -> tagged stream."""
+
+    def __init__(self, model_path, num_item_set, params=None):
+        with open(model_path, "rb") as f:
+            fmt, act, ext, _ = struct.unpack("<4B", f.read(4))
+        self.o = COracle(fmt, act, ext)
+        self.o.load_model(model_path)
+        self.o.set_params(params or {})
+        lib = self.o.lib
+        lib.svdo_init_ranker.argtypes = [C.c_void_p, C.c_int]
+        lib.svdo_rank_csr.restype = C.c_long
+        lib.svdo_rank_csr.argtypes = _RANK_CSR
+        lib.svdo_rank_ugroup.restype = C.c_long
+        lib.svdo_rank_ugroup.argtypes = _RANK_UG
+        lib.svdo_init_ranker(self.o.h, num_item_set)
+
+    def rank(self, stream, kind="csr", cap=1 << 20):
+        fn = self.o.lib.svdo_rank_csr if kind == "csr" else self.o.lib.svdo_rank_ugroup
+        return _rank_call(fn, self.o.h, stream, kind, cap)
+
+
+class RefRanker:
+    """The compiled reference's SVDFeatureRanker through create_svd_ranker (apex_svd.cpp:45-47)."""
+
+    def __init__(self, model_path, num_item_set, params=None):
+        build_oracle()
+        if RefTrainer.lib is None:
+            RefTrainer.lib = C.CDLL(REF_SO)
+            _declare(RefTrainer.lib, RefTrainer.prefix)
+        lib = self.lib = RefTrainer.lib
+        lib.svdrk_create_from_model.restype = C.c_void_p
+        lib.svdrk_create_from_model.argtypes = [C.c_char_p]
+        lib.svdrk_destroy.argtypes = [C.c_void_p]
+        lib.svdrk_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        lib.svdrk_init_ranker.argtypes = [C.c_void_p, C.c_int]
+        lib.svdrk_rank_csr.restype = C.c_long
+        lib.svdrk_rank_csr.argtypes = _RANK_CSR
+        lib.svdrk_rank_ugroup.restype = C.c_long
+        lib.svdrk_rank_ugroup.argtypes = _RANK_UG
+        # the fork's load_from_file dumps *.txt into the CWD (apex_svd_model.h:586-621)
+        cwd = os.getcwd()
+        os.chdir(os.path.dirname(os.path.abspath(model_path)))
+        try:
+            self.h = lib.svdrk_create_from_model(os.path.abspath(model_path).encode())
+        finally:
+            os.chdir(cwd)
+        assert self.h
+        for k, v in (params or {}).items():
+            lib.svdrk_set_param(self.h, str(k).encode(), str(v).encode())
+        lib.svdrk_init_ranker(self.h, num_item_set)
+
+    def rank(self, stream, kind="csr", cap=1 << 20):
+        fn = self.lib.svdrk_rank_csr if kind == "csr" else self.lib.svdrk_rank_ugroup
+        return _rank_call(fn, self.h, stream, kind, cap)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.svdrk_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
 # model-file reader (layout: SURVEY.md section 8b; apex_svd_model.h:638-660)
 # ---------------------------------------------------------------------------
 def parse_model(buf):

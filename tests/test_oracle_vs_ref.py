@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 import _cases
-from _oracle import COracle, RefTrainer, have_ref, build_oracle
+from _oracle import COracle, COracleRanker, RefRanker, RefTrainer, have_ref, build_oracle
+from svdfeature_b200 import synth
 
 build_oracle()
 CASES = _cases.cases()
@@ -73,3 +74,37 @@ def test_oracle_loads_reference_model_file(tmp_path):
     o.lib.svdo_init_trainer(o.h)
     assert np.array_equal(o.predict_ugroup(data), r.predict_ugroup(data))
     assert o.model_bytes(tmp_path) == open(path, "rb").read()
+
+
+RANK_CASES = _cases.rank_cases()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", sorted(RANK_CASES))
+def test_oracle_ranker_matches_compiled_reference(name, tmp_path):
+    """SVDFeatureRanker (base.h:597-813): the restatement returns the same item indices / rank positions
+    as the compiled reference's create_svd_ranker on the same model file and tagged stream."""
+    fmt, params, skw, rparams = RANK_CASES[name]
+    path = _cases.rank_model(fmt, params, tmp_path)
+    stream = synth.rank_stream(num_user=params["num_user"], num_item=params["num_item"], **skw)
+    kind = "ug" if skw.get("ugroup") else "csr"
+    ro = COracleRanker(path, skw["num_item_set"], rparams).rank(stream, kind)
+    rr = RefRanker(path, skw["num_item_set"], rparams).rank(stream, kind)
+    assert len(ro) > 0 and np.array_equal(ro, rr)
+    if rparams.get("top_k"):
+        assert len(ro) == rparams["top_k"] * skw["num_sections"]
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_oracle_ranker_side_features(tmp_path):
+    fmt, params, skw, rparams = RANK_CASES["rank_pos_k20"]
+    path = _cases.rank_model(fmt, params, tmp_path)
+    fu, fi = str(tmp_path / "user.side"), str(tmp_path / "item.side")
+    _cases.write_side_features(fu, params["num_user"], params["num_user"], seed=1)
+    _cases.write_side_features(fi, params["num_item"], params["num_item"], seed=2)
+    stream = synth.rank_stream(num_user=params["num_user"], num_item=params["num_item"], **skw)
+    rp = dict(rparams, feature_user=fu, feature_item=fi)
+    ro = COracleRanker(path, skw["num_item_set"], rp).rank(stream)
+    rr = RefRanker(path, skw["num_item_set"], rp).rank(stream)
+    assert np.array_equal(ro, rr)
+    assert not np.array_equal(ro, COracleRanker(path, skw["num_item_set"], rparams).rank(stream))
