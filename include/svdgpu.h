@@ -219,6 +219,32 @@ int svdgpu_batch_download(svdgpu_t *h, svdgpu_batch_t *b, int *num_row, long lon
                           int *row_ptr, float *label, unsigned *index, float *value,
                           int *blk_row_off);
 
+/* ---- ranking a fixed item set for many users (SVDFeatureRanker) ---------- */
+/* The reference's ranker (base.h:597-813) reads a TAGGED instance stream: the label field of a row
+ * holds a svdranker_tag (apex_svd.h:115-152): 0 ITEM (item + global features of the next candidate),
+ * 2 USER (user features; opens a user section), 1 POS / -1 BAN (candidate positions, in the
+ * user-feature field), 3 SPEC (candidate position in the user-feature field + extra item / global
+ * features scored for this user only), 4 PROCESS (rank now).  Every PROCESS row appends to the
+ * result: top_k > 0: the positions of the top_k candidates by score; top_k = 0: the rank position
+ * of every POS candidate, in the order they were given.  Equal scores: lower position first (the
+ * reference's std::sort leaves it unspecified).  The model is the one in the handle
+ * (svdgpu_upload_model); side features (svdgpu_set_side_features) apply as in base.h:703-707,735-738.
+ *
+ * replaces: SVDFeatureRanker::init_ranker (base.h:668-688; top_k is its "top_k" parameter) */
+int svdgpu_rank_init(svdgpu_t *h, int num_item_set, int top_k);
+/* replaces: for each row ISVDRanker::process(result, Elem) (base.h:802-804; the loop of
+ * svd_feature_infer.cpp:352-360).  The stream may be cut anywhere between calls; sections closed by
+ * a PROCESS row inside the call are ranked together on the device.  *num_result receives the
+ * number of results; if they do not fit result_cap the call fails and keeps them for the next call. */
+int svdgpu_rank_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label, const unsigned *index,
+                    const float *value, int *result, long long result_cap, long long *num_result);
+/* replaces: for each block ISVDRanker::process(result, SVDPlusBlock) (base.h:805-819): a DEFAULT or
+ * START block's feedback list becomes the implicit-feedback part of the following USER rows. */
+int svdgpu_rank_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
+                       const int *blk_tag, const unsigned *fb_index, const float *fb_value,
+                       const int *row_ptr, const float *label, const unsigned *index, const float *value,
+                       int *result, long long result_cap, long long *num_result);
+
 /* ---- synchronisation, timing, introspection ---------------------------- */
 /* wait for all queued work; reports device-side input errors (index out of
  * bound -- the reference's assert_true at base.h:320,327,343) */

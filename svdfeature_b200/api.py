@@ -77,6 +77,9 @@ SVDGPU_SYMBOLS = {
     "svdgpu_batch_update": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "svdgpu_batch_predict": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "svdgpu_batch_destroy": (None, [_vp, _vp]),
+    "svdgpu_rank_init": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "svdgpu_rank_csr": (C.c_int, [_vp, C.c_int] + [_vp] * 5 + [C.c_longlong, C.POINTER(C.c_longlong)]),
+    "svdgpu_rank_ugroup": (C.c_int, [_vp, C.c_int] + [_vp] * 10 + [C.c_longlong, C.POINTER(C.c_longlong)]),
     "svdgpu_sync": (C.c_int, [_vp]),
     "svdgpu_timer_start": (C.c_int, [_vp]),
     "svdgpu_timer_stop": (C.c_int, [_vp, _f32p]),
@@ -348,6 +351,26 @@ class SvdGpu:
         return bro, rp, lab, idx, val
 
     # sync / timing / introspection
+    # ranking (SVDFeatureRanker)
+    def rank_init(self, num_item_set, top_k=0):
+        self._ck(self.lib.svdgpu_rank_init(self.h, int(num_item_set), int(top_k)))
+
+    def rank(self, stream, kind="csr", cap=1 << 20):
+        """Feed a tagged ranker stream (CSR arrays, or the user-grouped tuple with kind="ug"); returns the
+        results of the sections closed inside it."""
+        out = np.empty(cap, np.int32)
+        n = C.c_longlong(0)
+        if kind == "csr":
+            row_ptr, label, index, value = stream
+            self._ck(self.lib.svdgpu_rank_csr(self.h, len(label), _ptr(row_ptr), _ptr(label), _ptr(index), _ptr(value),
+                                              _ptr(out), cap, C.byref(n)))
+        else:
+            bro, bfo, tag, fbi, fbv, row_ptr, label, index, value = stream
+            self._ck(self.lib.svdgpu_rank_ugroup(self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag), _ptr(fbi),
+                                                 _ptr(fbv), _ptr(row_ptr), _ptr(label), _ptr(index), _ptr(value),
+                                                 _ptr(out), cap, C.byref(n)))
+        return out[: n.value].copy()
+
     def sync(self):
         self._ck(self.lib.svdgpu_sync(self.h))
 
@@ -404,6 +427,13 @@ def load_trainer_library():
             "svdtr_load_model": (C.c_int, [vp, C.c_char_p]),
             "svdtr_sync": (None, [vp]),
             "svdtr_gpu_handle": (vp, [vp]),
+            # ISVDRanker behind the same shim (trainer_cabi.cpp)
+            "svdrk_create_from_model": (vp, [C.c_char_p]),
+            "svdrk_destroy": (None, [vp]),
+            "svdrk_set_param": (None, [vp, C.c_char_p, C.c_char_p]),
+            "svdrk_init_ranker": (None, [vp, C.c_int]),
+            "svdrk_rank_csr": (C.c_long, [vp, C.c_int] + [vp] * 5 + [C.c_long]),
+            "svdrk_rank_ugroup": (C.c_long, [vp, C.c_int] + [vp] * 10 + [C.c_long]),
         }
         for base in ("svdtr_update_csr", "svdtr_update_csr_bulk"):
             sig[base] = (None, [vp, C.c_int] + [vp] * 4)
@@ -492,6 +522,43 @@ class GpuTrainer:
     def close(self):
         if getattr(self, "h", None):
             self.lib.svdtr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GpuRanker:
+    """ISVDRanker on the GPU (GpuSVDRanker), driven row by row like svd_feature_infer.cpp:349-371:
+    create_svd_ranker(type of the model file) -> load_model -> set_param -> init_ranker -> process."""
+
+    def __init__(self, model_path, num_item_set, params=None):
+        self.lib = load_trainer_library()
+        self.h = self.lib.svdrk_create_from_model(model_path.encode())
+        if not self.h:
+            raise SvdGpuError("can not open model file %s" % model_path)
+        for k, v in (params or {}).items():
+            self.lib.svdrk_set_param(self.h, str(k).encode(), str(v).encode())
+        self.lib.svdrk_init_ranker(self.h, int(num_item_set))
+
+    def rank(self, stream, kind="csr", cap=1 << 20):
+        out = np.empty(cap, np.int32)
+        if kind == "csr":
+            row_ptr, label, index, value = stream
+            n = self.lib.svdrk_rank_csr(self.h, len(label), _ptr(row_ptr), _ptr(label), _ptr(index), _ptr(value),
+                                        _ptr(out), cap)
+        else:
+            bro, bfo, tag, fbi, fbv, row_ptr, label, index, value = stream
+            n = self.lib.svdrk_rank_ugroup(self.h, len(bro) - 1, _ptr(bro), _ptr(bfo), _ptr(tag), _ptr(fbi), _ptr(fbv),
+                                           _ptr(row_ptr), _ptr(label), _ptr(index), _ptr(value), _ptr(out), cap)
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            self.lib.svdrk_destroy(self.h)
             self.h = None
 
     def __del__(self):

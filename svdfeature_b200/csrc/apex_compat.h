@@ -16,7 +16,7 @@
 //   apex_svd::SVDPlusBlock                apex_svd_data.h:376-466
 //   apex_svd::svd_type / SVDTypeParam     apex_svd_model.h:50-57, 242-287
 //   apex_svd::ISVDTrainer                 apex_svd.h:33-107
-//   apex_svd::ISVDRanker                  apex_svd.h:160-197
+//   apex_svd::svdranker_tag / ISVDRanker  apex_svd.h:115-152, 160-197
 //   apex_svd::create_svd_trainer/_ranker  apex_svd.h:212,222
 //   apex_utils::error / assert_true       apex-utils/apex_utils.h:47-58
 //
@@ -162,8 +162,17 @@ class ISVDTrainer {
   virtual ~ISVDTrainer() {}
 };
 
-// Ranking utility interface (apex_svd.h:160-197); declared so that the factory pair the
-// reference's drivers link against is complete.  The GPU build provides no ranker.
+// Tags of the ranker's input rows, carried in the label field (apex_svd.h:115-152).
+namespace svdranker_tag {
+const int ITEM_TAG = 0;
+const int USER_TAG = 2;
+const int POS_SAMPLE = 1;
+const int BAN_SAMPLE = -1;
+const int SPEC_SAMPLE = 3;
+const int PROCESS_TAG = 4;
+}  // namespace svdranker_tag
+
+// Ranking utility interface (apex_svd.h:160-197); implemented by GpuSVDRanker (gpu_trainer.cpp).
 class ISVDRanker {
  public:
   virtual void load_model(FILE *fi) = 0;

@@ -528,11 +528,68 @@ ISVDTrainer *create_svd_trainer(SVDTypeParam mtype) {
   return new GpuSVDFeature(mtype);
 }
 
-// apex_svd.cpp:44-46.  SVDFeatureRanker (base.h:597-813) is inference-side dense scoring,
-// outside the SGD hot path: svd_feature_infer links, and says so if a ranker is requested.
+// SVDFeatureRanker (base.h:597-813) on the GPU: the model, side features and device handle are the
+// trainer's; every row goes straight to the C ABI's stream state machine (svdgpu_rank_csr), which
+// ranks a user section on the device when its PROCESS row arrives.
+class GpuSVDRanker : public ISVDRanker {
+ public:
+  explicit GpuSVDRanker(const SVDTypeParam &mtype) : tr_(mtype), mtype_(mtype) {}
+  virtual void load_model(FILE *fi) { tr_.load_model(fi); }  // base.h:662-664
+  virtual void set_param(const char *name, const char *val) {  // base.h:656-660 (+ the gpu: keys)
+    if (!strcmp(name, "top_k")) top_k_ = atoi(val);
+    if (!strcmp(name, "feature_user") || !strcmp(name, "feature_item") || !strncmp(name, "gpu:", 4))
+      tr_.set_param(name, val);
+  }
+  virtual void init_ranker(int num_item_set) {  // base.h:668-688
+    tr_.init_trainer();
+    check(tr_.handle(), svdgpu_rank_init(tr_.handle(), num_item_set, top_k_));
+  }
+  virtual void process(std::vector<int> &result, const SVDFeatureCSR::Elem &e) {  // base.h:802-804
+    CsrStage one;
+    one.push(e);
+    note(e);
+    collect(result, svdgpu_rank_csr(tr_.handle(), 1, one.row_ptr.data(), one.label.data(), one.index.data(),
+                                    one.value.data(), buf(), (long long)buf_.size(), &n_));
+  }
+  virtual void process(std::vector<int> &result, const SVDPlusBlock &b) {  // base.h:805-819
+    CsrStage rows;
+    for (int r = 0; r < b.data.num_row; ++r) {
+      rows.push(b.data[r]);
+      note(b.data[r]);
+    }
+    const int bro[2] = {0, rows.num_row()}, bfo[2] = {0, b.num_ufeedback}, tag[1] = {b.extend_tag};
+    collect(result, svdgpu_rank_ugroup(tr_.handle(), 1, bro, bfo, tag, b.index_ufeedback, b.value_ufeedback,
+                                       rows.row_ptr.data(), rows.label.data(), rows.index.data(), rows.value.data(),
+                                       buf(), (long long)buf_.size(), &n_));
+  }
+
+ private:
+  // results of one call never exceed top_k per PROCESS row or the POS entries seen since the last USER row
+  void note(const SVDFeatureCSR::Elem &e) {
+    const int tag = (int)e.label;
+    if (tag == svdranker_tag::USER_TAG) pending_ = 0;
+    if (tag == svdranker_tag::POS_SAMPLE) pending_ += e.num_ufactor;
+    if (tag == svdranker_tag::PROCESS_TAG) need_ += top_k_ > 0 ? top_k_ : pending_;
+  }
+  int *buf() {
+    if (buf_.size() < (size_t)need_ + 16) buf_.resize((size_t)need_ + 16);
+    need_ = 0;
+    return buf_.data();
+  }
+  void collect(std::vector<int> &result, int rc) {
+    check(tr_.handle(), rc);
+    result.insert(result.end(), buf_.begin(), buf_.begin() + n_);
+  }
+  GpuSVDFeature tr_;
+  SVDTypeParam mtype_;
+  int top_k_ = 0, pending_ = 0, need_ = 0;
+  long long n_ = 0;
+  std::vector<int> buf_;
+};
+
+// apex_svd.cpp:44-46
 ISVDRanker *create_svd_ranker(SVDTypeParam mtype) {
-  apex_utils::error("GPU build: SVDFeatureRanker is not provided (use the reference's svd_feature_infer for ranking)");
-  return NULL;
+  return new GpuSVDRanker(mtype);
 }
 
 }  // namespace apex_svd

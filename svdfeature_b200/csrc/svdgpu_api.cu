@@ -461,6 +461,7 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaSetDevice(h->device);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  rank_free(h);
   cudaFree(h->dm.W);
   cudaFree(h->dm.bias);
   cudaFree(h->dm.g_bias);

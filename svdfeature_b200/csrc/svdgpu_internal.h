@@ -56,6 +56,8 @@ struct Geometry {
 };
 }  // namespace svdk
 
+struct svdgpu_rank_state;  // svdgpu_rank.cu
+
 struct svdgpu {
   svdgpu_shape shape;
   svdgpu_hparams hp;
@@ -107,6 +109,8 @@ struct svdgpu {
     std::vector<float> val;
     bool on() const { return rp.size() > 1; }
   } side_u, side_i;
+  // SVDFeatureRanker state (svdgpu_rank_init)
+  svdgpu_rank_state *rank = nullptr;
   // multi-GPU exchange
   svdk::DeltaPlan plan;
   float *d_snap = nullptr, *d_delta = nullptr;
@@ -158,6 +162,7 @@ int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1
 int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
                   bool train, bool ordered, float *pred);
 int launch_delta(svdgpu *h, int mode, float scale);
+void rank_free(svdgpu *h);
 int launch_svdpp(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0, int u1, int warps,
                  const unsigned char **kind_out);
 }  // namespace svdk
