@@ -196,20 +196,23 @@ void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b);
 /* ---- pairwise-rank sample generation on the device ----------------------- */
 /* PairwiseRankGenerator's parameters (apex_svd_data.cpp:967-989), same names and defaults. */
 typedef struct {
-  int rank_sample_method;    /* 0: positives vs negatives, label 1; 10: same, label = p.label - n.label.
-                                Method 1 (label-gap pairs) is not provided on the device.       */
+  int rank_sample_method;    /* 0: positives vs negatives (sample_posneg); 1: every row against one random row
+                                of its block whose label differs by more than rank_sample_gap (sample_cmp).
+                                +10: label = p.label - n.label instead of 1 (genpair's second branch; the
+                                reference's own switch rejects 10/11, apex_svd_data.cpp:1007-1011)        */
   int rank_sample_num;       /* pairs per block; <= 0: one per negative row (reference: -1)     */
   int rank_sample_max;       /* cap on pairs per block; <= 0: none (reference: INT_MAX)         */
   int rank_sample_pointwise; /* emit (p, label 1) and (n, label 0) instead of the merged pair   */
   float pos_sample_lowerb;   /* reference default 0.8  */
   float neg_sample_upperb;   /* reference default 1e-6 */
+  float rank_sample_gap;     /* method 1 only; reference default 0.0001, must be > 0 */
   unsigned long long seed;   /* change it every round: the reference reshuffles on every pass   */
 } svdgpu_pair_params;
 /* From a resident user-grouped batch of rated rows make the resident batch of pair rows the
  * reference's host sampler would feed the trainer (same blocks and feedback lists, rows replaced).
  * Train on it with svdgpu_batch_update; free it with svdgpu_batch_destroy.
- * replaces: PairwiseRankGenerator::next -> sample_posneg / genpair / merge
- * (apex_svd_data.cpp:828-915, 946-965, 1001-1018); the rand()-driven shuffles become keyed
+ * replaces: PairwiseRankGenerator::next -> sample_posneg / sample_cmp / genpair / merge
+ * (apex_svd_data.cpp:828-965, 1001-1018); the rand()-driven shuffles become keyed
  * permutations, so parity with the host sampler is structural, not bit-level. */
 int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const svdgpu_pair_params *params,
                               svdgpu_batch_t **out);

@@ -44,7 +44,7 @@ class HParams(C.Structure):
 class PairParams(C.Structure):
     _fields_ = [("rank_sample_method", C.c_int), ("rank_sample_num", C.c_int), ("rank_sample_max", C.c_int),
                 ("rank_sample_pointwise", C.c_int), ("pos_sample_lowerb", C.c_float),
-                ("neg_sample_upperb", C.c_float), ("seed", C.c_ulonglong)]
+                ("neg_sample_upperb", C.c_float), ("rank_sample_gap", C.c_float), ("seed", C.c_ulonglong)]
 
 
 # every symbol include/svdgpu.h declares: (restype, argtypes)
@@ -326,8 +326,8 @@ class SvdGpu:
 
     # pairwise-rank samples on the device
     def batch_sample_pairs(self, batch, seed=0, method=0, num=-1, maxn=-1, pointwise=0, pos_lowerb=0.8,
-                           neg_upperb=1e-6):
-        pp = PairParams(method, num, maxn, pointwise, pos_lowerb, neg_upperb, seed)
+                           neg_upperb=1e-6, gap=1e-4):
+        pp = PairParams(method, num, maxn, pointwise, pos_lowerb, neg_upperb, gap, seed)
         out = _vp()
         self._ck(self.lib.svdgpu_batch_sample_pairs(self.h, batch.h, C.byref(pp), C.byref(out)))
         n, nv = C.c_int(), C.c_longlong()

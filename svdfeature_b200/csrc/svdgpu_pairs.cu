@@ -8,6 +8,12 @@
 // Once the SGD kernels run at GB/s speed that host loop is the bottleneck, so here the pairs are
 // generated from a user-grouped batch resident in HBM into another resident batch:
 //
+//   rank_sample_method 1 (sample_cmp, :920-944: every row pairs with one random row of the same
+//   block whose label differs by more than rank_sample_gap):
+//   (segmented sort) the rows of every block by label
+//   k_pair_cmp     one warp per block: per row two binary searches in the sorted labels give the
+//                  eligible partners, one is drawn; a scan compacts the pairs
+//   rank_sample_method 0 (sample_posneg):
 //   k_pair_split   one warp per block: stable compaction of the block's positive / negative rows
 //   (scan)         pair rows per block -> first pair row of every block
 //   k_pair_shape   one thread per pair row: pick (p, n), count the merged features
@@ -22,6 +28,7 @@
 #include "svdgpu_internal.h"
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 using namespace svdk;
 
@@ -29,7 +36,8 @@ namespace {
 
 struct PairCfg {
   int pointwise, label_diff, sample_num, sample_max;
-  float lowerb, upperb;
+  int explicit_pairs;  // method 1: pair row s is (pos_list[s], neg_list[s]) itself
+  float lowerb, upperb, gap;
   unsigned long long seed;
 };
 
@@ -89,6 +97,65 @@ __global__ void k_pair_split(const float *label, const int *blk_row_off, int num
   }
 }
 
+// ---- sample_cmp (:920-944): for every row (visited in a keyed pseudo-random order, the
+// reference shuffles) count the rows of the block with label < label - gap ("left") and with
+// label >= (label - gap) + 2*gap ("right" .. end) in the label-sorted block, draw one of them;
+// a lower-labelled partner makes this row the positive of the pair, a higher-labelled one the
+// negative.  has[slot] = a partner exists; pp / nn = the pair.
+__global__ void k_pair_cmp(const float *label, const int *blk_row_off, int num_block, const float *sorted_label,
+                           const int *sorted_row, PairCfg cfg, int *has, int *pp, int *nn) {
+  const int b = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (b >= num_block) return;
+  const int r0 = blk_row_off[b], n = blk_row_off[b + 1] - r0;
+  const float *sl = sorted_label + r0;
+  const unsigned long long key = cfg.seed * 0x100000001b3ULL + (unsigned long long)b;
+  auto lower_bound = [&](float x) {  // first position whose label is not < x
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sl[mid] < x) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  for (int t = lane; t < n; t += 32) {
+    const int r = r0 + (int)perm_at((unsigned)t, (unsigned)n, key);  // the row visited t-th
+    const float lo_lab = __fsub_rn(label[r], cfg.gap);
+    const int left = lower_bound(lo_lab);
+    const int right = lower_bound(__fadd_rn(lo_lab, __fmul_rn(cfg.gap, 2.0f)));
+    const unsigned rng = (unsigned)(left + n - right);
+    int ok = 0, p = 0, q = 0;
+    if (rng > 0) {
+      const unsigned idx = (unsigned)(mix64(key ^ (0x9e3779b97f4a7c15ULL * (unsigned long long)(t + 1))) % rng);
+      ok = 1;
+      if (idx < (unsigned)left) {
+        p = r;
+        q = sorted_row[r0 + idx];
+      } else {
+        p = sorted_row[r0 + right + (idx - left)];
+        q = r;
+      }
+    }
+    has[r0 + t] = ok;
+    pp[r0 + t] = p;
+    nn[r0 + t] = q;
+  }
+}
+// compact the pairs (slot -> pair row at[slot]) and derive every block's first pair row
+__global__ void k_pair_compact(const int *has, const int *at, const int *pp, const int *nn, int nrow, int *out_p,
+                               int *out_n, const int *blk_row_off, int num_block, int mult, int *out_off) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nrow && has[t]) {
+    out_p[at[t]] = pp[t];
+    out_n[at[t]] = nn[t];
+  }
+  if (t <= num_block) out_off[t] = mult * at[blk_row_off[t]];  // at[] has nrow + 1 entries
+}
+__global__ void k_iota(int *v, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) v[t] = t;
+}
+
 struct RowView {
   int g0, u0, i0, i1;  // segment bounds of a source row
 };
@@ -144,13 +211,21 @@ struct Pick {
 __device__ __forceinline__ Pick pick(long long s, const int *out_off, int num_block, const int *blk_row_off,
                                      const int *pos_list, const int *neg_list, const int *npos, const int *nneg,
                                      const PairCfg &cfg) {
+  Pick k;
+  if (cfg.explicit_pairs) {  // method 1: the pairs were drawn by k_pair_cmp
+    const long long pi = cfg.pointwise ? (s >> 1) : s;
+    k.b = 0;
+    k.half = cfg.pointwise ? (int)(s & 1) : 0;
+    k.p = pos_list[pi];
+    k.n = neg_list[pi];
+    return k;
+  }
   int lo = 0, hi = num_block;  // last block whose first pair row is <= s
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (out_off[mid] <= s) lo = mid;
     else hi = mid;
   }
-  Pick k;
   k.b = lo;
   const long long i = s - out_off[lo];
   const long long pi = cfg.pointwise ? (i >> 1) : i;
@@ -241,10 +316,14 @@ extern "C" int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const
   if (!src->ugroup) return fail(h, "sample_pairs: the source batch must be user grouped (svdgpu_batch_set_ugroup)");
   if (src->num_unit != src->num_block) return fail(h, "sample_pairs: START/MIDDLE/END blocks are not supported");
   if (src->has_value2) return fail(h, "sample_pairs: side features are not supported");
-  if (pp->rank_sample_method != 0 && pp->rank_sample_method != 10)
-    return fail(h, "sample_pairs: rank_sample_method %d is not provided on the device (0 / 10: positive vs negative)",
-                pp->rank_sample_method);
+  const int method = pp->rank_sample_method % 10;
+  if ((method != 0 && method != 1) || pp->rank_sample_method < 0 || pp->rank_sample_method > 11)
+    return fail(h, "unkown rank sample method\n");  // apex_svd_data.cpp:1010
+  if (method == 1 && !(pp->rank_sample_gap > 0.0f))
+    return fail(h, "must set rank_sample_gap to a value bigger than 0");  // apex_svd_data.cpp:994
   PairCfg cfg;
+  cfg.explicit_pairs = method == 1;
+  cfg.gap = pp->rank_sample_gap;
   cfg.pointwise = pp->rank_sample_pointwise != 0;
   cfg.label_diff = pp->rank_sample_method / 10 != 0;
   cfg.sample_num = pp->rank_sample_num;
@@ -257,7 +336,7 @@ extern "C" int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const
   const float *label = (const float *)src->d_label.p, *val = (const float *)src->d_value.p;
   const unsigned *idx = (const unsigned *)src->d_index.p;
 
-  DevBuf pos, neg, npos, nneg, orow, ooff, cnt;
+  DevBuf pos, neg, npos, nneg, orow, ooff, cnt, slab, srow, rowid, has, at, cp, cn, sort_tmp;
   int rc = 0;
   svdgpu_batch *b = nullptr;
   long long total = 0, nnz = 0;
@@ -267,13 +346,45 @@ extern "C" int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const
               dev_alloc(h, orow, (size_t)(nb + 1) * 4) | dev_alloc(h, ooff, (size_t)(nb + 2) * 4)))
       break;
     cudaMemsetAsync(orow.p, 0, (size_t)(nb + 1) * 4, h->stream);
-    if (nb > 0) {
-      k_pair_split<<<(int)(((long long)nb * 32 + 255) / 256), 256, 0, h->stream>>>(
-          label, bro, nb, cfg, (int *)pos.p, (int *)neg.p, (int *)npos.p, (int *)nneg.p, (int *)orow.p);
+    if (cfg.explicit_pairs) {
+      // sample_cmp: sort every block's rows by label, draw one partner per row, compact
+      const size_t rbytes = (size_t)std::max(nrow, 1) * 4;
+      if ((rc = dev_alloc(h, slab, rbytes) | dev_alloc(h, srow, rbytes) | dev_alloc(h, rowid, rbytes) |
+                dev_alloc(h, has, rbytes + 4) | dev_alloc(h, at, rbytes + 4) | dev_alloc(h, cp, rbytes) |
+                dev_alloc(h, cn, rbytes)))
+        break;
+      cudaMemsetAsync(has.p, 0, rbytes + 4, h->stream);
+      if (nrow > 0 && nb > 0) {
+        k_iota<<<(nrow + 255) / 256, 256, 0, h->stream>>>((int *)rowid.p, nrow);
+        size_t tb = 0;
+        cudaError_t e = cub::DeviceSegmentedSort::SortPairs(nullptr, tb, label, (float *)slab.p, (const int *)rowid.p,
+                                                            (int *)srow.p, nrow, nb, bro, bro + 1, h->stream);
+        if (e == cudaSuccess && !(rc = dev_alloc(h, sort_tmp, tb + 16)))
+          e = cub::DeviceSegmentedSort::SortPairs(sort_tmp.p, tb, label, (float *)slab.p, (const int *)rowid.p,
+                                                  (int *)srow.p, nrow, nb, bro, bro + 1, h->stream);
+        if (rc) break;
+        if (e != cudaSuccess) { rc = fail(h, "sample_pairs: segmented sort failed: %s", cudaGetErrorString(e)); break; }
+        k_pair_cmp<<<(int)(((long long)nb * 32 + 255) / 256), 256, 0, h->stream>>>(
+            label, bro, nb, (const float *)slab.p, (const int *)srow.p, cfg, (int *)has.p, (int *)pos.p, (int *)neg.p);
+        h->n_launch += 3;
+      }
+      if ((rc = scan_int<false>(h, (const int *)has.p, (int *)at.p, (long long)nrow + 1))) break;
+      const int work = std::max(nrow, nb + 1);
+      k_pair_compact<<<(work + 255) / 256, 256, 0, h->stream>>>((const int *)has.p, (const int *)at.p, (const int *)pos.p,
+                                                               (const int *)neg.p, nrow, (int *)cp.p, (int *)cn.p, bro, nb,
+                                                               cfg.pointwise ? 2 : 1, (int *)ooff.p);
       h->n_launch++;
+      std::swap(pos, cp);  // k_pair_rows reads the compacted pairs through pos / neg
+      std::swap(neg, cn);
+    } else {
+      if (nb > 0) {
+        k_pair_split<<<(int)(((long long)nb * 32 + 255) / 256), 256, 0, h->stream>>>(
+            label, bro, nb, cfg, (int *)pos.p, (int *)neg.p, (int *)npos.p, (int *)nneg.p, (int *)orow.p);
+        h->n_launch++;
+      }
+      // out_off[b] = first pair row of block b; out_off[nb] = total (orow[nb] is 0)
+      if ((rc = scan_int<false>(h, (const int *)orow.p, (int *)ooff.p, nb + 1))) break;
     }
-    // out_off[b] = first pair row of block b; out_off[nb] = total (orow[nb] is 0)
-    if ((rc = scan_int<false>(h, (const int *)orow.p, (int *)ooff.p, nb + 1))) break;
     int tot32 = 0;
     if (cudaMemcpy(&tot32, (const int *)ooff.p + nb, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(h, "sample_pairs: D2H failed"); break; }
     total = tot32;
@@ -326,7 +437,7 @@ extern "C" int svdgpu_batch_sample_pairs(svdgpu_t *h, svdgpu_batch_t *src, const
     if (rc) break;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(h, "sample_pairs: kernel failed");
   } while (0);
-  DevBuf *tmp[] = {&pos, &neg, &npos, &nneg, &orow, &ooff, &cnt};
+  DevBuf *tmp[] = {&pos, &neg, &npos, &nneg, &orow, &ooff, &cnt, &slab, &srow, &rowid, &has, &at, &cp, &cn, &sort_tmp};
   for (DevBuf *t : tmp)
     if (t->p) cudaFree(t->p);
   if (rc) {

@@ -114,8 +114,53 @@ def test_pair_count_options_and_pointwise(native):
     assert np.array_equal(lab, np.tile([1.0, 0.0], len(lab) // 2).astype(np.float32))  # (p, 1), (n, 0)
     bro, rp, lab, idx, val = g.batch_download(g.batch_sample_pairs(src, seed=1, method=10))
     assert np.all(lab == 1.0)  # p.label - n.label = 1 - 0
-    with pytest.raises(native.SvdGpuError, match="rank_sample_method"):
-        g.batch_sample_pairs(src, method=1)
+    with pytest.raises(native.SvdGpuError, match="unkown rank sample method"):  # apex_svd_data.cpp:1010
+        g.batch_sample_pairs(src, method=2)
+    with pytest.raises(native.SvdGpuError, match="rank_sample_gap"):  # apex_svd_data.cpp:994
+        g.batch_sample_pairs(src, method=1, gap=0.0)
+
+
+@pytest.mark.parametrize("with_globals", [False, True])
+def test_label_gap_pairs_have_the_reference_structure(native, with_globals):
+    """rank_sample_method = 1 (sample_cmp, apex_svd_data.cpp:920-944): every row of a block is paired with
+    one row of the same block whose label differs by more than rank_sample_gap; the higher-labelled
+    row is the positive.  A block yields one pair per row that has such a partner."""
+    nu, ni = 300, 500
+    csr, ug = _blocks(nu, ni, 11, with_globals)
+    g = native.SvdGpu(nu, ni, 16, num_global=6, num_ufeedback=1, no_user_bias=1, active_type=3, format_type=1)
+    g.set_hparams(learning_rate=0.01, base_score=0.0)
+    g.set_mode(native.MODE_HOGWILD)
+    src = g.batch_create(csr, ugroup=ug)
+    src_rows = _rows_of(csr)
+    f32 = lambda seg: [(x, np.float32(v)) for x, v in seg]
+    for method, gap in ((1, 1e-4), (11, 0.6)):
+        bro, rp, lab, idx, val = g.batch_download(g.batch_sample_pairs(src, seed=3, method=method, gap=gap))
+        out_rows = _rows_of((rp, lab, idx, val))
+        assert bro[0] == 0 and bro[-1] == len(out_rows)
+        seen_partner_sets = 0
+        for b in range(len(ug[0]) - 1):
+            rows = src_rows[ug[0][b]:ug[0][b + 1]]
+            labs = np.array([r[0] for r in rows], np.float32)
+            lo = labs - np.float32(gap)
+            hi = lo + np.float32(gap) * np.float32(2)
+            n_anchor = sum(int(((labs < lo[i]) | (labs >= hi[i])).any()) for i in range(len(rows)))
+            mine = out_rows[bro[b]:bro[b + 1]]
+            assert len(mine) == n_anchor, (b, len(mine), n_anchor)
+            for lab_o, og, ou, oi in mine:
+                cands = [(p, n) for p in rows for n in rows
+                         if p[0] - n[0] > gap * 0.999 and f32(_merge(p[3], n[3])) == f32(oi) and f32(_merge(p[1], n[1])) == f32(og)]
+                assert cands, (b, oi)
+                assert ou == [f for f in cands[0][0][2] if abs(f[1]) > 1e-6]
+                want = {np.float32(1.0)} if method == 1 else {np.float32(p[0]) - np.float32(n[0]) for p, n in cands}
+                assert np.float32(lab_o) in want
+                seen_partner_sets += 1
+        assert seen_partner_sets > 100
+    a = g.batch_download(g.batch_sample_pairs(src, seed=3, method=1))
+    b_ = g.batch_download(g.batch_sample_pairs(src, seed=3, method=1))
+    c = g.batch_download(g.batch_sample_pairs(src, seed=4, method=1))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b_)) and not np.array_equal(a[3], c[3])
+    pw = g.batch_download(g.batch_sample_pairs(src, seed=3, method=1, pointwise=1))
+    assert len(pw[2]) == 2 * len(a[2]) and np.array_equal(pw[2], np.tile([1.0, 0.0], len(a[2])).astype(np.float32))
 
 
 def test_training_on_device_pairs_learns_the_ranking(native):
