@@ -515,6 +515,8 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   if (!strcmp(name, "scatter_user")) h->scatter_user = v ? SCATTER_RED : SCATTER_STORE;
   else if (!strcmp(name, "scatter_item")) h->scatter_item = v ? SCATTER_RED : SCATTER_STORE;
   else if (!strcmp(name, "exact_dot")) h->exact_dot = v ? 1 : 0;
+  else if (!strcmp(name, "stream_tile")) h->stream_tile = (int)v;
+  else if (!strcmp(name, "rank_force_sort")) h->rank_force_sort = v ? 1 : 0;
   else if (!strcmp(name, "lanes")) {
     const int old = h->lanes_opt;
     h->lanes_opt = (int)v;
@@ -1072,6 +1074,7 @@ static DevCsr batch_csr(const svdgpu_batch *b) {
   c.ticket = b->has_ticket ? (const unsigned *)b->d_ticket.p : nullptr;
   c.val_base = 0;
   c.val_end = (int)b->num_val;
+  c.avg_nnz = b->num_row > 0 ? (float)((double)b->num_val / (double)b->num_row) : 0.0f;
   return c;
 }
 static DevUgroup batch_ug(const svdgpu_batch *b) {

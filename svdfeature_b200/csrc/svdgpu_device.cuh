@@ -80,6 +80,7 @@ struct DevCsr {
   const unsigned *ticket;  // exact mode: row version each feature waits for
   int val_base;
   int val_end;  // one past the last feature position the arrays hold (absolute)
+  float avg_nnz = 0.0f;  // features per row over the whole arrays, if the host knows it (tile sizing)
 };
 
 enum { SCATTER_STORE = 0, SCATTER_RED = 1 };

@@ -95,6 +95,7 @@ struct svdgpu {
   int ugroup_units = 0;  // option "ugroup_units": user units in flight in Hogwild user-group training (0 = auto: 64 with
                          // feedback lists -- more diverges, tools/hogwild_parity.py --svdpp -- else the occupancy limit)
   int l2_ahead = -1;   // option "l2_ahead": generic pass prefetches the next tile's rows into L2 (-1 auto)
+  int stream_tile = 0; // option "stream_tile": rows per tile of the generic pass (0 = auto: 64 / 32 / 16 / 8 by row width)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
   static constexpr int NSLOT = 3;
@@ -111,6 +112,7 @@ struct svdgpu {
   } side_u, side_i;
   // SVDFeatureRanker state (svdgpu_rank_init)
   svdgpu_rank_state *rank = nullptr;
+  int rank_force_sort = 0;  // option "rank_force_sort": top-k by the radix sort even for small top_k (testing)
   // multi-GPU exchange
   svdk::DeltaPlan plan;
   float *d_snap = nullptr, *d_delta = nullptr;

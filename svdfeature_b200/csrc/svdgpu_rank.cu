@@ -24,7 +24,8 @@
 //                  partial sums folded (l0+l2)+(l1+l3), then the k%4 tail, sse.h:88-97,289-317),
 //                  so scores -- and therefore ranks -- are bit-identical to the CPU's
 //   k_rank_pos     top_k = 0: one block per POS entry counts the candidates ranked before it
-//   k_rank_keys + cub::DeviceRadixSort   top_k > 0: one stable sort of (section, ~score) keys
+//   k_rank_select  0 < top_k <= 32: one block per section picks the best candidates one by one
+//   k_rank_keys + cub::DeviceRadixSort   larger top_k: one stable sort of (section, ~score) keys
 //
 // Equal scores: the reference's std::sort leaves their order unspecified; here (and in the
 // oracle) the lower item index comes first.  -0 and +0 compare equal, as they do for operator<.
@@ -288,6 +289,64 @@ __global__ void k_rank_pos(const Mark *pos, const float *score, int width, int *
   }
 }
 
+// top_k <= RANK_SELECT_MAX: one block per section picks its best candidates one after the other.
+// Pass t takes the best candidate that comes after pass t-1's pick in the order (score descending,
+// position ascending), so nothing is marked and the candidate row is only read (L2-resident).
+constexpr int RANK_SELECT_MAX = 32;
+__global__ void k_rank_select(const float *score, int width, int top_k, int *out) {
+  __shared__ float ws[32];
+  __shared__ int wi[32];
+  __shared__ float prev_s;
+  __shared__ int prev_i;
+  const float *row = score + (size_t)blockIdx.x * width;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int t = 0; t < top_k; ++t) {
+    const bool first = t == 0;
+    const float ps = first ? 0.0f : prev_s;
+    const int pi = first ? -1 : prev_i;
+    float bs = 0.0f;
+    int bi = -1;  // -1: nothing yet
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+      const float sc = row[i];
+      if (is_banned(sc)) continue;
+      if (!first && !(sc < ps || (sc == ps && i > pi))) continue;
+      if (bi < 0 || sc > bs) {  // (i ascends within a thread: an equal score never replaces an earlier one)
+        bs = sc;
+        bi = i;
+      }
+    }
+    auto better = [](float s1, int i1, float s2, int i2) {  // is (s1, i1) ranked before (s2, i2)?
+      if (i1 < 0) return false;
+      if (i2 < 0) return true;
+      return s1 > s2 || (s1 == s2 && i1 < i2);
+    };
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(os, oi, bs, bi)) {
+        bs = os;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      ws[warp] = bs;
+      wi[warp] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < nwarp; ++w)
+        if (better(ws[w], wi[w], bs, bi)) {
+          bs = ws[w];
+          bi = wi[w];
+        }
+      prev_s = bs;
+      prev_i = bi;
+      out[(size_t)blockIdx.x * top_k + t] = bi;
+    }
+    __syncthreads();
+  }
+}
+
 // sort keys: section-major, score descending, banned last; equal scores keep the index order
 __global__ void k_rank_keys(const float *score, long long n, int width, unsigned long long *key, int *val) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,7 +550,13 @@ int run_sections(svdgpu *h, int first, int n_sec, size_t pos0, size_t pos1, size
     h->n_launch++;
   }
   size_t n_out = 0;
-  if (s.top_k > 0) {
+  if (s.top_k > 0 && s.top_k <= RANK_SELECT_MAX && !h->rank_force_sort) {
+    n_out = (size_t)n_sec * s.top_k;
+    if (s.d_out.reserve(h, n_out)) return 1;
+    k_rank_select<<<(unsigned)n_sec, 256, 0, h->stream>>>(s.d_score.p, width, s.top_k, s.d_out.p);
+    CU(h, cudaGetLastError());
+    h->n_launch++;
+  } else if (s.top_k > 0) {
     n_out = (size_t)n_sec * s.top_k;
     if (s.d_key.reserve(h, cells) || s.d_key2.reserve(h, cells) || s.d_val.reserve(h, cells) ||
         s.d_val2.reserve(h, cells) || s.d_out.reserve(h, n_out))

@@ -22,7 +22,11 @@
 
 namespace svdk {
 
-constexpr int HW_TILE = 64;            // instances per tile (one tile belongs to ONE warp)
+constexpr int HW_TILE = 64;            // most instances per tile (one tile belongs to ONE warp); the launch picks
+                                       // 64, 32, 16 or 8 rows per tile so that a tile's index/value window fits
+                                       // HW_CAP entries (rows with ~10 features, configs[4]: 16 rows per tile --
+                                       // an unstaged tile reads its features from global memory on the critical
+                                       // path of every instance: 0.39 G inst/s there instead of ...)
 constexpr int HW_STAGES = 4;           // tiles in flight per warp
 constexpr int HW_CAP = 4 * HW_TILE;    // staged index/value entries per tile
 constexpr int HW_WARPS = 8;            // warps per CTA, every one a consumer with its own pipeline
@@ -49,14 +53,15 @@ template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN>
 __global__ void __launch_bounds__(HW_THREADS, 2)
 k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user,
          int scatter_item, float *pred_out, const unsigned *row_mask, const unsigned *any_left,
-         int *err_flag, int l2_ahead) {
+         int *err_flag, int l2_ahead, int tile_rows) {
   if (*any_left == 0u) return;  // pass 1 took every row
+  const int T = tile_rows;  // rows per tile: 64, 32, 16 or 8
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   HwWarp &sw = reinterpret_cast<HwWarp *>(smem_raw)[warp];
   float *dot_base = reinterpret_cast<float *>(smem_raw + sizeof(HwWarp) * HW_WARPS);
 
-  const int ntile = (row_end - row_begin + HW_TILE - 1) / HW_TILE;
+  const int ntile = (row_end - row_begin + T - 1) / T;
   const int wslot = blockIdx.x * HW_WARPS + warp;  // this warp's first tile
   const int wstride = gridDim.x * HW_WARPS;
   const int nlocal = ntile > wslot ? (ntile - wslot + wstride - 1) / wstride : 0;
@@ -82,19 +87,22 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
   // non-skipped tile and awaited exactly once, so the bits follow the barrier phases
   unsigned ph_a = 0, ph_b = 0;
   auto tile_of = [&](int j) { return wslot + j * wstride; };
-  // rows left by pass 1: one mask word per 32 rows, two per tile
-  auto skip_tile = [&](int j) -> bool {
-    const uint2 mk = *reinterpret_cast<const uint2 *>(row_mask + 2 * tile_of(j));
-    return (mk.x | mk.y) == 0u;
+  // rows left by pass 1: one mask bit per row (bit r - row_begin), T bits per tile
+  auto tile_mask = [&](int t) -> unsigned long long {
+    const long long bit0 = (long long)t * T;
+    const unsigned *w = row_mask + (bit0 >> 5);
+    if (T == 64) return (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+    return (unsigned long long)((w[0] >> (bit0 & 31)) & (T == 32 ? 0xffffffffu : ((1u << T) - 1u)));
   };
+  auto skip_tile = [&](int j) -> bool { return tile_mask(tile_of(j)) == 0ULL; };
   // phase A: row_ptr[3*r0 .. 3*(r0+nrow)] and label[r0 .. r0+nrow), 16-byte aligned windows
   auto issue_a = [&](int j) {
     if (j >= nlocal || skip_tile(j)) return;
     __syncwarp();  // every lane is done reading the stage being refilled
     if (lane == 0) {
       HwStage &st = sw.st[j % HW_STAGES];
-      const int r0 = row_begin + tile_of(j) * HW_TILE;
-      const int nrow = min(HW_TILE, row_end - r0);
+      const int r0 = row_begin + tile_of(j) * T;
+      const int nrow = min(T, row_end - r0);
       const int a_off = (3 * r0) & 3, l_off = r0 & 3;
       const unsigned bytesA = (unsigned)((a_off + 3 * nrow + 1 + 3) & ~3) * 4u;
       const unsigned bytesL = (unsigned)((l_off + nrow + 3) & ~3) * 4u;
@@ -109,8 +117,8 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
   };
   auto window = [&](int j) -> Win {
     const HwStage &st = sw.st[j % HW_STAGES];
-    const int r0 = row_begin + tile_of(j) * HW_TILE;
-    const int nrow = min(HW_TILE, row_end - r0);
+    const int r0 = row_begin + tile_of(j) * T;
+    const int nrow = min(T, row_end - r0);
     const int a_off = (3 * r0) & 3;
     Win w;
     w.v0 = st.rp[a_off] - csr.val_base;
@@ -156,15 +164,15 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
     if (skip_tile(j)) continue;
     const HwStage &st = sw.st[j % HW_STAGES];
     const int t = tile_of(j);
-    const int r0 = row_begin + t * HW_TILE;
-    const int nrow = min(HW_TILE, row_end - r0);
+    const int r0 = row_begin + t * T;
+    const int nrow = min(T, row_end - r0);
     const int *rp = st.rp + ((3 * r0) & 3);
     const float *lab = st.label + (r0 & 3);
     const Win w = window(j);  // A(j) and B(j) were awaited one tile ago
     const int sm_base = w.v0 - w.v_off + csr.val_base;  // absolute feature position held by idx[0]
     const int v_hi = w.v1 + csr.val_base;
 
-    const uint2 mk = *reinterpret_cast<const uint2 *>(row_mask + 2 * t);
+    const unsigned long long mk = tile_mask(t);
     const unsigned *idx = w.staged ? (st.idx - sm_base) : (csr.index - csr.val_base);
     const float *val = w.staged ? (st.val - sm_base) : (csr.value - csr.val_base);
     const float *val2 = csr.value2 ? csr.value2 - csr.val_base : nullptr;  // (not staged: side features only)
@@ -175,7 +183,7 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
     constexpr int L2_AHEAD = 2;
     auto l2_prefetch_row = [&](int q) {
       if (!l2_ahead || q >= nrow || !w.staged) return;
-      if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) return;
+      if (((mk >> q) & 1ULL) == 0ULL) return;
       const int rp0 = rp[3 * q], rp1 = rp[3 * q + 1], rp2 = rp[3 * q + 2], rp3 = rp[3 * q + 3];
       if (!(rp0 >= sm_base && rp0 <= rp1 && rp1 <= rp2 && rp2 <= rp3 && rp3 <= v_hi)) return;
       const int row_bytes = m.pitch * 4;
@@ -196,7 +204,7 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
     for (int a = 0; a < L2_AHEAD; ++a) l2_prefetch_row(gw + a * GPW);
     for (int q = gw; q < nrow; q += GPW) {
       l2_prefetch_row(q + L2_AHEAD * GPW);
-      if ((((q < 32 ? mk.x : mk.y) >> (q & 31)) & 1u) == 0u) continue;  // done by pass 1
+      if (((mk >> q) & 1ULL) == 0ULL) continue;  // done by pass 1
       if (!row_ok(rp[3 * q], rp[3 * q + 1], rp[3 * q + 2], rp[3 * q + 3], csr.val_base, csr.val_end)) {
         if (g.gl == 0) atomicCAS(err_flag, 0, ERR_ROW_PTR);
         continue;
@@ -212,7 +220,15 @@ k_stream(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatt
 
 template <int L, int V>
 static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
-  const long long ntile = ((long long)(r1 - r0) + HW_TILE - 1) / HW_TILE;
+  // rows per tile: the largest of 64 / 32 / 16 / 8 whose average feature window (+25 %) fits the stage
+  int tile_rows = h->stream_tile;
+  if (tile_rows != 64 && tile_rows != 32 && tile_rows != 16 && tile_rows != 8) {
+    const double avg = csr.avg_nnz > 0.0f ? (double)csr.avg_nnz
+                                          : (double)(csr.val_end - csr.val_base) / (double)std::max(1, r1 - r0);
+    tile_rows = 64;
+    while (tile_rows > 8 && tile_rows * avg * 1.25 > HW_CAP) tile_rows >>= 1;
+  }
+  const long long ntile = ((long long)(r1 - r0) + tile_rows - 1) / tile_rows;
   int grid = 1;
   // tile-ahead L2 prefetch of the gathered rows when the model cannot live in L2 (option "l2_ahead")
   const size_t model_bytes = h->rows * (size_t)h->dm.pitch * sizeof(float);
@@ -226,7 +242,7 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
     k<<<grid, HW_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
                                              h->scatter_item, pred, h->d_row_mask,               \
                                              h->d_row_mask + h->flag_for_generic, h->d_err,      \
-                                             l2_ahead);                                          \
+                                             l2_ahead, tile_rows);                               \
     h->n_launch++;                                                                               \
   }
   if (train) {

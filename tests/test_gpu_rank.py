@@ -83,7 +83,7 @@ def test_rank_side_features(native, top_k, tmp_path):
     assert np.array_equal(native.GpuRanker(path, skw["num_item_set"], rp).rank(stream), want)
 
 
-@pytest.mark.parametrize("top_k", [0, 10])
+@pytest.mark.parametrize("top_k", [0, 10, 40, -10])
 def test_rank_larger_set(native, top_k, tmp_path):
     """2 500 candidates x 400 users, k = 64 (one million scores): still bit-exact, and every top_k
     answer is a set of distinct, non-banned candidates."""
@@ -91,8 +91,11 @@ def test_rank_larger_set(native, top_k, tmp_path):
     path = _cases.rank_model(0, params, tmp_path)
     skw = dict(num_item_set=2500, num_sections=400, seed=9, max_pos=12, max_ban=40)
     stream = synth.rank_stream(num_user=3000, num_item=2000, **skw)
+    force_sort = top_k < 0  # small top_k normally takes the selection kernel: cover the sort path too
+    top_k = abs(top_k)
     want = COracleRanker(path, 2500, {"top_k": top_k}).rank(stream)
     g = _gpu_with_model(native, path, 0, params)
+    g.set_option("rank_force_sort", int(force_sort))
     g.rank_init(2500, top_k)
     got = g.rank(stream)
     assert np.array_equal(got, want)
