@@ -529,7 +529,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
     if (v < 1) return fail(h, "chunk_rows must be >= 1");
     h->chunk_rows = (int)std::min<long long>(v, 1LL << 28);
   } else if (!strcmp(name, "ctas_per_sm")) h->ctas_per_sm = (int)v;
-  else if (!strcmp(name, "pass1")) h->pass1 = (int)std::max<long long>(0, std::min<long long>(v, 2));
+  else if (!strcmp(name, "pass1")) h->pass1 = (int)std::max<long long>(0, std::min<long long>(v, 3));
   else if (!strcmp(name, "ring_depth")) h->ring_depth = (int)v;
   else if (!strcmp(name, "l2_ahead")) h->l2_ahead = (int)v;
   else if (!strcmp(name, "ugroup_units")) h->ugroup_units = (int)v;

@@ -84,10 +84,11 @@ struct svdgpu {
   float eval_scale = 1.0f;
   unsigned *d_row_mask = nullptr;  // Hogwild: rows the fast pass left to the generic pass (1 bit per row)
   size_t row_mask_cap = 0;
-  size_t flag_for_generic = 0;  // which of the two flag words gates the generic pass of this launch
-  size_t any_left_at = 0;  // index of the "pass 1 left something" word inside d_row_mask
-  int pass1 = 2;  // option "pass1": 0 sends every row through the generic pass, 1 first fast pass only,
-                  // 2 (default) first and second fast pass
+  size_t flag_for_generic = 0;  // which of the three flag words gates the generic pass of this launch
+  size_t any_left_at = 0;  // index of the LAST of the three "a fast pass left something" words inside d_row_mask
+  int pass1 = 3;  // option "pass1": 0 sends every row through the generic pass, 1 first fast pass only,
+                  // 2 first and second fast pass (rows with two item features), 3 (default) also the third
+                  // (basic rows with up to 16 global features)
 
   int svdpp_fast = 1;    // option "svdpp_fast": 0 keeps every user unit in k_ugroup
   unsigned char *d_unit_kind = nullptr;  // per unit of a launch: 1 = taken by k_svdpp
@@ -159,7 +160,7 @@ int grid_for(svdgpu *h, K kernel, int threads, long long work_items, int *grid, 
 // launchers (one translation unit each, so nvcc runs in parallel)
 int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred);
 int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred,
-              bool second);
+              int which, unsigned *flag_out, const unsigned *flag_gate);
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
 int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
                   bool train, bool ordered, float *pred);

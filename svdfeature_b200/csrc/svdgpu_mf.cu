@@ -25,6 +25,12 @@
 // EXACT_DOT the result is bit-identical to the generic routine; without it the dot uses the
 // shuffle-tree order and the "0 +" of prepare_tmp (base.h:357,372) is dropped (it can only
 // change the sign of a zero).
+//
+// NG > 0 (the third fast pass): rows (1..NG | 1 | 1) -- basic rows with a few global features, the
+// neighbourhood rows of configs[4] -- among the rows the earlier passes left.  Three staged tiles
+// per warp instead of two, so that the index/value window of the tile being computed is still
+// in shared memory: lane j of a group reads global feature j from it, fetches the 16-byte window
+// of g_bias holding its bias into the ring slot with the rows, and later updates that bias.
 #include "svdgpu_internal.h"
 
 namespace svdk {
@@ -41,29 +47,38 @@ constexpr int MF_CAP = MF_CAP_PER_ROW * MF_TILE;    // staged index/value entrie
 constexpr int MF_WARPS = MF_WARPS_PER_CTA;
 constexpr int MF_THREADS = MF_WARPS * 32;
 
-struct __align__(16) MfStage {
-  int rp[3 * MF_TILE + 8];
-  float label[MF_TILE + 4];
-  unsigned idx[MF_CAP + 8];
-  float val[MF_CAP + 8];
-};
-struct __align__(16) MfWarp {
-  MfStage st[MF_STAGES];
-  uint64_t barA[MF_STAGES], barB[MF_STAGES];
+// staged entries per tile / staged tiles per warp of a variant (NG = most global features per row it takes)
+template <int NG> struct MfCfg {
+  static constexpr int CAP = NG > 0 ? (NG + 2) * MF_TILE : MF_CAP;
+  static constexpr int STAGES = NG > 0 ? 3 : MF_STAGES;
 };
 
-template <int LANES, int VEC, int DEPTH, int NI>
+template <int CAP>
+struct __align__(16) MfStageT {
+  int rp[3 * MF_TILE + 8];
+  float label[MF_TILE + 4];
+  unsigned idx[CAP + 8];
+  float val[CAP + 8];
+};
+template <int CAP, int STAGES>
+struct __align__(16) MfWarpT {
+  MfStageT<CAP> st[STAGES];
+  uint64_t barA[STAGES], barB[STAGES];
+};
+
+template <int LANES, int VEC, int DEPTH, int NI, int NG>
 struct MfRing {
   static constexpr int GPW = 32 / LANES;
   static constexpr int NCH = LANES * VEC;
-  // per (iteration slot, group): user row | NI item rows | user-bias window | NI item-bias windows
-  static constexpr int SLOT_F4 = (1 + NI) * NCH + (1 + NI);
+  // per (iteration slot, group): user row | NI item rows | user-bias window | NI item-bias windows |
+  // NG global-bias windows
+  static constexpr int SLOT_F4 = (1 + NI) * NCH + (1 + NI) + NG;
   static constexpr size_t BYTES = (size_t)DEPTH * GPW * SLOT_F4 * sizeof(float4);
 };
 
-template <int LANES, int VEC, bool EXACT_DOT, int DEPTH, int NI>
+template <int LANES, int VEC, bool EXACT_DOT, int DEPTH, int NI, int NG>
 constexpr size_t mf_smem_bytes() {
-  return (sizeof(MfWarp) + MfRing<LANES, VEC, DEPTH, NI>::BYTES) * MF_WARPS +
+  return (sizeof(MfWarpT<MfCfg<NG>::CAP, MfCfg<NG>::STAGES>) + MfRing<LANES, VEC, DEPTH, NI, NG>::BYTES) * MF_WARPS +
          (EXACT_DOT ? sizeof(float) * MF_WARPS * (32 / LANES) * Group<LANES, VEC>::DOT_FLOATS : 0);
 }
 
@@ -83,6 +98,8 @@ struct MfDec {
   unsigned urow, irow;  // slab rows of the user / item feature (valid if the row is taken)
   unsigned irow2;       // NI = 2: slab row of the second item feature, 0xffffffff if the row has one
   float uval, ival, ival2, lab;
+  unsigned gp;          // NG > 0: (position of the row's first global feature in the staged window << 8) | count
+  int stage;            // warp-uniform: the stage that holds this tile's index/value window
   unsigned take;        // warp-uniform: bit q = the fast pass takes row q
   unsigned left;        // warp-uniform: bit q = row q exists and is left to the generic pass
   bool all_one;         // warp-uniform: every taken row has uval = ival = "one"
@@ -92,12 +109,20 @@ struct MfDec {
 // NI = 1: rows (0 | 1 | 1), every row is a candidate.  NI = 2 (the second fast pass): rows
 // (0 | 1 | 1..2) -- the pairwise-rank shape of configs[3], two distinct item features -- among the
 // rows the first pass left (`gate` = its "something left" flag: nothing left, nothing to do).
-template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB, int NI>
+// NG > 0 (the third fast pass): rows (1..NG | 1 | 1), strictly ascending global indices, among the
+// rows the earlier passes left.
+template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB, int NI, int NG>
 __global__ void __launch_bounds__(MF_THREADS, MINB)
 k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user, int scatter_item,
      float *pred_out, unsigned *row_mask, unsigned *any_left, const unsigned *gate) {
-  if (NI == 2 && *gate == 0u) return;
-  using Ring = MfRing<LANES, VEC, DEPTH, NI>;
+  constexpr bool FOLLOW = NI == 2 || NG > 0;  // a pass over what earlier passes left
+  static_assert(NG <= LANES, "lane j of a group handles global feature j");
+  static_assert(NG == 0 || NI == 1, "the global-feature pass takes one item feature");
+  if (FOLLOW && *gate == 0u) return;
+  using Ring = MfRing<LANES, VEC, DEPTH, NI, NG>;
+  constexpr int MF_STAGES = MfCfg<NG>::STAGES, MF_CAP = MfCfg<NG>::CAP;
+  using MfStage = MfStageT<MF_CAP>;
+  using MfWarp = MfWarpT<MF_CAP, MF_STAGES>;
   constexpr int GPW = Ring::GPW, NCH = Ring::NCH;
   constexpr int ITER = MF_TILE / GPW;  // iterations per tile
   static_assert(ITER % DEPTH == 0 && DEPTH <= ITER, "ring depth must divide the iterations of a tile");
@@ -188,6 +213,8 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     d.urow = d.irow = 0u;
     d.irow2 = 0xffffffffu;
     d.uval = d.ival = d.ival2 = d.lab = 0.0f;
+    d.gp = 0u;
+    d.stage = j % MF_STAGES;
     d.take = d.left = 0u;
     d.all_one = true;
     d.r0 = 0;
@@ -201,14 +228,27 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     const int *rp = st.rp + ((3 * d.r0) & 3) + 3 * lane;
     // candidates: every row of the tile (first pass) / the rows the first pass left (second pass)
     unsigned cand = nrow >= 32 ? 0xffffffffu : ((1u << nrow) - 1u);
-    if (NI == 2) cand &= row_mask[tile_of(j)];
+    if (FOLLOW) cand &= row_mask[tile_of(j)];
     bool ok = w.staged && ((cand >> lane) & 1u);
     bool one = true;
     if (ok) {
       const int rp0 = rp[0], rp1 = rp[1], rp2 = rp[2], rp3 = rp[3];
       // the basic-MF shape (0 | 1 | 1 features; 0 | 1 | 2 too when NI = 2), inside the staged window
       const bool two = NI == 2 && rp3 == rp2 + 2;
-      ok = rp1 == rp0 && rp2 == rp1 + 1 && (rp3 == rp2 + 1 || two) && rp1 >= sm_base && rp3 <= v_hi;
+      const int ngl = rp1 - rp0;
+      ok = (NG > 0 ? (ngl >= 1 && ngl <= NG) : ngl == 0) && rp2 == rp1 + 1 && (rp3 == rp2 + 1 || two) &&
+           rp0 >= sm_base && rp3 <= v_hi;
+      if (NG > 0 && ok) {  // global indices in range and strictly ascending (no repeats: the generic pass)
+        const int gpos = rp0 - sm_base;
+        unsigned prev = st.idx[gpos];
+        ok = prev < (unsigned)m.num_global;
+        for (int q = 1; q < ngl; ++q) {
+          const unsigned cur_g = st.idx[gpos + q];
+          ok = ok && cur_g > prev && cur_g < (unsigned)m.num_global;
+          prev = cur_g;
+        }
+        d.gp = ((unsigned)gpos << 8) | (unsigned)ngl;
+      }
       if (ok) {
         const int f = rp1 - sm_base;
         const unsigned uid = st.idx[f], iid = st.idx[f + 1];
@@ -244,6 +284,7 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     const unsigned urow = __shfl_sync(0xffffffffu, d.urow, src);
     const unsigned irow = __shfl_sync(0xffffffffu, d.irow, src);
     const unsigned irow2 = NI == 2 ? __shfl_sync(0xffffffffu, d.irow2, src) : 0xffffffffu;
+    const unsigned gp = NG > 0 ? __shfl_sync(0xffffffffu, d.gp, src) : 0u;
     if ((d.take >> src) & 1u) {
       float4 *dst = my_ring + slot * SLOT_STRIDE;
       const float *pu = m.W + (size_t)urow * (size_t)m.pitch, *pi = m.W + (size_t)irow * (size_t)m.pitch;
@@ -261,6 +302,10 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
       if (g.gl == 0 && !m.no_user_bias) cp_async16(dst + WIN, m.bias + (urow & ~3u));
       if (g.gl == LANES - 1) cp_async16(dst + WIN + 1, m.bias + (irow & ~3u));
       if (NI == 2 && g.gl == LANES - 2 && irow2 != 0xffffffffu) cp_async16(dst + WIN + 2, m.bias + (irow2 & ~3u));
+      if (NG > 0 && g.gl < (int)(gp & 0xffu)) {  // lane j: the g_bias window of global feature j
+        const unsigned gid = sw.st[d.stage].idx[(gp >> 8) + g.gl];
+        cp_async16(dst + WIN + 1 + NI + g.gl, m.g_bias + (gid & ~3u));
+      }
     }
     cp_async_commit();
   };
@@ -272,6 +317,10 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     float4 wu[VEC], wi[VEC], wi2[VEC];
     float ub, ib, ib2;
     unsigned urow, irow, irow2;
+    // NG > 0: lane j of the group holds global feature j of the instance
+    int ng;
+    unsigned gid;
+    float gval, gb;
   };
   auto load_slot = [&](const MfDec &d, int i, int slot, Rows &r) {
     const int src = i * GPW + gw;
@@ -299,6 +348,19 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
         r.wi2[v] = (two && ch < row_f4) ? rs[2 * NCH + ch] : f4_zero();  // (never garbage: it enters tmp_ifactor)
       }
       r.ib2 = two ? bw[8 + (r.irow2 & 3u)] : 0.0f;
+    }
+    r.ng = 0;
+    r.gid = 0u;
+    r.gval = r.gb = 0.0f;
+    if (NG > 0) {
+      const unsigned gp = __shfl_sync(0xffffffffu, d.gp, src);
+      r.ng = ((d.take >> src) & 1u) ? (int)(gp & 0xffu) : 0;
+      if (g.gl < r.ng) {
+        const MfStage &st = sw.st[d.stage];
+        r.gid = st.idx[(gp >> 8) + g.gl];
+        r.gval = st.val[(gp >> 8) + g.gl];
+        r.gb = bw[4 * (1 + NI + g.gl) + (r.gid & 3u)];
+      }
     }
   };
   auto compute = [&](const MfDec &d, int i, const Rows &r) {
@@ -341,6 +403,10 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     }
     // calc_bias (base.h:313-353) + pred (base.h:445-454)
     double bsum = 0.0;
+    if (NG > 0) {  // globals first, in feature order (base.h:318-322)
+      const float p = g.gl < r.ng ? __fmul_rn(r.gval, r.gb) : 0.0f;
+      for (int q = 0; q < r.ng; ++q) bsum = __dadd_rn(bsum, (double)g.bcast(p, q));
+    }
     if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, ub));
     bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
     if (NI == 2) bsum = __dadd_rn(bsum, two ? (double)__fmul_rn(ival2, r.ib2) : 0.0);
@@ -368,6 +434,12 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
       if (!hp.di_skip) ni[v] = f4_scale(ni[v], hp.di);
     }
     const float nub = __fmul_rn(__fadd_rn(ub, su), hp.dub), nib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
+    if (NG > 0 && g.gl < r.ng) {  // g_bias[gid] += lr*err*gval, then *= 1 - lr*wd_global (base.h:388-390,188-192)
+      float x = __fadd_rn(r.gb, __fmul_rn(lrerr, r.gval));
+      if (r.gid >= hp.regfree) x = __fmul_rn(x, hp.dg);
+      if (scatter_item == SCATTER_RED) red1(m.g_bias + r.gid, __fsub_rn(x, r.gb));
+      else __stcg(m.g_bias + r.gid, x);
+    }
     if (take) {
       if (scatter_user == SCATTER_RED) g.red_row(m, urow, nu, wu);
       else g.store_row(m, urow, nu);
@@ -419,9 +491,15 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     const MfDec nxt = decode(j + 1);
     issue_a(j + 3);
     issue_b(j + 2);
-    if (lane == 0 && (cur.left != 0u || (NI == 2 && cur.take != 0u))) {
-      row_mask[tile_of(j)] = cur.left;   // (second pass: also clears the rows it takes)
+    if (lane == 0 && (cur.left != 0u || (FOLLOW && cur.take != 0u))) {
+      row_mask[tile_of(j)] = cur.left;   // (later passes: also clear the rows they take)
       if (cur.left != 0u) *any_left = 1u;  // the generic pass has something to do
+    }
+    if (cur.take == 0u) {  // (warp-uniform) nothing of this tile is ours: its DEPTH pending groups are
+#pragma unroll             // empty; queue the next tile's first iterations behind them and move on
+      for (int i = 0; i < DEPTH; ++i) prefetch(nxt, i, i);
+      cur = nxt;
+      continue;
     }
 #pragma unroll 1
     for (int i = 0; i < ITER; ++i) {  // iteration i lives in ring slot i % DEPTH (one copy of the code:
@@ -440,21 +518,20 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
   cp_async_wait<0>();
 }
 
-template <int L, int V, int DEPTH, int MINB, int NI>
-static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred) {
+template <int L, int V, int DEPTH, int MINB, int NI, int NG>
+static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred, unsigned *flag_out,
+                         const unsigned *flag_gate) {
   const long long ntile = ((long long)(r1 - r0) + MF_TILE - 1) / MF_TILE;
   int grid = 1;
-  // flags behind the masks: [any_left_at - 1] set by the first pass, [any_left_at] by the second
-  unsigned *flag_a = h->d_row_mask + h->any_left_at - 1, *flag_b = h->d_row_mask + h->any_left_at;
 #define GO(ED, TR)                                                                               \
   {                                                                                              \
-    auto k = k_mf<L, V, ED, TR, DEPTH, MINB, NI>;                                                \
-    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH, NI>();                                    \
+    auto k = k_mf<L, V, ED, TR, DEPTH, MINB, NI, NG>;                                            \
+    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH, NI, NG>();                                \
     CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     if (grid_for(h, k, MF_THREADS, (ntile + MF_WARPS - 1) / MF_WARPS, &grid, smem)) return 1;    \
     k<<<grid, MF_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
                                              h->scatter_item, pred, h->d_row_mask,               \
-                                             NI == 2 ? flag_b : flag_a, flag_a);                 \
+                                             flag_out, flag_gate);                               \
     h->n_launch++;                                                                               \
   }
   if (train) {
@@ -470,18 +547,22 @@ static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool trai
 // The fast passes over rows [r0, r1); h->d_row_mask (one word per 32-row tile, zeroed by the
 // caller) receives the rows left for the generic pass.  First pass: rows (0|1|1).  Second pass
 // (`second`): rows (0|1|1..2) among those the first pass left; exits at once if it left none.
+// `which`: 0 first pass, 1 second pass (two item features), 2 third pass (global features).
+// flag_out receives "this pass left something"; a later pass exits at once when *flag_gate == 0.
 int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred,
-              bool second) {
+              int which, unsigned *flag_out, const unsigned *flag_gate) {
   // tuning knobs (options "ring_depth", "mf_ctas"): ring depth 2 or 4, 2 or 3 CTAs per SM
   const int depth = h->ring_depth == 2 ? 2 : 4;
   const int minb = h->mf_ctas == 3 ? 3 : 2;
 #define GEO(L, V)                                                                                      \
   if (g.lanes == L && g.vec == V) {                                                                    \
-    if (second) return launch_mf_geo<L, V, 2, 2, 2>(h, csr, r0, r1, train, pred);                      \
-    if (depth == 2 && minb == 3) return launch_mf_geo<L, V, 2, 3, 1>(h, csr, r0, r1, train, pred);     \
-    if (depth == 2) return launch_mf_geo<L, V, 2, 2, 1>(h, csr, r0, r1, train, pred);                  \
-    if (minb == 3) return launch_mf_geo<L, V, 4, 3, 1>(h, csr, r0, r1, train, pred);                   \
-    return launch_mf_geo<L, V, 4, 2, 1>(h, csr, r0, r1, train, pred);                                  \
+    constexpr int NGV = L < 16 ? L : 16;                                                               \
+    if (which == 2) return launch_mf_geo<L, V, 4, 1, 1, NGV>(h, csr, r0, r1, train, pred, flag_out, flag_gate); \
+    if (which == 1) return launch_mf_geo<L, V, 2, 2, 2, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate);   \
+    if (depth == 2 && minb == 3) return launch_mf_geo<L, V, 2, 3, 1, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate); \
+    if (depth == 2) return launch_mf_geo<L, V, 2, 2, 1, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate);   \
+    if (minb == 3) return launch_mf_geo<L, V, 4, 3, 1, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate);    \
+    return launch_mf_geo<L, V, 4, 2, 1, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate);                   \
   }
 #ifdef SVDGPU_TUNE_BUILD
   GEO(4, 4) GEO(8, 2) GEO(16, 2)

@@ -257,9 +257,9 @@ static int launch_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, 
 
 int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train,
                   float *pred) {
-  // row masks: one word per 32 rows (+ padding so that pass 2 may read them in pairs); the last
-  // word is the "pass 1 left something" flag
-  const long long nmask = (((long long)(r1 - r0) + 31) / 32 + 3) & ~1LL;
+  // row masks: one word per 32 rows (+ padding so that the generic pass may read them in pairs); the
+  // last three words are the "left something" flags of the three fast passes
+  const long long nmask = (((long long)(r1 - r0) + 31) / 32 + 5) & ~1LL;
   h->any_left_at = (size_t)nmask - 1;
   if ((size_t)nmask * sizeof(unsigned) > h->row_mask_cap) {
     if (h->d_row_mask) CU(h, cudaFree(h->d_row_mask));
@@ -273,11 +273,22 @@ int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r
   // reg_method / reg_global / user_nonnegative sends every row to the generic pass
   const bool pass1 = h->dhp.plain != 0 && h->pass1 != 0;
   CU(h, cudaMemsetAsync(h->d_row_mask, pass1 ? 0 : 0xff, (size_t)nmask * sizeof(unsigned), h->stream));
-  if (pass1 && launch_mf(h, g, csr, r0, r1, train, pred, false)) return 1;
+  unsigned *flags = h->d_row_mask + h->any_left_at - 2;  // [0] first, [1] second, [2] third pass
+  size_t last = h->any_left_at - 2;
+  if (pass1 && launch_mf(h, g, csr, r0, r1, train, pred, 0, flags, flags)) return 1;
   // second fast pass: rows with two item features (pairwise-rank rows) among those left
   const bool pass1b = pass1 && h->pass1 >= 2;
-  if (pass1b && launch_mf(h, g, csr, r0, r1, train, pred, true)) return 1;
-  h->flag_for_generic = pass1b ? h->any_left_at : h->any_left_at - 1;
+  if (pass1b) {
+    if (launch_mf(h, g, csr, r0, r1, train, pred, 1, flags + 1, flags)) return 1;
+    last = h->any_left_at - 1;
+  }
+  // third fast pass: basic rows with a few global features (neighbourhood rows) among those left
+  const bool pass1c = pass1 && h->pass1 >= 3 && h->shape.num_global > 0;
+  if (pass1c) {
+    if (launch_mf(h, g, csr, r0, r1, train, pred, 2, flags + 2, h->d_row_mask + last)) return 1;
+    last = h->any_left_at;
+  }
+  h->flag_for_generic = last;
 #define GEO(L, V) \
   if (g.lanes == L && g.vec == V) return launch_geo<L, V>(h, csr, r0, r1, train, pred);
 #ifdef SVDGPU_TUNE_BUILD

@@ -224,6 +224,68 @@ def test_hogwild_pairwise_rows_second_fast_pass(native, k):
     assert np.array_equal(W0, W1)  # fast and generic pass: the same arithmetic, bit for bit
 
 
+@pytest.mark.parametrize("k", [256, 64, 32, 128])
+def test_hogwild_global_feature_rows_third_fast_pass(native, k):
+    """Basic rows with a few global features (1..NG | 1 | 1: the neighbourhood rows of configs[4]) take
+    the third fast pass (k_mf, NG > 0); rows with more globals than it handles, with unsorted global
+    indices, and plain basic rows ride along.  On conflict-free input the model equals the sequential
+    oracle bit for bit whichever pass runs the rows."""
+    nu, ni, n = 5000, 6000, 2500
+    ngl = 24 * n
+    rng = np.random.default_rng(1000 + k)
+    users = rng.permutation(nu)[:n]
+    items = rng.permutation(ni)[:n]
+    gids = rng.permutation(ngl)
+    rows, gp = [], 0
+    for r in range(n):
+        kind = r % 10
+        ng = 0 if kind == 0 else (20 if kind == 1 else int(rng.integers(1, 17)))
+        mine = np.sort(gids[gp:gp + ng])
+        gp += ng
+        if kind == 2 and ng > 1:
+            mine = mine[::-1]  # descending: left to the generic pass
+        rows.append((float(rng.integers(1, 6)), [(int(x), float(np.float32(rng.normal(0, 0.5)))) for x in mine],
+                     [(int(users[r]), 1.0)], [(int(items[r]), 1.0 if kind != 3 else 0.7)]))
+    data = synth.ragged_csr(rows)
+    params = dict(num_user=nu, num_item=ni, num_global=ngl, num_factor=k, learning_rate=0.01, wd_user=0.004,
+                  wd_item=0.003, wd_user_bias=0.001, wd_item_bias=0.002, wd_global=0.002, num_regfree_global=ngl // 3,
+                  base_score=3.6)
+    o = COracle(0, 0, 0, params)
+    o.init(6)
+    o.arrays()[2][:] = np.random.default_rng(2).normal(0, 0.1, ngl).astype(np.float32)  # non-zero global biases
+    res = []
+    for p1 in (3, 2, 0):
+        g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+        g.set_hparams(**_cases.hparams_of(params, o.base_score))
+        g.set_mode(native.MODE_HOGWILD)
+        g.set_option("scatter_user", 0)
+        g.set_option("scatter_item", 0)
+        g.set_option("exact_dot", 1)
+        g.set_option("pass1", p1)
+        g.upload(*[a.copy() for a in o.arrays()])
+        for _ in range(2):
+            g.update_csr(data)
+        g.sync()
+        res.append(g)
+    for _ in range(2):
+        o.update_csr(data)
+    for g in res:
+        assert _maxdiff(o, g) == 0.0
+        assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
+    # default options (red scatter, tree-order dot): close, and the resident-batch path agrees
+    g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_mode(native.MODE_HOGWILD)
+    o2 = COracle(0, 0, 0, params)
+    o2.init(6)
+    g.upload(*[a.copy() for a in o2.arrays()])
+    b = g.batch_create(data)
+    g.batch_update(b)
+    g.sync()
+    o2.update_csr(data)
+    assert _maxdiff(o2, g) <= 1e-6
+
+
 def test_hogwild_fast_dot_close(native):
     o, g, data, kind = _pair(native, "basic_k64", native.MODE_HOGWILD, {"exact_dot": 0, "scatter_item": 0})
     data = _conflict_free(200, 100, 100, 5)
