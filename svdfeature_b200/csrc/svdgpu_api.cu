@@ -516,6 +516,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "scatter_item")) h->scatter_item = v ? SCATTER_RED : SCATTER_STORE;
   else if (!strcmp(name, "exact_dot")) h->exact_dot = v ? 1 : 0;
   else if (!strcmp(name, "stream_tile")) h->stream_tile = (int)v;
+  else if (!strcmp(name, "mfg")) h->mfg = (int)v;
   else if (!strcmp(name, "rank_force_sort")) h->rank_force_sort = v ? 1 : 0;
   else if (!strcmp(name, "lanes")) {
     const int old = h->lanes_opt;

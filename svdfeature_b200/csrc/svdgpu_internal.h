@@ -96,6 +96,9 @@ struct svdgpu {
   int ugroup_units = 0;  // option "ugroup_units": user units in flight in Hogwild user-group training (0 = auto: 64 with
                          // feedback lists -- more diverges, tools/hogwild_parity.py --svdpp -- else the occupancy limit)
   int l2_ahead = -1;   // option "l2_ahead": generic pass prefetches the next tile's rows into L2 (-1 auto)
+  int mfg = 1;         // option "mfg": third fast pass variant: 0 three stages / ring depth 4 / one CTA per SM
+                       // (configs[4]: 0.79 G inst/s), 1 (default) two stages with late window requests / ring
+                       // depth 2 / two CTAs per SM (1.17 G inst/s: the pass is short of warps, not of bytes in flight)
   int stream_tile = 0; // option "stream_tile": rows per tile of the generic pass (0 = auto: 64 / 32 / 16 / 8 by row width)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)

@@ -48,9 +48,12 @@ constexpr int MF_WARPS = MF_WARPS_PER_CTA;
 constexpr int MF_THREADS = MF_WARPS * 32;
 
 // staged entries per tile / staged tiles per warp of a variant (NG = most global features per row it takes)
-template <int NG> struct MfCfg {
-  static constexpr int CAP = NG > 0 ? (NG + 2) * MF_TILE : MF_CAP;
-  static constexpr int STAGES = NG > 0 ? 3 : MF_STAGES;
+// LATEB (NG > 0 only): two stages; the index/value window of tile j+2 is requested only after tile j
+// has been computed (it lands in the stage tile j occupied), which leaves its latency exposed once
+// per tile but costs a third less shared memory -- two CTAs per SM instead of one.
+template <int NG, bool LATEB> struct MfCfg {
+  static constexpr int CAP = NG > 0 ? (LATEB ? 14 * MF_TILE : (NG + 2) * MF_TILE) : MF_CAP;
+  static constexpr int STAGES = (NG > 0 && !LATEB) ? 3 : MF_STAGES;
 };
 
 template <int CAP>
@@ -76,9 +79,9 @@ struct MfRing {
   static constexpr size_t BYTES = (size_t)DEPTH * GPW * SLOT_F4 * sizeof(float4);
 };
 
-template <int LANES, int VEC, bool EXACT_DOT, int DEPTH, int NI, int NG>
+template <int LANES, int VEC, bool EXACT_DOT, int DEPTH, int NI, int NG, bool LATEB>
 constexpr size_t mf_smem_bytes() {
-  return (sizeof(MfWarpT<MfCfg<NG>::CAP, MfCfg<NG>::STAGES>) + MfRing<LANES, VEC, DEPTH, NI, NG>::BYTES) * MF_WARPS +
+  return (sizeof(MfWarpT<MfCfg<NG, LATEB>::CAP, MfCfg<NG, LATEB>::STAGES>) + MfRing<LANES, VEC, DEPTH, NI, NG>::BYTES) * MF_WARPS +
          (EXACT_DOT ? sizeof(float) * MF_WARPS * (32 / LANES) * Group<LANES, VEC>::DOT_FLOATS : 0);
 }
 
@@ -111,7 +114,7 @@ struct MfDec {
 // rows the first pass left (`gate` = its "something left" flag: nothing left, nothing to do).
 // NG > 0 (the third fast pass): rows (1..NG | 1 | 1), strictly ascending global indices, among the
 // rows the earlier passes left.
-template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB, int NI, int NG>
+template <int LANES, int VEC, bool EXACT_DOT, bool TRAIN, int DEPTH, int MINB, int NI, int NG, bool LATEB>
 __global__ void __launch_bounds__(MF_THREADS, MINB)
 k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_user, int scatter_item,
      float *pred_out, unsigned *row_mask, unsigned *any_left, const unsigned *gate) {
@@ -120,7 +123,8 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
   static_assert(NG == 0 || NI == 1, "the global-feature pass takes one item feature");
   if (FOLLOW && *gate == 0u) return;
   using Ring = MfRing<LANES, VEC, DEPTH, NI, NG>;
-  constexpr int MF_STAGES = MfCfg<NG>::STAGES, MF_CAP = MfCfg<NG>::CAP;
+  static_assert(!LATEB || NG > 0, "late B requests only exist for the global-feature pass");
+  constexpr int MF_STAGES = MfCfg<NG, LATEB>::STAGES, MF_CAP = MfCfg<NG, LATEB>::CAP;
   using MfStage = MfStageT<MF_CAP>;
   using MfWarp = MfWarpT<MF_CAP, MF_STAGES>;
   constexpr int GPW = Ring::GPW, NCH = Ring::NCH;
@@ -490,7 +494,7 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     wait_b(j + 1);
     const MfDec nxt = decode(j + 1);
     issue_a(j + 3);
-    issue_b(j + 2);
+    if (!LATEB) issue_b(j + 2);
     if (lane == 0 && (cur.left != 0u || (FOLLOW && cur.take != 0u))) {
       row_mask[tile_of(j)] = cur.left;   // (later passes: also clear the rows they take)
       if (cur.left != 0u) *any_left = 1u;  // the generic pass has something to do
@@ -498,6 +502,7 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
     if (cur.take == 0u) {  // (warp-uniform) nothing of this tile is ours: its DEPTH pending groups are
 #pragma unroll             // empty; queue the next tile's first iterations behind them and move on
       for (int i = 0; i < DEPTH; ++i) prefetch(nxt, i, i);
+      if (LATEB) issue_b(j + 2);
       cur = nxt;
       continue;
     }
@@ -513,20 +518,21 @@ k_mf(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, int scatter_u
       else prefetch(nxt, i + DEPTH - ITER, slot);
       compute(cur, i, r);
     }
+    if (LATEB) issue_b(j + 2);  // tile j's window is no longer needed: its stage takes tile j+2's
     cur = nxt;
   }
   cp_async_wait<0>();
 }
 
-template <int L, int V, int DEPTH, int MINB, int NI, int NG>
+template <int L, int V, int DEPTH, int MINB, int NI, int NG, bool LATEB = false>
 static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool train, float *pred, unsigned *flag_out,
                          const unsigned *flag_gate) {
   const long long ntile = ((long long)(r1 - r0) + MF_TILE - 1) / MF_TILE;
   int grid = 1;
 #define GO(ED, TR)                                                                               \
   {                                                                                              \
-    auto k = k_mf<L, V, ED, TR, DEPTH, MINB, NI, NG>;                                            \
-    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH, NI, NG>();                                \
+    auto k = k_mf<L, V, ED, TR, DEPTH, MINB, NI, NG, LATEB>;                                     \
+    const size_t smem = mf_smem_bytes<L, V, ED, DEPTH, NI, NG, LATEB>();                         \
     CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     if (grid_for(h, k, MF_THREADS, (ntile + MF_WARPS - 1) / MF_WARPS, &grid, smem)) return 1;    \
     k<<<grid, MF_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
@@ -557,6 +563,7 @@ int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, b
 #define GEO(L, V)                                                                                      \
   if (g.lanes == L && g.vec == V) {                                                                    \
     constexpr int NGV = L < 16 ? L : 16;                                                               \
+    if (which == 2 && h->mfg != 0) return launch_mf_geo<L, V, 2, 2, 1, NGV, true>(h, csr, r0, r1, train, pred, flag_out, flag_gate); \
     if (which == 2) return launch_mf_geo<L, V, 4, 1, 1, NGV>(h, csr, r0, r1, train, pred, flag_out, flag_gate); \
     if (which == 1) return launch_mf_geo<L, V, 2, 2, 2, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate);   \
     if (depth == 2 && minb == 3) return launch_mf_geo<L, V, 2, 3, 1, 0>(h, csr, r0, r1, train, pred, flag_out, flag_gate); \

@@ -254,7 +254,7 @@ def test_hogwild_global_feature_rows_third_fast_pass(native, k):
     o.init(6)
     o.arrays()[2][:] = np.random.default_rng(2).normal(0, 0.1, ngl).astype(np.float32)  # non-zero global biases
     res = []
-    for p1 in (3, 2, 0):
+    for p1, mfg in ((3, 0), (3, 1), (2, 0), (0, 0)):  # mfg: the two shared-memory layouts of the third pass
         g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
         g.set_hparams(**_cases.hparams_of(params, o.base_score))
         g.set_mode(native.MODE_HOGWILD)
@@ -262,6 +262,7 @@ def test_hogwild_global_feature_rows_third_fast_pass(native, k):
         g.set_option("scatter_item", 0)
         g.set_option("exact_dot", 1)
         g.set_option("pass1", p1)
+        g.set_option("mfg", mfg)
         g.upload(*[a.copy() for a in o.arrays()])
         for _ in range(2):
             g.update_csr(data)
