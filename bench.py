@@ -16,6 +16,9 @@ k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch
              bytes per launch from the committed ncu capture (profiles/)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref) timed on the host, 1 thread,
              on a bounded prefix of the same workload
+  parity     (N=1) the first --parity-rows of that prefix trained and predicted through the
+             ISVDTrainer seam on the GPU in both modes: RMSE / max-abs of the predictions
+             against the reference's own (ordered mode: 0.0; Hogwild: its measured distance)
 
 N>1 (torchrun): users are hash-partitioned (user mod N) so user rows are private to a
 rank; item rows/bias are replicated and their deltas are all-reduced over NCCL every
@@ -164,12 +167,21 @@ def ref_trainer():
     return t, kind
 
 
-def time_cpu(rows_total, rows_per_call):
-    """instances/s of the reference's single-threaded update() loop on host cores."""
+def time_cpu(rows_total, rows_per_call, parity_rows=0):
+    """instances/s of the reference's single-threaded update() loop on host cores.  With
+    parity_rows > 0 the first rows of the stream are first trained and predicted on a fresh
+    model (seed 10): (sample, predictions) come back as the yardstick of parity_leg()."""
     t, kind = ref_trainer()
     data = gen_rows_numpy(rows_total, seed=10)
     warm = min(rows_per_call, rows_total)
-    t.update_csr((data[0][:3 * warm + 1], data[1][:warm], data[2], data[3]))  # touch the model once
+    yard = None
+    if parity_rows > 0:
+        warm = min(parity_rows, rows_total)
+    nv = int(data[0][3 * warm])
+    sample = (data[0][:3 * warm + 1], data[1][:warm], data[2][:nv], data[3][:nv])
+    t.update_csr(sample)  # touches the model once before the timed loop
+    if parity_rows > 0:
+        yard = (sample, t.predict_csr(sample))
     t0 = time.perf_counter()
     done = 0
     for r0 in range(0, rows_total, rows_per_call):
@@ -177,7 +189,51 @@ def time_cpu(rows_total, rows_per_call):
         t.update_csr((data[0][3 * r0:3 * r1 + 1], data[1][r0:r1], data[2], data[3]))
         done += r1 - r0
     dt = time.perf_counter() - t0
-    return done / dt, kind, dt
+    return done / dt, kind, dt, yard
+
+
+def parity_leg(yard, kind, device):
+    """The north star's parity statement, measured in the same run: the first rows of the CPU
+    sample, trained once and predicted on a fresh model (seed 10, same order) through the
+    reference's own plug-in seam (create_svd_trainer -> GpuSVDFeature : ISVDTrainer), in both
+    execution modes, against what the reference's trainer predicted for them."""
+    from svdfeature_b200 import api
+
+    sample, want = yard
+    n = len(sample[1])
+    out = {"rows": n, "against": "%s ISVDTrainer, same seed and order" % kind, "north_star_tolerance_rmse": 1e-4}
+    for mode in ("exact", "hogwild"):
+        params = dict(num_user=NUM_USER, num_item=NUM_ITEM, num_factor=K, **HP)
+        params["gpu:device"] = device
+        params["gpu:mode"] = mode
+        t = api.GpuTrainer(0, 0, 0, params)
+        t.init(10)
+        t.update_csr(sample)
+        got = t.predict_csr(sample)
+        t.close()
+        d = got.astype(np.float64) - want.astype(np.float64)
+        out["ordered" if mode == "exact" else mode] = {
+            "rmse_vs_reference": float(np.sqrt(np.mean(d * d))), "max_abs": float(np.max(np.abs(d)))}
+    # throughput of the ordered mode (the one that meets the tolerance), batch resident in HBM,
+    # tickets already computed: bounded by the hand-off chain of the hottest item row
+    g = api.SvdGpu(NUM_USER, NUM_ITEM, K, device=device)
+    g.set_hparams(**HP)
+    g.set_mode(api.MODE_EXACT)
+    rng = np.random.default_rng(10)
+    g.upload(np.zeros(NUM_USER + NUM_ITEM, np.float32),
+             (rng.standard_normal((NUM_USER + NUM_ITEM, K)) * 0.01).astype(np.float32), np.zeros(1, np.float32))
+    b = g.batch_create(sample)
+    g.batch_update(b)
+    g.sync()
+    g.timer_start()
+    for _ in range(3):
+        g.batch_update(b)
+    ms = g.timer_stop() / 3
+    out["ordered"]["instances_per_s"] = n / (ms * 1e-3)
+    out["ordered"]["hottest_item_rows"] = int(np.bincount(sample[2][1:2 * n:2]).max())
+    b.close()
+    g.close()
+    return out
 
 
 def run_reference_arm(args):
@@ -235,6 +291,8 @@ def main():
     ap.add_argument("--rows-per-step", type=int, default=TOTAL_ROWS)
     ap.add_argument("--ref-rows-per-step", type=int, default=2_000_000)
     ap.add_argument("--cpu-rows", type=int, default=20_000_000, help="rows of the cpu_baseline sample")
+    ap.add_argument("--parity-rows", type=int, default=2_000_000,
+                    help="rows of the cpu_baseline sample that are also trained on the GPU and compared (N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to svdgpu_set_option")
@@ -440,9 +498,11 @@ def main():
                 "algorithmic_bytes_per_instance": BYTES_PER_INSTANCE, "launch_ms": kms, "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0}
 
-    cpu = None
+    cpu = parity = None
     if not args.no_cpu_baseline:
-        v, kind, dt = time_cpu(args.cpu_rows, 1_000_000)
+        v, kind, dt, yard = time_cpu(args.cpu_rows, 1_000_000, 0 if world > 1 else args.parity_rows)
+        if yard is not None:
+            parity = parity_leg(yard, kind, local)
         cpu = {"value": v, "unit": "instances/s", "cores": 1, "kind": kind,
                "sample": "first %d ratings of the same stream, ISVDTrainer::update loop, %.1f s, 1 thread of %d host cores"
                          % (args.cpu_rows, dt, os.cpu_count())}
@@ -454,6 +514,8 @@ def main():
         "config": workload_config(rows, args.mode), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
     }
+    if parity:
+        line["parity"] = parity
     if world > 1:
         line["config"]["parallelism"] = ("user-hash shards x%d (global problem %d users x %d items, %d ratings per step; "
                                          "each rank owns %d users), item-side delta allreduce (NCCL) every %d step(s)"

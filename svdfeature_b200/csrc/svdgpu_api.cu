@@ -536,6 +536,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "ugroup_units")) h->ugroup_units = (int)v;
   else if (!strcmp(name, "svdpp_fast")) h->svdpp_fast = v ? 1 : 0;
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
+  else if (!strcmp(name, "exact_opt")) h->exact_opt = (int)v;
   else return fail(h, "unknown option '%s'", name);
   return 0;
 }

@@ -101,6 +101,8 @@ struct svdgpu {
                        // depth 2 / two CTAs per SM (1.17 G inst/s: the pass is short of warps, not of bytes in flight)
   int stream_tile = 0; // option "stream_tile": rows per tile of the generic pass (0 = auto: 64 / 32 / 16 / 8 by row width)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
+  int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):
+                       // 1 no per-lane fence before the release, 2 spin before sleeping, 4 staged slice
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
   static constexpr int NSLOT = 3;
   Slot slot[NSLOT];

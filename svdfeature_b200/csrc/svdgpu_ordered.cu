@@ -17,6 +17,8 @@ namespace svdk {
 // k_exact
 // ---------------------------------------------------------------------------
 constexpr int EX_WARPS = 4;
+constexpr int EXOPT_NOFENCE = 1, EXOPT_SPIN = 2, EXOPT_STAGE = 4;  // option "exact_opt" (bit mask)
+constexpr int EX_STAGE = 32;  // features of an instance staged in shared memory
 
 __device__ __forceinline__ unsigned *version_of(const DevModel &m, int f, int rp1, int rp2, unsigned id) {
   if (f < rp1) return id < (unsigned)m.num_global ? m.ver_g + id : nullptr;
@@ -27,13 +29,17 @@ __device__ __forceinline__ unsigned *version_of(const DevModel &m, int f, int rp
 template <int LANES, int VEC>
 __device__ __forceinline__ void wait_tickets(const Group<LANES, VEC> &g, const DevModel &m, int rp0,
                                              int rp1, int rp2, int rp3, const unsigned *idx,
-                                             const unsigned *tk) {
+                                             const unsigned *tk, int opt = 0) {
   for (int f = rp0 + g.gl; f < rp3; f += LANES) {
     const unsigned *ver = version_of(m, f, rp1, rp2, idx[f]);
     if (ver) {
       const unsigned want = tk[f];
-      unsigned ns = 20;
+      unsigned ns = 20, spins = (opt & EXOPT_SPIN) ? 64u : 0u;
       while (ld_acquire_u32(ver) != want) {
+        if (spins) {  // the hand-off of a hot row is the critical path: poll back to back first
+          --spins;
+          continue;
+        }
         __nanosleep(ns);
         if (ns < 200) ns += 20;
       }
@@ -44,8 +50,12 @@ __device__ __forceinline__ void wait_tickets(const Group<LANES, VEC> &g, const D
 template <int LANES, int VEC>
 __device__ __forceinline__ void release_tickets(const Group<LANES, VEC> &g, const DevModel &m,
                                                 int rp0, int rp1, int rp2, int rp3,
-                                                const unsigned *idx) {
-  __threadfence();
+                                                const unsigned *idx, int opt = 0) {
+  // Every lane's row stores must be visible before any version moves.  Default: each lane fences
+  // its own stores, then the group meets.  EXOPT_NOFENCE: the group meets (the stores of all
+  // lanes then happen-before every lane's release), and red.release.gpu -- cumulative over what
+  // happens-before it -- publishes them: one fence less on the hand-off path.
+  if (!(opt & EXOPT_NOFENCE)) __threadfence();
   g.gsync();
   for (int f = rp0 + g.gl; f < rp3; f += LANES) {
     unsigned *ver = version_of(m, f, rp1, rp2, idx[f]);
@@ -56,8 +66,10 @@ __device__ __forceinline__ void release_tickets(const Group<LANES, VEC> &g, cons
 template <int LANES, int VEC>
 __global__ void __launch_bounds__(EX_WARPS * 32)
 k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *counter,
-        int *err_flag) {
+        int *err_flag, int opt) {
   __shared__ float dot_s[EX_WARPS][Group<LANES, VEC>::DOT_FLOATS];
+  __shared__ unsigned st_idx[EX_WARPS][EX_STAGE];
+  __shared__ float st_val[EX_WARPS][EX_STAGE], st_val2[EX_WARPS][EX_STAGE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane >= LANES) return;  // one group per warp
   Group<LANES, VEC> g;
@@ -77,11 +89,29 @@ k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *
     const int rp0 = csr.row_ptr[3 * r], rp1 = csr.row_ptr[3 * r + 1];
     const int rp2 = csr.row_ptr[3 * r + 2], rp3 = csr.row_ptr[3 * r + 3];
     // (row_ptr was validated on the host together with the tickets)
-    wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk);
-    process_instance<LANES, VEC, true, true, false>(g, m, hp, rp0, rp1, rp2, rp3, csr.label[r], idx,
-                                                    val, SCATTER_STORE, SCATTER_STORE, nullptr,
-                                                    err_flag, val2);
-    release_tickets(g, m, rp0, rp1, rp2, rp3, idx);
+    const float lab = csr.label[r];
+    // EXOPT_STAGE: the acquire below invalidates L1, so index/value loads issued after it are a
+    // full L2 round trip that the row gathers then depend on.  Copy the instance's slice to
+    // shared memory while it waits: after the hand-off the row addresses are already on chip.
+    const unsigned *pidx = idx;
+    const float *pval = val, *pval2 = val2;
+    if ((opt & EXOPT_STAGE) && rp3 - rp0 <= EX_STAGE) {
+      g.gsync();  // the previous instance of this warp has been read out of the stage
+      for (int f = rp0 + g.gl; f < rp3; f += LANES) {
+        st_idx[warp][f - rp0] = idx[f];
+        st_val[warp][f - rp0] = val[f];
+        if (val2) st_val2[warp][f - rp0] = val2[f];
+      }
+      g.gsync();
+      pidx = st_idx[warp] - rp0;
+      pval = st_val[warp] - rp0;
+      if (val2) pval2 = st_val2[warp] - rp0;
+    }
+    wait_tickets(g, m, rp0, rp1, rp2, rp3, idx, tk, opt);
+    process_instance<LANES, VEC, true, true, false>(g, m, hp, rp0, rp1, rp2, rp3, lab, pidx, pval,
+                                                    SCATTER_STORE, SCATTER_STORE, nullptr, err_flag,
+                                                    pval2);
+    release_tickets(g, m, rp0, rp1, rp2, rp3, pidx, opt);
   }
 }
 
@@ -514,7 +544,7 @@ static int exact_geo(svdgpu *h, const DevCsr &csr, int r0, int r1) {
   CU(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream));
   CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
   CU(h, cudaMemsetAsync(h->dm.ver_g, 0, sizeof(unsigned) * std::max(h->shape.num_global, 1), h->stream));
-  k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->d_counter, h->d_err);
+  k<<<grid, EX_WARPS * 32, 0, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->d_counter, h->d_err, h->exact_opt);
   CU(h, cudaGetLastError());
   h->n_launch++;
   return 0;
