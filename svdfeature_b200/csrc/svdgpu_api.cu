@@ -5,12 +5,14 @@
 #include "svdgpu_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace svdk;
@@ -69,6 +71,7 @@ int dev_reserve(svdgpu *h, DevBuf &b, size_t bytes) {
   if (b.p) CU(h, cudaFree(b.p));
   b.p = nullptr;
   b.cap = 0;
+  b.fill_n = 0;
   size_t cap = bytes + bytes / 4;
   CU(h, cudaMalloc(&b.p, cap));
   b.cap = cap;
@@ -109,6 +112,7 @@ bool is_pinned(const void *p) {
 int h2d(svdgpu *h, DevBuf &d, HostBuf &stage, const void *src, size_t bytes) {
   if (dev_reserve(h, d, bytes)) return 1;
   if (bytes == 0) return 0;
+  d.fill_n = 0;
   const void *from = src;
   if (!is_pinned(src)) {
     if (host_reserve(h, stage, bytes)) return 1;
@@ -537,6 +541,8 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "svdpp_fast")) h->svdpp_fast = v ? 1 : 0;
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else if (!strcmp(name, "exact_opt")) h->exact_opt = (int)v;
+  else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
+  else if (!strcmp(name, "compact_min_rows")) h->compact_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
   else return fail(h, "unknown option '%s'", name);
   return 0;
 }
@@ -686,6 +692,113 @@ void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats) {
 }
 
 // ---------------------------------------------------------------------------
+// Compact H2D for the Hogwild / predict host-pointer calls.  The reference's CSR costs 32 bytes
+// per basic-MF instance on the bus (12 row_ptr + 4 label + 8 index + 8 value) and the call is
+// PCIe-bound, yet two of the four arrays usually carry no information: row_ptr is an arithmetic
+// progression when every row of a chunk has the same feature counts, and the values of
+// indicator features are all 1.0f.  Host threads check this per chunk (exactly: every element is
+// compared) while earlier chunks are being copied; an array that passes is not copied but
+// rebuilt in the slot by a fill kernel.  What the kernels read is bit-identical either way.
+// ---------------------------------------------------------------------------
+struct ChunkScan {
+  bool rp_regular = false, val_ones = false;
+  int a = 0, b = 0, c = 0;  // global / user / item features per row when rp_regular
+};
+
+// rows [0,n) of p (p[0..3n]) all have the feature counts of row 0
+bool scan_rp_regular(const int *p, long long n, int &a, int &b, int &c) {
+  if (n <= 0) return false;
+  const long long v0 = p[0];
+  a = p[1] - p[0];
+  b = p[2] - p[1];
+  c = p[3] - p[2];
+  if (v0 < 0 || a < 0 || b < 0 || c < 0) return false;
+  const long long w = (long long)a + b + c;
+  if (v0 + n * w != (long long)p[3 * n]) return false;  // (also rules out int overflow below)
+  constexpr long long BLK = 2048;
+  for (long long r0 = 0; r0 < n; r0 += BLK) {
+    const long long r1 = std::min(n, r0 + BLK);
+    unsigned diff = 0;
+    for (long long r = r0; r < r1; ++r) {
+      const int base = (int)(v0 + r * w);
+      const int *q = p + 3 * r;
+      diff |= (unsigned)(q[0] ^ base) | (unsigned)(q[1] ^ (base + a)) | (unsigned)(q[2] ^ (base + a + b));
+    }
+    if (diff) return false;
+  }
+  return true;
+}
+// every one of the nv values is the bit pattern of 1.0f
+bool scan_ones(const float *v, long long nv) {
+  constexpr long long BLK = 8192;
+  for (long long i0 = 0; i0 < nv; i0 += BLK) {
+    const long long i1 = std::min(nv, i0 + BLK);
+    unsigned diff = 0;
+    for (long long i = i0; i < i1; ++i) {
+      unsigned u;
+      memcpy(&u, v + i, 4);
+      diff |= u ^ 0x3f800000u;
+    }
+    if (diff) return false;
+  }
+  return true;
+}
+
+__global__ void k_fill_row_ptr(int *rp, int n, int a, int b, int c) {
+  const int w = a + b + c;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r <= n; r += (long long)gridDim.x * blockDim.x) {
+    const int base = (int)(r * w);
+    rp[3 * r] = base;
+    if (r < n) {
+      rp[3 * r + 1] = base + a;
+      rp[3 * r + 2] = base + a + b;
+    }
+  }
+}
+__global__ void k_fill_ones(float *v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] = 1.0f;
+}
+
+// the scanning threads of one call: chunk c's verdict is in scan[c] once ready[c] != 0
+struct ScanPool {
+  std::vector<ChunkScan> scan;
+  std::vector<std::atomic<int>> ready;
+  std::atomic<int> next{0};
+  std::atomic<bool> stop{false};
+  std::vector<std::thread> threads;
+  explicit ScanPool(int nchunk) : scan((size_t)nchunk), ready((size_t)nchunk) {
+    for (auto &r : ready) r.store(0, std::memory_order_relaxed);
+  }
+  void start(int num_row, int chunk_rows, const int *row_ptr, const float *value) {
+    const int nchunk = (int)scan.size();
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(std::min(nt, 16), nchunk));
+    for (int t = 0; t < nt; ++t)
+      threads.emplace_back([=]() {
+        for (;;) {
+          const int c = next.fetch_add(1);
+          if (c >= nchunk || stop.load(std::memory_order_relaxed)) break;
+          const long long r0 = (long long)c * chunk_rows, r1 = std::min<long long>(num_row, r0 + chunk_rows);
+          ChunkScan &s = scan[(size_t)c];
+          const long long v0 = row_ptr[3 * r0], v1 = row_ptr[3 * r1];
+          s.rp_regular = scan_rp_regular(row_ptr + 3 * r0, r1 - r0, s.a, s.b, s.c);
+          s.val_ones = value && v0 >= 0 && v1 > v0 && scan_ones(value + v0, v1 - v0);
+          ready[(size_t)c].store(1, std::memory_order_release);
+        }
+      });
+  }
+  const ChunkScan &wait(int c) {
+    while (!ready[(size_t)c].load(std::memory_order_acquire)) std::this_thread::yield();
+    return scan[(size_t)c];
+  }
+  ~ScanPool() {
+    stop.store(true);
+    for (auto &t : threads) t.join();
+  }
+};
+
+// ---------------------------------------------------------------------------
 // random-order CSR, host buffers
 // ---------------------------------------------------------------------------
 static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const float *label,
@@ -701,7 +814,11 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
   // the ordered mode walks every row on the host anyway (tickets); Hogwild leaves the
   // row_ptr checks to the kernels so that the host never touches the batch
   if (exact && validate_csr(h, num_row, row_ptr)) return 1;
-  for (int r0 = 0; r0 < num_row; r0 += h->chunk_rows) {
+  const int nchunk = (int)(((long long)num_row + h->chunk_rows - 1) / h->chunk_rows);
+  const bool compact = h->compact_h2d && !exact && !sides_on(h) && num_row >= h->compact_min_rows;
+  ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
+  if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value);
+  for (int r0 = 0, ci = 0; r0 < num_row; r0 += h->chunk_rows, ++ci) {
     const int r1 = (int)std::min<long long>(num_row, (long long)r0 + h->chunk_rows);
     const int n = r1 - r0;
     // the chunk's arrays: the caller's, or their side-feature expansion (0-based)
@@ -714,11 +831,38 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     const size_t nv = (size_t)(v1 - v0);
     const unsigned *c_idx = side ? ex.idx.data() : index + v0;
     const float *c_val = side ? ex.val.data() : value + v0;
-    Slot &s = next_slot(h);
-    if (h2d(h, s.d_rp, s.h_rp, c_rp, (3 * (size_t)n + 1) * 4)) return 1;
+    ChunkScan sc;
+    if (compact) sc = pool.wait(ci);
+    Slot &s = next_slot(h);  // (the kernels that last read this slot are done)
+    if (sc.rp_regular) {
+      // not copied: rebuilt 0-based on the launch stream unless the slot still holds this very fill
+      if (dev_reserve(h, s.d_rp, (3 * (size_t)n + 1) * 4)) return 1;
+      if (s.d_rp.fill_n != n || s.d_rp.fill_a != sc.a || s.d_rp.fill_b != sc.b || s.d_rp.fill_c != sc.c) {
+        k_fill_row_ptr<<<std::min(h->num_sm * 8, (n + 256) / 256), 256, 0, h->stream>>>((int *)s.d_rp.p, n, sc.a, sc.b, sc.c);
+        CU(h, cudaGetLastError());
+        h->n_launch++;
+        s.d_rp.fill_n = n;
+        s.d_rp.fill_a = sc.a;
+        s.d_rp.fill_b = sc.b;
+        s.d_rp.fill_c = sc.c;
+      }
+    } else if (h2d(h, s.d_rp, s.h_rp, c_rp, (3 * (size_t)n + 1) * 4)) {
+      return 1;
+    }
     if (h2d(h, s.d_label, s.h_label, label + r0, (size_t)n * 4)) return 1;
     if (h2d(h, s.d_index, s.h_index, c_idx, nv * 4)) return 1;
-    if (h2d(h, s.d_value, s.h_value, c_val, nv * 4)) return 1;
+    if (sc.val_ones) {
+      if (dev_reserve(h, s.d_value, nv * 4)) return 1;
+      if (s.d_value.fill_n < (long long)nv) {
+        k_fill_ones<<<(int)std::min<long long>(h->num_sm * 8, ((long long)nv + 255) / 256), 256, 0, h->stream>>>(
+            (float *)s.d_value.p, (long long)nv);
+        CU(h, cudaGetLastError());
+        h->n_launch++;
+        s.d_value.fill_n = (long long)nv;
+      }
+    } else if (h2d(h, s.d_value, s.h_value, c_val, nv * 4)) {
+      return 1;
+    }
     if (side && h2d(h, s.d_value2, s.h_value2, ex.val2.data(), nv * 4)) return 1;
     DevCsr csr;
     csr.row_ptr = (const int *)s.d_rp.p;
@@ -727,8 +871,8 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     csr.value = (const float *)s.d_value.p;
     csr.value2 = side ? (const float *)s.d_value2.p : nullptr;
     csr.ticket = nullptr;
-    csr.val_base = v0;
-    csr.val_end = v1;
+    csr.val_base = sc.rp_regular ? 0 : v0;  // a rebuilt row_ptr counts from 0
+    csr.val_end = sc.rp_regular ? (int)nv : v1;
     if (exact) {
       if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
       reset_ticket_counters(h);

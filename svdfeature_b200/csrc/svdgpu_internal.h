@@ -12,6 +12,10 @@
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
+  // what a device-side fill left in the buffer (compact H2D of regular chunks, svdgpu_api.cu):
+  // fill_n = 0 when the content came from a copy
+  long long fill_n = 0;
+  int fill_a = 0, fill_b = 0, fill_c = 0;
 };
 struct HostBuf {
   void *p = nullptr;
@@ -101,6 +105,10 @@ struct svdgpu {
                        // depth 2 / two CTAs per SM (1.17 G inst/s: the pass is short of warps, not of bytes in flight)
   int stream_tile = 0; // option "stream_tile": rows per tile of the generic pass (0 = auto: 64 / 32 / 16 / 8 by row width)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
+  int compact_h2d = 1;  // option "compact_h2d": Hogwild / predict host-pointer calls do not copy a chunk's
+                        // row_ptr when every row has the same feature counts, nor its values when all are 1.0f
+                        // (checked on host threads while earlier chunks are copied; rebuilt on the device)
+  int compact_min_rows = 1 << 18;  // option "compact_min_rows": calls with fewer rows skip the check
   int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):
                        // 1 no per-lane fence before the release, 2 spin before sleeping, 4 staged slice
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)

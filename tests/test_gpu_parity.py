@@ -695,3 +695,56 @@ def test_ranged_wd_errors(native):
     g.set_wd_ranges(0, [], [])  # cleared: the default wd_user applies again
     g.update_csr(data)
     g.sync()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_rows", [1000, 777, 1 << 20])
+def test_compact_h2d_is_invisible(native, chunk_rows):
+    """Host-pointer calls leave out a chunk's row_ptr when every row has the same feature counts
+    and its values when all are 1.0f, and rebuild them on the device (option compact_h2d).  A batch
+    whose chunks are partly regular (basic rows, unit values), partly not (non-unit values, a
+    ragged tail) must give the oracle's model and predictions with the option on and off, and
+    move fewer bytes with it on."""
+    nu, ni, k, n = 9000, 9000, 64, 6000
+    rng = np.random.default_rng(21)
+    users = rng.permutation(nu)
+    items = rng.permutation(ni)
+    rows = []
+    for r in range(n):
+        lab = float(rng.integers(1, 6))
+        if r < 3500:  # regular and unit-valued
+            rows.append((lab, [], [(users[r], 1.0)], [(items[r], 1.0)]))
+        elif r < 4800:  # regular, other values
+            rows.append((lab, [], [(users[r], 0.5)], [(items[r], -1.25)]))
+        elif r % 3:  # ragged: some rows without a user feature
+            rows.append((lab, [], [(users[r], 1.0)], [(items[r], 1.0)]))
+        else:
+            rows.append((lab, [], [], [(items[r], 1.0)]))
+    data = synth.ragged_csr(rows)
+    params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.01, wd_user=0.004, wd_item=0.003,
+                  wd_user_bias=0.001, wd_item_bias=0.002, base_score=3.6)
+    moved = {}
+    for compact in (1, 0):
+        o = COracle(0, 0, 0, params)
+        o.init(5)
+        g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+        g.set_hparams(**_cases.hparams_of(params, o.base_score))
+        g.set_mode(native.MODE_HOGWILD)
+        for name, v in (("scatter_user", 0), ("scatter_item", 0), ("exact_dot", 1), ("chunk_rows", chunk_rows),
+                        ("compact_h2d", compact), ("compact_min_rows", 1)):
+            g.set_option(name, v)
+        g.upload(*[a.copy() for a in o.arrays()])
+        o.update_csr(data)
+        h0 = g.counter("h2d_bytes")
+        g.update_csr(data)
+        g.sync()
+        moved[compact] = g.counter("h2d_bytes") - h0
+        assert _maxdiff(o, g) == 0.0
+        assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
+        g.close()
+    if chunk_rows >= n:  # one chunk holding the ragged tail and the other values: nothing to leave out
+        assert moved[1] == moved[0]
+    else:
+        assert moved[1] < moved[0]
+    if chunk_rows == 1000:  # chunks 0-2 leave out both arrays, chunk 3 (rows 3000-3999) its row_ptr only
+        assert moved[0] - moved[1] >= 3 * 1000 * 20 + 1000 * 12
