@@ -42,7 +42,7 @@ def _sources(*names):
 
 GPU_UNITS = ["svdgpu_api.cu", "svdgpu_stream.cu", "svdgpu_mf.cu", "svdgpu_ordered.cu", "svdgpu_ingest.cu", "svdgpu_pairs.cu", "svdgpu_svdpp.cu",
              "svdgpu_rank.cu"]
-GPU_HEADERS = ["svdgpu_internal.h", "svdgpu_device.cuh", "svdgpu_fb.cuh"]
+GPU_HEADERS = ["svdgpu_internal.h", "svdgpu_device.cuh", "svdgpu_fb.cuh", "svdgpu_scan.h"]
 
 
 def build_gpu(force=False, verbose=False):

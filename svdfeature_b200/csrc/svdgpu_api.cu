@@ -3,6 +3,7 @@
 // dispatch.  No CPU compute path exists here: every update/predict call ends in
 // a kernel launch or fails.
 #include "svdgpu_internal.h"
+#include "svdgpu_scan.h"
 
 #include <algorithm>
 #include <atomic>
@@ -542,6 +543,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else if (!strcmp(name, "exact_opt")) h->exact_opt = (int)v;
   else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
+  else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));
   else if (!strcmp(name, "compact_min_rows")) h->compact_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
   else return fail(h, "unknown option '%s'", name);
   return 0;
@@ -705,45 +707,6 @@ struct ChunkScan {
   int a = 0, b = 0, c = 0;  // global / user / item features per row when rp_regular
 };
 
-// rows [0,n) of p (p[0..3n]) all have the feature counts of row 0
-bool scan_rp_regular(const int *p, long long n, int &a, int &b, int &c) {
-  if (n <= 0) return false;
-  const long long v0 = p[0];
-  a = p[1] - p[0];
-  b = p[2] - p[1];
-  c = p[3] - p[2];
-  if (v0 < 0 || a < 0 || b < 0 || c < 0) return false;
-  const long long w = (long long)a + b + c;
-  if (v0 + n * w != (long long)p[3 * n]) return false;  // (also rules out int overflow below)
-  constexpr long long BLK = 2048;
-  for (long long r0 = 0; r0 < n; r0 += BLK) {
-    const long long r1 = std::min(n, r0 + BLK);
-    unsigned diff = 0;
-    for (long long r = r0; r < r1; ++r) {
-      const int base = (int)(v0 + r * w);
-      const int *q = p + 3 * r;
-      diff |= (unsigned)(q[0] ^ base) | (unsigned)(q[1] ^ (base + a)) | (unsigned)(q[2] ^ (base + a + b));
-    }
-    if (diff) return false;
-  }
-  return true;
-}
-// every one of the nv values is the bit pattern of 1.0f
-bool scan_ones(const float *v, long long nv) {
-  constexpr long long BLK = 8192;
-  for (long long i0 = 0; i0 < nv; i0 += BLK) {
-    const long long i1 = std::min(nv, i0 + BLK);
-    unsigned diff = 0;
-    for (long long i = i0; i < i1; ++i) {
-      unsigned u;
-      memcpy(&u, v + i, 4);
-      diff |= u ^ 0x3f800000u;
-    }
-    if (diff) return false;
-  }
-  return true;
-}
-
 __global__ void k_fill_row_ptr(int *rp, int n, int a, int b, int c) {
   const int w = a + b + c;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r <= n; r += (long long)gridDim.x * blockDim.x) {
@@ -770,10 +733,10 @@ struct ScanPool {
   explicit ScanPool(int nchunk) : scan((size_t)nchunk), ready((size_t)nchunk) {
     for (auto &r : ready) r.store(0, std::memory_order_relaxed);
   }
-  void start(int num_row, int chunk_rows, const int *row_ptr, const float *value) {
+  void start(int num_row, int chunk_rows, const int *row_ptr, const float *value, int max_threads) {
     const int nchunk = (int)scan.size();
-    int nt = (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(std::min(nt, 16), nchunk));
+    int nt = max_threads > 0 ? max_threads : std::min((int)std::thread::hardware_concurrency(), 16);
+    nt = std::max(1, std::min(nt, nchunk));
     for (int t = 0; t < nt; ++t)
       threads.emplace_back([=]() {
         for (;;) {
@@ -782,8 +745,8 @@ struct ScanPool {
           const long long r0 = (long long)c * chunk_rows, r1 = std::min<long long>(num_row, r0 + chunk_rows);
           ChunkScan &s = scan[(size_t)c];
           const long long v0 = row_ptr[3 * r0], v1 = row_ptr[3 * r1];
-          s.rp_regular = scan_rp_regular(row_ptr + 3 * r0, r1 - r0, s.a, s.b, s.c);
-          s.val_ones = value && v0 >= 0 && v1 > v0 && scan_ones(value + v0, v1 - v0);
+          s.rp_regular = svdscan::rp_regular(row_ptr + 3 * r0, r1 - r0, s.a, s.b, s.c);
+          s.val_ones = value && v0 >= 0 && v1 > v0 && svdscan::all_ones(value + v0, v1 - v0);
           ready[(size_t)c].store(1, std::memory_order_release);
         }
       });
@@ -817,7 +780,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
   const int nchunk = (int)(((long long)num_row + h->chunk_rows - 1) / h->chunk_rows);
   const bool compact = h->compact_h2d && !exact && !sides_on(h) && num_row >= h->compact_min_rows;
   ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
-  if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value);
+  if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value, h->scan_threads);
   for (int r0 = 0, ci = 0; r0 < num_row; r0 += h->chunk_rows, ++ci) {
     const int r1 = (int)std::min<long long>(num_row, (long long)r0 + h->chunk_rows);
     const int n = r1 - r0;

@@ -108,6 +108,7 @@ struct svdgpu {
   int compact_h2d = 1;  // option "compact_h2d": Hogwild / predict host-pointer calls do not copy a chunk's
                         // row_ptr when every row has the same feature counts, nor its values when all are 1.0f
                         // (checked on host threads while earlier chunks are copied; rebuilt on the device)
+  int scan_threads = 0;            // option "scan_threads": host threads of that check (0 = min(cores, 16))
   int compact_min_rows = 1 << 18;  // option "compact_min_rows": calls with fewer rows skip the check
   int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):
                        // 1 no per-lane fence before the release, 2 spin before sleeping, 4 staged slice
