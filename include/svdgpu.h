@@ -91,7 +91,14 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *   "ring_depth", "mf_ctas" : fast-pass tuning (gather ring depth 2|4, CTAs per SM 2|3)
  *   "lanes"       : lanes per instance in hogwild mode (0 = auto = pitch/4, max 32)
  *   "chunk_rows"  : rows per launch for host-pointer calls
- *   "ctas_per_sm" : persistent CTAs per SM (0 = auto) */
+ *   "ctas_per_sm" : persistent CTAs per SM (0 = auto)
+ *   "compact_h2d" : 1 (default): Hogwild / predict host-pointer calls of at least "compact_min_rows"
+ *                   rows (default 262144) do not copy a chunk's row_ptr when all its rows have the same
+ *                   feature counts, nor its values when all are 1.0f; host threads ("scan_threads",
+ *                   0 = min(cores, 16)) verify every element while earlier chunks are copied, the
+ *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
+ *   "exact_opt"   : ordered kernel hand-off variants, bit mask (default 5): 1 release without a
+ *                   per-lane fence, 2 poll back to back, 4 instance slice staged in shared memory */
 int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
 int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);
