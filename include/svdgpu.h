@@ -95,7 +95,7 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *   "compact_h2d" : 1 (default): Hogwild / predict host-pointer calls of at least "compact_min_rows"
  *                   rows (default 262144) do not copy a chunk's row_ptr when all its rows have the same
  *                   feature counts, nor its values when all are 1.0f; host threads ("scan_threads",
- *                   0 = min(cores, 16)) verify every element while earlier chunks are copied, the
+ *                   0 = this process's share of the cores, at most 16; fewer than 5: no scan) verify every element while earlier chunks are copied, the
  *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
  *   "exact_opt"   : ordered kernel hand-off variants, bit mask (default 5): 1 release without a
  *                   per-lane fence, 2 poll back to back, 4 instance slice staged in shared memory */

@@ -731,7 +731,7 @@ def test_compact_h2d_is_invisible(native, chunk_rows):
         g.set_hparams(**_cases.hparams_of(params, o.base_score))
         g.set_mode(native.MODE_HOGWILD)
         for name, v in (("scatter_user", 0), ("scatter_item", 0), ("exact_dot", 1), ("chunk_rows", chunk_rows),
-                        ("compact_h2d", compact), ("compact_min_rows", 1)):
+                        ("compact_h2d", compact), ("compact_min_rows", 1), ("scan_threads", 4)):
             g.set_option(name, v)
         g.upload(*[a.copy() for a in o.arrays()])
         o.update_csr(data)
