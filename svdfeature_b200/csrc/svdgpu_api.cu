@@ -14,6 +14,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -703,10 +704,6 @@ void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats) {
 // compared) while earlier chunks are being copied; an array that passes is not copied but
 // rebuilt in the slot by a fill kernel.  What the kernels read is bit-identical either way.
 // ---------------------------------------------------------------------------
-struct ChunkScan {
-  bool rp_regular = false, val_ones = false;
-  int a = 0, b = 0, c = 0;  // global / user / item features per row when rp_regular
-};
 
 __global__ void k_fill_row_ptr(int *rp, int n, int a, int b, int c) {
   const int w = a + b + c;
@@ -723,43 +720,6 @@ __global__ void k_fill_ones(float *v, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     v[i] = 1.0f;
 }
-
-// the scanning threads of one call: chunk c's verdict is in scan[c] once ready[c] != 0
-struct ScanPool {
-  std::vector<ChunkScan> scan;
-  std::vector<std::atomic<int>> ready;
-  std::atomic<int> next{0};
-  std::atomic<bool> stop{false};
-  std::vector<std::thread> threads;
-  explicit ScanPool(int nchunk) : scan((size_t)nchunk), ready((size_t)nchunk) {
-    for (auto &r : ready) r.store(0, std::memory_order_relaxed);
-  }
-  void start(int num_row, int chunk_rows, const int *row_ptr, const float *value, int max_threads) {
-    const int nchunk = (int)scan.size();
-    const int nt = std::max(1, std::min(max_threads, nchunk));
-    for (int t = 0; t < nt; ++t)
-      threads.emplace_back([=]() {
-        for (;;) {
-          const int c = next.fetch_add(1);
-          if (c >= nchunk || stop.load(std::memory_order_relaxed)) break;
-          const long long r0 = (long long)c * chunk_rows, r1 = std::min<long long>(num_row, r0 + chunk_rows);
-          ChunkScan &s = scan[(size_t)c];
-          const long long v0 = row_ptr[3 * r0], v1 = row_ptr[3 * r1];
-          s.rp_regular = svdscan::rp_regular(row_ptr + 3 * r0, r1 - r0, s.a, s.b, s.c);
-          s.val_ones = value && v0 >= 0 && v1 > v0 && svdscan::all_ones(value + v0, v1 - v0);
-          ready[(size_t)c].store(1, std::memory_order_release);
-        }
-      });
-  }
-  const ChunkScan &wait(int c) {
-    while (!ready[(size_t)c].load(std::memory_order_acquire)) std::this_thread::yield();
-    return scan[(size_t)c];
-  }
-  ~ScanPool() {
-    stop.store(true);
-    for (auto &t : threads) t.join();
-  }
-};
 
 // ---------------------------------------------------------------------------
 // random-order CSR, host buffers
@@ -790,7 +750,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     if (scan_threads < 5) scan_threads = 0;
   }
   const bool compact = h->compact_h2d && scan_threads > 0 && !exact && !sides_on(h) && num_row >= h->compact_min_rows;
-  ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
+  svdscan::ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
   if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value, scan_threads);
   for (int r0 = 0, ci = 0; r0 < num_row; r0 += h->chunk_rows, ++ci) {
     const int r1 = (int)std::min<long long>(num_row, (long long)r0 + h->chunk_rows);
@@ -805,7 +765,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     const size_t nv = (size_t)(v1 - v0);
     const unsigned *c_idx = side ? ex.idx.data() : index + v0;
     const float *c_val = side ? ex.val.data() : value + v0;
-    ChunkScan sc;
+    svdscan::ChunkScan sc;
     if (compact) sc = pool.wait(ci);
     Slot &s = next_slot(h);  // (the kernels that last read this slot are done)
     if (sc.rp_regular) {

@@ -5,7 +5,11 @@
 // (tests/test_scan_host.py).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <system_error>
+#include <thread>
+#include <vector>
 
 namespace svdscan {
 
@@ -69,5 +73,66 @@ inline bool all_ones(const float *v, long long nv) {
   }
   return true;
 }
+
+// verdict of the two checks for one chunk of a call
+struct ChunkScan {
+  bool rp_regular = false, val_ones = false;
+  int a = 0, b = 0, c = 0;  // global / user / item features per row when rp_regular
+};
+
+// the scanning threads of one call: chunk c's verdict is in scan[c] once ready[c] != 0.  Chunks are
+// claimed in input order, so the verdicts the caller waits for come first.
+struct ScanPool {
+  std::vector<ChunkScan> scan;
+  std::vector<std::atomic<int>> ready;
+  std::atomic<int> next{0};
+  std::atomic<bool> stop{false};
+  std::vector<std::thread> threads;
+  int num_row = 0, chunk_rows = 1;
+  const int *row_ptr = nullptr;
+  const float *value = nullptr;
+  explicit ScanPool(int nchunk) : scan((size_t)nchunk), ready((size_t)nchunk) {
+    for (auto &r : ready) r.store(0, std::memory_order_relaxed);
+  }
+  // claim the next unclaimed chunk and scan it; false when none is left
+  bool scan_one() {
+    const int c = next.fetch_add(1);
+    if (c >= (int)scan.size()) return false;
+    const long long r0 = (long long)c * chunk_rows, r1 = std::min<long long>(num_row, r0 + chunk_rows);
+    ChunkScan &s = scan[(size_t)c];
+    const long long v0 = row_ptr[3 * r0], v1 = row_ptr[3 * r1];
+    s.rp_regular = rp_regular(row_ptr + 3 * r0, r1 - r0, s.a, s.b, s.c);
+    s.val_ones = value && v0 >= 0 && v1 > v0 && all_ones(value + v0, v1 - v0);
+    ready[(size_t)c].store(1, std::memory_order_release);
+    return true;
+  }
+  void start(int num_row_, int chunk_rows_, const int *row_ptr_, const float *value_, int max_threads) {
+    num_row = num_row_;
+    chunk_rows = chunk_rows_;
+    row_ptr = row_ptr_;
+    value = value_;
+    const int nt = std::max(0, std::min(max_threads, (int)scan.size()));  // 0: the caller scans in wait()
+    try {
+      for (int t = 0; t < nt; ++t)
+        threads.emplace_back([this]() {
+          while (!stop.load(std::memory_order_relaxed) && scan_one()) {
+          }
+        });
+    } catch (const std::system_error &) {
+      // out of threads: the ones that started (or, with none, the calling thread in wait()) do the work
+    }
+  }
+  const ChunkScan &wait(int c) {
+    while (!ready[(size_t)c].load(std::memory_order_acquire)) {
+      if (threads.empty()) scan_one();  // (claims are in order: this reaches chunk c)
+      else std::this_thread::yield();
+    }
+    return scan[(size_t)c];
+  }
+  ~ScanPool() {
+    stop.store(true);
+    for (auto &t : threads) t.join();
+  }
+};
 
 }  // namespace svdscan

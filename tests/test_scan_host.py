@@ -12,6 +12,27 @@ SHIM = r"""
 #include "svdgpu_scan.h"
 extern "C" int scan_rp(const int *p, long long n, int *abc) { return svdscan::rp_regular(p, n, abc[0], abc[1], abc[2]) ? 1 : 0; }
 extern "C" int scan_ones(const float *v, long long n) { return svdscan::all_ones(v, n) ? 1 : 0; }
+// what run_csr_host does with the pool: start, take the verdicts in chunk order
+extern "C" void scan_pool(const int *rp, const float *v, int num_row, int chunk_rows, int threads, int *out) {
+  const int nchunk = (num_row + chunk_rows - 1) / chunk_rows;
+  svdscan::ScanPool pool(nchunk);
+  pool.start(num_row, chunk_rows, rp, v, threads);
+  for (int c = 0; c < nchunk; ++c) {
+    const svdscan::ChunkScan &s = pool.wait(c);
+    out[5 * c] = s.rp_regular;
+    out[5 * c + 1] = s.val_ones;
+    out[5 * c + 2] = s.a;
+    out[5 * c + 3] = s.b;
+    out[5 * c + 4] = s.c;
+  }
+}
+// leaving early (an error return of the caller) must join the workers
+extern "C" void scan_pool_abandon(const int *rp, const float *v, int num_row, int chunk_rows, int threads) {
+  const int nchunk = (num_row + chunk_rows - 1) / chunk_rows;
+  svdscan::ScanPool pool(nchunk);
+  pool.start(num_row, chunk_rows, rp, v, threads);
+  if (nchunk > 0) pool.wait(0);
+}
 """
 
 
@@ -21,7 +42,7 @@ def lib(tmp_path_factory):
     src = d / "shim.cpp"
     src.write_text(SHIM)
     so = d / "libscan.so"
-    subprocess.check_call(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "svdfeature_b200", "csrc"),
+    subprocess.check_call(["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "svdfeature_b200", "csrc"),
                            "-o", str(so), str(src)])
     lib = C.CDLL(str(so))
     lib.scan_rp.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
@@ -101,3 +122,42 @@ def test_all_ones(lib, n):
             w = v.copy()
             w[j] = bad
             assert lib.scan_ones(w.ctypes.data, n) == 0, (n, j, bad)
+
+
+@pytest.mark.parametrize("threads", [0, 1, 3, 16])
+@pytest.mark.parametrize("chunk_rows", [1000, 777, 100000])
+def test_scan_pool_verdicts_per_chunk(lib, threads, chunk_rows):
+    """The batch of test_compact_h2d_is_invisible: unit-valued basic rows, basic rows with other
+    values, a ragged tail -- per chunk the pool must say exactly what numpy says."""
+    n = 6000
+    nf = np.array([2] * 4800 + [2 if r % 3 else 1 for r in range(4800, n)], np.int64)
+    nu = np.array([1] * 4800 + [1 if r % 3 else 0 for r in range(4800, n)], np.int64)
+    start = np.concatenate([[0], np.cumsum(nf)]) + 40  # (the slice does not start at entry 0)
+    rp = np.empty(3 * n + 1, np.int32)
+    rp[0::3] = start
+    rp[1::3] = start[:-1]
+    rp[2::3] = start[:-1] + nu
+    val = np.ones(int(start[-1]), np.float32)
+    val[start[3500]:start[4800]] = 0.5
+    nchunk = (n + chunk_rows - 1) // chunk_rows
+    out = np.full(5 * nchunk, -1, np.int32)
+    lib.scan_pool.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.scan_pool(rp.ctypes.data, val.ctypes.data, n, chunk_rows, threads, out.ctypes.data)
+    for c in range(nchunk):
+        r0, r1 = c * chunk_rows, min(n, (c + 1) * chunk_rows)
+        regular = bool(np.all(nf[r0:r1] == nf[r0]) and np.all(nu[r0:r1] == nu[r0]))
+        ones = bool(np.all(val[start[r0]:start[r1]] == 1.0))
+        assert bool(out[5 * c]) == regular, (c, "row_ptr")
+        assert bool(out[5 * c + 1]) == ones, (c, "values")
+        if regular:
+            assert tuple(out[5 * c + 2:5 * c + 5]) == (0, int(nu[r0]), int(nf[r0] - nu[r0]))
+
+
+@pytest.mark.parametrize("threads", [0, 2, 8])
+def test_scan_pool_can_be_abandoned(lib, threads):
+    n = 200000
+    rp = _rp(n, 0, 1, 1)
+    val = np.ones(2 * n, np.float32)
+    lib.scan_pool_abandon.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    for _ in range(20):
+        lib.scan_pool_abandon(rp.ctypes.data, val.ctypes.data, n, 1000, threads)
