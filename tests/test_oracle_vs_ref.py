@@ -108,3 +108,51 @@ def test_oracle_ranker_side_features(tmp_path):
     rr = RefRanker(path, skw["num_item_set"], rp).rank(stream)
     assert np.array_equal(ro, rr)
     assert not np.array_equal(ro, COracleRanker(path, skw["num_item_set"], rparams).rank(stream))
+
+
+def _random_config(seed):
+    """A random point of the hot path's configuration space: factor count (any residue mod 4),
+    loss, regulariser, decays (zero, tiny = the "scalar is one" shortcut, ordinary), bias switches,
+    learning-rate decay, ragged rows with duplicates; user-grouped (SVD++) for odd seeds."""
+    rng = np.random.default_rng(1000 + seed)
+    act = int(rng.choice([0, 0, 1, 2, 3, 5, 6, 7]))
+    wd = lambda: float(rng.choice([0.0, 1e-5, 0.004, 0.05]))  # noqa: E731
+    params = dict(num_user=NU_R, num_item=NI_R, num_global=NG_R, num_factor=int(rng.integers(1, 41)),
+                  learning_rate=float(rng.choice([0.001, 0.01, 0.05])), wd_user=wd(), wd_item=wd(),
+                  wd_user_bias=wd(), wd_item_bias=wd(), wd_global=wd(),
+                  base_score=0.6 if act in (1, 2, 3, 7) else float(rng.choice([0.0, 3.6])),
+                  no_user_bias=int(rng.integers(0, 2)), num_regfree_global=int(rng.choice([0, 5])),
+                  reg_method=int(rng.choice([0, 0, 1, 2, 3])), reg_global=int(rng.choice([0, 1])),
+                  user_nonnegative=int(rng.choice([0, 0, 1])),
+                  u_init_sigma=float(rng.choice([0.01, 0.1])), i_init_sigma=float(rng.choice([0.01, 0.1])))
+    if rng.random() < 0.3:
+        params.update(decay_learning_rate=1, decay_rate=0.8)
+    ug = seed % 2 == 1
+    if ug:
+        params.update(num_ufeedback=NI_R, wd_ufeedback=wd(), wd_ufeedback_bias=wd(),
+                      scale_lr_ufeedback=float(rng.choice([1.0, 0.3])), ufeedback_init_sigma=0.01)
+        data = synth.user_grouped(600, NU_R, NI_R, avg_fb=int(rng.integers(1, 12)), seed=seed)
+        if rng.random() < 0.5:
+            data = _cases.split_tags(data, every=2)
+        if act in (1, 2, 3, 7):  # labels in [0,1] for the sigmoid losses
+            data = data[:6] + ((data[6] > 3).astype(np.float32),) + data[7:]
+        return 1, act, params, data, "ug"
+    data = synth.random_general(500, NU_R, NI_R, NG_R, seed=seed, max_g=int(rng.integers(0, 6)),
+                                max_u=int(rng.integers(1, 4)), max_i=int(rng.integers(1, 5)),
+                                allow_dup=bool(rng.integers(0, 2)))
+    if act in (1, 2, 3, 7):
+        data = _cases._binary(data)
+    return 0, act, params, data, "csr"
+
+
+NU_R, NI_R, NG_R = 60, 40, 12
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(48))
+def test_oracle_matches_reference_on_random_configurations(seed, tmp_path):
+    fmt, act, params, data, kind = _random_config(seed)
+    mo, po = _train(COracle, fmt, act, params, data, kind, tmp_path, rounds=3)
+    mr, pr = _train(RefTrainer, fmt, act, params, data, kind, tmp_path, rounds=3)
+    assert mo == mr, ("model bytes differ", params, act)
+    assert np.array_equal(po, pr, equal_nan=True), ("predictions differ", params, act)
