@@ -98,7 +98,9 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   0 = this process's share of the cores, at most 16; fewer than 5: no scan) verify every element while earlier chunks are copied, the
  *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
  *   "exact_opt"   : ordered kernel hand-off variants, bit mask (default 5): 1 release without a
- *                   per-lane fence, 2 poll back to back, 4 instance slice staged in shared memory */
+ *                   per-lane fence, 2 poll back to back, 4 instance slice staged in shared memory
+ *   "exact_owner" : EXPERIMENTAL, default 0: ordered mode on resident basic-MF batches through
+ *                   item-owner warps (set before svdgpu_batch_create) */
 int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
 int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);

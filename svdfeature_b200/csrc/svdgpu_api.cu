@@ -3,6 +3,7 @@
 // dispatch.  No CPU compute path exists here: every update/predict call ends in
 // a kernel launch or fails.
 #include "svdgpu_internal.h"
+#include "svdgpu_owner.h"
 #include "svdgpu_scan.h"
 
 #include <algorithm>
@@ -544,6 +545,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "svdpp_fast")) h->svdpp_fast = v ? 1 : 0;
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else if (!strcmp(name, "exact_opt")) h->exact_opt = (int)v;
+  else if (!strcmp(name, "exact_owner")) h->exact_owner = v ? 1 : 0;
   else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
   else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));
   else if (!strcmp(name, "compact_min_rows")) h->compact_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
@@ -1103,6 +1105,18 @@ int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const in
     if (!rc) rc |= upload_plain(h, b->d_ticket, tk.data(), nv * 4);
     if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
     b->has_ticket = !rc;
+    if (!rc && h->exact_owner && !side && num_row > 0) {  // experimental: per-owner queues for k_owner
+      Geometry geo;
+      int cap = 0;
+      svdowner::Plan plan;
+      if (!pick_geometry(h, geo) && !launch_owner(h, geo, DevCsr(), nullptr, nullptr, 0, &cap) && cap > 0 &&
+          svdowner::build_plan(num_row, row_ptr, index, h->shape.num_item, cap, plan)) {
+        rc |= upload_plain(h, b->d_queue_off, plan.queue_off.data(), plan.queue_off.size() * 4);
+        rc |= upload_plain(h, b->d_queue, plan.queue.data(), plan.queue.size() * 4);
+        if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
+        if (!rc) b->owner_warps = cap;
+      }
+    }
   }
   if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
   if (rc) {
@@ -1201,7 +1215,13 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
     if (!b->has_ticket) return fail(h, "batch was created in hogwild mode: no tickets for the ordered mode");
     if (begin != 0 || end != b->num_row)
       return fail(h, "ordered mode needs the whole resident batch (tickets are per batch)");
-    if (launch_exact(h, geo, batch_csr(b), begin, end)) return 1;
+    if (h->exact_owner && b->owner_warps > 0) {
+      if (launch_owner(h, geo, batch_csr(b), (const int *)b->d_queue_off.p, (const int *)b->d_queue.p, b->owner_warps,
+                       nullptr))
+        return 1;
+    } else if (launch_exact(h, geo, batch_csr(b), begin, end)) {
+      return 1;
+    }
   } else {
     if (launch_stream(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
   }
@@ -1255,7 +1275,7 @@ void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b) {
     cudaStreamSynchronize(h->stream);
   }
   DevBuf *db[] = {&b->d_rp, &b->d_label, &b->d_index, &b->d_value, &b->d_value2, &b->d_ticket, &b->d_pred,
-                  &b->d_unit_off, &b->d_blk_row_off, &b->d_blk_fb_off, &b->d_fbi, &b->d_fbv, &b->d_fbt, &b->d_order};
+                  &b->d_queue, &b->d_queue_off, &b->d_unit_off, &b->d_blk_row_off, &b->d_blk_fb_off, &b->d_fbi, &b->d_fbv, &b->d_fbt, &b->d_order};
   for (DevBuf *d : db) dev_free(*d);
   delete b;
 }

@@ -110,6 +110,8 @@ struct svdgpu {
                         // (checked on host threads while earlier chunks are copied; rebuilt on the device)
   int scan_threads = 0;            // option "scan_threads": host threads of that check (0 = min(cores, 16))
   int compact_min_rows = 1 << 18;  // option "compact_min_rows": calls with fewer rows skip the check
+  int exact_owner = 0;  // option "exact_owner" (EXPERIMENTAL): ordered mode on resident basic-MF batches through
+                        // item-owner warps (k_owner, svdgpu_ordered.cu)
   int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):
                        // 1 no per-lane fence before the release, 2 spin before sleeping, 4 staged slice
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
@@ -143,6 +145,9 @@ struct svdgpu_batch {
   long long num_val = 0;
   DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_pred;
   bool has_ticket = false, has_value2 = false;
+  // experimental item-owner ordered mode (option "exact_owner"): per-owner row queues
+  DevBuf d_queue, d_queue_off;
+  int owner_warps = 0;
   // user-group structure
   bool ugroup = false, has_fb = false;
   int num_block = 0, num_unit = 0;
@@ -176,6 +181,9 @@ int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r
 int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred,
               int which, unsigned *flag_out, const unsigned *flag_gate);
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
+// experimental item-owner ordered kernel: capacity != nullptr only queries how many owners fit
+int launch_owner(svdgpu *h, const Geometry &g, const DevCsr &csr, const int *queue_off, const int *queue,
+                 int num_owner, int *capacity);
 int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
                   bool train, bool ordered, float *pred);
 int launch_delta(svdgpu *h, int mode, float scale);

@@ -9,6 +9,8 @@ Bars (north_star: predictions within 1e-4 RMSE of the reference CPU path):
   * Hogwild mode on conflicting input: prediction RMSE vs sequential <= 1e-2 after
     an epoch and held-out RMSE within 1e-3 (statistical parity; documented).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -748,3 +750,32 @@ def test_compact_h2d_is_invisible(native, chunk_rows):
         assert moved[1] < moved[0]
     if chunk_rows == 1000:  # chunks 0-2 leave out both arrays, chunk 3 (rows 3000-3999) its row_ptr only
         assert moved[0] - moved[1] >= 3 * 1000 * 20 + 1000 * 12
+
+
+@pytest.mark.skipif(not os.environ.get("SVDGPU_TEST_EXPERIMENTAL"),
+                    reason="experimental item-owner ordered kernel (option exact_owner): written after this round's "
+                           "GPU budget was spent; set SVDGPU_TEST_EXPERIMENTAL=1 to run it")
+@pytest.mark.parametrize("k", [64, 16, 128])
+def test_exact_owner_matches_oracle(native, k):
+    """Ordered mode through item-owner warps (k_owner) on a resident basic-MF batch with hot items:
+    model and predictions bit-identical to the sequential oracle, like k_exact."""
+    nu, ni, n = 3000, 200, 60000
+    params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.01, wd_user=0.004, wd_item=0.003,
+                  wd_user_bias=0.001, wd_item_bias=0.002, base_score=3.6)
+    data = synth.basic_mf(n, nu, ni, seed=31, zipf_q=2.0)
+    o = COracle(0, 0, 0, params)
+    o.init(5)
+    g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_mode(native.MODE_EXACT)
+    g.set_option("exact_owner", 1)
+    g.upload(*[a.copy() for a in o.arrays()])
+    b = g.batch_create(data)
+    for _ in range(2):
+        o.update_csr(data)
+        g.batch_update(b)
+    g.sync()
+    assert _maxdiff(o, g) == 0.0
+    assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
+    b.close()
+    g.close()

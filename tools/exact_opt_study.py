@@ -20,11 +20,15 @@ data = synth.basic_mf(N, NU, NI, seed=3, zipf_q=70.0)
 top = int(np.bincount(data[2][1::2]).max())
 out = open(os.path.join(ROOT, "gpurun_out", "exact_opt_study.jsonl"), "a")
 ref = None
-for opt in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 3, 5, 6, 7]:
+# "owner" = the experimental item-owner kernel (option exact_owner) on top of the default exact_opt
+for arg in sys.argv[1:] or ["0", "1", "2", "4", "3", "5", "6", "7"]:
+    owner = arg == "owner"
+    opt = 5 if owner else int(arg)
     g = api.SvdGpu(NU, NI, K)
     g.set_hparams(learning_rate=0.005, wd_user=0.004, wd_item=0.004, base_score=3.6)
     g.set_mode(api.MODE_EXACT)
     g.set_option("exact_opt", opt)
+    g.set_option("exact_owner", 1 if owner else 0)
     g.upload(np.zeros(NU + NI, np.float32), W, np.zeros(1, np.float32))
     b = g.batch_create(data)
     g.batch_update(b)
@@ -37,7 +41,7 @@ for opt in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 3, 5, 6, 7]:
     for _ in range(3):
         g.batch_update(b)
     ms = g.timer_stop() / 3
-    line = dict(exact_opt=opt, rows=N, hottest_item_rows=top, ms=ms, minst_s=N / ms / 1e3,
+    line = dict(exact_opt=opt, exact_owner=owner, rows=N, hottest_item_rows=top, ms=ms, minst_s=N / ms / 1e3,
                 us_per_hot_row=1e3 * ms / top, same_model_as_first=bool(same))
     print(json.dumps(line), flush=True)
     out.write(json.dumps(line) + "\n")
