@@ -240,17 +240,17 @@ int svdgpu_batch_download(svdgpu_t *h, svdgpu_batch_t *b, int *num_row, long lon
  * result: top_k > 0: the positions of the top_k candidates by score; top_k = 0: the rank position
  * of every POS candidate, in the order they were given.  Equal scores: lower position first (the
  * reference's std::sort leaves it unspecified).  The model is the one in the handle
- * (svdgpu_upload_model); side features (svdgpu_set_side_features) apply as in base.h:703-707,735-738.
+ * (svdgpu_upload_model); side features (svdgpu_set_side_features) apply as in base.h:698-702,731-734.
  *
- * replaces: SVDFeatureRanker::init_ranker (base.h:668-688; top_k is its "top_k" parameter) */
+ * replaces: SVDFeatureRanker::init_ranker (base.h:666-685; top_k is its "top_k" parameter) */
 int svdgpu_rank_init(svdgpu_t *h, int num_item_set, int top_k);
-/* replaces: for each row ISVDRanker::process(result, Elem) (base.h:802-804; the loop of
+/* replaces: for each row ISVDRanker::process(result, Elem) (base.h:795-797; the loop of
  * svd_feature_infer.cpp:352-360).  The stream may be cut anywhere between calls; sections closed by
  * a PROCESS row inside the call are ranked together on the device.  *num_result receives the
  * number of results; if they do not fit result_cap the call fails and keeps them for the next call. */
 int svdgpu_rank_csr(svdgpu_t *h, int num_row, const int *row_ptr, const float *label, const unsigned *index,
                     const float *value, int *result, long long result_cap, long long *num_result);
-/* replaces: for each block ISVDRanker::process(result, SVDPlusBlock) (base.h:805-819): a DEFAULT or
+/* replaces: for each block ISVDRanker::process(result, SVDPlusBlock) (base.h:798-812): a DEFAULT or
  * START block's feedback list becomes the implicit-feedback part of the following USER rows. */
 int svdgpu_rank_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const int *blk_fb_off,
                        const int *blk_tag, const unsigned *fb_index, const float *fb_value,

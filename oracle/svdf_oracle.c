@@ -963,7 +963,7 @@ float svdo_learning_rate(svdo_t *m) { return m->learning_rate; }
  * ====================================================================================== */
 enum { RK_ITEM = 0, RK_POS = 1, RK_USER = 2, RK_SPEC = 3, RK_PROCESS = 4, RK_BAN = -1 };
 
-void svdo_init_ranker(svdo_t *m, int num_item_set) { /* base.h:668-688 */
+void svdo_init_ranker(svdo_t *m, int num_item_set) { /* base.h:666-685 */
   size_t n = (size_t)(m->pitch > 0 ? m->pitch : 1), ns = (size_t)(num_item_set > 0 ? num_item_set : 1);
   if (strcmp(m->name_feat_user, "NULL"))
     sparse_load(m->name_feat_user, &m->feat_user.num_row, &m->feat_user.row_ptr, &m->feat_user.index, &m->feat_user.value);
@@ -981,7 +981,7 @@ void svdo_init_ranker(svdo_t *m, int num_item_set) { /* base.h:668-688 */
   m->rk.init_end = 1;
 }
 
-static void rk_prepare_ifactor(svdo_t *m, float *ifactor, float *bias_out, const elem_t *e) { /* base.h:690-716 */
+static void rk_prepare_ifactor(svdo_t *m, float *ifactor, float *bias_out, const elem_t *e) { /* base.h:687-710 */
   const int k = m->num_factor;
   float bias = 0.0f;
   int i;
@@ -1015,13 +1015,13 @@ static void rk_prepare_ifactor(svdo_t *m, float *ifactor, float *bias_out, const
   *bias_out = bias;
 }
 
-static void rk_proc_item(svdo_t *m, const elem_t *e) { /* base.h:718-723 */
+static void rk_proc_item(svdo_t *m, const elem_t *e) { /* base.h:712-717 */
   const int idx = m->rk.num_item_processed++;
   if (!(m->rk.num_item_processed <= m->rk.num_item_set)) die("item instance exceed specified item set size");
   rk_prepare_ifactor(m, m->rk.tmp_ifactors + (size_t)idx * m->pitch, &m->rk.bias_ifactors[idx], e);
 }
 
-static void rk_proc_user(svdo_t *m, const elem_t *e) { /* base.h:725-746 */
+static void rk_proc_user(svdo_t *m, const elem_t *e) { /* base.h:719-740 */
   const int k = m->num_factor;
   int i;
   if (m->format_type == FMT_USER_GROUP) memcpy(m->rk.tmp_ufactor, m->rk.tmp_ufeedback, sizeof(float) * (size_t)k);
@@ -1039,7 +1039,7 @@ static void rk_proc_user(svdo_t *m, const elem_t *e) { /* base.h:725-746 */
   for (i = 0; i < m->rk.num_item_processed; ++i) m->rk.item_tag[i] = 0;
 }
 
-static void rk_proc_tag(svdo_t *m, const elem_t *e, int tag) { /* base.h:747-755 */
+static void rk_proc_tag(svdo_t *m, const elem_t *e, int tag) { /* base.h:741-749 */
   int i;
   for (i = 0; i < e->nu; ++i) {
     const int idx = (int)e->ui[i];
@@ -1056,7 +1056,7 @@ static void rk_proc_tag(svdo_t *m, const elem_t *e, int tag) { /* base.h:747-755
   }
 }
 
-static void rk_proc_spec(svdo_t *m, const elem_t *e) { /* base.h:756-764 */
+static void rk_proc_spec(svdo_t *m, const elem_t *e) { /* base.h:750-758 */
   float bias, d;
   int idx;
   if (!(e->nu == 1)) die("must specify item index of sample in user feature field\n");
@@ -1068,7 +1068,7 @@ static void rk_proc_spec(svdo_t *m, const elem_t *e) { /* base.h:756-764 */
 }
 
 typedef struct { int iid; float score; } rk_entry;
-/* Entry::operator< (base.h:621): higher score first.  std::sort leaves the order of equal scores
+/* Entry::operator< (base.h:622): higher score first.  std::sort leaves the order of equal scores
  * to the implementation; this restatement puts the lower item index first (stable). */
 static int rk_cmp(const void *a, const void *b) {
   const rk_entry *x = (const rk_entry *)a, *y = (const rk_entry *)b;
@@ -1077,7 +1077,7 @@ static int rk_cmp(const void *a, const void *b) {
   return x->iid < y->iid ? -1 : (x->iid > y->iid ? 1 : 0);
 }
 
-static long rk_proc_rank(svdo_t *m, int *rst, long cap, long n_out) { /* base.h:765-789 */
+static long rk_proc_rank(svdo_t *m, int *rst, long cap, long n_out) { /* base.h:759-782 */
   const int n = m->rk.num_item_processed;
   rk_entry *entry = (rk_entry *)malloc(sizeof(rk_entry) * (size_t)(n > 0 ? n : 1));
   int ne = 0, i;
@@ -1109,7 +1109,7 @@ static long rk_proc_rank(svdo_t *m, int *rst, long cap, long n_out) { /* base.h:
   return n_out;
 }
 
-static long rk_proc(svdo_t *m, const elem_t *e, int *rst, long cap, long n_out) { /* base.h:790-800 */
+static long rk_proc(svdo_t *m, const elem_t *e, int *rst, long cap, long n_out) { /* base.h:783-793 */
   const int tag = (int)e->label;
   switch (tag) {
     case RK_ITEM: rk_proc_item(m, e); break;
@@ -1123,7 +1123,7 @@ static long rk_proc(svdo_t *m, const elem_t *e, int *rst, long cap, long n_out) 
   return n_out;
 }
 
-/* for each row ISVDRanker::process(result, Elem) (base.h:802-804); returns the number of results
+/* for each row ISVDRanker::process(result, Elem) (base.h:795-797); returns the number of results
  * (those beyond cap are counted but not stored) */
 long svdo_rank_csr(svdo_t *m, int num_row, const int *row_ptr, const float *label, const unsigned *index,
                    const float *value, int *result, long cap) {
@@ -1136,7 +1136,7 @@ long svdo_rank_csr(svdo_t *m, int num_row, const int *row_ptr, const float *labe
   return n_out;
 }
 
-/* for each block ISVDRanker::process(result, SVDPlusBlock) (base.h:805-819) */
+/* for each block ISVDRanker::process(result, SVDPlusBlock) (base.h:798-812) */
 long svdo_rank_ugroup(svdo_t *m, int num_block, const int *blk_row_off, const int *blk_fb_off, const int *blk_tag,
                       const unsigned *fb_index, const float *fb_value, const int *row_ptr, const float *label,
                       const unsigned *index, const float *value, int *result, long cap) {

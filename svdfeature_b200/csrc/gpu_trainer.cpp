@@ -540,18 +540,18 @@ class GpuSVDRanker : public ISVDRanker {
     if (!strcmp(name, "feature_user") || !strcmp(name, "feature_item") || !strncmp(name, "gpu:", 4))
       tr_.set_param(name, val);
   }
-  virtual void init_ranker(int num_item_set) {  // base.h:668-688
+  virtual void init_ranker(int num_item_set) {  // base.h:666-685
     tr_.init_trainer();
     check(tr_.handle(), svdgpu_rank_init(tr_.handle(), num_item_set, top_k_));
   }
-  virtual void process(std::vector<int> &result, const SVDFeatureCSR::Elem &e) {  // base.h:802-804
+  virtual void process(std::vector<int> &result, const SVDFeatureCSR::Elem &e) {  // base.h:795-797
     CsrStage one;
     one.push(e);
     note(e);
     collect(result, svdgpu_rank_csr(tr_.handle(), 1, one.row_ptr.data(), one.label.data(), one.index.data(),
                                     one.value.data(), buf(), (long long)buf_.size(), &n_));
   }
-  virtual void process(std::vector<int> &result, const SVDPlusBlock &b) {  // base.h:805-819
+  virtual void process(std::vector<int> &result, const SVDPlusBlock &b) {  // base.h:798-812
     CsrStage rows;
     for (int r = 0; r < b.data.num_row; ++r) {
       rows.push(b.data[r]);

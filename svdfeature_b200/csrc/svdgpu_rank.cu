@@ -3,10 +3,10 @@
 // The reference's ranker (base.h:597-813) consumes a TAGGED instance stream (svdranker_tag,
 // apex_svd.h:115-152; the tag sits in the label field): ITEM rows define the candidate set
 // (prepare_ifactor: tmp_ifactors[idx] = sum ival*W_item[iid], bias_ifactors[idx] = sum
-// ival*i_bias[iid] + sum gval*g_bias[gid], base.h:690-723), then every user section
+// ival*i_bias[iid] + sum gval*g_bias[gid], base.h:687-717), then every user section
 // USER / POS* / BAN* / SPEC* / PROCESS ranks the whole set for one user: score[i] = spec[i] +
 // (bias_ifactors[i] + dot(tmp_ufactor, tmp_ifactors[i])) for every item that is not banned,
-// sorted by score (base.h:765-789); the answer is the top_k item indices or, with top_k = 0, the
+// sorted by score (base.h:759-782); the answer is the top_k item indices or, with top_k = 0, the
 // rank position of every POS item.  On the CPU that is one k-length dot per (user, item) pair.
 //
 // Here the host only walks the stream (a state machine over tiny rows, with the reference's
@@ -45,7 +45,7 @@ constexpr unsigned BANNED_BITS = 0x7fc0dead;  // a quiet NaN no arithmetic produ
 
 // one expanded feature entry: factor scale sf, bias factors b1, b2 (bias += (b*b1)*b2).
 // Plain item entry: sf = ival, b1 = ival, b2 = 1.  Side-feature entry of item feature (iid, ival)
-// (base.h:703-707): sf = float(double(v)*double(ival)) (the two scalars fold in double,
+// (base.h:698-702): sf = float(double(v)*double(ival)) (the two scalars fold in double,
 // apex_exp_template.h:500-503), b1 = v, b2 = ival.
 struct Entry {
   unsigned idx;
@@ -184,7 +184,7 @@ __device__ __forceinline__ float4 gather_chunk(const DevModel &m, int row_off, c
   return acc;
 }
 
-// bias of a feature row (base.h:699-715): item entries first, then globals
+// bias of a feature row (base.h:691-709): item entries first, then globals
 __device__ __forceinline__ float row_bias(const DevModel &m, const Entry *ent, const GEntry *g, const FRow &r) {
   float bias = 0.f;
   for (int e = r.e0; e < r.e1; ++e) {
@@ -214,13 +214,13 @@ __global__ void k_rank_users(DevModel m, const Sec *secs, const Entry *uent, con
   const Sec s = secs[warp];
   const int chunks = m.pitch >> 2;
   for (int c = lane; c < chunks; c += 32) {
-    float4 acc = gather_chunk(m, 0, fent, s.f0, s.f1, c, f4_zero());  // tmp_ufeedback (base.h:807-815)
-    acc = gather_chunk(m, m.user_off, uent, s.u0, s.u1, c, acc);      // proc_user (base.h:725-741)
+    float4 acc = gather_chunk(m, 0, fent, s.f0, s.f1, c, f4_zero());  // tmp_ufeedback (base.h:800-808)
+    acc = gather_chunk(m, m.user_off, uent, s.u0, s.u1, c, acc);      // proc_user (base.h:719-735)
     U[(size_t)warp * chunks + c] = acc;
   }
 }
 
-// SPEC rows (base.h:756-764): item_score[idx] = bias + dot(tmp_ufactor, ifactor of this row)
+// SPEC rows (base.h:750-758): item_score[idx] = bias + dot(tmp_ufactor, ifactor of this row)
 __global__ void k_rank_spec(DevModel m, const Spec *spec, const Entry *ent, const GEntry *g, int n_spec,
                             const float4 *U, float *score, int width) {
   extern __shared__ float4 sh[];  // one ifactor per warp
@@ -247,7 +247,7 @@ __global__ void k_rank_mark(const Mark *ban, int n_ban, float *score, int width)
 
 __device__ __forceinline__ bool is_banned(float s) { return __float_as_uint(s) == BANNED_BITS; }
 
-// proc_rank's scoring loop (base.h:767-771) for every (section, item) pair
+// proc_rank's scoring loop (base.h:761-765) for every (section, item) pair
 __global__ void k_rank_score(DevModel m, const Sec *secs, const float4 *U, const float4 *IF, const float *ibias,
                              int cap, float *score, int width) {
   extern __shared__ float4 su[];
@@ -267,7 +267,7 @@ __global__ void k_rank_score(DevModel m, const Sec *secs, const float4 *U, const
   *out = __fadd_rn(base, __fadd_rn(ibias[i], d));
 }
 
-// rank position of one POS item = number of candidates the sort puts before it (base.h:782-788)
+// rank position of one POS item = number of candidates the sort puts before it (base.h:774-780)
 __global__ void k_rank_pos(const Mark *pos, const float *score, int width, int *out) {
   __shared__ int part[32];
   const Mark p = pos[blockIdx.x];
@@ -404,7 +404,7 @@ int expand_item_row(svdgpu *h, const Row &r, std::vector<Entry> &ent, std::vecto
 int feed_row(svdgpu *h, const Row &r) {
   svdgpu_rank_state &s = *h->rank;
   switch (r.tag) {
-    case TAG_ITEM: {  // proc_item, base.h:718-723
+    case TAG_ITEM: {  // proc_item, base.h:712-717
       if (s.open) return fail(h, "ranker: ITEM rows inside a user section are not supported");
       if (!(s.n_items + 1 <= s.cap_items)) return fail(h, "item instance exceed specified item set size");
       FRow fr;
@@ -414,7 +414,7 @@ int feed_row(svdgpu *h, const Row &r) {
       s.stamp.push_back(-1);
       break;
     }
-    case TAG_USER: {  // proc_user, base.h:725-746
+    case TAG_USER: {  // proc_user, base.h:719-740
       if (s.open) {  // a section abandoned without PROCESS: drop what it collected
         s.secs.pop_back();
         while (!s.pos.empty() && s.pos.back().sec == s.n_closed) s.pos.pop_back();
@@ -443,7 +443,7 @@ int feed_row(svdgpu *h, const Row &r) {
       break;
     }
     case TAG_POS:
-    case TAG_BAN: {  // proc_tag, base.h:747-755
+    case TAG_BAN: {  // proc_tag, base.h:741-749
       if (!s.open) return fail(h, "ranker: POS/BAN row outside a user section");
       for (int i = 0; i < r.nu; ++i) {
         const int idx = (int)r.ui[i];
@@ -454,7 +454,7 @@ int feed_row(svdgpu *h, const Row &r) {
       }
       break;
     }
-    case TAG_SPEC: {  // proc_spec, base.h:756-764
+    case TAG_SPEC: {  // proc_spec, base.h:750-758
       if (!s.open) return fail(h, "ranker: SPEC row outside a user section");
       if (!(r.nu == 1)) return fail(h, "must specify item index of sample in user feature field\n");
       const int idx = (int)r.ui[0];
@@ -463,13 +463,13 @@ int feed_row(svdgpu *h, const Row &r) {
       sp.sec = s.n_closed;
       sp.item = idx;
       if (expand_item_row(h, r, s.sp_ent, s.sp_g, sp.row)) return 1;
-      // a later SPEC row of the same item replaces the earlier one (plain assignment, base.h:763)
+      // a later SPEC row of the same item replaces the earlier one (plain assignment, base.h:757)
       for (size_t j = s.spec.size(); j-- > 0 && s.spec[j].sec == sp.sec;)
         if (s.spec[j].item == idx) s.spec.erase(s.spec.begin() + (long)j);
       s.spec.push_back(sp);
       break;
     }
-    case TAG_PROCESS: {  // proc_rank, base.h:765-789
+    case TAG_PROCESS: {  // proc_rank, base.h:759-782
       if (!s.open) return fail(h, "ranker: PROCESS row outside a user section");
       s.secs.back().n_cand = s.n_items;
       if (s.top_k > 0) {
@@ -481,7 +481,7 @@ int feed_row(svdgpu *h, const Row &r) {
       s.n_closed++;
       break;
     }
-    default: break;  // unknown tags are ignored (base.h:792-799)
+    default: break;  // unknown tags are ignored (base.h:785-792)
   }
   return 0;
 }
@@ -526,7 +526,7 @@ int run_sections(svdgpu *h, int first, int n_sec, size_t pos0, size_t pos1, size
   h->n_launch++;
   const size_t cells = (size_t)n_sec * width;
   if (s.d_score.reserve(h, cells)) return 1;
-  CU(h, cudaMemsetAsync(s.d_score.p, 0, cells * sizeof(float), h->stream));  // item_score = 0 (base.h:743)
+  CU(h, cudaMemsetAsync(s.d_score.p, 0, cells * sizeof(float), h->stream));  // item_score = 0 (base.h:738)
   if (!spec.empty()) {
     if (s.d_spec.upload(h, spec) || s.d_spent.upload(h, s.sp_ent) || s.d_spg.upload(h, s.sp_g)) return 1;
     const int wpb = 4;
@@ -725,7 +725,7 @@ int svdgpu_rank_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const
   svdgpu_rank_state &s = *h->rank;
   for (int b = 0; b < num_block; ++b) {
     const int tag = blk_tag ? blk_tag[b] : 0;
-    if (tag == 0 || tag == 1) {  // DEFAULT / START_TAG: a new feedback list (base.h:806-815)
+    if (tag == 0 || tag == 1) {  // DEFAULT / START_TAG: a new feedback list (base.h:799-808)
       s.cur_fbi.clear();
       s.cur_fbv.clear();
       for (int i = blk_fb_off[b]; i < blk_fb_off[b + 1]; ++i) {
