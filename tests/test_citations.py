@@ -64,3 +64,55 @@ def test_citations_point_into_the_reference():
                 bad.append((doc, m.group(0), "beyond the file's %d lines" % lengths[path]))
     assert checked > 150, checked
     assert not bad, bad[:20]
+
+
+ANCHORS = [  # (file, first line, last line, text that must occur inside)
+    ("solvers/base-solver/apex_svd_base.h", 33, 75, "class ParameterSet"),
+    ("solvers/base-solver/apex_svd_base.h", 188, 210, "reg_global"),
+    ("solvers/base-solver/apex_svd_base.h", 211, 250, "reg_user"),
+    ("solvers/base-solver/apex_svd_base.h", 251, 283, "reg_item"),
+    ("solvers/base-solver/apex_svd_base.h", 286, 311, "regularize"),
+    ("solvers/base-solver/apex_svd_base.h", 313, 353, "calc_bias"),
+    ("solvers/base-solver/apex_svd_base.h", 354, 381, "prepare_tmp"),
+    ("solvers/base-solver/apex_svd_base.h", 383, 427, "update_no_decay"),
+    ("solvers/base-solver/apex_svd_base.h", 445, 454, "float pred("),
+    ("solvers/base-solver/apex_svd_base.h", 456, 462, "update_inner"),
+    ("solvers/base-solver/apex_svd_base.h", 470, 478, "set_round"),
+    ("solvers/base-solver/apex_svd_base.h", 512, 520, "update_svdpp"),
+    ("solvers/base-solver/apex_svd_base.h", 523, 538, "prepare_ufeedback"),
+    ("solvers/base-solver/apex_svd_base.h", 539, 554, "update_ufeedback"),
+    ("solvers/base-solver/apex_svd_base.h", 568, 582, "update( const SVDPlusBlock"),
+    ("solvers/base-solver/apex_svd_base.h", 583, 591, "predict("),
+    ("solvers/base-solver/apex_svd_base.h", 666, 685, "init_ranker"),
+    ("solvers/base-solver/apex_svd_base.h", 687, 710, "prepare_ifactor"),
+    ("solvers/base-solver/apex_svd_base.h", 712, 717, "proc_item"),
+    ("solvers/base-solver/apex_svd_base.h", 719, 740, "proc_user"),
+    ("solvers/base-solver/apex_svd_base.h", 741, 749, "proc_tag"),
+    ("solvers/base-solver/apex_svd_base.h", 750, 758, "proc_spec"),
+    ("solvers/base-solver/apex_svd_base.h", 759, 782, "proc_rank"),
+    ("solvers/base-solver/apex_svd_base.h", 795, 797, "process("),
+    ("solvers/base-solver/apex_svd_base.h", 798, 812, "const SVDPlusBlock &data"),
+    ("apex_svd_model.h", 112, 123, "map_active"),
+    ("apex_svd_model.h", 132, 156, "cal_grad"),
+    ("apex_svd_model.h", 220, 237, "calc_base_score"),
+    ("apex_svd_model.h", 511, 556, "alloc_space"),
+    ("apex_svd_model.h", 638, 660, "save_to_file"),
+    ("apex_svd_model.h", 665, 705, "rand_init"),
+    ("apex_svd.h", 33, 107, "class ISVDTrainer"),
+    ("apex_svd.h", 160, 197, "class ISVDRanker"),
+    ("apex_svd.cpp", 32, 47, "create_svd_trainer"),
+    ("apex-tensor/apex_tensor_sse.h", 289, 317, "sdot"),
+    ("apex_svd_data.cpp", 812, 1025, "class PairwiseRankGenerator"),
+    ("apex_svd_data.cpp", 886, 915, "genpair"),
+    ("apex_svd_data.cpp", 920, 944, "sample_cmp"),
+    ("apex_svd_data.cpp", 946, 965, "sample_posneg"),
+    ("svd_feature.cpp", 231, 247, "update("),
+    ("apex-utils/apex_utils.h", 141, 196, "SparseFeatureArray"),
+]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+@pytest.mark.parametrize("path,first,last,text", ANCHORS)
+def test_cited_ranges_hold_what_they_are_cited_for(path, first, last, text):
+    lines = open(os.path.join(REF, path), errors="replace").read().split("\n")
+    assert text in "\n".join(lines[first - 1:last]), (path, first, last, text)
