@@ -459,25 +459,39 @@ def main():
             return g.predict_csr(probe)  # D2H read of the step's result (probe predictions)
 
         g.set_option("chunk_rows", 1 << 20)
-        for s in range(max(1, args.warmup)):
-            e2e_step(s)
-        g.sync()
-        if dist:
-            dist.barrier()
-        h0, d0 = g.counter("h2d_bytes"), g.counter("d2h_bytes")
-        t0 = time.perf_counter()
-        for s in range(args.steps):
-            e2e_step(args.warmup + s)
-        g.sync()
-        dt = time.perf_counter() - t0
-        if dist:
-            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        e2e = {"value": world * rows * args.steps / dt, "unit": "instances/s",
-               "h2d_bytes_per_step": (g.counter("h2d_bytes") - h0) // args.steps,
-               "d2h_bytes_per_step": (g.counter("d2h_bytes") - d0) // args.steps,
-               "timing": "wall clock around K calls of svdgpu_update_csr (pinned host buffers) + probe predict"}
+
+        def measure_e2e():
+            for s in range(max(1, args.warmup)):
+                e2e_step(s)
+            g.sync()
+            if dist:
+                dist.barrier()
+            h0, d0 = g.counter("h2d_bytes"), g.counter("d2h_bytes")
+            t0 = time.perf_counter()
+            for s in range(args.steps):
+                e2e_step(args.warmup + s)
+            g.sync()
+            dt = time.perf_counter() - t0
+            if dist:
+                tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            return {"value": world * rows * args.steps / dt, "unit": "instances/s",
+                    "h2d_bytes_per_step": (g.counter("h2d_bytes") - h0) // args.steps,
+                    "d2h_bytes_per_step": (g.counter("d2h_bytes") - d0) // args.steps}
+
+        e2e = measure_e2e()
+        e2e["timing"] = "wall clock around K calls of svdgpu_update_csr (pinned host buffers) + probe predict"
+        e2e["compact_h2d"] = ("inside the timed region host threads verify, element by element, that a chunk's row_ptr is "
+                              "the progression of constant feature counts and that its values are all 1.0f; such arrays "
+                              "are rebuilt on the device instead of copied (12 of the reference layout's 32 bytes per "
+                              "instance cross PCIe); full_copy = the same call with the option off")
+        try:
+            g.set_option("compact_h2d", 0)
+            full = measure_e2e()
+            e2e["full_copy"] = {"value": full["value"], "h2d_bytes_per_step": full["h2d_bytes_per_step"]}
+        finally:
+            g.set_option("compact_h2d", 1)
 
     if dist:
         dist.barrier()
