@@ -99,8 +99,15 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
  *   "exact_opt"   : ordered kernel hand-off variants, bit mask (default 5): 1 release without a
  *                   per-lane fence, 2 poll back to back, 4 instance slice staged in shared memory
- *   "exact_owner" : EXPERIMENTAL, default 0: ordered mode on resident basic-MF batches through
- *                   item-owner warps (set before svdgpu_batch_create) */
+ *   "exact_owner" : 1 (default): in the ordered mode, launches made only of basic-MF rows (0 | 1 | 1
+ *                   features) under plain L2 decay take the item-owner kernel (k_own: every item row
+ *                   stays on one warp, user rows travel under version counters; bit-identical to
+ *                   k_exact and to the reference); 0 keeps every row in k_exact.  Tuning:
+ *                   "own_min_rows" (4096: smaller launches keep k_exact), "own_batch" (16: version
+ *                   publishes the busiest owner holds back per release fence, <= 32),
+ *                   "own_urgent_gap" (16384: a user whose next rating follows within this many rows
+ *                   is published at once), "own_slots" (0 = auto: item rows per owner kept in
+ *                   shared memory, <= 32; the rest of an owner's rows stay in L2) */
 int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
 int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);
@@ -264,7 +271,7 @@ int svdgpu_sync(svdgpu_t *h);
 /* CUDA-event stopwatch on the launch stream */
 int svdgpu_timer_start(svdgpu_t *h);
 int svdgpu_timer_stop(svdgpu_t *h, float *elapsed_ms);
-/* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm", "lanes",
+/* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm", "lanes", "own_launches", "own_rows",
  * "ingest_read_us", "ingest_call_us" (bulk ingest: time reading the file / inside the hot-path calls) */
 long long svdgpu_get_counter(const svdgpu_t *h, const char *name);
 /* device pointers of the model slabs (for peer / collective plumbing): 0 ui_bias,

@@ -40,9 +40,9 @@ def _sources(*names):
     return [os.path.join(CSRC, n) for n in names]
 
 
-GPU_UNITS = ["svdgpu_api.cu", "svdgpu_stream.cu", "svdgpu_mf.cu", "svdgpu_ordered.cu", "svdgpu_ingest.cu", "svdgpu_pairs.cu", "svdgpu_svdpp.cu",
+GPU_UNITS = ["svdgpu_api.cu", "svdgpu_stream.cu", "svdgpu_mf.cu", "svdgpu_ordered.cu", "svdgpu_own.cu", "svdgpu_ingest.cu", "svdgpu_pairs.cu", "svdgpu_svdpp.cu",
              "svdgpu_rank.cu"]
-GPU_HEADERS = ["svdgpu_internal.h", "svdgpu_device.cuh", "svdgpu_fb.cuh", "svdgpu_scan.h"]
+GPU_HEADERS = ["svdgpu_internal.h", "svdgpu_device.cuh", "svdgpu_fb.cuh", "svdgpu_scan.h", "svdgpu_ownplan.h"]
 
 
 def build_gpu(force=False, verbose=False):

@@ -3,7 +3,6 @@
 // dispatch.  No CPU compute path exists here: every update/predict call ends in
 // a kernel launch or fails.
 #include "svdgpu_internal.h"
-#include "svdgpu_owner.h"
 #include "svdgpu_scan.h"
 
 #include <algorithm>
@@ -452,6 +451,7 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
   CUC(cudaMalloc(&h->d_err, sizeof(int)));
   CUC(cudaMemset(h->d_err, 0, sizeof(int)));
   CUC(cudaMalloc(&h->d_counter, sizeof(unsigned)));
+  CUC(cudaMalloc(&h->d_abort, sizeof(unsigned)));
   CUC(cudaMalloc(&h->d_eval, 2 * sizeof(double)));
 #undef CUC
   Geometry g;
@@ -477,6 +477,9 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->dm.ver_g);
   cudaFree(h->d_err);
   cudaFree(h->d_counter);
+  cudaFree(h->d_abort);
+  own_scratch_free(h->own);
+  for (int i = 0; i < svdgpu::NSLOT; ++i) own_plan_free(h->slot[i].own);
   cudaFree(h->d_eval);
   cudaFree(h->d_row_mask);
   cudaFree(h->d_unit_kind);
@@ -546,6 +549,10 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "mf_ctas")) h->mf_ctas = (int)v;
   else if (!strcmp(name, "exact_opt")) h->exact_opt = (int)v;
   else if (!strcmp(name, "exact_owner")) h->exact_owner = v ? 1 : 0;
+  else if (!strcmp(name, "own_min_rows")) h->own_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
+  else if (!strcmp(name, "own_urgent_gap")) h->own_urgent_gap = (int)std::max<long long>(0, std::min<long long>(v, 1LL << 30));
+  else if (!strcmp(name, "own_batch")) h->own_batch = (int)std::max<long long>(1, std::min<long long>(v, 32));
+  else if (!strcmp(name, "own_slots")) h->own_slots = (int)std::max<long long>(0, std::min<long long>(v, 32));
   else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
   else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));
   else if (!strcmp(name, "compact_min_rows")) h->compact_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
@@ -651,6 +658,7 @@ int svdgpu_sync(svdgpu_t *h) {
       case ERR_FB_INDEX: return fail(h, "ufeedback id exceed bound");
       case ERR_ROW_PTR: return fail(h, "row_ptr must be non-decreasing and inside the batch");
       case ERR_WD_BOUND: return fail(h, "bound set err");  // base.h:72
+      case ERR_TIMEOUT: return fail(h, "ordered mode: a wait inside k_own timed out (internal error; the model is unusable)");
       default: return fail(h, "device error %d", e);
     }
   }
@@ -677,6 +685,8 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
   if (!strcmp(name, "h2d_bytes")) return h->n_h2d;
   if (!strcmp(name, "d2h_bytes")) return h->n_d2h;
   if (!strcmp(name, "num_sm")) return h->num_sm;
+  if (!strcmp(name, "own_launches")) return h->n_own;  // ordered mode: launches of the item-owner kernel
+  if (!strcmp(name, "own_rows")) return h->n_own_rows;
   if (!strcmp(name, "ingest_read_us")) return (long long)(h->ingest_read_s * 1e6);  // file -> pinned chunk
   if (!strcmp(name, "ingest_call_us")) return (long long)(h->ingest_call_s * 1e6);  // hot-path calls
   if (!strcmp(name, "lanes")) {
@@ -736,9 +746,16 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
   Geometry geo;
   if (pick_geometry(h, geo)) return 1;
   const bool exact = train && h->mode == SVDGPU_MODE_EXACT;
-  // the ordered mode walks every row on the host anyway (tickets); Hogwild leaves the
-  // row_ptr checks to the kernels so that the host never touches the batch
-  if (exact && validate_csr(h, num_row, row_ptr)) return 1;
+  // Ordered mode: chunks of basic-MF rows under plain L2 decay take the item-owner kernel, whose
+  // plan (checks, tickets, queues) is built on the device; everything else takes k_exact, whose
+  // tickets the host computes walking every row.  Hogwild leaves the row_ptr checks to the
+  // kernels so that the host never touches the batch.
+  const bool own_ok = exact && h->exact_owner && own_supported(h) && !sides_on(h);
+  bool validated = false;
+  if (exact && !own_ok) {
+    if (validate_csr(h, num_row, row_ptr)) return 1;
+    validated = true;
+  }
   const int nchunk = (int)(((long long)num_row + h->chunk_rows - 1) / h->chunk_rows);
   // Host threads for the scan: what the option says, else this process's share of the cores (the
   // ranks of one box split them: torchrun's LOCAL_WORLD_SIZE) minus the calling thread, at most 16.
@@ -809,7 +826,23 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     csr.ticket = nullptr;
     csr.val_base = sc.rp_regular ? 0 : v0;  // a rebuilt row_ptr counts from 0
     csr.val_end = sc.rp_regular ? (int)nv : v1;
-    if (exact) {
+    bool owned = false;
+    if (exact && own_ok && n >= h->own_min_rows) {
+      if (slot_copied(h, s)) return 1;
+      int bad = 0;
+      if (own_plan_build(h, csr, 0, n, s.own, h->stream, &bad)) return 1;
+      if (s.own.valid) {
+        if (launch_own(h, s.own, h->stream)) return 1;
+        owned = true;
+      } else if (!(bad & 3)) {  // every row has the basic shape, but an index is out of range (base.h:327,343)
+        return fail(h, (bad & 4) ? "user feature index exceed bound" : "item feature index exceed bound");
+      }
+    }
+    if (exact && !owned) {
+      if (!validated) {
+        if (validate_csr(h, num_row, row_ptr)) return 1;
+        validated = true;
+      }
       if (host_reserve(h, s.h_ticket, nv * 4 + 4)) return 1;
       reset_ticket_counters(h);
       if (side ? make_tickets(h, 0, n, ex.rp.data(), ex.idx.data(), (unsigned *)s.h_ticket.p)
@@ -821,7 +854,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
       if (slot_copied(h, s)) return 1;
       // row_ptr on the device is the slice [3*r0, 3*r1]: rows are 0..n there
       if (launch_exact(h, geo, csr, 0, n)) return 1;
-    } else {
+    } else if (!exact) {
       float *pred = nullptr;
       if (!train) {
         if (dev_reserve(h, s.d_pred, (size_t)n * 4)) return 1;
@@ -1062,6 +1095,7 @@ int svdgpu_eval_ugroup(svdgpu_t *h, int num_block, const int *blk_row_off, const
 // ---------------------------------------------------------------------------
 // resident batches
 // ---------------------------------------------------------------------------
+static DevCsr batch_csr(const svdgpu_batch *b);
 static int upload_plain(svdgpu *h, DevBuf &d, const void *src, size_t bytes) {
   if (dev_reserve(h, d, bytes)) return 1;
   if (bytes) {
@@ -1099,23 +1133,24 @@ int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const in
   if (side) rc |= upload_plain(h, b->d_value2, ex.val2.data(), nv * 4);
   b->has_value2 = side;
   if (!rc && h->mode == SVDGPU_MODE_EXACT && h->shape.format_type == 0) {
-    std::vector<unsigned> tk(nv + 1);
-    reset_ticket_counters(h);
-    rc |= make_tickets(h, 0, num_row, row_ptr, index, tk.data());
-    if (!rc) rc |= upload_plain(h, b->d_ticket, tk.data(), nv * 4);
-    if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
-    b->has_ticket = !rc;
-    if (!rc && h->exact_owner && !side && num_row > 0) {  // experimental: per-owner queues for k_owner
-      Geometry geo;
-      int cap = 0;
-      svdowner::Plan plan;
-      if (!pick_geometry(h, geo) && !launch_owner(h, geo, DevCsr(), nullptr, nullptr, 0, &cap) && cap > 0 &&
-          svdowner::build_plan(num_row, row_ptr, index, h->shape.num_item, cap, plan)) {
-        rc |= upload_plain(h, b->d_queue_off, plan.queue_off.data(), plan.queue_off.size() * 4);
-        rc |= upload_plain(h, b->d_queue, plan.queue.data(), plan.queue.size() * 4);
-        if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
-        if (!rc) b->owner_warps = cap;
+    // ordered mode: the owner plan when the rows qualify (built on the device), else the
+    // per-feature tickets of k_exact (host)
+    bool need_tickets = true;
+    if (h->exact_owner && !side && num_row >= h->own_min_rows && h->hp_set && own_supported(h)) {
+      int bad = 0;
+      rc |= own_plan_build(h, batch_csr(b), 0, num_row, b->own, h->stream, &bad);
+      if (!rc && b->own.valid) need_tickets = false;
+      else if (!rc && !(bad & 3) && bad) {
+        rc = fail(h, (bad & 4) ? "user feature index exceed bound" : "item feature index exceed bound");
       }
+    }
+    if (!rc && need_tickets) {
+      std::vector<unsigned> tk(nv + 1);
+      reset_ticket_counters(h);
+      rc |= make_tickets(h, 0, num_row, row_ptr, index, tk.data());
+      if (!rc) rc |= upload_plain(h, b->d_ticket, tk.data(), nv * 4);
+      if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
+      b->has_ticket = !rc;
     }
   }
   if (!rc) rc |= (cudaStreamSynchronize(h->stream) != cudaSuccess);
@@ -1212,15 +1247,16 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
   if (begin < 0 || end > b->num_row || begin > end) return fail(h, "batch_update: row range out of bounds");
   if (begin == end) return 0;
   if (h->mode == SVDGPU_MODE_EXACT) {
-    if (!b->has_ticket) return fail(h, "batch was created in hogwild mode: no tickets for the ordered mode");
     if (begin != 0 || end != b->num_row)
       return fail(h, "ordered mode needs the whole resident batch (tickets are per batch)");
-    if (h->exact_owner && b->owner_warps > 0) {
-      if (launch_owner(h, geo, batch_csr(b), (const int *)b->d_queue_off.p, (const int *)b->d_queue.p, b->owner_warps,
-                       nullptr))
-        return 1;
-    } else if (launch_exact(h, geo, batch_csr(b), begin, end)) {
-      return 1;
+    if (h->exact_owner && b->own.valid && own_supported(h)) {
+      if (launch_own(h, b->own, h->stream)) return 1;
+    } else {
+      if (!b->has_ticket)
+        return fail(h, b->own.valid ? "batch was created for the item-owner kernel (plain L2 decay): re-create it after "
+                                      "changing the regulariser or the exact_owner option"
+                                    : "batch was created in hogwild mode: no tickets for the ordered mode");
+      if (launch_exact(h, geo, batch_csr(b), begin, end)) return 1;
     }
   } else {
     if (launch_stream(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
@@ -1275,8 +1311,9 @@ void svdgpu_batch_destroy(svdgpu_t *h, svdgpu_batch_t *b) {
     cudaStreamSynchronize(h->stream);
   }
   DevBuf *db[] = {&b->d_rp, &b->d_label, &b->d_index, &b->d_value, &b->d_value2, &b->d_ticket, &b->d_pred,
-                  &b->d_queue, &b->d_queue_off, &b->d_unit_off, &b->d_blk_row_off, &b->d_blk_fb_off, &b->d_fbi, &b->d_fbv, &b->d_fbt, &b->d_order};
+                  &b->d_unit_off, &b->d_blk_row_off, &b->d_blk_fb_off, &b->d_fbi, &b->d_fbv, &b->d_fbt, &b->d_order};
   for (DevBuf *d : db) dev_free(*d);
+  own_plan_free(b->own);
   delete b;
 }
 

@@ -85,7 +85,7 @@ struct DevCsr {
 
 enum { SCATTER_STORE = 0, SCATTER_RED = 1 };
 enum { ERR_NONE = 0, ERR_GLOBAL_INDEX = 1, ERR_USER_INDEX = 2, ERR_ITEM_INDEX = 3, ERR_FB_INDEX = 4, ERR_ROW_PTR = 5,
-       ERR_WD_BOUND = 6 };
+       ERR_WD_BOUND = 6, ERR_TIMEOUT = 7 };
 
 // a row's four segment bounds must be ordered and inside the batch (checked on the
 // device so that the host never walks row_ptr)

@@ -21,9 +21,27 @@ struct HostBuf {
   void *p = nullptr;
   size_t cap = 0;
 };
+// Ordered mode with item-owner warps (svdgpu_own.cu).  A plan = the per-owner queues of one set
+// of rows; the scratch = what building a plan needs (shared by all plans of a handle: builds are
+// stream-ordered on one stream).
+struct OwnPlan {
+  DevBuf entries, queue_off, item_off, items, batch;
+  HostBuf stage;  // pinned source of the small host-made arrays
+  int num_owner = 0;
+  long long rows = 0, max_load = 0;
+  bool valid = false;
+};
+struct OwnScratch {
+  DevBuf cnt_item, cnt_user, start_user, flag, keyA, keyB, valA, valB, key_item, tick, tmp, item_owner, item_slot;
+  void *h_cnt = nullptr;  // pinned: item counts + flag word
+  size_t h_cnt_cap = 0;
+  cudaEvent_t ev = nullptr;
+};
+
 // One staging slot for host-pointer calls: pinned mirrors + device arrays.
 struct Slot {
   HostBuf h_rp, h_label, h_index, h_value, h_value2, h_ticket, h_misc, h_fbi, h_fbv, h_fbt;
+  OwnPlan own;  // ordered mode: the chunk's owner plan
   DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
   cudaEvent_t done = nullptr;    // last kernel that read this slot
   cudaEvent_t copied = nullptr;  // the slot's H2D copies have landed (recorded on the copy stream)
@@ -110,8 +128,15 @@ struct svdgpu {
                         // (checked on host threads while earlier chunks are copied; rebuilt on the device)
   int scan_threads = 0;            // option "scan_threads": host threads of that check (0 = min(cores, 16))
   int compact_min_rows = 1 << 18;  // option "compact_min_rows": calls with fewer rows skip the check
-  int exact_owner = 0;  // option "exact_owner" (EXPERIMENTAL): ordered mode on resident basic-MF batches through
-                        // item-owner warps (k_owner, svdgpu_ordered.cu)
+  int exact_owner = 1;  // option "exact_owner": ordered mode sends basic-MF rows under plain L2 decay through the
+                        // item-owner kernel (k_own, svdgpu_own.cu); 0 keeps every row in k_exact
+  int own_min_rows = 4096;   // option "own_min_rows": launches with fewer rows keep k_exact (no plan to build)
+  int own_urgent_gap = 16384;  // option "own_urgent_gap": a user whose next rating follows within this many rows
+                               // is published at once instead of with the owner's batch
+  int own_batch = 16;        // option "own_batch": version publishes the most loaded owner holds back (<= 32)
+  int own_slots = 0;         // option "own_slots": item rows an owner keeps in shared memory (0 = auto, <= 32)
+  OwnScratch own;
+  unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
   int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):
                        // 1 no per-lane fence before the release, 2 spin before sleeping, 4 staged slice
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
@@ -137,6 +162,7 @@ struct svdgpu {
   std::vector<unsigned> cnt_ui, cnt_g;
   std::string err;
   long long n_launch = 0, n_inst = 0, n_h2d = 0, n_d2h = 0;
+  long long n_own = 0, n_own_rows = 0;  // k_own launches and the rows they trained
 };
 
 // an instance batch resident in HBM (svdgpu_batch_create / svdgpu_batch_sample_pairs)
@@ -145,9 +171,7 @@ struct svdgpu_batch {
   long long num_val = 0;
   DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_pred;
   bool has_ticket = false, has_value2 = false;
-  // experimental item-owner ordered mode (option "exact_owner"): per-owner row queues
-  DevBuf d_queue, d_queue_off;
-  int owner_warps = 0;
+  OwnPlan own;  // ordered mode through k_own: the batch's owner plan (valid when the rows qualify)
   // user-group structure
   bool ugroup = false, has_fb = false;
   int num_block = 0, num_unit = 0;
@@ -181,9 +205,12 @@ int launch_stream(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r
 int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred,
               int which, unsigned *flag_out, const unsigned *flag_gate);
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
-// experimental item-owner ordered kernel: capacity != nullptr only queries how many owners fit
-int launch_owner(svdgpu *h, const Geometry &g, const DevCsr &csr, const int *queue_off, const int *queue,
-                 int num_owner, int *capacity);
+// ordered mode with item-owner warps (svdgpu_own.cu)
+bool own_supported(const svdgpu *h);
+int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad);
+int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st);
+void own_plan_free(OwnPlan &p);
+void own_scratch_free(OwnScratch &s);
 int launch_ugroup(svdgpu *h, const Geometry &g, const DevCsr &csr, const DevUgroup &ug, int u0, int u1,
                   bool train, bool ordered, float *pred);
 int launch_delta(svdgpu *h, int mode, float scale);

@@ -116,61 +116,6 @@ k_exact(DevModel m, DevHP hp, DevCsr csr, int row_begin, int row_end, unsigned *
 }
 
 // ---------------------------------------------------------------------------
-// k_owner -- EXPERIMENTAL (option "exact_owner", off by default; not yet run on a GPU when this
-// was written: DESIGN.md section 8, item 1; host side and protocol tests: svdgpu_owner.h,
-// tests/test_owner_plan.py).  Ordered training of basic-MF rows where every ITEM belongs to one
-// persistent warp: warp w takes the rows queue[queue_off[w] .. queue_off[w+1]) -- the instances of
-// its items, in input order -- so an item row is only ever touched by one warp, in program order,
-// and needs no hand-off.  User rows still move between warps through the version counters.  The
-// oldest unfinished instance is always at the head of its owner's queue with its user ticket
-// satisfied, so some warp can always proceed -- provided all owners are resident, which the
-// cooperative launch checks.
-// ---------------------------------------------------------------------------
-template <int LANES, int VEC>
-__global__ void __launch_bounds__(EX_WARPS * 32)
-k_owner(DevModel m, DevHP hp, DevCsr csr, const int *queue_off, const int *queue, int num_owner, int *err_flag) {
-  __shared__ float dot_s[EX_WARPS][Group<LANES, VEC>::DOT_FLOATS];
-  __shared__ unsigned st_idx[EX_WARPS][4];
-  __shared__ float st_val[EX_WARPS][4];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * EX_WARPS + warp;
-  if (lane >= LANES || w >= num_owner) return;
-  Group<LANES, VEC> g;
-  g.gl = lane;
-  g.gmask = (LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u);
-  g.dot_s = dot_s[warp];
-  const unsigned *idx = csr.index - csr.val_base;
-  const float *val = csr.value - csr.val_base;
-  const unsigned *tk = csr.ticket - csr.val_base;
-  const int q1 = queue_off[w + 1];
-  for (int q = queue_off[w]; q < q1; ++q) {
-    const long long r = queue[q];
-    const int rp0 = csr.row_ptr[3 * r];  // the host checked the shape: (0 | 1 | 1)
-    const float lab = csr.label[r];
-    const unsigned uid = idx[rp0], want = tk[rp0];
-    g.gsync();  // the previous instance has been read out of the stage
-    if (g.gl < 2) {
-      st_idx[warp][g.gl] = idx[rp0 + g.gl];
-      st_val[warp][g.gl] = val[rp0 + g.gl];
-    }
-    unsigned *ver = uid < (unsigned)m.num_user ? m.ver_ui + m.user_off + uid : nullptr;
-    if (g.gl == 0 && ver) {
-      unsigned ns = 20;
-      while (ld_acquire_u32(ver) != want) {
-        __nanosleep(ns);
-        if (ns < 200) ns += 20;
-      }
-    }
-    g.gsync();
-    process_instance<LANES, VEC, true, true, false>(g, m, hp, rp0, rp0, rp0 + 1, rp0 + 2, lab, st_idx[warp] - rp0,
-                                                    st_val[warp] - rp0, SCATTER_STORE, SCATTER_STORE, nullptr,
-                                                    err_flag, nullptr);
-    g.gsync();  // the group's stores happen-before the release below (cumulative)
-    if (g.gl == 0 && ver) red_release_add_u32(ver, 1u);
-  }
-}
-
-// ---------------------------------------------------------------------------
 // k_ugroup
 // ---------------------------------------------------------------------------
 template <int LANES, int VEC>
@@ -663,38 +608,6 @@ static int ugroup_geo(svdgpu *h, const DevCsr &csr, const DevUgroup &ug, int u0,
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1) {
 #define GEO(L, V) \
   if (g.lanes == L && g.vec == V) return exact_geo<L, V>(h, csr, r0, r1);
-  ORDERED_GEOS(GEO)
-#undef GEO
-  return fail(h, "ordered mode: no kernel for lanes=%d vec=%d (unset option lanes)", g.lanes, g.vec);
-}
-
-template <int L, int V>
-static int owner_geo(svdgpu *h, const DevCsr &csr, const int *queue_off, const int *queue, int num_owner,
-                     int *capacity) {
-  auto k = k_owner<L, V>;
-  if (capacity) {  // how many owner warps can be resident at once
-    int per_sm = 0;
-    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, EX_WARPS * 32, 0));
-    *capacity = std::max(0, per_sm) * h->num_sm * EX_WARPS;
-    return 0;
-  }
-  CU(h, cudaMemsetAsync(h->dm.ver_ui, 0, sizeof(unsigned) * std::max<size_t>(h->rows, 1), h->stream));
-  DevModel dm = h->dm;
-  DevHP dhp = h->dhp;
-  DevCsr c = csr;
-  int *err = h->d_err;
-  void *args[] = {&dm, &dhp, &c, &queue_off, &queue, &num_owner, &err};
-  // cooperative: the launch fails instead of deadlocking if the owners cannot all be resident
-  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3((num_owner + EX_WARPS - 1) / EX_WARPS), dim3(EX_WARPS * 32), args,
-                                    0, h->stream));
-  h->n_launch++;
-  return 0;
-}
-
-int launch_owner(svdgpu *h, const Geometry &g, const DevCsr &csr, const int *queue_off, const int *queue,
-                 int num_owner, int *capacity) {
-#define GEO(L, V) \
-  if (g.lanes == L && g.vec == V) return owner_geo<L, V>(h, csr, queue_off, queue, num_owner, capacity);
   ORDERED_GEOS(GEO)
 #undef GEO
   return fail(h, "ordered mode: no kernel for lanes=%d vec=%d (unset option lanes)", g.lanes, g.vec);

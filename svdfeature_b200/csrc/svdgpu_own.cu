@@ -1,0 +1,668 @@
+// svdgpu_own.cu -- ordered ("exact") training of basic-MF rows with ITEM-OWNER warps.
+//
+// The reference's loop is strictly sequential (base.h:456-462): instance n+1 sees what instance n
+// wrote.  Instances that share no row commute exactly, so the result of the sequential loop is
+// reproduced bit for bit by any schedule that keeps, per row, the input order of the instances
+// touching it.  k_exact (svdgpu_ordered.cu) hands every row from warp to warp through L2 and is
+// bound by the hand-off chain of the hottest item (5.9 us per hand-off, 67 M instances/s on
+// configs[1]).  Here the hot rows never move:
+//
+//   * every ITEM belongs to one persistent warp (its owner; LPT by popularity, svdgpu_ownplan.h)
+//     which takes the instances of its items in input order from its own queue and keeps the item
+//     rows in shared memory / registers for the whole launch: the chain of the hottest item runs
+//     at register speed, one dot + update per link;
+//   * USER rows travel between owners through L2 under a version counter per user: an instance
+//     carries a ticket (= number of earlier instances of its user) and its user row may only be
+//     fetched once the counter has reached it.  Checking, waiting and fetching is done by LOADER
+//     lanes, never by the owner: loader lane (c, s) feeds ring slot s of owner c -- it reads the
+//     queue entry, polls the version (ld.acquire.gpu), and when the row is final issues one TMA
+//     bulk copy (cp.async.bulk, 256 B at k = 64) that lands in the slot and completes its
+//     mbarrier.  The owner only ever waits on shared memory;
+//   * an owner publishes the user rows it has written with one release per BATCH of instances
+//     (st.release.gpu of ticket+1; the fence is what costs), at once when the plan says the user
+//     comes back soon, and always before it blocks -- so the oldest unfinished instance of the
+//     whole launch can always proceed (all CTAs are co-resident: cooperative launch).
+//
+// Arithmetic = process_instance (svdgpu_device.cuh) specialised to the shape (0 | 1 | 1) with
+// plain L2 decay: the same operations in the same order, the reference's dot order included.
+//
+// The plan (queues, tickets, item lists) is built on the device from the CSR batch: two radix
+// sorts (by user for the tickets, by owner for the queues) around a host LPT of the item counts.
+#include "svdgpu_internal.h"
+#include "svdgpu_ownplan.h"
+
+#include <cub/cub.cuh>
+
+#include <cstring>
+
+namespace svdk {
+
+// ---------------------------------------------------------------------------
+// plan kernels
+// ---------------------------------------------------------------------------
+enum { OWN_BAD_ROWPTR = 1, OWN_NOT_BASIC = 2, OWN_BAD_USER = 4, OWN_BAD_ITEM = 8 };
+
+// shape / bound checks (the reference's asserts, base.h:327,343), per-item and per-user counts
+__global__ void k_own_scan(DevCsr csr, int r0, int n, int num_user, int num_item, unsigned *cnt_item,
+                           unsigned *cnt_user, unsigned *key_user, unsigned *key_item, unsigned *row_id,
+                           int *flag) {
+  const unsigned *idx = csr.index - csr.val_base;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = r0 + i;
+    const int rp0 = csr.row_ptr[3 * r], rp1 = csr.row_ptr[3 * r + 1], rp2 = csr.row_ptr[3 * r + 2],
+              rp3 = csr.row_ptr[3 * r + 3];
+    unsigned u = 0, it = 0;
+    int bad = 0;
+    if (!row_ok(rp0, rp1, rp2, rp3, csr.val_base, csr.val_end)) bad = OWN_BAD_ROWPTR;
+    else if (!(rp1 == rp0 && rp2 == rp1 + 1 && rp3 == rp2 + 1)) bad = OWN_NOT_BASIC;
+    else {
+      u = idx[rp1];
+      it = idx[rp2];
+      if (u >= (unsigned)num_user) bad = OWN_BAD_USER;
+      else if (it >= (unsigned)num_item) bad = OWN_BAD_ITEM;
+    }
+    if (bad) {
+      atomicOr(flag, bad);
+      u = it = 0;
+    } else {
+      atomicAdd(cnt_item + it, 1u);
+      atomicAdd(cnt_user + u, 1u);
+    }
+    key_user[i] = u;
+    key_item[i] = it;
+    row_id[i] = (unsigned)i;
+  }
+}
+
+// rows sorted by user (stable: input order inside a user): ticket = rank inside the user's run;
+// bit 31 = the user's next instance follows within `gap` rows (publish at once)
+__global__ void k_own_ticket(const unsigned *ku, const unsigned *rows, const unsigned *start_user, int n,
+                             unsigned gap, unsigned *tick) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned u = ku[i], r = rows[i];
+    unsigned t = (unsigned)i - start_user[u];
+    if (i + 1 < n && ku[i + 1] == u && rows[i + 1] - r < gap) t |= 0x80000000u;
+    tick[r] = t;
+  }
+}
+
+__global__ void k_own_keyowner(const unsigned *key_item, const int *item_owner, int n, unsigned *key, unsigned *row_id) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    key[i] = (unsigned)item_owner[key_item[i]];
+    row_id[i] = (unsigned)i;
+  }
+}
+
+// one queue entry per instance, 32 bytes, in owner order (= the stable sort's output order)
+struct OwnEntry {
+  unsigned user, ticket;
+  float label;
+  unsigned item;
+  unsigned slot;  // position of the item in its owner's list
+  float uval, ival;
+  unsigned flags;  // bit 0: publish the user row at once
+};
+static_assert(sizeof(OwnEntry) == 32, "queue entries are two 16-byte words");
+
+__global__ void k_own_entries(DevCsr csr, int r0, int n, const unsigned *rows, const unsigned *tick,
+                              const unsigned *item_slot, OwnEntry *out) {
+  const unsigned *idx = csr.index - csr.val_base;
+  const float *val = csr.value - csr.val_base;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    const long long r = r0 + (long long)rows[q];
+    const int rp1 = csr.row_ptr[3 * r + 1];
+    const unsigned t = tick[rows[q]];
+    OwnEntry e;
+    e.user = idx[rp1];
+    e.ticket = t & 0x7fffffffu;
+    e.label = csr.label[r];
+    e.item = idx[rp1 + 1];
+    e.slot = item_slot[e.item];
+    e.uval = val[rp1];
+    e.ival = val[rp1 + 1];
+    e.flags = t >> 31;
+    uint4 *o = reinterpret_cast<uint4 *>(out + q);
+    o[0] = make_uint4(e.user, e.ticket, __float_as_uint(e.label), e.item);
+    o[1] = make_uint4(e.slot, __float_as_uint(e.uval), __float_as_uint(e.ival), e.flags);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_own
+// ---------------------------------------------------------------------------
+constexpr int OWN_C = 16;                      // owner (compute) warps per CTA
+constexpr int OWN_D = 8;                       // ring slots per owner
+constexpr int OWN_LW = OWN_C * OWN_D / 32;     // loader warps per CTA: one lane per ring slot
+constexpr int OWN_THREADS = (OWN_C + OWN_LW) * 32;
+constexpr int OWN_SLOT_EXTRA = 48;             // [row | 16-byte bias window | 32-byte entry]
+constexpr long long OWN_TIMEOUT = 6000000000LL;  // cycles (~3 s): a wait this long is a bug, not load
+
+struct OwnArgs {
+  DevModel m;
+  DevHP hp;
+  const OwnEntry *entries;
+  const int *queue_off;
+  const int *item_off;
+  const unsigned *items;
+  const int *batch;
+  int S;                  // item rows an owner keeps in shared memory (the rest stay in L2)
+  unsigned region_bytes;  // shared memory per owner
+  unsigned off_items, off_ibias, off_dot, off_bars;
+  int *err_flag;
+  unsigned *abort_flag;
+};
+
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {  // non-blocking
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, unsigned parity) {  // may suspend briefly
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// the version was read through the generic proxy; the row is read by the TMA unit (async proxy)
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// One instance of the shape (0 | 1 | 1) with plain L2 decay: process_instance (svdgpu_device.cuh)
+// with everything that cannot happen removed; same operations, same order (base.h:313-462).
+template <int VEC>
+__device__ __forceinline__ void own_step(const Group<32, VEC> &g, const DevModel &m, const DevHP &hp,
+                                         float4 (&wu)[VEC], float &ub, float4 (&wi)[VEC], float &ib,
+                                         float uval, float ival, float label) {
+  const bool uone = scalar_is_one(uval), ione = scalar_is_one(ival);
+  float4 tu[VEC], ti[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {  // prepare_tmp, base.h:354-381
+    tu[v] = f4_add_scaled(f4_zero(), wu[v], uval, uone);
+    ti[v] = f4_add_scaled(f4_zero(), wi[v], ival, ione);
+  }
+  double bsum = 0.0;  // calc_bias, base.h:313-353
+  if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, ub));
+  bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+  const float d = g.template dot<true>(m, tu, ti);
+  double sum = __dadd_rn((double)hp.base_score, bsum);  // pred, base.h:445-454
+  sum = __dadd_rn(sum, (double)d);
+  const float p = map_active((float)sum, m.active_type);
+  const float err = cal_grad(label, p, m.active_type);
+  const float lrerr = __fmul_rn(hp.lr, err);
+  const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);  // base.h:391,412
+  const bool su1 = scalar_is_one(su), si1 = scalar_is_one(si);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {  // update_no_decay + regularize(after), base.h:383-427,211-283
+    float4 nu = f4_add_scaled(wu[v], ti[v], su, su1);
+    float4 ni = f4_add_scaled(wi[v], tu[v], si, si1);
+    if (!hp.du_skip) nu = f4_scale(nu, hp.du);
+    if (!hp.di_skip) ni = f4_scale(ni, hp.di);
+    wu[v] = nu;
+    wi[v] = ni;
+  }
+  if (!m.no_user_bias) ub = __fmul_rn(__fadd_rn(ub, su), hp.dub);
+  ib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(OWN_THREADS, 1) k_own(const OwnArgs a) {
+  extern __shared__ __align__(128) unsigned char own_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DevModel &m = a.m;
+  const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
+  const int S = a.S;
+  // every owner's barriers: full[D] then empty[D], one arrival each
+  if (warp < OWN_C && lane < 2 * OWN_D)
+    mbar_init(reinterpret_cast<uint64_t *>(own_smem + (size_t)warp * a.region_bytes + a.off_bars) + lane, 1);
+  mbar_fence_init();
+  __syncthreads();
+  unsigned *const ver = m.ver_ui + m.user_off;
+
+  if (warp >= OWN_C) {
+    // =========================== loader lane: ring slot s of owner c ===========================
+    const int t = (int)threadIdx.x - OWN_C * 32;
+    const int c = t / OWN_D, s = t % OWN_D;
+    const int w = c * (int)gridDim.x + (int)blockIdx.x;
+    unsigned char *reg = own_smem + (size_t)c * a.region_bytes;
+    unsigned char *slot = reg + (size_t)s * slot_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(reg + a.off_bars) + s;
+    uint64_t *empty = full + OWN_D;
+    const int q0 = a.queue_off[w], n = a.queue_off[w + 1] - q0;
+    int j = s;  // this lane loads entries s, s+D, s+2D, ... of the owner's queue
+    unsigned fill = 0, idle = 0;
+    bool have = false, ready = false, vacant = false;
+    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
+    for (unsigned it = 0;; ++it) {
+      const bool active = j < n;
+      if (!__any_sync(0xffffffffu, active)) break;
+      bool prog = false;
+      if (active) {
+        if (!have) {
+          const uint4 *ep = reinterpret_cast<const uint4 *>(a.entries + q0 + j);
+          e0 = __ldg(ep);
+          e1 = __ldg(ep + 1);
+          have = true;
+        }
+        // the slot is vacant once the owner has read fill-1 out of it (a fresh barrier passes parity 1)
+        if (!vacant) vacant = mbar_test(empty, (fill & 1u) ^ 1u);
+        // the row is final once every earlier instance of this user has been published; nobody
+        // writes it again before this very instance does
+        if (!ready) ready = ld_acquire_u32(ver + e0.x) == e0.y;
+        if (vacant && ready) {
+          *reinterpret_cast<uint4 *>(slot + row_bytes + 16) = e0;
+          *reinterpret_cast<uint4 *>(slot + row_bytes + 32) = e1;
+          fence_proxy_async_global();
+          const size_t row = (size_t)m.user_off + e0.x;
+          mbar_arrive_expect_tx(full, row_bytes + (m.no_user_bias ? 0u : 16u));
+          bulk_g2s(slot, m.W + row * (size_t)m.pitch, row_bytes, full);
+          if (!m.no_user_bias) bulk_g2s(slot + row_bytes, m.bias + (row & ~(size_t)3), 16u, full);
+          j += OWN_D;
+          ++fill;
+          have = ready = vacant = false;
+          prog = true;
+        }
+      }
+      if (__any_sync(0xffffffffu, prog)) {
+        idle = 0;
+      } else {
+        ++idle;
+        __nanosleep(idle < 16 ? 20 : 200);
+      }
+      if ((it & 63u) == 63u && ld_relaxed_u32(a.abort_flag)) break;
+    }
+    return;
+  }
+
+  // ================================ owner warp ================================================
+  const int w = warp * (int)gridDim.x + (int)blockIdx.x;
+  unsigned char *reg = own_smem + (size_t)warp * a.region_bytes;
+  float *items_s = reinterpret_cast<float *>(reg + a.off_items);
+  float *ibias_s = reinterpret_cast<float *>(reg + a.off_ibias);
+  uint64_t *full = reinterpret_cast<uint64_t *>(reg + a.off_bars);
+  uint64_t *empty = full + OWN_D;
+  Group<32, VEC> g;
+  g.gl = lane;
+  g.gmask = 0xffffffffu;
+  g.dot_s = reinterpret_cast<float *>(reg + a.off_dot);
+
+  // the owner's item rows: the first S (its most popular) live in shared memory for the launch
+  const int it0 = a.item_off[w], nit = a.item_off[w + 1] - it0, nres = min(nit, S);
+  for (int sl = 0; sl < nres; ++sl) {
+    const size_t row = (size_t)m.item_off + a.items[it0 + sl];
+    const float *src = m.W + row * (size_t)m.pitch;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int ch = lane + v * 32;
+      if (4 * ch < m.pitch) *reinterpret_cast<float4 *>(items_s + (size_t)sl * m.pitch + 4 * ch) = ldcg4(src + 4 * ch);
+    }
+    if (lane == 0) ibias_s[sl] = __ldcg(m.bias + row);
+  }
+  __syncwarp();
+
+  float4 wi[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) wi[v] = f4_zero();
+  float ib = 0.0f;
+  unsigned cur_item = 0xffffffffu, cur_slot = 0;
+  auto put_item = [&]() {  // the current item row leaves the registers
+    if (cur_item == 0xffffffffu) return;
+    if ((int)cur_slot < S) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int ch = lane + v * 32;
+        if (4 * ch < m.pitch) *reinterpret_cast<float4 *>(items_s + (size_t)cur_slot * m.pitch + 4 * ch) = wi[v];
+      }
+      if (lane == 0) ibias_s[cur_slot] = ib;
+    } else {
+      g.store_row(m, (size_t)m.item_off + cur_item, wi);
+      if (lane == 0) __stcg(m.bias + m.item_off + cur_item, ib);
+    }
+    __syncwarp();
+  };
+  auto get_item = [&](unsigned item, unsigned sl) {
+    if ((int)sl < S) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int ch = lane + v * 32;
+        wi[v] = (4 * ch < m.pitch) ? *reinterpret_cast<const float4 *>(items_s + (size_t)sl * m.pitch + 4 * ch) : f4_zero();
+      }
+      ib = ibias_s[sl];
+    } else {
+      g.load_row(m, (size_t)m.item_off + item, wi);
+      ib = __ldcg(m.bias + m.item_off + item);
+    }
+    cur_item = item;
+    cur_slot = sl;
+  };
+
+  const int q0 = a.queue_off[w], n = a.queue_off[w + 1] - q0;
+  const int B = a.batch[w];
+  int pend = 0;
+  unsigned my_u = 0, my_t = 0;
+  auto flush = [&]() {  // publish the user rows written since the last flush: one release fence
+    if (pend) {
+      __syncwarp();  // the row stores of all lanes happen-before the releases (cumulative)
+      if (lane < pend) st_release_u32(ver + my_u, my_t);
+      pend = 0;
+    }
+  };
+  bool dead = false;
+  for (int j = 0; j < n && !dead; ++j) {
+    const int s = j & (OWN_D - 1);
+    const unsigned par = (unsigned)(j / OWN_D) & 1u;
+    if (!mbar_try(full + s, par)) {
+      flush();  // never block with unpublished rows: somebody may be waiting for them
+      const long long t0 = clock64();
+      for (unsigned it = 0; !mbar_try(full + s, par); ++it) {
+        if ((it & 63u) == 63u) {
+          if (ld_relaxed_u32(a.abort_flag)) dead = true;
+          else if (clock64() - t0 > OWN_TIMEOUT) {
+            if (lane == 0) {
+              atomicCAS(a.err_flag, 0, ERR_TIMEOUT);
+              st_relaxed_u32(a.abort_flag, 1u);
+            }
+            dead = true;
+          }
+          if (dead) break;
+        }
+      }
+      if (dead) break;
+    }
+    const unsigned char *slot = reg + (size_t)s * slot_bytes;
+    const uint4 e0 = *reinterpret_cast<const uint4 *>(slot + row_bytes + 16);
+    const uint4 e1 = *reinterpret_cast<const uint4 *>(slot + row_bytes + 32);
+    const unsigned user = e0.x;
+    float4 wu[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int ch = lane + v * 32;
+      wu[v] = (4 * ch < m.pitch) ? *reinterpret_cast<const float4 *>(slot + 16 * ch) : f4_zero();
+    }
+    const size_t urow = (size_t)m.user_off + user;
+    float ub = m.no_user_bias ? 0.0f : *reinterpret_cast<const float *>(slot + row_bytes + 4 * (urow & 3));
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);  // the slot may be refilled
+    if (e0.w != cur_item) {
+      put_item();
+      get_item(e0.w, e1.x);
+    }
+    own_step<VEC>(g, m, a.hp, wu, ub, wi, ib, __uint_as_float(e1.y), __uint_as_float(e1.z), __uint_as_float(e0.z));
+    g.store_row(m, urow, wu);
+    if (!m.no_user_bias && lane == 0) __stcg(m.bias + urow, ub);
+    if (lane == pend) {
+      my_u = user;
+      my_t = e0.y + 1u;
+    }
+    ++pend;
+    if ((e1.w & 1u) || pend >= B) flush();
+  }
+  flush();
+  put_item();
+  // resident item rows go home
+  for (int sl = 0; sl < nres; ++sl) {
+    const size_t row = (size_t)m.item_off + a.items[it0 + sl];
+    float *dst = m.W + row * (size_t)m.pitch;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int ch = lane + v * 32;
+      if (4 * ch < m.pitch) stcg4(dst + 4 * ch, *reinterpret_cast<const float4 *>(items_s + (size_t)sl * m.pitch + 4 * ch));
+    }
+    if (lane == 0) __stcg(m.bias + row, ibias_s[sl]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int own_reserve(svdgpu *h, DevBuf &b, size_t bytes) {
+  bytes += 64;
+  if (bytes <= b.cap) return 0;
+  if (b.p) CU(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  CU(h, cudaMalloc(&b.p, bytes + bytes / 8));
+  b.cap = bytes + bytes / 8;
+  return 0;
+}
+
+static int bits_for(unsigned n) {  // key bits needed for values < n
+  int b = 1;
+  while (b < 32 && (1ull << b) < (unsigned long long)n) ++b;
+  return b;
+}
+
+bool own_supported(const svdgpu *h) {
+  // plain L2 decay only (the other regularisers keep k_exact), rows of at most 256 floats
+  return h->dhp.plain && h->dm.pitch <= 256 && h->shape.format_type == 0 && h->dm.num_user > 0 && h->dm.num_item > 0;
+}
+
+void own_plan_free(OwnPlan &p) {
+  DevBuf *db[] = {&p.entries, &p.queue_off, &p.item_off, &p.items, &p.batch};
+  for (DevBuf *d : db) {
+    if (d->p) cudaFree(d->p);
+    d->p = nullptr;
+    d->cap = 0;
+  }
+  if (p.stage.p) cudaFreeHost(p.stage.p);
+  p.stage.p = nullptr;
+  p.stage.cap = 0;
+  p.valid = false;
+}
+void own_scratch_free(OwnScratch &s) {
+  DevBuf *db[] = {&s.cnt_item, &s.cnt_user, &s.start_user, &s.flag, &s.keyA, &s.keyB, &s.valA, &s.valB,
+                  &s.key_item, &s.tick, &s.tmp, &s.item_owner, &s.item_slot};
+  for (DevBuf *d : db) {
+    if (d->p) cudaFree(d->p);
+    d->p = nullptr;
+    d->cap = 0;
+  }
+  if (s.h_cnt) cudaFreeHost(s.h_cnt);
+  s.h_cnt = nullptr;
+  s.h_cnt_cap = 0;
+  if (s.ev) cudaEventDestroy(s.ev);
+  s.ev = nullptr;
+}
+
+// Build the plan of rows [r0, r0+n) of a device CSR on `st`.  Returns non-zero on failure (message
+// set).  p.valid tells whether the rows can take k_own; *bad receives the OWN_* bits otherwise.
+int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad) {
+  p.valid = false;
+  if (bad) *bad = 0;
+  if (n <= 0) return 0;
+  OwnScratch &s = h->own;
+  const DevModel &m = h->dm;
+  const int W = h->num_sm * OWN_C;
+  const size_t nn = (size_t)n;
+  if (own_reserve(h, s.cnt_item, (size_t)m.num_item * 4) || own_reserve(h, s.cnt_user, (size_t)m.num_user * 4) ||
+      own_reserve(h, s.start_user, (size_t)m.num_user * 4) || own_reserve(h, s.flag, 4) ||
+      own_reserve(h, s.keyA, nn * 4) || own_reserve(h, s.keyB, nn * 4) || own_reserve(h, s.valA, nn * 4) ||
+      own_reserve(h, s.valB, nn * 4) || own_reserve(h, s.key_item, nn * 4) || own_reserve(h, s.tick, nn * 4) ||
+      own_reserve(h, s.item_owner, (size_t)m.num_item * 4) || own_reserve(h, s.item_slot, (size_t)m.num_item * 4))
+    return 1;
+  if (!s.ev) CU(h, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  if (s.h_cnt_cap < (size_t)m.num_item * 4 + 4) {
+    if (s.h_cnt) cudaFreeHost(s.h_cnt);
+    s.h_cnt = nullptr;
+    s.h_cnt_cap = 0;
+    CU(h, cudaMallocHost(&s.h_cnt, (size_t)m.num_item * 4 + 64));
+    s.h_cnt_cap = (size_t)m.num_item * 4 + 4;
+  }
+  const int blocks = (int)std::min<long long>((long long)h->num_sm * 16, ((long long)n + 255) / 256);
+  CU(h, cudaMemsetAsync(s.cnt_item.p, 0, (size_t)m.num_item * 4, st));
+  CU(h, cudaMemsetAsync(s.cnt_user.p, 0, (size_t)m.num_user * 4, st));
+  CU(h, cudaMemsetAsync(s.flag.p, 0, 4, st));
+  unsigned *keyA = (unsigned *)s.keyA.p, *keyB = (unsigned *)s.keyB.p, *valA = (unsigned *)s.valA.p,
+           *valB = (unsigned *)s.valB.p;
+  k_own_scan<<<blocks, 256, 0, st>>>(csr, r0, n, m.num_user, m.num_item, (unsigned *)s.cnt_item.p,
+                                     (unsigned *)s.cnt_user.p, keyA, (unsigned *)s.key_item.p, valA, (int *)s.flag.p);
+  CU(h, cudaGetLastError());
+  h->n_launch++;
+  // item counts (+ the flag word behind them) to the host: the LPT runs there while the device sorts by user
+  CU(h, cudaMemcpyAsync(s.h_cnt, s.cnt_item.p, (size_t)m.num_item * 4, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync((char *)s.h_cnt + (size_t)m.num_item * 4, s.flag.p, 4, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaEventRecord(s.ev, st));
+  h->n_d2h += (long long)m.num_item * 4 + 4;
+
+  // tickets: stable sort by user, rank inside the user's run
+  size_t tmp_scan = 0, tmp_sort = 0;
+  CU(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (unsigned *)s.cnt_user.p, (unsigned *)s.start_user.p, m.num_user, st));
+  {
+    cub::DoubleBuffer<unsigned> dk(keyA, keyB), dv(valA, valB);
+    CU(h, cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, n, 0, 32, st));
+  }
+  if (own_reserve(h, s.tmp, std::max(tmp_scan, tmp_sort))) return 1;
+  size_t tmp_bytes = s.tmp.cap;
+  CU(h, cub::DeviceScan::ExclusiveSum(s.tmp.p, tmp_bytes, (unsigned *)s.cnt_user.p, (unsigned *)s.start_user.p, m.num_user, st));
+  {
+    cub::DoubleBuffer<unsigned> dk(keyA, keyB), dv(valA, valB);
+    tmp_bytes = s.tmp.cap;
+    CU(h, cub::DeviceRadixSort::SortPairs(s.tmp.p, tmp_bytes, dk, dv, n, 0, bits_for((unsigned)m.num_user), st));
+    k_own_ticket<<<blocks, 256, 0, st>>>(dk.Current(), dv.Current(), (const unsigned *)s.start_user.p, n,
+                                         (unsigned)h->own_urgent_gap, (unsigned *)s.tick.p);
+    CU(h, cudaGetLastError());
+    h->n_launch += 3;
+  }
+
+  // host: deal the items out
+  CU(h, cudaEventSynchronize(s.ev));
+  const unsigned *hc = (const unsigned *)s.h_cnt;
+  const int fl = (int)hc[m.num_item];
+  if (fl) {
+    if (bad) *bad = fl;
+    return 0;  // not for k_own (the caller reports bound errors / falls back to k_exact)
+  }
+  svdown::HostPlan hp;
+  svdown::assign(hc, m.num_item, W, h->own_batch, hp);
+  if (own_reserve(h, p.queue_off, (size_t)(W + 1) * 4) || own_reserve(h, p.item_off, (size_t)(W + 1) * 4) ||
+      own_reserve(h, p.items, std::max<size_t>(hp.items.size(), 1) * 4) || own_reserve(h, p.batch, (size_t)W * 4) ||
+      own_reserve(h, p.entries, nn * sizeof(OwnEntry)))
+    return 1;
+  // the host-made arrays go through the plan's own pinned buffer (it stays untouched until the
+  // plan is rebuilt, which is stream-ordered after everything that reads it)
+  {
+    const size_t ni = (size_t)m.num_item, nw = (size_t)W + 1, nit = hp.items.size();
+    const size_t words = 2 * ni + 2 * nw + nit + (size_t)W;
+    if (p.stage.cap < words * 4) {
+      if (p.stage.p) CU(h, cudaFreeHost(p.stage.p));
+      p.stage.p = nullptr;
+      p.stage.cap = 0;
+      CU(h, cudaMallocHost(&p.stage.p, words * 4 + words));
+      p.stage.cap = words * 4 + words;
+    }
+    unsigned *sp = (unsigned *)p.stage.p;
+    unsigned *s_owner = sp, *s_slot = s_owner + ni, *s_qoff = s_slot + ni, *s_ioff = s_qoff + nw,
+             *s_items = s_ioff + nw, *s_batch = s_items + nit;
+    memcpy(s_owner, hp.item_owner.data(), ni * 4);
+    memcpy(s_slot, hp.item_slot.data(), ni * 4);
+    memcpy(s_qoff, hp.queue_off.data(), nw * 4);
+    memcpy(s_ioff, hp.item_off.data(), nw * 4);
+    if (nit) memcpy(s_items, hp.items.data(), nit * 4);
+    memcpy(s_batch, hp.batch.data(), (size_t)W * 4);
+    CU(h, cudaMemcpyAsync(s.item_owner.p, s_owner, ni * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(s.item_slot.p, s_slot, ni * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(p.queue_off.p, s_qoff, nw * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(p.item_off.p, s_ioff, nw * 4, cudaMemcpyHostToDevice, st));
+    if (nit) CU(h, cudaMemcpyAsync(p.items.p, s_items, nit * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(p.batch.p, s_batch, (size_t)W * 4, cudaMemcpyHostToDevice, st));
+    h->n_h2d += (long long)words * 4;
+  }
+
+  // queues: stable sort by owner; the sorted position is the queue position
+  k_own_keyowner<<<blocks, 256, 0, st>>>((const unsigned *)s.key_item.p, (const int *)s.item_owner.p, n, keyA, valA);
+  CU(h, cudaGetLastError());
+  {
+    cub::DoubleBuffer<unsigned> dk(keyA, keyB), dv(valA, valB);
+    tmp_bytes = s.tmp.cap;
+    CU(h, cub::DeviceRadixSort::SortPairs(s.tmp.p, tmp_bytes, dk, dv, n, 0, bits_for((unsigned)W), st));
+    k_own_entries<<<blocks, 256, 0, st>>>(csr, r0, n, dv.Current(), (const unsigned *)s.tick.p,
+                                          (const unsigned *)s.item_slot.p, (OwnEntry *)p.entries.p);
+    CU(h, cudaGetLastError());
+    h->n_launch += 3;
+  }
+  p.num_owner = W;
+  p.rows = n;
+  p.max_load = hp.max_load;
+  p.valid = true;
+  return 0;
+}
+
+template <int VEC>
+static int own_launch_vec(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
+  const DevModel &m = h->dm;
+  const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
+  const unsigned ring = OWN_D * slot_bytes;
+  const unsigned dot = (unsigned)Group<32, VEC>::DOT_FLOATS * 4u;
+  const unsigned bars = 2u * OWN_D * 8u;
+  int max_smem = 0;
+  CU(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const long long fixed = (long long)ring + dot + bars + 128;
+  long long S = ((long long)max_smem / OWN_C - fixed) / (long long)(row_bytes + 4);
+  S = std::min<long long>(S, h->own_slots > 0 ? h->own_slots : 32);
+  if (S < 0) return fail(h, "ordered mode: shared memory too small for k_own at num_factor %d", m.k);
+  OwnArgs a;
+  a.m = m;
+  a.hp = h->dhp;
+  a.entries = (const OwnEntry *)p.entries.p;
+  a.queue_off = (const int *)p.queue_off.p;
+  a.item_off = (const int *)p.item_off.p;
+  a.items = (const unsigned *)p.items.p;
+  a.batch = (const int *)p.batch.p;
+  a.S = (int)S;
+  a.off_items = ring;
+  a.off_ibias = a.off_items + (unsigned)S * row_bytes;
+  a.off_dot = (a.off_ibias + (unsigned)S * 4u + 15u) & ~15u;
+  a.off_bars = a.off_dot + dot;
+  a.region_bytes = (a.off_bars + bars + 127u) & ~127u;
+  a.err_flag = h->d_err;
+  a.abort_flag = h->d_abort;
+  const size_t smem = (size_t)a.region_bytes * OWN_C;
+  auto k = k_own<VEC>;
+  CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(h, cudaMemsetAsync(m.ver_ui + m.user_off, 0, sizeof(unsigned) * (size_t)m.num_user, st));
+  CU(h, cudaMemsetAsync(h->d_abort, 0, sizeof(unsigned), st));
+  void *args[] = {&a};
+  // cooperative: the launch fails instead of deadlocking if the CTAs cannot all be resident
+  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3(h->num_sm), dim3(OWN_THREADS), args, smem, st));
+  h->n_launch++;
+  h->n_own++;
+  h->n_own_rows += p.rows;
+  return 0;
+}
+
+int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
+  if (!p.valid) return fail(h, "ordered mode: no owner plan");
+  if (p.num_owner != h->num_sm * OWN_C) return fail(h, "ordered mode: plan was built for another device");
+  const int chunks = h->dm.pitch / 4;
+  if (chunks <= 32) return own_launch_vec<1>(h, p, st);
+  if (chunks <= 64) return own_launch_vec<2>(h, p, st);
+  return fail(h, "ordered mode: k_own supports num_factor <= 256");
+}
+
+}  // namespace svdk

@@ -1,0 +1,81 @@
+// svdgpu_ownplan.h -- host part of the plan for the ordered mode with item-owner warps
+// (k_own, svdgpu_own.cu).  Plain C++: unit-tested on the CPU
+// (tests/test_own_plan.py) and compiled into libsvdgpu.so.
+//
+// The reference's SGD loop is strictly sequential (base.h:456-462).  Two instances that share
+// neither a user row nor an item row commute exactly, so the ordered mode only has to keep, for
+// every row, the order of the instances that touch it.  k_own does this by giving every ITEM to
+// one persistent warp (its "owner"), which takes the instances of its items in input order and
+// keeps the item rows on chip; user rows travel between owners through version counters.
+//
+// The device counts the ratings of every item; this header deals the items out: in decreasing
+// popularity to the least loaded owner (LPT), so the heaviest owner carries little more than the
+// hottest item -- whose chain of dependent updates is the critical path of the whole launch.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <queue>
+#include <utility>
+#include <vector>
+
+namespace svdown {
+
+struct HostPlan {
+  int num_owner = 0;
+  std::vector<int> item_owner;       // [num_item] owner of an item, -1 if the batch never touches it
+  std::vector<unsigned> item_slot;   // [num_item] position of the item in its owner's list
+  std::vector<int> queue_off;        // [num_owner + 1] first queue entry of an owner
+  std::vector<int> item_off;         // [num_owner + 1] first entry of an owner in `items`
+  std::vector<unsigned> items;       // items by owner, most popular first (slot order)
+  std::vector<int> batch;            // [num_owner] user-row publishes an owner may hold back
+  int64_t max_load = 0;
+};
+
+// cnt[i] = ratings of item i in the batch.  Owner w of the launch is warp (w / grid) of block
+// (w % grid): consecutive owners sit on different SMs, so the hottest items never share one.
+// max_batch: how many user-row version publishes the most loaded owner may collect before one
+// release fence; slower owners hold back proportionally fewer, so the delay is about the same
+// stretch of the input order for everybody.
+inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_batch, HostPlan &p) {
+  p.num_owner = num_owner;
+  p.item_owner.assign((size_t)num_item, -1);
+  p.item_slot.assign((size_t)num_item, 0u);
+  std::vector<int> order;
+  order.reserve((size_t)num_item);
+  for (int i = 0; i < num_item; ++i)
+    if (cnt[i] > 0) order.push_back(i);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+  typedef std::pair<int64_t, int> Load;  // (rows, owner): smallest load first, then smallest owner id
+  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  for (int w = 0; w < num_owner; ++w) heap.push(Load(0, w));
+  std::vector<int64_t> load((size_t)num_owner, 0);
+  std::vector<int> nitem((size_t)num_owner, 0);
+  for (int i : order) {
+    Load l = heap.top();
+    heap.pop();
+    p.item_owner[(size_t)i] = l.second;
+    p.item_slot[(size_t)i] = (unsigned)nitem[(size_t)l.second]++;
+    l.first += cnt[i];
+    load[(size_t)l.second] = l.first;
+    heap.push(l);
+  }
+  p.queue_off.assign((size_t)num_owner + 1, 0);
+  p.item_off.assign((size_t)num_owner + 1, 0);
+  p.max_load = 0;
+  for (int w = 0; w < num_owner; ++w) {
+    p.queue_off[(size_t)w + 1] = p.queue_off[(size_t)w] + (int)load[(size_t)w];
+    p.item_off[(size_t)w + 1] = p.item_off[(size_t)w] + nitem[(size_t)w];
+    p.max_load = std::max(p.max_load, load[(size_t)w]);
+  }
+  p.items.assign(order.size(), 0u);
+  for (int i : order)
+    p.items[(size_t)p.item_off[(size_t)p.item_owner[(size_t)i]] + p.item_slot[(size_t)i]] = (unsigned)i;
+  p.batch.assign((size_t)num_owner, 1);
+  for (int w = 0; w < num_owner; ++w) {
+    const int64_t b = p.max_load > 0 ? (int64_t)max_batch * load[(size_t)w] / p.max_load : 1;
+    p.batch[(size_t)w] = (int)std::max<int64_t>(1, std::min<int64_t>(b, max_batch));
+  }
+}
+
+}  // namespace svdown

@@ -752,30 +752,132 @@ def test_compact_h2d_is_invisible(native, chunk_rows):
         assert moved[0] - moved[1] >= 3 * 1000 * 20 + 1000 * 12
 
 
-@pytest.mark.skipif(not os.environ.get("SVDGPU_TEST_EXPERIMENTAL"),
-                    reason="experimental item-owner ordered kernel (option exact_owner): written after this round's "
-                           "GPU budget was spent; set SVDGPU_TEST_EXPERIMENTAL=1 to run it")
-@pytest.mark.parametrize("k", [64, 16, 128])
-def test_exact_owner_matches_oracle(native, k):
-    """Ordered mode through item-owner warps (k_owner) on a resident basic-MF batch with hot items:
-    model and predictions bit-identical to the sequential oracle, like k_exact."""
+def _own_setup(native, params, act=0, options=None, seed=5):
+    o = COracle(0, act, 0, params)
+    o.init(seed)
+    g = native.SvdGpu(**_cases.shape_of(params, 0, act))
+    g.set_hparams(**_cases.hparams_of(params, o.base_score))
+    g.set_mode(native.MODE_EXACT)
+    for name, v in (options or {}).items():
+        g.set_option(name, v)
+    g.upload(*[a.copy() for a in o.arrays()])
+    return o, g
+
+
+@pytest.mark.parametrize("k", [64, 16, 128, 256, 20, 3])
+@pytest.mark.parametrize("resident", [True, False])
+def test_exact_owner_matches_oracle(native, k, resident):
+    """Ordered mode through the item-owner kernel (k_own) on basic-MF rows with hot items (the top
+    item holds ~8 % of the rows): model and predictions bit-identical to the sequential oracle, as
+    a resident batch and through the host-pointer call (several chunks)."""
     nu, ni, n = 3000, 200, 60000
     params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.01, wd_user=0.004, wd_item=0.003,
                   wd_user_bias=0.001, wd_item_bias=0.002, base_score=3.6)
     data = synth.basic_mf(n, nu, ni, seed=31, zipf_q=2.0)
-    o = COracle(0, 0, 0, params)
-    o.init(5)
-    g = native.SvdGpu(**_cases.shape_of(params, 0, 0))
-    g.set_hparams(**_cases.hparams_of(params, o.base_score))
-    g.set_mode(native.MODE_EXACT)
-    g.set_option("exact_owner", 1)
-    g.upload(*[a.copy() for a in o.arrays()])
-    b = g.batch_create(data)
+    o, g = _own_setup(native, params, options={"chunk_rows": 25000})
+    b = g.batch_create(data) if resident else None
     for _ in range(2):
         o.update_csr(data)
-        g.batch_update(b)
+        if resident:
+            g.batch_update(b)
+        else:
+            g.update_csr(data)
     g.sync()
+    assert g.counter("own_launches") == (2 if resident else 6)  # the owner kernel did the work
+    assert g.counter("own_rows") == 2 * n
     assert _maxdiff(o, g) == 0.0
     assert np.array_equal(o.predict_csr(data), g.predict_csr(data))
-    b.close()
+    if b:
+        b.close()
     g.close()
+
+
+@pytest.mark.parametrize("options", [dict(own_slots=1), dict(own_batch=1), dict(own_batch=32, own_urgent_gap=0),
+                                     dict(own_urgent_gap=1 << 30), dict(own_min_rows=1, chunk_rows=37),
+                                     dict(own_min_rows=1, chunk_rows=1)])
+def test_exact_owner_options_do_not_change_the_result(native, options):
+    """Item rows beyond an owner's shared-memory slots (own_slots=1: most of them live in L2),
+    publish batching, the urgent-publish rule and tiny launches: all bit-identical."""
+    nu, ni, n = 500, 2000, 20000 if options.get("chunk_rows", 0) != 1 else 300
+    params = dict(num_user=nu, num_item=ni, num_factor=32, learning_rate=0.02, wd_user=0.004, wd_item=0.003,
+                  wd_user_bias=0.001, wd_item_bias=0.002, base_score=3.6)
+    data = synth.basic_mf(n, nu, ni, seed=32, zipf_q=20.0)  # 500 users: the same user comes back within a few rows
+    o, g = _own_setup(native, params, options=options)
+    o.update_csr(data)
+    g.update_csr(data)
+    g.sync()
+    assert g.counter("own_rows") == n
+    assert _maxdiff(o, g) == 0.0
+    g.close()
+
+
+def test_exact_owner_values_bias_switch_and_sigmoid(native):
+    """Non-unit feature values, no_user_bias, zero decay (the scalar-is-one shortcut) and a sigmoid
+    loss through the owner kernel."""
+    nu, ni, n = 800, 300, 12000
+    rng = np.random.default_rng(7)
+    u, i, lab = synth.ratings(n, nu, ni, seed=33, zipf_q=3.0)
+    uval = rng.choice(np.array([1.0, 0.5, -1.25, 2.0], np.float32), n)
+    ival = rng.choice(np.array([1.0, 1.0, 0.75, -0.5], np.float32), n)
+    data = synth.fixed_csr(lab, uidx=u, uval=uval, iidx=i, ival=ival)
+    for extra, act in ((dict(no_user_bias=1), 0), (dict(wd_user=0.0, wd_item=0.0), 0), (dict(base_score=0.6), 2),
+                       (dict(base_score=0.6), 3)):
+        params = dict(num_user=nu, num_item=ni, num_factor=24, learning_rate=0.01, wd_user=0.004, wd_item=0.003,
+                      wd_user_bias=0.001, wd_item_bias=0.002, base_score=3.6)
+        params.update(extra)
+        d = data if act == 0 else (data[0], (data[1] > 3).astype(np.float32), data[2], data[3])
+        o, g = _own_setup(native, params, act=act)
+        for _ in range(2):
+            o.update_csr(d)
+            g.update_csr(d)
+        g.sync()
+        assert g.counter("own_rows") == 2 * n
+        diff = _maxdiff(o, g)
+        assert diff == 0.0 if act == 0 else diff <= 2e-6, (extra, act, diff)
+        g.close()
+
+
+def test_exact_owner_equals_exact_kernel_and_falls_back(native):
+    """exact_owner on / off give the same bits; rows of other shapes, other regularisers and bad
+    indices keep k_exact's behaviour."""
+    nu, ni, n = 1000, 150, 10000
+    params = dict(num_user=nu, num_item=ni, num_factor=64, learning_rate=0.01, wd_user=0.004, wd_item=0.003,
+                  base_score=3.6)
+    data = synth.basic_mf(n, nu, ni, seed=34, zipf_q=1.0)
+    models = []
+    for own in (1, 0):
+        o, g = _own_setup(native, params, options={"exact_owner": own})
+        g.update_csr(data)
+        g.sync()
+        assert (g.counter("own_launches") > 0) == bool(own)
+        models.append(g.download())
+        g.close()
+    for a, b in zip(models[0], models[1]):
+        assert np.array_equal(a, b)
+    # a launch with one row of another shape: the whole launch takes k_exact, still bit-exact
+    rp, lab, idx, val = data
+    rows = [(float(lab[r]), [], [(int(idx[2 * r]), 1.0)], [(int(idx[2 * r + 1]), 1.0)]) for r in range(5000)]
+    rows[1234] = (4.0, [], [(3, 1.0), (7, 0.5)], [(9, 1.0)])
+    mixed = synth.ragged_csr(rows)
+    o, g = _own_setup(native, params)
+    o.update_csr(mixed)
+    g.update_csr(mixed)
+    g.sync()
+    assert g.counter("own_launches") == 0 and _maxdiff(o, g) == 0.0
+    g.close()
+    # projection regulariser: not plain decay -> k_exact
+    o, g = _own_setup(native, dict(params, reg_method=2, wd_user=0.005, wd_item=0.006))
+    o.update_csr(data)
+    g.update_csr(data)
+    g.sync()
+    assert g.counter("own_launches") == 0 and _maxdiff(o, g) == 0.0
+    g.close()
+    # an index out of range is the reference's assert (base.h:327,343)
+    for pos, msg in ((2 * 4321, "user feature index exceed bound"), (2 * 4321 + 1, "item feature index exceed bound")):
+        bad = (rp, lab, idx.copy(), val)
+        bad[2][pos] = 1 << 20
+        o, g = _own_setup(native, params)
+        with pytest.raises(native.SvdGpuError, match=msg):
+            g.update_csr(bad)
+            g.sync()
+        g.close()

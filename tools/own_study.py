@@ -1,0 +1,87 @@
+"""GPU experiment: the ordered mode through the item-owner kernel (k_own, svdgpu_own.cu) on the
+configs[1] shape.  Checks on a small prefix that k_own leaves the same model bytes as k_exact
+(which the parity tests pin to the oracle), then times the plan build and the epochs at full size.
+
+    python tools/own_study.py [rows] [name=value ...]      options: own_batch, own_urgent_gap, own_slots
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from svdfeature_b200 import api, synth  # noqa: E402
+
+NU, NI, K = 480000, 18000, 64
+N = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20_000_000
+opts = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+rng = np.random.default_rng(1)
+W = (rng.standard_normal((NU + NI, K)) * 0.01).astype(np.float32)
+data = synth.basic_mf(N, NU, NI, seed=3, zipf_q=70.0)
+top = int(np.bincount(data[2][1::2]).max())
+out = open(os.path.join(ROOT, "gpurun_out", "own_study.jsonl"), "a")
+
+
+def trainer(owner):
+    g = api.SvdGpu(NU, NI, K)
+    g.set_hparams(learning_rate=0.005, wd_user=0.004, wd_item=0.004, base_score=3.6)
+    g.set_mode(api.MODE_EXACT)
+    g.set_option("exact_owner", owner)
+    for k, v in opts.items():
+        g.set_option(k, int(v))
+    g.upload(np.zeros(NU + NI, np.float32), W, np.zeros(1, np.float32))
+    return g
+
+
+# ---- same bytes as k_exact on a prefix ---------------------------------------------------------
+M = min(N, 1_000_000)
+sub = (data[0][:3 * M + 1], data[1][:M], data[2][:2 * M], data[3][:2 * M])
+models = []
+for owner in (0, 1):
+    g = trainer(owner)
+    b = g.batch_create(sub)
+    g.timer_start()
+    g.batch_update(b)
+    ms = g.timer_stop()
+    g.sync()
+    models.append([a.copy() for a in g.download()])
+    print(json.dumps(dict(check_rows=M, exact_owner=owner, ms=ms, minst_s=M / ms / 1e3,
+                          own_launches=g.counter("own_launches"))), flush=True)
+    b.close()
+    g.close()
+same = all(np.array_equal(a, c) for a, c in zip(*models))
+print(json.dumps(dict(same_model_as_k_exact=bool(same))), flush=True)
+
+# ---- full size ------------------------------------------------------------------------------------
+g = trainer(1)
+t0 = time.perf_counter()
+b = g.batch_create(data)
+g.sync()
+t_create = time.perf_counter() - t0
+times = []
+for _ in range(4):
+    g.timer_start()
+    g.batch_update(b)
+    times.append(g.timer_stop())
+g.sync()
+ms = float(np.median(times[1:]))
+line = dict(rows=N, hottest_item_rows=top, batch_create_s=t_create, ms_epochs=times, ms=ms, minst_s=N / ms / 1e3,
+            us_per_hot_row=1e3 * ms / top, same_model_as_k_exact=bool(same), options=opts,
+            own_launches=g.counter("own_launches"))
+print(json.dumps(line), flush=True)
+out.write(json.dumps(line) + "\n")
+# host-pointer call (plan per chunk inside the call)
+for chunk in (1 << 20, 1 << 23):
+    g.set_option("chunk_rows", chunk)
+    t0 = time.perf_counter()
+    g.update_csr(data)
+    g.sync()
+    dt = time.perf_counter() - t0
+    line = dict(host_call_rows=N, chunk_rows=chunk, s=dt, minst_s=N / dt / 1e6)
+    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+b.close()
+g.close()
