@@ -103,7 +103,7 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   features) under plain L2 decay take the item-owner kernel (k_own: every item row
  *                   stays on one warp, user rows travel under version counters; bit-identical to
  *                   k_exact and to the reference); 0 keeps every row in k_exact.  Tuning:
- *                   "own_min_rows" (4096: smaller launches keep k_exact), "own_batch" (16: version
+ *                   "own_min_rows" (4096: smaller launches keep k_exact), "own_batch" (32: version
  *                   publishes the busiest owner holds back per release fence, <= 32),
  *                   "own_urgent_gap" (16384: a user whose next rating follows within this many rows
  *                   is published at once), "own_slots" (0 = auto: item rows per owner kept in
@@ -274,6 +274,10 @@ int svdgpu_timer_stop(svdgpu_t *h, float *elapsed_ms);
 /* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm", "lanes", "own_launches", "own_rows",
  * "ingest_read_us", "ingest_call_us" (bulk ingest: time reading the file / inside the hot-path calls) */
 long long svdgpu_get_counter(const svdgpu_t *h, const char *name);
+/* Diagnostics of the last item-owner launch (option "own_stats" = 1 before it): per owner warp
+ * {cycles in its queue loop, cycles waiting for a ring slot, cycles in publish fences, number of
+ * waits}; out holds 4 * cap_owners values, *num_owner receives the owner count. */
+int svdgpu_own_stats(svdgpu_t *h, long long *out, int cap_owners, int *num_owner);
 /* device pointers of the model slabs (for peer / collective plumbing): 0 ui_bias,
  * 1 W_uiset, 2 g_bias; *pitch_floats receives the device row stride */
 void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats);

@@ -84,6 +84,7 @@ SVDGPU_SYMBOLS = {
     "svdgpu_timer_start": (C.c_int, [_vp]),
     "svdgpu_timer_stop": (C.c_int, [_vp, _f32p]),
     "svdgpu_get_counter": (C.c_longlong, [_vp, C.c_char_p]),
+    "svdgpu_own_stats": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "svdgpu_device_ptr": (_vp, [_vp, C.c_int, C.POINTER(C.c_size_t)]),
     "svdgpu_items_snapshot": (C.c_int, [_vp]),
     "svdgpu_items_pack_delta": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
@@ -384,6 +385,15 @@ class SvdGpu:
 
     def counter(self, name):
         return int(self.lib.svdgpu_get_counter(self.h, name.encode()))
+
+    def own_stats(self):
+        """Per-owner counters of the last item-owner launch (option own_stats=1 before it):
+        int64[num_owner, 4] = cycles in the queue loop, waiting for a slot, in publish fences, waits."""
+        n = C.c_int()
+        self._ck(self.lib.svdgpu_own_stats(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), np.int64)
+        self._ck(self.lib.svdgpu_own_stats(self.h, out.ctypes.data, n.value, C.byref(n)))
+        return out
 
     def device_ptr(self, which):
         pitch = C.c_size_t()

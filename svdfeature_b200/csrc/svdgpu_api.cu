@@ -552,6 +552,9 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_min_rows")) h->own_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_urgent_gap")) h->own_urgent_gap = (int)std::max<long long>(0, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_batch")) h->own_batch = (int)std::max<long long>(1, std::min<long long>(v, 32));
+  else if (!strcmp(name, "own_stats")) h->own_stats = v ? 1 : 0;
+  else if (!strcmp(name, "own_depth")) h->own_depth = v >= 16 ? 16 : 8;
+  else if (!strcmp(name, "own_fast")) h->own_fast = v ? 1 : 0;
   else if (!strcmp(name, "own_slots")) h->own_slots = (int)std::max<long long>(0, std::min<long long>(v, 32));
   else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
   else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));
@@ -694,6 +697,19 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
     return pick_geometry(const_cast<svdgpu *>(h), g) ? -1 : g.lanes;
   }
   return -1;
+}
+
+int svdgpu_own_stats(svdgpu_t *h, long long *out, int cap_owners, int *num_owner) {
+  if (!h || !num_owner) return 1;
+  CU(h, cudaSetDevice(h->device));
+  const int W = h->num_sm * 16;
+  *num_owner = W;
+  if (!h->own.stats.p) return fail(h, "own_stats: set option own_stats before the ordered launch");
+  if (out && cap_owners >= W) {
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(out, h->own.stats.p, (size_t)W * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  return 0;
 }
 
 void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats) {

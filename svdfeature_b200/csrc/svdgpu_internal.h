@@ -32,7 +32,7 @@ struct OwnPlan {
   bool valid = false;
 };
 struct OwnScratch {
-  DevBuf cnt_item, cnt_user, start_user, flag, keyA, keyB, valA, valB, key_item, tick, tmp, item_owner, item_slot;
+  DevBuf cnt_item, cnt_user, start_user, flag, keyA, keyB, valA, valB, key_item, tick, tmp, item_owner, item_slot, stats;
   void *h_cnt = nullptr;  // pinned: item counts + flag word
   size_t h_cnt_cap = 0;
   cudaEvent_t ev = nullptr;
@@ -133,8 +133,11 @@ struct svdgpu {
   int own_min_rows = 4096;   // option "own_min_rows": launches with fewer rows keep k_exact (no plan to build)
   int own_urgent_gap = 16384;  // option "own_urgent_gap": a user whose next rating follows within this many rows
                                // is published at once instead of with the owner's batch
-  int own_batch = 16;        // option "own_batch": version publishes the most loaded owner holds back (<= 32)
+  int own_batch = 32;        // option "own_batch": version publishes the most loaded owner holds back (<= 32)
   int own_slots = 0;         // option "own_slots": item rows an owner keeps in shared memory (0 = auto, <= 32)
+  int own_depth = 8;         // option "own_depth": ring slots per owner (8 or 16)
+  int own_fast = 1;          // option "own_fast": 0 keeps the generic link for every shape (testing)
+  int own_stats = 0;         // option "own_stats": k_own records per-owner cycle counters (svdgpu_own_stats)
   OwnScratch own;
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
   int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):

@@ -131,16 +131,14 @@ __global__ void k_own_entries(DevCsr csr, int r0, int n, const unsigned *rows, c
 // k_own
 // ---------------------------------------------------------------------------
 constexpr int OWN_C = 16;                      // owner (compute) warps per CTA
-constexpr int OWN_D = 8;                       // ring slots per owner
-constexpr int OWN_LW = OWN_C * OWN_D / 32;     // loader warps per CTA: one lane per ring slot
-constexpr int OWN_THREADS = (OWN_C + OWN_LW) * 32;
 constexpr int OWN_SLOT_EXTRA = 48;             // [row | 16-byte bias window | 32-byte entry]
 constexpr long long OWN_TIMEOUT = 6000000000LL;  // cycles (~3 s): a wait this long is a bug, not load
+constexpr int own_threads(int D) { return (OWN_C + OWN_C * D / 32) * 32; }  // + one loader lane per ring slot
 
 struct OwnArgs {
   DevModel m;
   DevHP hp;
-  const OwnEntry *entries;
+  const uint4 *entries;  // OwnEntry[], two 16-byte words each
   const int *queue_off;
   const int *item_off;
   const unsigned *items;
@@ -150,6 +148,7 @@ struct OwnArgs {
   unsigned off_items, off_ibias, off_dot, off_bars;
   int *err_flag;
   unsigned *abort_flag;
+  long long *stats;  // option "own_stats": per owner {cycles, cycles waiting for a slot, cycles in flushes, waits} or null
 };
 
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {  // non-blocking
@@ -231,69 +230,144 @@ __device__ __forceinline__ void own_step(const Group<32, VEC> &g, const DevModel
   ib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(OWN_THREADS, 1) k_own(const OwnArgs a) {
+// The same instance for rows of exactly CH float4 chunks (num_factor = 4*CH <= 128), linear loss:
+// branch-free and with compile-time trip counts -- this is the link of the hot item's chain.
+//   * "s is one => no multiply" (sse.h:231-242) becomes a multiply by exactly 1.0f (x*1.0f == x);
+//     a skipped decay likewise;
+//   * the dot keeps the reference's order (sse.h:289-317): the products go to shared memory
+//     transposed, every lane adds the CH products of component (lane & 3) in order (lanes with
+//     the same component read the same words: broadcast), then (l0+l2)+(l1+l3).
+template <int CH>
+__device__ __forceinline__ void own_step_fast(const DevModel &m, const DevHP &hp, float *dotT, int lane, float4 &wu,
+                                              float &ub, float4 &wi, float &ib, float uval, float ival, float label,
+                                              float du, float di, uint64_t *release_slot) {
+  constexpr int STRIDE = CH + 4;
+  const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
+  const float4 tu = f4_add_scaled(f4_zero(), wu, um, false);  // prepare_tmp, base.h:354-381
+  const float4 ti = f4_add_scaled(f4_zero(), wi, im, false);
+  if (lane < CH) {
+    dotT[0 * STRIDE + lane] = __fmul_rn(tu.x, ti.x);
+    dotT[1 * STRIDE + lane] = __fmul_rn(tu.y, ti.y);
+    dotT[2 * STRIDE + lane] = __fmul_rn(tu.z, ti.z);
+    dotT[3 * STRIDE + lane] = __fmul_rn(tu.w, ti.w);
+  }
+  double bsum = 0.0;  // calc_bias, base.h:313-353 (off the critical path: needs no dot)
+  if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, ub));
+  bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+  const double s0 = __dadd_rn((double)hp.base_score, bsum);
+  __syncwarp();
+  // (every lane has read the next entry out of its ring slot by now: the slot may be refilled)
+  if (release_slot && lane == 0) mbar_arrive(release_slot);
+  float acc = 0.0f;
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(dotT + (lane & 3) * STRIDE);
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+      const float4 q = src[i];
+      acc = __fadd_rn(acc, q.x);
+      acc = __fadd_rn(acc, q.y);
+      acc = __fadd_rn(acc, q.z);
+      acc = __fadd_rn(acc, q.w);
+    }
+  }
+  const float l0 = __shfl_sync(0xffffffffu, acc, 0), l1 = __shfl_sync(0xffffffffu, acc, 1),
+              l2 = __shfl_sync(0xffffffffu, acc, 2), l3 = __shfl_sync(0xffffffffu, acc, 3);
+  const float d = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
+  const float p = (float)__dadd_rn(s0, (double)d);  // pred, base.h:445-454 (linear: map_active is the identity)
+  const float err = __fsub_rn(label, p);           // cal_grad, model.h:132-156
+  const float lrerr = __fmul_rn(hp.lr, err);
+  const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);  // base.h:391,412
+  const float sum_ = scalar_is_one(su) ? 1.0f : su, sim = scalar_is_one(si) ? 1.0f : si;
+  wu = f4_scale(f4_add_scaled(wu, ti, sum_, false), du);  // update_no_decay + regularize(after)
+  wi = f4_scale(f4_add_scaled(wi, tu, sim, false), di);
+  if (!m.no_user_bias) ub = __fmul_rn(__fadd_rn(ub, su), hp.dub);
+  ib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
+}
+
+// CH > 0: rows of exactly CH chunks, linear loss (fast link); CH = 0: any row width up to
+// 32*VEC chunks, any loss.  D = ring slots per owner (a power of two).
+template <int CH, int VEC, int D>
+__global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
   extern __shared__ __align__(128) unsigned char own_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DevModel &m = a.m;
   const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
   const int S = a.S;
   // every owner's barriers: full[D] then empty[D], one arrival each
-  if (warp < OWN_C && lane < 2 * OWN_D)
-    mbar_init(reinterpret_cast<uint64_t *>(own_smem + (size_t)warp * a.region_bytes + a.off_bars) + lane, 1);
+  if (warp < OWN_C) {
+    uint64_t *bars = reinterpret_cast<uint64_t *>(own_smem + (size_t)warp * a.region_bytes + a.off_bars);
+    for (int i = lane; i < 2 * D; i += 32) mbar_init(bars + i, 1);
+  }
   mbar_fence_init();
   __syncthreads();
   unsigned *const ver = m.ver_ui + m.user_off;
 
   if (warp >= OWN_C) {
     // =========================== loader lane: ring slot s of owner c ===========================
+    // Per iteration ONE round trip to L2 for the whole warp: the poll of the version the current
+    // entry waits for and the fetch of the entry after it are issued together, consumed together.
     const int t = (int)threadIdx.x - OWN_C * 32;
-    const int c = t / OWN_D, s = t % OWN_D;
+    const int c = t / D, s = t % D;
     const int w = c * (int)gridDim.x + (int)blockIdx.x;
     unsigned char *reg = own_smem + (size_t)c * a.region_bytes;
     unsigned char *slot = reg + (size_t)s * slot_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(reg + a.off_bars) + s;
-    uint64_t *empty = full + OWN_D;
+    uint64_t *empty = full + D;
     const int q0 = a.queue_off[w], n = a.queue_off[w + 1] - q0;
+    const uint4 *q = a.entries + 2 * (size_t)q0;
     int j = s;  // this lane loads entries s, s+D, s+2D, ... of the owner's queue
     unsigned fill = 0, idle = 0;
-    bool have = false, ready = false, vacant = false;
-    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
+    bool ready = false, vacant = false, have_nxt = false;
+    uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0, n0 = e0, n1 = e0;
+    if (j < n) {
+      e0 = __ldg(q + 2 * (size_t)j);
+      e1 = __ldg(q + 2 * (size_t)j + 1);
+    }
     for (unsigned it = 0;; ++it) {
       const bool active = j < n;
       if (!__any_sync(0xffffffffu, active)) break;
       bool prog = false;
-      if (active) {
-        if (!have) {
-          const uint4 *ep = reinterpret_cast<const uint4 *>(a.entries + q0 + j);
-          e0 = __ldg(ep);
-          e1 = __ldg(ep + 1);
-          have = true;
+      // ---- issue
+      const bool want_nxt = active && !have_nxt && j + D < n;
+      if (want_nxt) {
+        n0 = __ldg(q + 2 * (size_t)(j + D));
+        n1 = __ldg(q + 2 * (size_t)(j + D) + 1);
+      }
+      // the row is final once every earlier instance of this user has been published; nobody
+      // writes it again before this very instance does
+      unsigned v = 0;
+      const bool poll = active && !ready;
+      if (poll) v = ld_acquire_u32(ver + e0.x);
+      // the slot is vacant once the owner has read fill-1 out of it (a fresh barrier passes parity 1)
+      if (active && !vacant) vacant = mbar_test(empty, (fill & 1u) ^ 1u);
+      // ---- consume
+      if (want_nxt) have_nxt = true;
+      if (poll) ready = v == e0.y;
+      if (active && vacant && ready) {
+        *reinterpret_cast<uint4 *>(slot + row_bytes + 16) = e0;
+        *reinterpret_cast<uint4 *>(slot + row_bytes + 32) = e1;
+        fence_proxy_async_global();
+        const size_t row = (size_t)m.user_off + e0.x;
+        mbar_arrive_expect_tx(full, row_bytes + (m.no_user_bias ? 0u : 16u));
+        bulk_g2s(slot, m.W + row * (size_t)m.pitch, row_bytes, full);
+        if (!m.no_user_bias) bulk_g2s(slot + row_bytes, m.bias + (row & ~(size_t)3), 16u, full);
+        j += D;
+        ++fill;
+        e0 = n0;
+        e1 = n1;
+        ready = vacant = false;
+        if (!have_nxt && j < n) {  // (the entry after was not fetched yet: cold start)
+          e0 = __ldg(q + 2 * (size_t)j);
+          e1 = __ldg(q + 2 * (size_t)j + 1);
         }
-        // the slot is vacant once the owner has read fill-1 out of it (a fresh barrier passes parity 1)
-        if (!vacant) vacant = mbar_test(empty, (fill & 1u) ^ 1u);
-        // the row is final once every earlier instance of this user has been published; nobody
-        // writes it again before this very instance does
-        if (!ready) ready = ld_acquire_u32(ver + e0.x) == e0.y;
-        if (vacant && ready) {
-          *reinterpret_cast<uint4 *>(slot + row_bytes + 16) = e0;
-          *reinterpret_cast<uint4 *>(slot + row_bytes + 32) = e1;
-          fence_proxy_async_global();
-          const size_t row = (size_t)m.user_off + e0.x;
-          mbar_arrive_expect_tx(full, row_bytes + (m.no_user_bias ? 0u : 16u));
-          bulk_g2s(slot, m.W + row * (size_t)m.pitch, row_bytes, full);
-          if (!m.no_user_bias) bulk_g2s(slot + row_bytes, m.bias + (row & ~(size_t)3), 16u, full);
-          j += OWN_D;
-          ++fill;
-          have = ready = vacant = false;
-          prog = true;
-        }
+        have_nxt = false;
+        prog = true;
       }
       if (__any_sync(0xffffffffu, prog)) {
         idle = 0;
       } else {
         ++idle;
-        __nanosleep(idle < 16 ? 20 : 200);
+        if (idle > 4) __nanosleep(idle < 64 ? 20 : 100);
       }
       if ((it & 63u) == 63u && ld_relaxed_u32(a.abort_flag)) break;
     }
@@ -306,7 +380,7 @@ __global__ void __launch_bounds__(OWN_THREADS, 1) k_own(const OwnArgs a) {
   float *items_s = reinterpret_cast<float *>(reg + a.off_items);
   float *ibias_s = reinterpret_cast<float *>(reg + a.off_ibias);
   uint64_t *full = reinterpret_cast<uint64_t *>(reg + a.off_bars);
-  uint64_t *empty = full + OWN_D;
+  uint64_t *empty = full + D;
   Group<32, VEC> g;
   g.gl = lane;
   g.gmask = 0xffffffffu;
@@ -366,65 +440,115 @@ __global__ void __launch_bounds__(OWN_THREADS, 1) k_own(const OwnArgs a) {
   const int B = a.batch[w];
   int pend = 0;
   unsigned my_u = 0, my_t = 0;
+  long long st_wait = 0, st_flush = 0, st_nwait = 0;
+  const long long st_begin = clock64();
   auto flush = [&]() {  // publish the user rows written since the last flush: one release fence
     if (pend) {
+      const long long tf = a.stats ? clock64() : 0;
       __syncwarp();  // the row stores of all lanes happen-before the releases (cumulative)
       if (lane < pend) st_release_u32(ver + my_u, my_t);
       pend = 0;
+      if (a.stats) st_flush += clock64() - tf;
     }
   };
-  bool dead = false;
-  for (int j = 0; j < n && !dead; ++j) {
-    const int s = j & (OWN_D - 1);
-    const unsigned par = (unsigned)(j / OWN_D) & 1u;
-    if (!mbar_try(full + s, par)) {
-      flush();  // never block with unpublished rows: somebody may be waiting for them
-      const long long t0 = clock64();
-      for (unsigned it = 0; !mbar_try(full + s, par); ++it) {
-        if ((it & 63u) == 63u) {
-          if (ld_relaxed_u32(a.abort_flag)) dead = true;
-          else if (clock64() - t0 > OWN_TIMEOUT) {
-            if (lane == 0) {
-              atomicCAS(a.err_flag, 0, ERR_TIMEOUT);
-              st_relaxed_u32(a.abort_flag, 1u);
-            }
-            dead = true;
+  // wait until ring slot s holds fill number `par`; false: the launch is being aborted
+  auto wait_full = [&](int s, unsigned par) -> bool {
+    if (mbar_try(full + s, par)) return true;
+    flush();  // never block with unpublished rows: somebody may be waiting for them
+    const long long t0 = clock64();
+    for (unsigned it = 0; !mbar_try(full + s, par); ++it) {
+      if ((it & 63u) == 63u) {
+        if (ld_relaxed_u32(a.abort_flag)) return false;
+        if (clock64() - t0 > OWN_TIMEOUT) {
+          if (lane == 0) {
+            atomicCAS(a.err_flag, 0, ERR_TIMEOUT);
+            st_relaxed_u32(a.abort_flag, 1u);
           }
-          if (dead) break;
+          return false;
         }
       }
-      if (dead) break;
     }
-    const unsigned char *slot = reg + (size_t)s * slot_bytes;
-    const uint4 e0 = *reinterpret_cast<const uint4 *>(slot + row_bytes + 16);
-    const uint4 e1 = *reinterpret_cast<const uint4 *>(slot + row_bytes + 32);
-    const unsigned user = e0.x;
+    st_wait += clock64() - t0;
+    ++st_nwait;
+    return true;
+  };
+  // what an owner keeps of a ring slot: the entry, its lane's chunk(s) of the user row, the bias
+  struct Inst {
+    uint4 e0, e1;
     float4 wu[VEC];
+    float ub;
+  };
+  auto read_slot = [&](int s, Inst &x) {
+    const unsigned char *slot = reg + (size_t)s * slot_bytes;
+    x.e0 = *reinterpret_cast<const uint4 *>(slot + row_bytes + 16);
+    x.e1 = *reinterpret_cast<const uint4 *>(slot + row_bytes + 32);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const int ch = lane + v * 32;
-      wu[v] = (4 * ch < m.pitch) ? *reinterpret_cast<const float4 *>(slot + 16 * ch) : f4_zero();
+      x.wu[v] = (CH ? ch < CH : 4 * ch < m.pitch) ? *reinterpret_cast<const float4 *>(slot + 16 * ch) : f4_zero();
     }
-    const size_t urow = (size_t)m.user_off + user;
-    float ub = m.no_user_bias ? 0.0f : *reinterpret_cast<const float *>(slot + row_bytes + 4 * (urow & 3));
+    const float4 bw = *reinterpret_cast<const float4 *>(slot + row_bytes);
+    const unsigned k = (unsigned)(m.user_off + x.e0.x) & 3u;
+    x.ub = m.no_user_bias ? 0.0f : (k == 0 ? bw.x : k == 1 ? bw.y : k == 2 ? bw.z : bw.w);
+  };
+  const float du = a.hp.du_skip ? 1.0f : a.hp.du, di = a.hp.di_skip ? 1.0f : a.hp.di;
+
+  Inst cur, nxt;
+  bool alive = n > 0;
+  if (alive) {
+    alive = wait_full(0, 0u);
+    read_slot(0, cur);
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty + s);  // the slot may be refilled
-    if (e0.w != cur_item) {
+    if (lane == 0) mbar_arrive(empty + 0);  // the slot may be refilled
+  }
+  for (int j = 0; j < n && alive; ++j) {
+    // the next entry is read out of its slot (if it has landed) while this one is computed
+    const int s1 = (j + 1) & (D - 1);
+    const unsigned par1 = (unsigned)((j + 1) / D) & 1u;
+    const bool more = j + 1 < n;
+    const bool nready = more && mbar_test(full + s1, par1);
+    read_slot(s1, nxt);  // (garbage when !nready: read again below)
+    if (cur.e0.w != cur_item) {
       put_item();
-      get_item(e0.w, e1.x);
+      get_item(cur.e0.w, cur.e1.x);
     }
-    own_step<VEC>(g, m, a.hp, wu, ub, wi, ib, __uint_as_float(e1.y), __uint_as_float(e1.z), __uint_as_float(e0.z));
-    g.store_row(m, urow, wu);
-    if (!m.no_user_bias && lane == 0) __stcg(m.bias + urow, ub);
+    if (CH) {
+      own_step_fast<CH ? CH : 4>(m, a.hp, g.dot_s + (j & 1) * 4 * ((CH ? CH : 4) + 4), lane, cur.wu[0], cur.ub, wi[0], ib,
+                                 __uint_as_float(cur.e1.y), __uint_as_float(cur.e1.z), __uint_as_float(cur.e0.z), du, di,
+                                 nready ? empty + s1 : nullptr);
+    } else {
+      own_step<VEC>(g, m, a.hp, cur.wu, cur.ub, wi, ib, __uint_as_float(cur.e1.y), __uint_as_float(cur.e1.z),
+                    __uint_as_float(cur.e0.z));
+    }
+    const size_t urow = (size_t)m.user_off + cur.e0.x;
+    g.store_row(m, urow, cur.wu);
+    if (!m.no_user_bias && lane == 0) __stcg(m.bias + urow, cur.ub);
+    if (!CH && nready) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s1);
+    }
     if (lane == pend) {
-      my_u = user;
-      my_t = e0.y + 1u;
+      my_u = cur.e0.x;
+      my_t = cur.e0.y + 1u;
     }
     ++pend;
-    if ((e1.w & 1u) || pend >= B) flush();
+    if ((cur.e1.w & 1u) || pend >= B) flush();
+    if (more && !nready) {
+      alive = wait_full(s1, par1);
+      read_slot(s1, nxt);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s1);
+    }
+    cur = nxt;
   }
   flush();
   put_item();
+  if (a.stats && lane == 0) {
+    a.stats[4 * w + 0] = clock64() - st_begin;
+    a.stats[4 * w + 1] = st_wait;
+    a.stats[4 * w + 2] = st_flush;
+    a.stats[4 * w + 3] = st_nwait;
+  }
   // resident item rows go home
   for (int sl = 0; sl < nres; ++sl) {
     const size_t row = (size_t)m.item_off + a.items[it0 + sl];
@@ -477,7 +601,7 @@ void own_plan_free(OwnPlan &p) {
 }
 void own_scratch_free(OwnScratch &s) {
   DevBuf *db[] = {&s.cnt_item, &s.cnt_user, &s.start_user, &s.flag, &s.keyA, &s.keyB, &s.valA, &s.valB,
-                  &s.key_item, &s.tick, &s.tmp, &s.item_owner, &s.item_slot};
+                  &s.key_item, &s.tick, &s.tmp, &s.item_owner, &s.item_slot, &s.stats};
   for (DevBuf *d : db) {
     if (d->p) cudaFree(d->p);
     d->p = nullptr;
@@ -613,13 +737,14 @@ int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cuda
   return 0;
 }
 
-template <int VEC>
-static int own_launch_vec(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
+template <int CH, int VEC, int D>
+static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   const DevModel &m = h->dm;
   const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
-  const unsigned ring = OWN_D * slot_bytes;
-  const unsigned dot = (unsigned)Group<32, VEC>::DOT_FLOATS * 4u;
-  const unsigned bars = 2u * OWN_D * 8u;
+  const unsigned ring = D * slot_bytes;
+  // dot scratch: the generic routine's, or two transposed product buffers of the fast link
+  const unsigned dot = std::max<unsigned>((unsigned)Group<32, VEC>::DOT_FLOATS * 4u, 2u * 4u * (32u + 4u) * 4u);
+  const unsigned bars = 2u * D * 8u;
   int max_smem = 0;
   CU(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const long long fixed = (long long)ring + dot + bars + 128;
@@ -629,7 +754,7 @@ static int own_launch_vec(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   OwnArgs a;
   a.m = m;
   a.hp = h->dhp;
-  a.entries = (const OwnEntry *)p.entries.p;
+  a.entries = (const uint4 *)p.entries.p;
   a.queue_off = (const int *)p.queue_off.p;
   a.item_off = (const int *)p.item_off.p;
   a.items = (const unsigned *)p.items.p;
@@ -642,26 +767,46 @@ static int own_launch_vec(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   a.region_bytes = (a.off_bars + bars + 127u) & ~127u;
   a.err_flag = h->d_err;
   a.abort_flag = h->d_abort;
+  a.stats = nullptr;
+  if (h->own_stats) {
+    if (own_reserve(h, h->own.stats, (size_t)p.num_owner * 4 * sizeof(long long))) return 1;
+    CU(h, cudaMemsetAsync(h->own.stats.p, 0, (size_t)p.num_owner * 4 * sizeof(long long), st));
+    a.stats = (long long *)h->own.stats.p;
+  }
   const size_t smem = (size_t)a.region_bytes * OWN_C;
-  auto k = k_own<VEC>;
+  auto k = k_own<CH, VEC, D>;
   CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(h, cudaMemsetAsync(m.ver_ui + m.user_off, 0, sizeof(unsigned) * (size_t)m.num_user, st));
   CU(h, cudaMemsetAsync(h->d_abort, 0, sizeof(unsigned), st));
   void *args[] = {&a};
   // cooperative: the launch fails instead of deadlocking if the CTAs cannot all be resident
-  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3(h->num_sm), dim3(OWN_THREADS), args, smem, st));
+  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3(h->num_sm), dim3(own_threads(D)), args, smem, st));
   h->n_launch++;
   h->n_own++;
   h->n_own_rows += p.rows;
   return 0;
 }
 
+template <int CH, int VEC>
+static int own_launch_d(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
+  if (h->own_depth == 16 && h->dm.pitch <= 128) return own_launch_as<CH, VEC, 16>(h, p, st);
+  return own_launch_as<CH, VEC, 8>(h, p, st);
+}
+
 int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   if (!p.valid) return fail(h, "ordered mode: no owner plan");
   if (p.num_owner != h->num_sm * OWN_C) return fail(h, "ordered mode: plan was built for another device");
-  const int chunks = h->dm.pitch / 4;
-  if (chunks <= 32) return own_launch_vec<1>(h, p, st);
-  if (chunks <= 64) return own_launch_vec<2>(h, p, st);
+  const DevModel &m = h->dm;
+  const int chunks = m.pitch / 4;
+  // the fast link: linear loss, rows of exactly 4 / 8 / 16 / 32 chunks (num_factor 16, 32, 64, 128)
+  if (h->own_fast && m.active_type == 0 && m.k == m.pitch) {
+    if (chunks == 16) return own_launch_d<16, 1>(h, p, st);
+    if (chunks == 32) return own_launch_d<32, 1>(h, p, st);
+    if (chunks == 8) return own_launch_d<8, 1>(h, p, st);
+    if (chunks == 4) return own_launch_d<4, 1>(h, p, st);
+  }
+  if (chunks <= 32) return own_launch_d<0, 1>(h, p, st);
+  if (chunks <= 64) return own_launch_d<0, 2>(h, p, st);
   return fail(h, "ordered mode: k_own supports num_factor <= 256");
 }
 

@@ -18,6 +18,7 @@ from svdfeature_b200 import api, synth  # noqa: E402
 NU, NI, K = 480000, 18000, 64
 N = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20_000_000
 opts = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+FLAGS = set(a for a in sys.argv[1:] if a in ("nocheck", "nohost", "stats"))
 rng = np.random.default_rng(1)
 W = (rng.standard_normal((NU + NI, K)) * 0.01).astype(np.float32)
 data = synth.basic_mf(N, NU, NI, seed=3, zipf_q=70.0)
@@ -40,7 +41,7 @@ def trainer(owner):
 M = min(N, 1_000_000)
 sub = (data[0][:3 * M + 1], data[1][:M], data[2][:2 * M], data[3][:2 * M])
 models = []
-for owner in (0, 1):
+for owner in (() if "nocheck" in FLAGS else (0, 1)):
     g = trainer(owner)
     b = g.batch_create(sub)
     g.timer_start()
@@ -52,8 +53,8 @@ for owner in (0, 1):
                           own_launches=g.counter("own_launches"))), flush=True)
     b.close()
     g.close()
-same = all(np.array_equal(a, c) for a, c in zip(*models))
-print(json.dumps(dict(same_model_as_k_exact=bool(same))), flush=True)
+same = all(np.array_equal(a, c) for a, c in zip(*models)) if models else None
+print(json.dumps(dict(same_model_as_k_exact=same)), flush=True)
 
 # ---- full size ------------------------------------------------------------------------------------
 g = trainer(1)
@@ -69,12 +70,30 @@ for _ in range(4):
 g.sync()
 ms = float(np.median(times[1:]))
 line = dict(rows=N, hottest_item_rows=top, batch_create_s=t_create, ms_epochs=times, ms=ms, minst_s=N / ms / 1e3,
-            us_per_hot_row=1e3 * ms / top, same_model_as_k_exact=bool(same), options=opts,
+            us_per_hot_row=1e3 * ms / top, same_model_as_k_exact=same, options=opts,
             own_launches=g.counter("own_launches"))
 print(json.dumps(line), flush=True)
 out.write(json.dumps(line) + "\n")
+if "stats" in FLAGS:
+    g.set_option("own_stats", 1)
+    g.timer_start()
+    g.batch_update(b)
+    ms1 = g.timer_stop()
+    st = g.own_stats()
+    cnt = np.bincount(data[2][1::2], minlength=NI)
+    order = np.argsort(-st[:, 0])
+    rep = dict(ms_with_stats=ms1, mhz_assumed=1965)
+    for name, sel in (("slowest16", order[:16]), ("owners0_15", np.arange(16)), ("median16", order[len(order) // 2 - 8:len(order) // 2 + 8])):
+        rep[name] = dict(owner=sel.tolist(), us_total=(st[sel, 0] / 1965).round(0).tolist(), us_wait=(st[sel, 1] / 1965).round(0).tolist(),
+                         us_flush=(st[sel, 2] / 1965).round(0).tolist(), waits=st[sel, 3].tolist())
+    rep["all"] = dict(us_total_max=float(st[:, 0].max() / 1965), us_total_mean=float(st[:, 0].mean() / 1965),
+                      us_wait_mean=float(st[:, 1].mean() / 1965), us_flush_mean=float(st[:, 2].mean() / 1965),
+                      waits_total=int(st[:, 3].sum()))
+    print(json.dumps(rep), flush=True)
+    out.write(json.dumps(rep) + "\n")
+    g.set_option("own_stats", 0)
 # host-pointer call (plan per chunk inside the call)
-for chunk in (1 << 20, 1 << 23):
+for chunk in (() if "nohost" in FLAGS else (1 << 20, 1 << 23)):
     g.set_option("chunk_rows", chunk)
     t0 = time.perf_counter()
     g.update_csr(data)
