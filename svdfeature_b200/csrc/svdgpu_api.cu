@@ -555,6 +555,8 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_stats")) h->own_stats = v ? 1 : 0;
   else if (!strcmp(name, "own_depth")) h->own_depth = v >= 16 ? 16 : 8;
   else if (!strcmp(name, "own_fast")) h->own_fast = v ? 1 : 0;
+  else if (!strcmp(name, "own_acquire")) h->own_acquire = v ? 1 : 0;
+  else if (!strcmp(name, "own_reverse")) h->own_reverse = v ? 1 : 0;
   else if (!strcmp(name, "own_slots")) h->own_slots = (int)std::max<long long>(0, std::min<long long>(v, 32));
   else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
   else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));
@@ -702,7 +704,7 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
 int svdgpu_own_stats(svdgpu_t *h, long long *out, int cap_owners, int *num_owner) {
   if (!h || !num_owner) return 1;
   CU(h, cudaSetDevice(h->device));
-  const int W = h->num_sm * 16;
+  const int W = h->num_sm * svdk::own_owners_per_cta();
   *num_owner = W;
   if (!h->own.stats.p) return fail(h, "own_stats: set option own_stats before the ordered launch");
   if (out && cap_owners >= W) {

@@ -137,6 +137,8 @@ struct svdgpu {
   int own_slots = 0;         // option "own_slots": item rows an owner keeps in shared memory (0 = auto, <= 32)
   int own_depth = 8;         // option "own_depth": ring slots per owner (8 or 16)
   int own_fast = 1;          // option "own_fast": 0 keeps the generic link for every shape (testing)
+  int own_acquire = 0;       // option "own_acquire": loaders poll versions with ld.acquire.gpu (adds CCTL.IVALL per poll)
+  int own_reverse = 1;       // option "own_reverse": busiest owners on the highest warp ids (the arbiter prefers them)
   int own_stats = 0;         // option "own_stats": k_own records per-owner cycle counters (svdgpu_own_stats)
   OwnScratch own;
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
@@ -210,6 +212,7 @@ int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, b
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
 // ordered mode with item-owner warps (svdgpu_own.cu)
 bool own_supported(const svdgpu *h);
+int own_owners_per_cta();
 int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad);
 int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st);
 void own_plan_free(OwnPlan &p);

@@ -130,7 +130,7 @@ __global__ void k_own_entries(DevCsr csr, int r0, int n, const unsigned *rows, c
 // ---------------------------------------------------------------------------
 // k_own
 // ---------------------------------------------------------------------------
-constexpr int OWN_C = 16;                      // owner (compute) warps per CTA
+constexpr int OWN_C = 12;                      // owner (compute) warps per CTA (12 + 3 loader warps: 136 registers each)
 constexpr int OWN_SLOT_EXTRA = 48;             // [row | 16-byte bias window | 32-byte entry]
 constexpr long long OWN_TIMEOUT = 6000000000LL;  // cycles (~3 s): a wait this long is a bug, not load
 constexpr int own_threads(int D) { return (OWN_C + OWN_C * D / 32) * 32; }  // + one loader lane per ring slot
@@ -149,7 +149,10 @@ struct OwnArgs {
   int *err_flag;
   unsigned *abort_flag;
   long long *stats;  // option "own_stats": per owner {cycles, cycles waiting for a slot, cycles in flushes, waits} or null
+  int flags;         // OWN_F_*
 };
+enum { OWN_F_ACQUIRE = 1,   // loaders poll with ld.acquire.gpu (LDG + CCTL.IVALL) instead of ld.relaxed.gpu
+       OWN_F_REVERSE = 2 }; // busiest owners on the highest warp ids of a CTA
 
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity) {  // non-blocking
   unsigned ok;
@@ -169,11 +172,11 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, unsigned parity) {  // m
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)  // suspend-time hint (ns): a waiting owner stays out of the issue slots
       : "memory");
   return ok != 0;
 }
@@ -191,6 +194,56 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
 // the version was read through the generic proxy; the row is read by the TMA unit (async proxy)
 __device__ __forceinline__ void fence_proxy_async_global() {
   asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// Shared memory through 32-bit addresses (the generic pointers of the rest of this file make the
+// compiler rebuild the shared window base inside the loop), and loop constants pinned in registers
+// (kernel parameters are otherwise re-read from the constant bank every iteration).
+__device__ __forceinline__ float4 lds128f(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32f(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32f(unsigned a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+// (a warp shuffle: neither the compiler nor ptxas can rematerialise its result from the constant bank)
+__device__ __forceinline__ unsigned pin(unsigned x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+__device__ __forceinline__ float pin(float x) { return __uint_as_float(pin(__float_as_uint(x))); }
+__device__ __forceinline__ double pin(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return __longlong_as_double((long long)(((unsigned long long)pin((unsigned)(b >> 32)) << 32) | pin((unsigned)b)));
+}
+template <typename T>
+__device__ __forceinline__ T *pin(T *p) {
+  const unsigned long long b = (unsigned long long)p;
+  return reinterpret_cast<T *>(((unsigned long long)pin((unsigned)(b >> 32)) << 32) | pin((unsigned)b));
+}
+__device__ __forceinline__ bool mbar_test_s(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_s(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // One instance of the shape (0 | 1 | 1) with plain L2 decay: process_instance (svdgpu_device.cuh)
@@ -230,60 +283,6 @@ __device__ __forceinline__ void own_step(const Group<32, VEC> &g, const DevModel
   ib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
 }
 
-// The same instance for rows of exactly CH float4 chunks (num_factor = 4*CH <= 128), linear loss:
-// branch-free and with compile-time trip counts -- this is the link of the hot item's chain.
-//   * "s is one => no multiply" (sse.h:231-242) becomes a multiply by exactly 1.0f (x*1.0f == x);
-//     a skipped decay likewise;
-//   * the dot keeps the reference's order (sse.h:289-317): the products go to shared memory
-//     transposed, every lane adds the CH products of component (lane & 3) in order (lanes with
-//     the same component read the same words: broadcast), then (l0+l2)+(l1+l3).
-template <int CH>
-__device__ __forceinline__ void own_step_fast(const DevModel &m, const DevHP &hp, float *dotT, int lane, float4 &wu,
-                                              float &ub, float4 &wi, float &ib, float uval, float ival, float label,
-                                              float du, float di, uint64_t *release_slot) {
-  constexpr int STRIDE = CH + 4;
-  const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
-  const float4 tu = f4_add_scaled(f4_zero(), wu, um, false);  // prepare_tmp, base.h:354-381
-  const float4 ti = f4_add_scaled(f4_zero(), wi, im, false);
-  if (lane < CH) {
-    dotT[0 * STRIDE + lane] = __fmul_rn(tu.x, ti.x);
-    dotT[1 * STRIDE + lane] = __fmul_rn(tu.y, ti.y);
-    dotT[2 * STRIDE + lane] = __fmul_rn(tu.z, ti.z);
-    dotT[3 * STRIDE + lane] = __fmul_rn(tu.w, ti.w);
-  }
-  double bsum = 0.0;  // calc_bias, base.h:313-353 (off the critical path: needs no dot)
-  if (!m.no_user_bias) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, ub));
-  bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
-  const double s0 = __dadd_rn((double)hp.base_score, bsum);
-  __syncwarp();
-  // (every lane has read the next entry out of its ring slot by now: the slot may be refilled)
-  if (release_slot && lane == 0) mbar_arrive(release_slot);
-  float acc = 0.0f;
-  {
-    const float4 *src = reinterpret_cast<const float4 *>(dotT + (lane & 3) * STRIDE);
-#pragma unroll
-    for (int i = 0; i < CH / 4; ++i) {
-      const float4 q = src[i];
-      acc = __fadd_rn(acc, q.x);
-      acc = __fadd_rn(acc, q.y);
-      acc = __fadd_rn(acc, q.z);
-      acc = __fadd_rn(acc, q.w);
-    }
-  }
-  const float l0 = __shfl_sync(0xffffffffu, acc, 0), l1 = __shfl_sync(0xffffffffu, acc, 1),
-              l2 = __shfl_sync(0xffffffffu, acc, 2), l3 = __shfl_sync(0xffffffffu, acc, 3);
-  const float d = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
-  const float p = (float)__dadd_rn(s0, (double)d);  // pred, base.h:445-454 (linear: map_active is the identity)
-  const float err = __fsub_rn(label, p);           // cal_grad, model.h:132-156
-  const float lrerr = __fmul_rn(hp.lr, err);
-  const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);  // base.h:391,412
-  const float sum_ = scalar_is_one(su) ? 1.0f : su, sim = scalar_is_one(si) ? 1.0f : si;
-  wu = f4_scale(f4_add_scaled(wu, ti, sum_, false), du);  // update_no_decay + regularize(after)
-  wi = f4_scale(f4_add_scaled(wi, tu, sim, false), di);
-  if (!m.no_user_bias) ub = __fmul_rn(__fadd_rn(ub, su), hp.dub);
-  ib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
-}
-
 // CH > 0: rows of exactly CH chunks, linear loss (fast link); CH = 0: any row width up to
 // 32*VEC chunks, any loss.  D = ring slots per owner (a power of two).
 template <int CH, int VEC, int D>
@@ -308,7 +307,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
     // entry waits for and the fetch of the entry after it are issued together, consumed together.
     const int t = (int)threadIdx.x - OWN_C * 32;
     const int c = t / D, s = t % D;
-    const int w = c * (int)gridDim.x + (int)blockIdx.x;
+    const int w = ((a.flags & OWN_F_REVERSE) ? OWN_C - 1 - c : c) * (int)gridDim.x + (int)blockIdx.x;
     unsigned char *reg = own_smem + (size_t)c * a.region_bytes;
     unsigned char *slot = reg + (size_t)s * slot_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(reg + a.off_bars) + s;
@@ -337,7 +336,10 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       // writes it again before this very instance does
       unsigned v = 0;
       const bool poll = active && !ready;
-      if (poll) v = ld_acquire_u32(ver + e0.x);
+      // (relaxed poll: the row itself is then read by the TMA unit straight from L2, after this load
+      // has returned the awaited value -- an acquire would only add an L1 invalidation, CCTL.IVALL,
+      // per poll, which stalls the shared-memory pipe of the owners on this SM)
+      if (poll) v = (a.flags & OWN_F_ACQUIRE) ? ld_acquire_u32(ver + e0.x) : ld_relaxed_u32(ver + e0.x);
       // the slot is vacant once the owner has read fill-1 out of it (a fresh barrier passes parity 1)
       if (active && !vacant) vacant = mbar_test(empty, (fill & 1u) ^ 1u);
       // ---- consume
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
   }
 
   // ================================ owner warp ================================================
-  const int w = warp * (int)gridDim.x + (int)blockIdx.x;
+  const int w = ((a.flags & OWN_F_REVERSE) ? OWN_C - 1 - warp : warp) * (int)gridDim.x + (int)blockIdx.x;
   unsigned char *reg = own_smem + (size_t)warp * a.region_bytes;
   float *items_s = reinterpret_cast<float *>(reg + a.off_items);
   float *ibias_s = reinterpret_cast<float *>(reg + a.off_ibias);
@@ -442,13 +444,15 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
   unsigned my_u = 0, my_t = 0;
   long long st_wait = 0, st_flush = 0, st_nwait = 0;
   const long long st_begin = clock64();
+  unsigned *const pver = pin(ver);
+  const bool want_stats = pin((unsigned)(a.stats != nullptr)) != 0u;
   auto flush = [&]() {  // publish the user rows written since the last flush: one release fence
     if (pend) {
-      const long long tf = a.stats ? clock64() : 0;
+      const long long tf = want_stats ? clock64() : 0;
       __syncwarp();  // the row stores of all lanes happen-before the releases (cumulative)
-      if (lane < pend) st_release_u32(ver + my_u, my_t);
+      if (lane < pend) st_release_u32(pver + my_u, my_t);
       pend = 0;
-      if (a.stats) st_flush += clock64() - tf;
+      if (want_stats) st_flush += clock64() - tf;
     }
   };
   // wait until ring slot s holds fill number `par`; false: the launch is being aborted
@@ -493,53 +497,167 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
   };
   const float du = a.hp.du_skip ? 1.0f : a.hp.du, di = a.hp.di_skip ? 1.0f : a.hp.di;
 
-  Inst cur, nxt;
-  bool alive = n > 0;
-  if (alive) {
-    alive = wait_full(0, 0u);
-    read_slot(0, cur);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + 0);  // the slot may be refilled
-  }
-  for (int j = 0; j < n && alive; ++j) {
-    // the next entry is read out of its slot (if it has landed) while this one is computed
-    const int s1 = (j + 1) & (D - 1);
-    const unsigned par1 = (unsigned)((j + 1) / D) & 1u;
-    const bool more = j + 1 < n;
-    const bool nready = more && mbar_test(full + s1, par1);
-    read_slot(s1, nxt);  // (garbage when !nready: read again below)
-    if (cur.e0.w != cur_item) {
-      put_item();
-      get_item(cur.e0.w, cur.e1.x);
+  if (CH) {
+    // ---------------------------------------------------------------------------------------
+    // The fast link: rows of exactly CH chunks (lane c < CH holds chunk c), linear loss.  This
+    // loop is one dependent chain per instance of the owner's item -- what bounds the whole
+    // launch -- so it is kept lean: branch-free arithmetic, constants in registers, the next entry
+    // read out of its slot while this one is computed, two entries per trip (no register moves).
+    //   * "s is one => no multiply" (sse.h:231-242) becomes a multiply by exactly 1.0f
+    //     (x * 1.0f == x bit for bit); a skipped decay likewise;
+    //   * the dot keeps the reference's order (sse.h:289-317): the products go to shared memory
+    //     transposed, every lane adds the CH products of component (lane & 3) in order (lanes with
+    //     the same component read the same words: broadcast), then (l0+l2)+(l1+l3);
+    //   * lanes >= CH run along on whatever their registers hold; they neither store nor are read.
+    // ---------------------------------------------------------------------------------------
+    constexpr int LOG_D = D == 16 ? 4 : 3;
+    constexpr unsigned ROW = CH * 16u, SLOT = ROW + OWN_SLOT_EXTRA, DOTROW = 36u * 4u, DOTBUF = 4u * DOTROW;
+    const unsigned reg_s = pin(smem_u32(reg));
+    const unsigned full_s = pin(reg_s + a.off_bars), empty_s = pin(reg_s + a.off_bars + 8u * D);
+    const unsigned dot_w = pin(reg_s + a.off_dot + 4u * (unsigned)lane);          // this lane's column of the products
+    const unsigned dot_r = pin(reg_s + a.off_dot + DOTROW * ((unsigned)lane & 3u));  // the row this lane adds up
+    const unsigned lane16 = pin(16u * (unsigned)lane);
+    char *const wbase = pin(reinterpret_cast<char *>(m.W + (size_t)m.user_off * (size_t)m.pitch) + 16 * lane);
+    float *const bbase = pin(m.bias + m.user_off);
+    const unsigned koff = pin((unsigned)m.user_off & 3u);
+    const float lr = pin(a.hp.lr), dub = pin(a.hp.dub), dib = pin(a.hp.dib), pdu = pin(du), pdi = pin(di);
+    const double base = pin((double)a.hp.base_score);
+    const bool has_ub = pin((unsigned)(m.no_user_bias == 0)) != 0u;
+    const bool row_lane = lane < CH, lane0 = lane == 0;
+    const bool st_ub = has_ub && lane0;
+    struct Link {
+      uint4 e0, e1;  // {user, ticket, label, item}, {slot, uval, ival, flags}
+      float4 wu;
+      float ub;
+    };
+    auto read_link = [&](int s, Link &x) {
+      const unsigned sa = reg_s + (unsigned)s * SLOT;
+      x.e0 = lds128u(sa + ROW + 16u);
+      x.e1 = lds128u(sa + ROW + 32u);
+      x.wu = lds128f(sa + lane16);
+      x.ub = lds32f(sa + ROW + 4u * ((x.e0.x + koff) & 3u));
+    };
+    float4 &wi0 = wi[0];
+    // one link; returns false when the launch is being aborted
+    auto link = [&](Link &cur, Link &nxt, int j) -> bool {
+      const int j1 = j + 1, s1 = j1 & (D - 1);
+      const unsigned par1 = (unsigned)(j1 >> LOG_D) & 1u;
+      const bool more = j1 < n;
+      const bool nready = more && mbar_test_s(full_s + 8u * (unsigned)s1, par1);
+      read_link(s1, nxt);  // (garbage when !nready: read again below)
+      if (cur.e0.w != cur_item) {
+        put_item();
+        get_item(cur.e0.w, cur.e1.x);
+      }
+      const float uval = __uint_as_float(cur.e1.y), ival = __uint_as_float(cur.e1.z), label = __uint_as_float(cur.e0.z);
+      const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
+      const float4 tu = f4_add_scaled(f4_zero(), cur.wu, um, false);  // prepare_tmp, base.h:354-381
+      const float4 ti = f4_add_scaled(f4_zero(), wi0, im, false);
+      const unsigned dw = dot_w + ((unsigned)j & 1u) * DOTBUF, dr = dot_r + ((unsigned)j & 1u) * DOTBUF;
+      sts32f(dw, __fmul_rn(tu.x, ti.x));
+      sts32f(dw + DOTROW, __fmul_rn(tu.y, ti.y));
+      sts32f(dw + 2u * DOTROW, __fmul_rn(tu.z, ti.z));
+      sts32f(dw + 3u * DOTROW, __fmul_rn(tu.w, ti.w));
+      double bsum = 0.0;  // calc_bias, base.h:313-353 (needs no dot: off the chain)
+      if (has_ub) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, cur.ub));
+      bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+      const double s0 = __dadd_rn(base, bsum);
+      __syncwarp();
+      // every lane has read the next entry out of its ring slot by now: the slot may be refilled
+      if (nready && lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
+      float acc = 0.0f;
+      constexpr int NQ = CH ? CH / 4 : 1;
+      float4 q[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) q[i] = lds128f(dr + 16u * i);  // (all in flight before the first add)
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        acc = __fadd_rn(acc, q[i].x);
+        acc = __fadd_rn(acc, q[i].y);
+        acc = __fadd_rn(acc, q[i].z);
+        acc = __fadd_rn(acc, q[i].w);
+      }
+      const float l0 = __shfl_sync(0xffffffffu, acc, 0), l1 = __shfl_sync(0xffffffffu, acc, 1),
+                  l2 = __shfl_sync(0xffffffffu, acc, 2), l3 = __shfl_sync(0xffffffffu, acc, 3);
+      const float d = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
+      const float p = (float)__dadd_rn(s0, (double)d);  // pred, base.h:445-454 (linear: map_active is the identity)
+      const float err = __fsub_rn(label, p);           // cal_grad, model.h:132-156
+      const float lrerr = __fmul_rn(lr, err);
+      const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);  // base.h:391,412
+      const float sum_ = scalar_is_one(su) ? 1.0f : su, sim = scalar_is_one(si) ? 1.0f : si;
+      wi0 = f4_scale(f4_add_scaled(wi0, tu, sim, false), pdi);  // update_no_decay + regularize(after)
+      ib = __fmul_rn(__fadd_rn(ib, si), dib);
+      const float4 nwu = f4_scale(f4_add_scaled(cur.wu, ti, sum_, false), pdu);
+      const unsigned user = cur.e0.x;
+      if (row_lane) stcg4(reinterpret_cast<float *>(wbase + (size_t)user * ROW), nwu);
+      if (st_ub) __stcg(bbase + user, __fmul_rn(__fadd_rn(cur.ub, su), dub));
+      if (lane == pend) {
+        my_u = user;
+        my_t = cur.e0.y + 1u;
+      }
+      ++pend;
+      if ((cur.e1.w & 1u) || pend >= B) flush();
+      if (more && !nready) {
+        if (!wait_full(s1, par1)) return false;
+        read_link(s1, nxt);
+        __syncwarp();
+        if (lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
+      }
+      return true;
+    };
+    Link la, lb;
+    if (n > 0 && wait_full(0, 0u)) {
+      read_link(0, la);
+      __syncwarp();
+      if (lane0) mbar_arrive_s(empty_s);
+      for (int j = 0; j < n; j += 2) {
+        if (!link(la, lb, j)) break;
+        if (j + 1 < n && !link(lb, la, j + 1)) break;
+      }
     }
-    if (CH) {
-      own_step_fast<CH ? CH : 4>(m, a.hp, g.dot_s + (j & 1) * 4 * ((CH ? CH : 4) + 4), lane, cur.wu[0], cur.ub, wi[0], ib,
-                                 __uint_as_float(cur.e1.y), __uint_as_float(cur.e1.z), __uint_as_float(cur.e0.z), du, di,
-                                 nready ? empty + s1 : nullptr);
-    } else {
+  } else {
+    Inst cur, nxt;
+    bool alive = n > 0;
+    if (alive) {
+      alive = wait_full(0, 0u);
+      read_slot(0, cur);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + 0);  // the slot may be refilled
+    }
+    for (int j = 0; j < n && alive; ++j) {
+      // the next entry is read out of its slot (if it has landed) while this one is computed
+      const int s1 = (j + 1) & (D - 1);
+      const unsigned par1 = (unsigned)((j + 1) / D) & 1u;
+      const bool more = j + 1 < n;
+      const bool nready = more && mbar_test(full + s1, par1);
+      read_slot(s1, nxt);  // (garbage when !nready: read again below)
+      if (cur.e0.w != cur_item) {
+        put_item();
+        get_item(cur.e0.w, cur.e1.x);
+      }
       own_step<VEC>(g, m, a.hp, cur.wu, cur.ub, wi, ib, __uint_as_float(cur.e1.y), __uint_as_float(cur.e1.z),
                     __uint_as_float(cur.e0.z));
+      const size_t urow = (size_t)m.user_off + cur.e0.x;
+      g.store_row(m, urow, cur.wu);
+      if (!m.no_user_bias && lane == 0) __stcg(m.bias + urow, cur.ub);
+      if (nready) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s1);
+      }
+      if (lane == pend) {
+        my_u = cur.e0.x;
+        my_t = cur.e0.y + 1u;
+      }
+      ++pend;
+      if ((cur.e1.w & 1u) || pend >= B) flush();
+      if (more && !nready) {
+        alive = wait_full(s1, par1);
+        read_slot(s1, nxt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s1);
+      }
+      cur = nxt;
     }
-    const size_t urow = (size_t)m.user_off + cur.e0.x;
-    g.store_row(m, urow, cur.wu);
-    if (!m.no_user_bias && lane == 0) __stcg(m.bias + urow, cur.ub);
-    if (!CH && nready) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s1);
-    }
-    if (lane == pend) {
-      my_u = cur.e0.x;
-      my_t = cur.e0.y + 1u;
-    }
-    ++pend;
-    if ((cur.e1.w & 1u) || pend >= B) flush();
-    if (more && !nready) {
-      alive = wait_full(s1, par1);
-      read_slot(s1, nxt);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s1);
-    }
-    cur = nxt;
   }
   flush();
   put_item();
@@ -581,6 +699,8 @@ static int bits_for(unsigned n) {  // key bits needed for values < n
   while (b < 32 && (1ull << b) < (unsigned long long)n) ++b;
   return b;
 }
+
+int own_owners_per_cta() { return OWN_C; }
 
 bool own_supported(const svdgpu *h) {
   // plain L2 decay only (the other regularisers keep k_exact), rows of at most 256 floats
@@ -743,7 +863,7 @@ static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
   const unsigned ring = D * slot_bytes;
   // dot scratch: the generic routine's, or two transposed product buffers of the fast link
-  const unsigned dot = std::max<unsigned>((unsigned)Group<32, VEC>::DOT_FLOATS * 4u, 2u * 4u * (32u + 4u) * 4u);
+  const unsigned dot = std::max<unsigned>((unsigned)Group<32, VEC>::DOT_FLOATS * 4u, 2u * 4u * 36u * 4u);
   const unsigned bars = 2u * D * 8u;
   int max_smem = 0;
   CU(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -767,6 +887,7 @@ static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   a.region_bytes = (a.off_bars + bars + 127u) & ~127u;
   a.err_flag = h->d_err;
   a.abort_flag = h->d_abort;
+  a.flags = (h->own_acquire ? OWN_F_ACQUIRE : 0) | (h->own_reverse ? OWN_F_REVERSE : 0);
   a.stats = nullptr;
   if (h->own_stats) {
     if (own_reserve(h, h->own.stats, (size_t)p.num_owner * 4 * sizeof(long long))) return 1;

@@ -18,6 +18,7 @@ from svdfeature_b200 import api, synth  # noqa: E402
 NU, NI, K = 480000, 18000, 64
 N = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20_000_000
 opts = dict(a.split("=") for a in sys.argv[1:] if "=" in a)
+NI = int(opts.pop("ni", NI))  # ni=1: every rating on one item = the bare chain of one owner
 FLAGS = set(a for a in sys.argv[1:] if a in ("nocheck", "nohost", "stats"))
 rng = np.random.default_rng(1)
 W = (rng.standard_normal((NU + NI, K)) * 0.01).astype(np.float32)
