@@ -7,13 +7,22 @@ Workload (BASELINE.json configs[1]): Netflix-shaped basicMF, 480k users x 18k it
 k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch of
 --rows-per-step ratings (default: all 100M, i.e. one step = one epoch).  Prints ONE JSON line.
 
+  The headline is the ORDERED mode (--mode exact, the default): the execution mode whose
+  predictions equal the reference's sequential loop (north star: <= 1e-4 RMSE; measured 0.0,
+  `parity.ordered`).  Hogwild -- faster, but 1e-2 away from the sequential order -- is reported
+  as the labelled secondary `hogwild` of the same line (or as the headline with --mode hogwild).
+
   value      whole-job instances/s with the batches resident in HBM (device-timed, CUDA
-             events on the launch stream, max over ranks)
+             events on the launch stream, max over ranks).  The ordered mode's plan (per-owner
+             queues, tickets: a function of the batch, not of the model) is built when the batch
+             is made resident; `plan` carries what it costs and the value with it rebuilt every step
   e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D of every
-             step's batch and a D2H read of a probe prediction inside the timed region
-  roofline   dominant kernel (k_mf, the basic-MF fast pass): algorithmic bytes (1072 B/instance,
-             SURVEY 8d) / measured launch time vs the measured HBM copy peak; `traffic` = DRAM
-             bytes per launch from the committed ncu capture (profiles/)
+             step's batch, the plan, and a D2H read of a probe prediction inside the timed region
+  roofline   dominant kernel (ordered: k_own, the item-owner kernel; Hogwild: k_mf): algorithmic
+             bytes (1072 B/instance) / measured launch time vs the measured HBM copy
+             peak.  k_own is bound by the chain of dependent updates of the hottest item
+             (`chain`), not by bytes; `traffic` = DRAM bytes per launch from the committed ncu
+             capture (profiles/)
   cpu_baseline  the UNMODIFIED reference (oracle/_ref) timed on the host, 1 thread,
              on a bounded prefix of the same workload
   parity     (N=1) the first --parity-rows of that prefix trained and predicted through the
@@ -46,6 +55,9 @@ BYTES_PER_INSTANCE = 8 * K * 2 + 8 * 2 + 16 + 8 * 2  # = 1072, SURVEY.md section
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_mf launch over 100M ratings, from
 # `ncu --set full` (profiles/r1_kmf_v5_100M_ncu_full_summary.txt): 7.549 GB + 8.126 GB
 NCU_DRAM_BYTES_PER_INSTANCE = (7.548526e9 + 8.126198e9) / 100e6
+# the same for ONE k_own launch (ordered mode); None until the capture is committed
+NCU_OWN_DRAM_BYTES_PER_INSTANCE = None
+NCU_OWN_TRAFFIC_SOURCE = "no ncu --set full capture of k_own committed yet"
 
 
 def log(*a):
@@ -264,7 +276,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "sgd_training_instances_per_sec", "value": v, "unit": "instances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(rows, "cpu"),
+        "config": workload_config(args.rows_per_step), "mode": "sequential (the reference's own loop)",
         "cpu_baseline": {"value": v, "unit": "instances/s", "cores": 1, "kind": kind,
                          "sample": "%d steps x %d ratings of the 480kx18k k=64 stream, ISVDTrainer::update loop, 1 thread of %d host cores"
                                    % (args.steps, rows, os.cpu_count())},
@@ -274,10 +286,12 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(rows_per_step, mode):
+def workload_config(rows_per_step):
+    """The same dictionary for both arms (the reference arm times a bounded sample of it, described
+    in its cpu_baseline.sample)."""
     return {"workload": "configs[1] Netflix-shaped basicMF: 480k users x 18k items, k=64, 100M synthetic ratings "
                         "(users lognormal, items Zipf-Mandelbrot s=1 q=70, shuffled)",
-            "rows_per_step": rows_per_step, "mode": mode, "l2_policy": "inputs larger than L2 (batch+model > 126 MB per step)",
+            "rows_per_step": rows_per_step, "l2_policy": "inputs larger than L2 (batch+model > 126 MB per step)",
             "hparams": HP}
 
 
@@ -290,7 +304,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="hogwild", choices=["hogwild", "exact"])
+    ap.add_argument("--mode", default="exact", choices=["hogwild", "exact"],
+                    help="exact = ordered (bit-identical to the sequential reference; the headline), hogwild = throughput mode")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Hogwild secondary of an ordered run")
     ap.add_argument("--rows-per-step", type=int, default=TOTAL_ROWS)
     ap.add_argument("--ref-rows-per-step", type=int, default=2_000_000)
     ap.add_argument("--cpu-rows", type=int, default=20_000_000, help="rows of the cpu_baseline sample")
@@ -300,6 +316,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to svdgpu_set_option")
     ap.add_argument("--allreduce-every", type=int, default=1)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 22, help="rows per launch of the ordered e2e call")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -345,155 +362,203 @@ def main():
     torch.cuda.empty_cache()
     h_rp, h_lab, h_idx, h_val = host
 
-    g = api.SvdGpu(NUM_USER, NUM_ITEM, K, device=local)
-    g.set_hparams(**HP)
-    g.set_mode(api.MODE_HOGWILD if args.mode == "hogwild" else api.MODE_EXACT)
-    for o in args.opt:
-        name, v = o.split("=")
-        g.set_option(name, int(v))
     stream = torch.cuda.Stream(device=dev)
-    g.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(10)
     rows_model = NUM_USER + NUM_ITEM
     W0 = (rng.standard_normal((rows_model, K)) * 0.01).astype(np.float32)  # N(0, 0.01^2) as rand_init
-    g.upload(np.zeros(rows_model, np.float32), W0, np.zeros(1, np.float32))
-
-    # ---- resident batches (value) ----
-    if args.mode == "exact":
-        batches = []
-        for c in range(nchunk):
-            sl = (h_rp[3 * c * rows:3 * (c + 1) * rows + 1] - int(h_rp[3 * c * rows])).contiguous().numpy()
-            batches.append(g.batch_create((sl, h_lab[c * rows:(c + 1) * rows].numpy(),
-                                           h_idx[2 * c * rows:2 * (c + 1) * rows].numpy(),
-                                           h_val[2 * c * rows:2 * (c + 1) * rows].numpy())))
-
-        def step(s):
-            g.batch_update(batches[s % nchunk])
-    else:
-        batch = g.batch_create((h_rp, h_lab, h_idx, h_val))
-
-        def step(s):
-            c = s % nchunk
-            g.batch_update(batch, c * rows, (c + 1) * rows)
-    log("[rank %d] setup %.1fs: %d rows in %d chunks" % (rank, time.perf_counter() - t_setup, total, nchunk))
-
     use_allreduce = world > 1
-    xchg = [None]
+    probe_n = 1024
+    probe = (h_rp[:3 * probe_n + 1].numpy(), h_lab[:probe_n].numpy(), h_idx.numpy(), h_val.numpy())
+    check_n = min(rows, 1_000_000)  # rows of the post-run model check
+    check = (h_rp[:3 * check_n + 1].numpy(), h_lab[:check_n].numpy(), h_idx.numpy(), h_val.numpy())
 
-    def exchange():
-        if use_allreduce:
-            xchg[0].sync()  # pack item-side deltas, ONE NCCL all-reduce, apply (svdfeature_b200/parallel.py)
+    def measure(mode, steps, warmup, want_e2e):
+        """One trainer in `mode` ("exact" = ordered, "hogwild"): resident `value`, kernel-only time,
+        e2e through host buffers, and the state of the model afterwards."""
+        g = api.SvdGpu(NUM_USER, NUM_ITEM, K, device=local)
+        g.set_hparams(**HP)
+        g.set_mode(api.MODE_HOGWILD if mode == "hogwild" else api.MODE_EXACT)
+        for o in args.opt:
+            name, v = o.split("=")
+            g.set_option(name, int(v))
+        g.set_stream(stream.cuda_stream)
+        g.upload(np.zeros(rows_model, np.float32), W0, np.zeros(1, np.float32))
+        res = {"mode": mode}
 
-    with torch.cuda.stream(stream):
-        if use_allreduce:
-            from svdfeature_b200 import parallel
+        # ---- resident batches (value) ----
+        t_b = time.perf_counter()
+        if mode == "exact":  # the ordered mode trains whole resident batches (its plan is per batch)
+            batches = []
+            for c in range(nchunk):
+                sl = (h_rp[3 * c * rows:3 * (c + 1) * rows + 1] - int(h_rp[3 * c * rows])).contiguous().numpy()
+                batches.append(g.batch_create((sl, h_lab[c * rows:(c + 1) * rows].numpy(),
+                                               h_idx[2 * c * rows:2 * (c + 1) * rows].numpy(),
+                                               h_val[2 * c * rows:2 * (c + 1) * rows].numpy())))
 
-            xchg[0] = parallel.ItemExchange(g, dist, dev, scale=1.0)
-        for s in range(args.warmup):
-            step(s)
-            if (s + 1) % args.allreduce_every == 0:
-                exchange()
+            def step(s):
+                g.batch_update(batches[s % nchunk])
+        else:
+            batches = [g.batch_create((h_rp, h_lab, h_idx, h_val))]
+
+            def step(s):
+                c = s % nchunk
+                g.batch_update(batches[0], c * rows, (c + 1) * rows)
         g.sync()
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
-            time.sleep(0.2)  # let nvidia-smi attach before the timed region
-        if dist:
-            dist.barrier()  # (after rank 0's sleep: every rank enters the timed region together)
-        torch.cuda.synchronize()
-        l0 = g.counter("kernel_launches")
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for s in range(args.steps):
-            step(args.warmup + s)
-            if (s + 1) % args.allreduce_every == 0:
-                exchange()
-        ev1.record(stream)
-        g.sync()
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        clk = clocks.stop() if rank == 0 else None
-        ms = ev0.elapsed_time(ev1)
-        launches = g.counter("kernel_launches") - l0
+        log("[rank %d] %s: %d rows resident in %d batch(es), %.2f s" % (rank, mode, total, len(batches), time.perf_counter() - t_b))
 
-        # kernel-only duration of k_stream launches (roofline numerator), same stream
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for s in range(args.steps):
-            kev[s][0].record(stream)
-            step(args.warmup + s)
-            kev[s][1].record(stream)
-        g.sync()
-        kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-        if use_allreduce:  # per-rank diagnostics (stderr): the exchange alone, back to back
-            xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            dist.barrier()
-            xe0.record(stream)
-            for _ in range(5):
-                exchange()
-            xe1.record(stream)
+        xchg = [None]
+
+        def exchange():
+            if use_allreduce:
+                xchg[0].sync()  # pack item-side deltas, ONE NCCL all-reduce, apply (svdfeature_b200/parallel.py)
+
+        with torch.cuda.stream(stream):
+            if use_allreduce:
+                from svdfeature_b200 import parallel
+
+                xchg[0] = parallel.ItemExchange(g, dist, dev, scale=1.0)
+            for s in range(warmup):
+                step(s)
+                if (s + 1) % args.allreduce_every == 0:
+                    exchange()
+            g.sync()
+            clocks = ClockSampler(local)
+            if rank == 0:
+                clocks.start()
+                time.sleep(0.2)  # let nvidia-smi attach before the timed region
+            if dist:
+                dist.barrier()  # (after rank 0's sleep: every rank enters the timed region together)
+            torch.cuda.synchronize()
+            l0, o0 = g.counter("kernel_launches"), g.counter("own_launches")
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for s in range(steps):
+                step(warmup + s)
+                if (s + 1) % args.allreduce_every == 0:
+                    exchange()
+            ev1.record(stream)
             g.sync()
             torch.cuda.synchronize()
-            log("[rank %d] kernel-only %.3f ms/step, exchange-only %.3f ms, timed loop %.3f ms/step"
-                % (rank, kms, xe0.elapsed_time(xe1) / 5, ms / args.steps))
-
-    if dist:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    value = world * rows * args.steps / (ms * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers ----
-    e2e = None
-    if not args.no_e2e and args.mode == "hogwild":
-        probe_n = 1024
-        probe = (h_rp[:3 * probe_n + 1].numpy(), h_lab[:probe_n].numpy(), h_idx.numpy(), h_val.numpy())
-
-        def e2e_step(s):
-            c = s % nchunk
-            r0, r1 = c * rows, (c + 1) * rows
-            g.update_csr((h_rp[3 * r0:3 * r1 + 1], h_lab[r0:r1], h_idx, h_val))
-            if use_allreduce:
-                with torch.cuda.stream(stream):
-                    exchange()
-            return g.predict_csr(probe)  # D2H read of the step's result (probe predictions)
-
-        g.set_option("chunk_rows", 1 << 20)
-
-        def measure_e2e():
-            for s in range(max(1, args.warmup)):
-                e2e_step(s)
-            g.sync()
             if dist:
                 dist.barrier()
-            h0, d0 = g.counter("h2d_bytes"), g.counter("d2h_bytes")
-            t0 = time.perf_counter()
-            for s in range(args.steps):
-                e2e_step(args.warmup + s)
-            g.sync()
-            dt = time.perf_counter() - t0
-            if dist:
-                tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
-            return {"value": world * rows * args.steps / dt, "unit": "instances/s",
-                    "h2d_bytes_per_step": (g.counter("h2d_bytes") - h0) // args.steps,
-                    "d2h_bytes_per_step": (g.counter("d2h_bytes") - d0) // args.steps}
+            res["clocks"] = clocks.stop() if rank == 0 else None
+            ms = ev0.elapsed_time(ev1)
+            res["launches"] = g.counter("kernel_launches") - l0
+            res["own_launches"] = g.counter("own_launches") - o0
 
-        e2e = measure_e2e()
-        e2e["timing"] = "wall clock around K calls of svdgpu_update_csr (pinned host buffers) + probe predict"
-        e2e["compact_h2d"] = ("inside the timed region host threads verify, element by element, that a chunk's row_ptr is "
-                              "the progression of constant feature counts and that its values are all 1.0f; such arrays "
-                              "are rebuilt on the device instead of copied (12 of the reference layout's 32 bytes per "
-                              "instance cross PCIe); full_copy = the same call with the option off")
+            # kernel-only duration of the training launches (roofline numerator), same stream
+            kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for s in range(steps):
+                kev[s][0].record(stream)
+                step(warmup + s)
+                kev[s][1].record(stream)
+            g.sync()
+            res["kms"] = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+            if use_allreduce:  # per-rank diagnostics (stderr): the exchange alone, back to back
+                xe0, xe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                xe0.record(stream)
+                for _ in range(5):
+                    exchange()
+                xe1.record(stream)
+                g.sync()
+                torch.cuda.synchronize()
+                log("[rank %d] %s kernel-only %.3f ms/step, exchange-only %.3f ms, timed loop %.3f ms/step"
+                    % (rank, mode, res["kms"], xe0.elapsed_time(xe1) / 5, ms / steps))
+        if dist:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        res["ms"] = ms
+        res["value"] = world * rows * steps / (ms * 1e-3)
+
+        # ---- the ordered mode's plan: what rebuilding it every step would cost ----
+        if mode == "exact" and res["own_launches"] > 0:
+            ksteps = max(1, min(steps, 5))
+            g.sync()
+            t0 = time.perf_counter()
+            for s in range(ksteps):
+                g.batch_plan(batches[s % nchunk])
+            g.sync()
+            plan_ms = 1e3 * (time.perf_counter() - t0) / ksteps
+            res["plan"] = {"ms_per_batch": plan_ms, "what": "device: shape/bound checks, item and user histograms, two radix sorts "
+                           "(by user: tickets; by owner: queues), queue entries; host: LPT of the item counts",
+                           "value_with_plan_rebuilt_every_step": world * rows / ((ms / steps + plan_ms) * 1e-3)}
+
+        # ---- end to end through the C ABI with host buffers ----
+        if want_e2e:
+            def e2e_step(s):
+                c = s % nchunk
+                r0, r1 = c * rows, (c + 1) * rows
+                g.update_csr((h_rp[3 * r0:3 * r1 + 1], h_lab[r0:r1], h_idx, h_val))
+                if use_allreduce:
+                    with torch.cuda.stream(stream):
+                        exchange()
+                return g.predict_csr(probe)  # D2H read of the step's result (probe predictions)
+
+            g.set_option("chunk_rows", args.e2e_chunk_rows if mode == "exact" else 1 << 20)
+
+            def measure_e2e():
+                for s in range(max(1, min(warmup, 3))):
+                    e2e_step(s)
+                g.sync()
+                if dist:
+                    dist.barrier()
+                h0, d0 = g.counter("h2d_bytes"), g.counter("d2h_bytes")
+                t0 = time.perf_counter()
+                for s in range(steps):
+                    e2e_step(warmup + s)
+                g.sync()
+                dt = time.perf_counter() - t0
+                if dist:
+                    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt = float(tt.item())
+                return {"value": world * rows * steps / dt, "unit": "instances/s",
+                        "h2d_bytes_per_step": (g.counter("h2d_bytes") - h0) // steps,
+                        "d2h_bytes_per_step": (g.counter("d2h_bytes") - d0) // steps}
+
+            e2e = measure_e2e()
+            e2e["timing"] = "wall clock around K calls of svdgpu_update_csr (pinned host buffers) + probe predict"
+            if mode == "exact":
+                e2e["includes"] = "H2D of the batch, the ordered mode's plan of every chunk (device sorts + host LPT), k_own, D2H of the probe"
+            e2e["compact_h2d"] = ("inside the timed region host threads verify, element by element, that a chunk's row_ptr is "
+                                  "the progression of constant feature counts and that its values are all 1.0f; such arrays "
+                                  "are rebuilt on the device instead of copied (12 of the reference layout's 32 bytes per "
+                                  "instance cross PCIe); full_copy = the same call with the option off")
+            try:
+                g.set_option("compact_h2d", 0)
+                full = measure_e2e()
+                e2e["full_copy"] = {"value": full["value"], "h2d_bytes_per_step": full["h2d_bytes_per_step"]}
+            except api.SvdGpuError as e:  # (a side measurement must not cost the run its line)
+                e2e["full_copy"] = {"error": str(e)}
+            finally:
+                g.set_option("compact_h2d", 1)
+            res["e2e"] = e2e
+
+        # ---- the model after all those epochs: finite, and still fitting the labels ----
         try:
-            g.set_option("compact_h2d", 0)
-            full = measure_e2e()
-            e2e["full_copy"] = {"value": full["value"], "h2d_bytes_per_step": full["h2d_bytes_per_step"]}
-        except api.SvdGpuError as e:  # (a side measurement must not cost the run its line)
-            e2e["full_copy"] = {"error": str(e)}
-        finally:
-            g.set_option("compact_h2d", 1)
+            sse, cnt = g.eval_csr(check)
+            ub, Wm, _ = g.download()
+            res["model_check"] = {"finite": bool(np.isfinite(Wm).all() and np.isfinite(ub).all()),
+                                  "rmse_vs_labels": float(np.sqrt(sse / max(cnt, 1))), "rows": int(cnt),
+                                  "note": "first rows of the training stream, after every timed and untimed epoch of this run"}
+        except Exception as e:
+            res["model_check"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        for b_ in batches:
+            b_.close()
+        g.close()
+        return res
+
+    main_res = measure(args.mode, args.steps, args.warmup, not args.no_e2e)
+    second = None
+    if args.mode == "exact" and not args.no_secondary:
+        try:
+            second = measure("hogwild", max(1, min(args.steps, 10)), 3, not args.no_e2e and world == 1)
+        except Exception as e:  # the secondary must not cost the run its line
+            second = {"error": "%s: %s" % (type(e).__name__, e)}
+    ms, kms, value, launches, clk, e2e = (main_res["ms"], main_res["kms"], main_res["value"], main_res["launches"],
+                                          main_res["clocks"], main_res.get("e2e"))
 
     if dist:
         dist.barrier()
@@ -508,15 +573,28 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = rows * BYTES_PER_INSTANCE / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": rows * NCU_DRAM_BYTES_PER_INSTANCE if args.mode == "hogwild" else None,
-                "traffic_source": "ncu --set full, profiles/r1_kmf_v5_100M_ncu_full_summary.txt (156.7 B/instance: the "
-                                  "128 MB model is L2-resident, so DRAM moves less than the algorithmic bytes)",
-                "kernel": "k_mf" if args.mode == "hogwild" else "k_exact",
-                "algorithmic_bytes_per_instance": BYTES_PER_INSTANCE, "launch_ms": kms, "peak_source": peak_src,
-                "frac_of_nominal_8000": achieved / 8000.0}
 
+    def roof(kms_, mode):
+        achieved = rows * BYTES_PER_INSTANCE / (kms_ * 1e-3) / 1e9
+        r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+             "kernel": "k_mf" if mode == "hogwild" else "k_own",
+             "algorithmic_bytes_per_instance": BYTES_PER_INSTANCE, "launch_ms": kms_, "peak_source": peak_src,
+             "frac_of_nominal_8000": achieved / 8000.0}
+        if mode == "hogwild":
+            r["traffic"] = rows * NCU_DRAM_BYTES_PER_INSTANCE
+            r["traffic_source"] = ("ncu --set full, profiles/r1_kmf_v5_100M_ncu_full_summary.txt (156.7 B/instance: the "
+                                   "128 MB model is L2-resident, so DRAM moves less than the algorithmic bytes)")
+        else:
+            hot = int(np.bincount(h_idx[1:2 * rows:2].numpy()).max())
+            r["traffic"] = rows * NCU_OWN_DRAM_BYTES_PER_INSTANCE if NCU_OWN_DRAM_BYTES_PER_INSTANCE else None
+            r["traffic_source"] = NCU_OWN_TRAFFIC_SOURCE
+            r["chain"] = {"hottest_item_rows": hot, "us_per_link": 1e3 * kms_ / hot,
+                          "note": "the ordered mode is bound by latency, not bytes: the updates of one item are a chain of "
+                                  "dependent dot products (the reference's sequential semantics), so a launch cannot finish "
+                                  "before (rows of the hottest item) x (time of one link); every other row overlaps with it"}
+        return r
+
+    roofline = roof(kms, args.mode)
     cpu = parity = None
     if not args.no_cpu_baseline:
         v, kind, dt, yard = time_cpu(args.cpu_rows, 1_000_000, 0 if world > 1 else args.parity_rows)
@@ -529,13 +607,27 @@ def main():
                "sample": "first %d ratings of the same stream, ISVDTrainer::update loop, %.1f s, 1 thread of %d host cores"
                          % (args.cpu_rows, dt, os.cpu_count())}
 
+    cfg = workload_config(rows)
     line = {
         "metric": "sgd_training_instances_per_sec", "value": value, "unit": "instances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(rows, args.mode), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "config": cfg, "mode": ("ordered: bit-identical to the reference's sequential loop (k_own, item-owner warps)"
+                                if args.mode == "exact" else "hogwild: no ordering between the instances of a launch"),
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "model_check": main_res.get("model_check"),
     }
+    if "plan" in main_res:
+        line["plan"] = main_res["plan"]
+    if second is not None:
+        if "error" in second:
+            line["hogwild"] = second
+        else:
+            line["hogwild"] = {"what": "secondary: the throughput mode on the same workload; NOT within the north star's 1e-4 "
+                                       "of the sequential order (see parity.hogwild)",
+                               "value": second["value"], "ms_per_step": second["ms"] / max(1, min(args.steps, 10)),
+                               "e2e": second.get("e2e"), "roofline": roof(second["kms"], "hogwild"),
+                               "gpu_launches": int(second["launches"]), "model_check": second.get("model_check")}
     if parity:
         line["parity"] = parity
     if world > 1:

@@ -105,7 +105,7 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   k_exact and to the reference); 0 keeps every row in k_exact.  Tuning:
  *                   "own_min_rows" (4096: smaller launches keep k_exact), "own_batch" (32: version
  *                   publishes the busiest owner holds back per release fence, <= 32),
- *                   "own_urgent_gap" (16384: a user whose next rating follows within this many rows
+ *                   "own_urgent_gap" (4096: a user whose next rating follows within this many rows
  *                   is published at once), "own_slots" (0 = auto: item rows per owner kept in
  *                   shared memory, <= 32; the rest of an owner's rows stay in L2) */
 int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
@@ -202,6 +202,11 @@ int svdgpu_batch_set_ugroup(svdgpu_t *h, svdgpu_batch_t *b, int num_block, const
                             const float *fb_value);
 /* rows [row_begin,row_end) (blocks [begin,end) for a user-grouped batch) */
 int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end);
+/* (Re)build the ordered mode's item-owner plan of a resident batch (svdgpu_batch_create builds it
+ * already when the trainer is in the ordered mode; this entry exists to time the plan and to plan a
+ * batch created in Hogwild mode).  *planned = 1 when the batch qualifies (basic-MF rows, plain L2
+ * decay), else 0 and the ordered mode keeps k_exact. */
+int svdgpu_batch_plan(svdgpu_t *h, svdgpu_batch_t *b, int *planned);
 /* out_host may be NULL (predictions stay on the device; see svdgpu_batch_pred_ptr) */
 int svdgpu_batch_predict(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end, float *out_host);
 /* squared error of rows [begin,end) of a resident batch (see svdgpu_eval_csr) */

@@ -75,6 +75,7 @@ SVDGPU_SYMBOLS = {
     "svdgpu_batch_create": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, _vp, _vp, _vp, _vp]),
     "svdgpu_batch_set_ugroup": (C.c_int, [_vp, _vp, C.c_int] + [_vp] * 5),
     "svdgpu_batch_update": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "svdgpu_batch_plan": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "svdgpu_batch_predict": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "svdgpu_batch_destroy": (None, [_vp, _vp]),
     "svdgpu_rank_init": (C.c_int, [_vp, C.c_int, C.c_int]),
@@ -316,6 +317,12 @@ class SvdGpu:
         if end is None:
             end = batch.num_unit if batch.num_unit is not None else batch.num_row
         self._ck(self.lib.svdgpu_batch_update(self.h, batch.h, begin, end))
+
+    def batch_plan(self, batch):
+        """(Re)build the ordered mode's owner plan of a resident batch; True if the batch qualifies."""
+        ok = C.c_int()
+        self._ck(self.lib.svdgpu_batch_plan(self.h, batch.h, C.byref(ok)))
+        return bool(ok.value)
 
     def batch_predict(self, batch, begin=0, end=None, fetch=True):
         if end is None:

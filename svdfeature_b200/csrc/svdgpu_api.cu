@@ -786,7 +786,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     scan_threads = std::min(16, std::max(1, hw) / lw - 1);
     if (scan_threads < 5) scan_threads = 0;
   }
-  const bool compact = h->compact_h2d && scan_threads > 0 && !exact && !sides_on(h) && num_row >= h->compact_min_rows;
+  const bool compact = h->compact_h2d && scan_threads > 0 && (!exact || own_ok) && !sides_on(h) && num_row >= h->compact_min_rows;
   svdscan::ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
   if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value, scan_threads);
   for (int r0 = 0, ci = 0; r0 < num_row; r0 += h->chunk_rows, ++ci) {
@@ -1280,6 +1280,18 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
     if (launch_stream(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
   }
   h->n_inst += end - begin;
+  return 0;
+}
+
+int svdgpu_batch_plan(svdgpu_t *h, svdgpu_batch_t *b, int *planned) {
+  if (check_ready(h)) return 1;
+  if (!b) return fail(h, "null batch");
+  CU(h, cudaSetDevice(h->device));
+  if (planned) *planned = 0;
+  if (b->ugroup || b->has_value2 || !h->exact_owner || !own_supported(h) || b->num_row <= 0) return 0;
+  int bad = 0;
+  if (own_plan_build(h, batch_csr(b), 0, b->num_row, b->own, h->stream, &bad)) return 1;
+  if (planned) *planned = b->own.valid ? 1 : 0;
   return 0;
 }
 

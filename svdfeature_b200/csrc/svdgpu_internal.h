@@ -131,7 +131,7 @@ struct svdgpu {
   int exact_owner = 1;  // option "exact_owner": ordered mode sends basic-MF rows under plain L2 decay through the
                         // item-owner kernel (k_own, svdgpu_own.cu); 0 keeps every row in k_exact
   int own_min_rows = 4096;   // option "own_min_rows": launches with fewer rows keep k_exact (no plan to build)
-  int own_urgent_gap = 16384;  // option "own_urgent_gap": a user whose next rating follows within this many rows
+  int own_urgent_gap = 4096;   // option "own_urgent_gap": a user whose next rating follows within this many rows
                                // is published at once instead of with the owner's batch
   int own_batch = 32;        // option "own_batch": version publishes the most loaded owner holds back (<= 32)
   int own_slots = 0;         // option "own_slots": item rows an owner keeps in shared memory (0 = auto, <= 32)

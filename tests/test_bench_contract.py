@@ -30,6 +30,11 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "configs[1]" in d["config"]["workload"] and "model" not in d["config"]
+    # the same config dictionary as our arm prints (the bounded sample is described in cpu_baseline.sample)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.workload_config(bench.TOTAL_ROWS)
 
 
 def test_reference_arm_other_ranks_stay_silent():

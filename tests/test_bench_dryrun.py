@@ -42,14 +42,15 @@ class _FakeGpu:
     """What bench.py calls on api.SvdGpu; predictions are the base score."""
 
     def __init__(self, *a, **k):
-        self.c = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        self.c = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0, "own_launches": 0}
         self.compact = 1
+        self.mode = 1
 
     def set_hparams(self, **kw):
         pass
 
     def set_mode(self, m):
-        pass
+        self.mode = m
 
     def set_option(self, name, v):
         if name == "compact_h2d":
@@ -66,6 +67,18 @@ class _FakeGpu:
 
     def batch_update(self, b, begin=0, end=None):
         self.c["kernel_launches"] += 3
+        if self.mode == 0:  # ordered: the item-owner kernel
+            self.c["own_launches"] += 1
+
+    def batch_plan(self, b):
+        return True
+
+    def eval_csr(self, csr, scale=1.0):
+        n = len(csr[1])
+        return 1.21 * n, n
+
+    def download(self):
+        return np.zeros(4, np.float32), np.zeros((4, 2), np.float32), np.zeros(1, np.float32)
 
     def update_csr(self, csr):
         n = len(csr[1])
@@ -147,6 +160,12 @@ def test_bench_main_runs_against_stand_ins(monkeypatch, capfd):
                 "parity"):
         assert key in d, key
     assert d["steps"] == 2 and d["warmup"] == 1 and d["gpu_launches"] == 6
+    # the headline is the ordered mode; Hogwild is the labelled secondary of the same line
+    assert d["mode"].startswith("ordered") and d["roofline"]["kernel"] == "k_own" and "chain" in d["roofline"]
+    assert d["plan"]["value_with_plan_rebuilt_every_step"] > 0
+    assert d["model_check"]["finite"] is True and abs(d["model_check"]["rmse_vs_labels"] - 1.1) < 1e-6
+    assert d["hogwild"]["value"] > 0 and d["hogwild"]["roofline"]["kernel"] == "k_mf"
+    assert "mode" not in d["config"] and d["config"]["rows_per_step"] == 20000
     assert d["e2e"]["h2d_bytes_per_step"] == 20000 * 12 and d["e2e"]["full_copy"]["h2d_bytes_per_step"] == 20000 * 32
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
