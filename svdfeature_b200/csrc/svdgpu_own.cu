@@ -530,8 +530,12 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       float4 wu;
       float ub;
     };
-    auto read_link = [&](int s, Link &x) {
-      const unsigned sa = reg_s + (unsigned)s * SLOT;
+    // `landed` = what the barrier test returned, 1 or 0: it enters the address (0: the owner's first
+    // slot, whose content is then discarded), so the reads cannot be issued before the test has
+    // answered.  (Reads issued unconditionally behind a test_wait may be performed BEFORE it: they
+    // then see the slot as it was, while the test already sees the bulk copy complete.)
+    auto read_link = [&](int s, Link &x, unsigned landed = 1u) {
+      const unsigned sa = reg_s + landed * ((unsigned)s * SLOT);
       x.e0 = lds128u(sa + ROW + 16u);
       x.e1 = lds128u(sa + ROW + 32u);
       x.wu = lds128f(sa + lane16);
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       const unsigned par1 = (unsigned)(j1 >> LOG_D) & 1u;
       const bool more = j1 < n;
       const bool nready = more && mbar_test_s(full_s + 8u * (unsigned)s1, par1);
-      read_link(s1, nxt);  // (garbage when !nready: read again below)
+      read_link(s1, nxt, nready ? 1u : 0u);  // (not landed yet: read again below)
       if (cur.e0.w != cur_item) {
         put_item();
         get_item(cur.e0.w, cur.e1.x);
@@ -630,7 +634,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       const unsigned par1 = (unsigned)((j + 1) / D) & 1u;
       const bool more = j + 1 < n;
       const bool nready = more && mbar_test(full + s1, par1);
-      read_slot(s1, nxt);  // (garbage when !nready: read again below)
+      if (nready) read_slot(s1, nxt);  // (behind the branch: never before the test has answered)
       if (cur.e0.w != cur_item) {
         put_item();
         get_item(cur.e0.w, cur.e1.x);

@@ -881,3 +881,34 @@ def test_exact_owner_equals_exact_kernel_and_falls_back(native):
             g.update_csr(bad)
             g.sync()
         g.close()
+
+
+@pytest.mark.parametrize("compact", [0, 1])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_exact_owner_host_call_at_scale(native, compact, pinned):
+    """The ordered host-pointer call the trainer seam uses (several chunks in flight, the compact
+    H2D path, pageable and pinned caller arrays) on a model larger than L2's hot set: bit-identical
+    to the sequential oracle."""
+    nu, ni, n, k = 120000, 5000, 700000, 64
+    params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.005, wd_user=0.004, wd_item=0.004,
+                  base_score=3.6)
+    data = synth.basic_mf(n, nu, ni, seed=41, zipf_q=20.0)
+    opts = {"chunk_rows": 150000, "compact_h2d": compact, "compact_min_rows": 1, "scan_threads": 4}
+    for kv in os.environ.get("SVDGPU_TEST_OPTS", "").split():
+        opts[kv.split("=")[0]] = int(kv.split("=")[1])
+    o, g = _own_setup(native, params, options=opts)
+    gdata = data
+    if pinned:
+        import torch
+
+        keep = [torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory() for a in data]
+        gdata = tuple(keep)
+    o.update_csr(data)
+    g.update_csr(gdata)
+    g.sync()
+    assert g.counter("own_rows") == n
+    assert _maxdiff(o, g) == 0.0
+    o.update_csr(data)
+    g.update_csr(gdata)
+    assert _maxdiff(o, g) == 0.0
+    g.close()
