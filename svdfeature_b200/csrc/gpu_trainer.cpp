@@ -179,6 +179,7 @@ class GpuSVDFeature : public ISVDTrainer {
     if (!strcmp("gpu:batch", name)) batch_rows_ = atoi(val) > 0 ? atoi(val) : batch_rows_;
     if (!strncmp("gpu:opt:", name, 8)) options_.push_back(std::make_pair(std::string(name + 8), atoll(val)));
     if (h_) {
+      flush();  // rows staged so far were handed over under the old hyper-parameters (the reference applies them per row)
       push_hparams();
       if (!strcmp("gpu:mode", name)) check(h_, svdgpu_set_mode(h_, mode_));
       if (!strncmp("gpu:opt:", name, 8)) check(h_, svdgpu_set_option(h_, name + 8, atoll(val)));
@@ -324,17 +325,22 @@ class GpuSVDFeature : public ISVDTrainer {
     apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
     if (!svdpp_) apex_utils::error("GPU trainer: a random-order model takes SVDFeatureCSR::Elem input");
     flush();
-    // a MIDDLE/END block predicts with the feedback sum of its START block in the
-    // reference (trainer state); here each call is self-contained, which is the same
-    // for DEFAULT blocks and for split users carrying their feedback list in every block.
-    push_block(data);
-    blk_tag_.back() = svdpp_tag::DEFAULT;
-    pred.resize((size_t)rows_.num_row());
-    check(h_, svdgpu_predict_ugroup(h_, 1, blk_row_off_.data(), blk_fb_off_.data(), blk_tag_.data(),
-                                    fb_index_.data(), fb_value_.data(), rows_.row_ptr.data(),
-                                    rows_.label.data(), rows_.index.data(), rows_.value.data(),
+    // The reference prepares the feedback sum on DEFAULT / START blocks only and predicts the rows
+    // of MIDDLE / END blocks with the state the last of those left (base.h:583-591): keep that
+    // block's feedback list and predict every block of the user with it.
+    const bool opens = data.extend_tag == svdpp_tag::DEFAULT || data.extend_tag == svdpp_tag::START_TAG;
+    if (opens) {
+      pred_fb_index_.assign(data.index_ufeedback, data.index_ufeedback + data.num_ufeedback);
+      pred_fb_value_.assign(data.value_ufeedback, data.value_ufeedback + data.num_ufeedback);
+    }
+    // (own buffers: the training stage may hold the blocks of a run that is still open)
+    CsrStage rows;
+    for (int r = 0; r < data.data.num_row; ++r) rows.push(data.data[r]);
+    const int bro[2] = {0, rows.num_row()}, bfo[2] = {0, (int)pred_fb_index_.size()}, tag[1] = {svdpp_tag::DEFAULT};
+    pred.resize((size_t)rows.num_row());
+    check(h_, svdgpu_predict_ugroup(h_, 1, bro, bfo, tag, pred_fb_index_.data(), pred_fb_value_.data(),
+                                    rows.row_ptr.data(), rows.label.data(), rows.index.data(), rows.value.data(),
                                     pred.data()));
-    clear_stage();
   }
 
   // ---- bulk extensions (whole batches in one call) ----------
@@ -438,13 +444,35 @@ class GpuSVDFeature : public ISVDTrainer {
   }
   void upload() { check(h_, svdgpu_upload_model(h_, ui_bias_.data(), W_.data(), (size_t)pitch_, g_bias_.data())); }
 
-  void push_block(const SVDPlusBlock &b) {
-    fb_index_.insert(fb_index_.end(), b.index_ufeedback, b.index_ufeedback + b.num_ufeedback);
-    fb_value_.insert(fb_value_.end(), b.value_ufeedback, b.value_ufeedback + b.num_ufeedback);
+  void push_block(const SVDPlusBlock &b) { stage_block(b, b.index_ufeedback, b.value_ufeedback, b.num_ufeedback); }
+  void stage_block(const SVDPlusBlock &b, const unsigned *fbi, const float *fbv, int nfb) {
+    fb_index_.insert(fb_index_.end(), fbi, fbi + nfb);
+    fb_value_.insert(fb_value_.end(), fbv, fbv + nfb);
     blk_fb_off_.push_back((int)fb_index_.size());
     for (int r = 0; r < b.data.num_row; ++r) rows_.push(b.data[r]);
     blk_row_off_.push_back(rows_.num_row());
     blk_tag_.push_back(b.extend_tag);
+  }
+  // drop the first nb staged blocks, keep the (open) rest
+  void keep_open_run(int nb) {
+    const int r0 = blk_row_off_[(size_t)nb], f0 = blk_fb_off_[(size_t)nb], v0 = rows_.row_ptr[3 * (size_t)r0];
+    CsrStage rest;
+    rest.label.assign(rows_.label.begin() + r0, rows_.label.end());
+    rest.index.assign(rows_.index.begin() + v0, rows_.index.end());
+    rest.value.assign(rows_.value.begin() + v0, rows_.value.end());
+    rest.row_ptr.clear();
+    for (size_t i = 3 * (size_t)r0; i < rows_.row_ptr.size(); ++i) rest.row_ptr.push_back(rows_.row_ptr[i] - v0);
+    rows_ = rest;
+    std::vector<int> bro(1, 0), bfo(1, 0);
+    for (size_t b = (size_t)nb + 1; b < blk_row_off_.size(); ++b) {
+      bro.push_back(blk_row_off_[b] - r0);
+      bfo.push_back(blk_fb_off_[b] - f0);
+    }
+    blk_row_off_ = bro;
+    blk_fb_off_ = bfo;
+    blk_tag_.erase(blk_tag_.begin(), blk_tag_.begin() + nb);
+    fb_index_.erase(fb_index_.begin(), fb_index_.begin() + f0);
+    fb_value_.erase(fb_value_.begin(), fb_value_.begin() + f0);
   }
   void clear_stage() {
     rows_.clear();
@@ -457,11 +485,18 @@ class GpuSVDFeature : public ISVDTrainer {
   void flush() {
     if (!h_) return;
     if (svdpp_) {
-      if (!blk_tag_.empty())
-        check(h_, svdgpu_update_ugroup(h_, (int)blk_tag_.size(), blk_row_off_.data(), blk_fb_off_.data(),
-                                       blk_tag_.data(), fb_index_.data(), fb_value_.data(),
-                                       rows_.row_ptr.data(), rows_.label.data(), rows_.index.data(),
-                                       rows_.value.data()));
+      // a user unit (START .. END) is trained as a whole: blocks of a run that has not been closed
+      // yet stay staged until its END block arrives
+      int nb = (int)blk_tag_.size();
+      while (nb > 0 && blk_tag_[(size_t)nb - 1] != svdpp_tag::DEFAULT && blk_tag_[(size_t)nb - 1] != svdpp_tag::END_TAG) --nb;
+      if (nb > 0)
+        check(h_, svdgpu_update_ugroup(h_, nb, blk_row_off_.data(), blk_fb_off_.data(), blk_tag_.data(),
+                                       fb_index_.data(), fb_value_.data(), rows_.row_ptr.data(),
+                                       rows_.label.data(), rows_.index.data(), rows_.value.data()));
+      if (nb < (int)blk_tag_.size()) {
+        keep_open_run(nb);
+        return;
+      }
     } else if (rows_.num_row() > 0) {
       check(h_, svdgpu_update_csr(h_, rows_.num_row(), rows_.row_ptr.data(), rows_.label.data(),
                                   rows_.index.data(), rows_.value.data()));
@@ -519,6 +554,9 @@ class GpuSVDFeature : public ISVDTrainer {
   std::vector<int> blk_row_off_, blk_fb_off_, blk_tag_;
   std::vector<unsigned> fb_index_;
   std::vector<float> fb_value_;
+  // feedback list of the last DEFAULT / START block handed to predict (base.h:583-591)
+  std::vector<unsigned> pred_fb_index_;
+  std::vector<float> pred_fb_value_;
 };
 
 // apex_svd.cpp:32-45 -- the link-time seam
@@ -548,8 +586,12 @@ class GpuSVDRanker : public ISVDRanker {
     CsrStage one;
     one.push(e);
     note(e);
+    // (buf() may grow buf_: take the pointer and the capacity in this order, not as two arguments
+    // of one call, whose evaluation order is unspecified)
+    int *out = buf();
+    const long long cap = (long long)buf_.size();
     collect(result, svdgpu_rank_csr(tr_.handle(), 1, one.row_ptr.data(), one.label.data(), one.index.data(),
-                                    one.value.data(), buf(), (long long)buf_.size(), &n_));
+                                    one.value.data(), out, cap, &n_));
   }
   virtual void process(std::vector<int> &result, const SVDPlusBlock &b) {  // base.h:798-812
     CsrStage rows;
@@ -558,9 +600,11 @@ class GpuSVDRanker : public ISVDRanker {
       note(b.data[r]);
     }
     const int bro[2] = {0, rows.num_row()}, bfo[2] = {0, b.num_ufeedback}, tag[1] = {b.extend_tag};
+    int *out = buf();
+    const long long cap = (long long)buf_.size();
     collect(result, svdgpu_rank_ugroup(tr_.handle(), 1, bro, bfo, tag, b.index_ufeedback, b.value_ufeedback,
                                        rows.row_ptr.data(), rows.label.data(), rows.index.data(), rows.value.data(),
-                                       buf(), (long long)buf_.size(), &n_));
+                                       out, cap, &n_));
   }
 
  private:

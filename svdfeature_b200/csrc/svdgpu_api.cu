@@ -420,9 +420,12 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
   CUC(cudaEventCreate(&h->ev1));
   CUC(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
   CUC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming));
   for (int i = 0; i < svdgpu::NSLOT; ++i) {
     CUC(cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&h->slot[i].copied, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->slot[i].planned, cudaEventDisableTiming));
   }
 
   DevModel &m = h->dm;
@@ -468,6 +471,7 @@ void svdgpu_destroy(svdgpu_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->plan_stream) cudaStreamSynchronize(h->plan_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
   rank_free(h);
   cudaFree(h->dm.W);
@@ -497,11 +501,14 @@ void svdgpu_destroy(svdgpu_t *h) {
     for (DevBuf *b : db) dev_free(*b);
     if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
+    if (s.planned) cudaEventDestroy(s.planned);
   }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->plan_stream) cudaStreamDestroy(h->plan_stream);
+  if (h->ev_plan) cudaEventDestroy(h->ev_plan);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -553,6 +560,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_urgent_gap")) h->own_urgent_gap = (int)std::max<long long>(0, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_batch")) h->own_batch = (int)std::max<long long>(1, std::min<long long>(v, 32));
   else if (!strcmp(name, "own_stats")) h->own_stats = v ? 1 : 0;
+  else if (!strcmp(name, "own_spare_sms")) h->own_spare_sms = (int)std::max<long long>(0, std::min<long long>(v, 64));
   else if (!strcmp(name, "own_depth")) h->own_depth = v >= 16 ? 16 : 8;
   else if (!strcmp(name, "own_fast")) h->own_fast = v ? 1 : 0;
   else if (!strcmp(name, "own_acquire")) h->own_acquire = v ? 1 : 0;
@@ -751,6 +759,22 @@ __global__ void k_fill_ones(float *v, long long n) {
     v[i] = 1.0f;
 }
 
+// Build an owner plan on the plan stream: it starts once `after` has happened (the chunk's copies, or
+// whatever the launch stream had queued), and the launch stream waits for it.  The plan scratch of
+// the handle is only ever touched on the plan stream.
+static int plan_on_side(svdgpu *h, const DevCsr &csr, int n, OwnPlan &p, int *bad, int ctas, cudaEvent_t after,
+                        cudaEvent_t done) {
+  if (!after) {
+    CU(h, cudaEventRecord(h->ev_plan, h->stream));
+    after = h->ev_plan;
+  }
+  CU(h, cudaStreamWaitEvent(h->plan_stream, after, 0));
+  if (own_plan_build(h, csr, 0, n, p, h->plan_stream, bad, ctas)) return 1;
+  CU(h, cudaEventRecord(done, h->plan_stream));
+  CU(h, cudaStreamWaitEvent(h->stream, done, 0));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // random-order CSR, host buffers
 // ---------------------------------------------------------------------------
@@ -805,11 +829,15 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     svdscan::ChunkScan sc;
     if (compact) sc = pool.wait(ci);
     Slot &s = next_slot(h);  // (the kernels that last read this slot are done)
+    // ordered mode through k_own: the chunk's fills and plan run on the plan stream, beside the
+    // k_own launch of the chunk before (which leaves them own_spare_sms SMs)
+    const bool try_own = exact && own_ok && n >= h->own_min_rows;
+    cudaStream_t aux = try_own ? h->plan_stream : h->stream;
     if (sc.rp_regular) {
       // not copied: rebuilt 0-based on the launch stream unless the slot still holds this very fill
       if (dev_reserve(h, s.d_rp, (3 * (size_t)n + 1) * 4)) return 1;
       if (s.d_rp.fill_n != n || s.d_rp.fill_a != sc.a || s.d_rp.fill_b != sc.b || s.d_rp.fill_c != sc.c) {
-        k_fill_row_ptr<<<std::min(h->num_sm * 8, (n + 256) / 256), 256, 0, h->stream>>>((int *)s.d_rp.p, n, sc.a, sc.b, sc.c);
+        k_fill_row_ptr<<<std::min(h->num_sm * 8, (n + 256) / 256), 256, 0, aux>>>((int *)s.d_rp.p, n, sc.a, sc.b, sc.c);
         CU(h, cudaGetLastError());
         h->n_launch++;
         s.d_rp.fill_n = n;
@@ -825,7 +853,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     if (sc.val_ones) {
       if (dev_reserve(h, s.d_value, nv * 4)) return 1;
       if (s.d_value.fill_n < (long long)nv) {
-        k_fill_ones<<<(int)std::min<long long>(h->num_sm * 8, ((long long)nv + 255) / 256), 256, 0, h->stream>>>(
+        k_fill_ones<<<(int)std::min<long long>(h->num_sm * 8, ((long long)nv + 255) / 256), 256, 0, aux>>>(
             (float *)s.d_value.p, (long long)nv);
         CU(h, cudaGetLastError());
         h->n_launch++;
@@ -845,10 +873,11 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     csr.val_base = sc.rp_regular ? 0 : v0;  // a rebuilt row_ptr counts from 0
     csr.val_end = sc.rp_regular ? (int)nv : v1;
     bool owned = false;
-    if (exact && own_ok && n >= h->own_min_rows) {
-      if (slot_copied(h, s)) return 1;
+    if (try_own) {
+      CU(h, cudaEventRecord(s.copied, h->copy_stream));
       int bad = 0;
-      if (own_plan_build(h, csr, 0, n, s.own, h->stream, &bad)) return 1;
+      const int ctas = nchunk > 1 ? std::max(1, h->num_sm - h->own_spare_sms) : h->num_sm;
+      if (plan_on_side(h, csr, n, s.own, &bad, ctas, s.copied, s.planned)) return 1;
       if (s.own.valid) {
         if (launch_own(h, s.own, h->stream)) return 1;
         owned = true;
@@ -916,6 +945,14 @@ static int fb_tickets(svdgpu *h, const std::vector<int> &unit_off, int u0, int u
   for (int u = u0; u < u1; ++u) {
     const int b0 = unit_off[u], b1 = unit_off[u + 1];
     const int f0 = blk_fb_off[b0], f1 = blk_fb_off[b0 + 1];
+    // The unit holds the rows of its FIRST block's list from gather to scatter; the scatter goes to
+    // the LAST block's list (base.h:539-554).  The reference's loader repeats a split user's list in
+    // every piece; a unit whose END list differs would scatter to rows it does not hold.
+    if (b1 - 1 != b0) {
+      const int g0 = blk_fb_off[b1 - 1], g1 = blk_fb_off[b1];
+      if (g1 - g0 != f1 - f0 || (f1 > f0 && memcmp(fb_index + g0, fb_index + f0, (size_t)(f1 - f0) * sizeof(unsigned)) != 0))
+        return fail(h, "ordered mode: the END block of a split user must carry the START block's feedback list");
+    }
     for (int f = f0; f < f1; ++f) {
       if (fb_index[f] >= (unsigned)h->dm.num_ufeedback) return fail(h, "ufeedback id exceed bound");
       fb_ticket[f - fb_base] = cf[fb_index[f]];
@@ -1156,7 +1193,7 @@ int svdgpu_batch_create(svdgpu_t *h, svdgpu_batch_t **out, int num_row, const in
     bool need_tickets = true;
     if (h->exact_owner && !side && num_row >= h->own_min_rows && h->hp_set && own_supported(h)) {
       int bad = 0;
-      rc |= own_plan_build(h, batch_csr(b), 0, num_row, b->own, h->stream, &bad);
+      rc |= plan_on_side(h, batch_csr(b), num_row, b->own, &bad, h->num_sm, nullptr, h->ev_plan);
       if (!rc && b->own.valid) need_tickets = false;
       else if (!rc && !(bad & 3) && bad) {
         rc = fail(h, (bad & 4) ? "user feature index exceed bound" : "item feature index exceed bound");
@@ -1290,7 +1327,7 @@ int svdgpu_batch_plan(svdgpu_t *h, svdgpu_batch_t *b, int *planned) {
   if (planned) *planned = 0;
   if (b->ugroup || b->has_value2 || !h->exact_owner || !own_supported(h) || b->num_row <= 0) return 0;
   int bad = 0;
-  if (own_plan_build(h, batch_csr(b), 0, b->num_row, b->own, h->stream, &bad)) return 1;
+  if (plan_on_side(h, batch_csr(b), b->num_row, b->own, &bad, h->num_sm, nullptr, h->ev_plan)) return 1;
   if (planned) *planned = b->own.valid ? 1 : 0;
   return 0;
 }

@@ -45,6 +45,7 @@ struct Slot {
   DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_misc, d_fbi, d_fbv, d_fbt, d_pred;
   cudaEvent_t done = nullptr;    // last kernel that read this slot
   cudaEvent_t copied = nullptr;  // the slot's H2D copies have landed (recorded on the copy stream)
+  cudaEvent_t planned = nullptr;  // ordered mode: the slot's arrays and plan are complete (recorded on the plan stream)
   bool used = false;
 };
 
@@ -95,6 +96,9 @@ struct svdgpu {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   // host-pointer calls stage chunk c+1 on this stream while the kernels of chunk c run on `stream`
   cudaStream_t copy_stream = nullptr;
+  // ordered host-pointer calls build the plan of chunk c+1 here while k_own trains chunk c on `stream`
+  cudaStream_t plan_stream = nullptr;
+  cudaEvent_t ev_plan = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
   svdk::DevModel dm;
   svdk::DevHP dhp{};
@@ -139,6 +143,8 @@ struct svdgpu {
   int own_fast = 1;          // option "own_fast": 0 keeps the generic link for every shape (testing)
   int own_acquire = 0;       // option "own_acquire": loaders poll versions with ld.acquire.gpu (adds CCTL.IVALL per poll)
   int own_reverse = 1;       // option "own_reverse": busiest owners on the highest warp ids (the arbiter prefers them)
+  int own_spare_sms = 16;    // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
+                             // fills of the next chunk (k_own then runs on num_sm - this many CTAs)
   int own_stats = 0;         // option "own_stats": k_own records per-owner cycle counters (svdgpu_own_stats)
   OwnScratch own;
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
@@ -213,7 +219,8 @@ int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1
 // ordered mode with item-owner warps (svdgpu_own.cu)
 bool own_supported(const svdgpu *h);
 int own_owners_per_cta();
-int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad);
+// ctas: CTAs (= SMs) the launch will occupy, 12 owners each; 0 = every SM
+int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad, int ctas = 0);
 int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st);
 void own_plan_free(OwnPlan &p);
 void own_scratch_free(OwnScratch &s);

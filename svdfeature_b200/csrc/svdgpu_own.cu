@@ -740,13 +740,14 @@ void own_scratch_free(OwnScratch &s) {
 
 // Build the plan of rows [r0, r0+n) of a device CSR on `st`.  Returns non-zero on failure (message
 // set).  p.valid tells whether the rows can take k_own; *bad receives the OWN_* bits otherwise.
-int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad) {
+int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad, int ctas) {
   p.valid = false;
   if (bad) *bad = 0;
   if (n <= 0) return 0;
   OwnScratch &s = h->own;
   const DevModel &m = h->dm;
-  const int W = h->num_sm * OWN_C;
+  if (ctas <= 0 || ctas > h->num_sm) ctas = h->num_sm;
+  const int W = ctas * OWN_C;
   const size_t nn = (size_t)n;
   if (own_reserve(h, s.cnt_item, (size_t)m.num_item * 4) || own_reserve(h, s.cnt_user, (size_t)m.num_user * 4) ||
       own_reserve(h, s.start_user, (size_t)m.num_user * 4) || own_reserve(h, s.flag, 4) ||
@@ -905,7 +906,7 @@ static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   CU(h, cudaMemsetAsync(h->d_abort, 0, sizeof(unsigned), st));
   void *args[] = {&a};
   // cooperative: the launch fails instead of deadlocking if the CTAs cannot all be resident
-  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3(h->num_sm), dim3(own_threads(D)), args, smem, st));
+  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3(p.num_owner / OWN_C), dim3(own_threads(D)), args, smem, st));
   h->n_launch++;
   h->n_own++;
   h->n_own_rows += p.rows;
@@ -920,7 +921,8 @@ static int own_launch_d(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
 
 int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   if (!p.valid) return fail(h, "ordered mode: no owner plan");
-  if (p.num_owner != h->num_sm * OWN_C) return fail(h, "ordered mode: plan was built for another device");
+  if (p.num_owner <= 0 || p.num_owner % OWN_C || p.num_owner > h->num_sm * OWN_C)
+    return fail(h, "ordered mode: plan was built for another device");
   const DevModel &m = h->dm;
   const int chunks = m.pitch / 4;
   // the fast link: linear loss, rows of exactly 4 / 8 / 16 / 32 chunks (num_factor 16, 32, 64, 128)

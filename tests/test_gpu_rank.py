@@ -106,6 +106,19 @@ def test_rank_larger_set(native, top_k, tmp_path):
         assert got.min() >= 0 and got.max() < 2500
 
 
+@pytest.mark.parametrize("top_k", [0, 40])
+def test_gpu_ranker_class_large_results(native, top_k, tmp_path):
+    """GpuSVDRanker's result buffer grows with the stream: top_k = 40 and users with up to 60 POS
+    items (a PROCESS row then returns more than any earlier one) through the ISVDRanker virtuals."""
+    params = dict(_cases.BASE, num_user=3000, num_item=2000, num_factor=16)
+    path = _cases.rank_model(0, params, tmp_path)
+    skw = dict(num_item_set=300, num_sections=40, seed=11, max_pos=60, max_ban=10)
+    stream = synth.rank_stream(num_user=3000, num_item=2000, **skw)
+    want = COracleRanker(path, 300, {"top_k": top_k}).rank(stream)
+    got = native.GpuRanker(path, 300, {"top_k": top_k}).rank(stream)
+    assert len(want) > 40 * 16 and np.array_equal(got, want)
+
+
 def test_rank_errors(native, tmp_path):
     """The reference's assert messages (base.h:720,751-752,758,760,775)."""
     fmt, params, skw, rparams, path, stream, kind = _case("rank_pos_k20", tmp_path)

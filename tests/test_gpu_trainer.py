@@ -89,3 +89,30 @@ def test_hogwild_through_trainer(native, tmp_path):
         preds.append(t.predict_csr(test))
     rmse = float(np.sqrt(np.mean((preds[0] - preds[1]) ** 2)))
     assert rmse <= 1e-2, rmse
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_split_user_predict_uses_the_start_blocks_feedback(native, bulk, tmp_path):
+    """The reference prepares the feedback sum on DEFAULT / START blocks only (base.h:583-591): the
+    rows of MIDDLE / END blocks are predicted with the START block's list, whatever their own list
+    says (here: empty).  Training across a flush with an open START run stays byte-identical."""
+    fmt, act, params, data, kind = CASES["svdpp_k64_tags"]
+    bro, bfo, tag, fi, fv = data[:5]
+    nfi, nfv, nbfo = [], [], [0]
+    for b in range(len(tag)):  # MIDDLE / END blocks lose their copy of the list
+        if tag[b] in (0, 1):
+            nfi.append(fi[bfo[b]:bfo[b + 1]])
+            nfv.append(fv[bfo[b]:bfo[b + 1]])
+        nbfo.append(nbfo[-1] + (int(bfo[b + 1] - bfo[b]) if tag[b] in (0, 1) else 0))
+    stripped = (bro, np.asarray(nbfo, np.int32), tag, np.concatenate(nfi).astype(np.uint32),
+                np.concatenate(nfv).astype(np.float32)) + tuple(data[5:])
+    assert (np.asarray(tag) == 3).any() or (np.asarray(tag) == 2).any()
+    o = COracle(fmt, act, 0, params)
+    g = native.GpuTrainer(fmt, act, 0, dict(params, **{"gpu:mode": "exact", "gpu:batch": 7}), bulk=bulk)
+    for t in (o, g):
+        t.init(10)
+        t.update_ugroup(data)  # (training scatters to the END block's list: keep the full lists here)
+        if hasattr(t, "finish_round"):
+            t.finish_round()
+    assert o.model_bytes(tmp_path) == g.model_bytes(tmp_path)
+    assert np.array_equal(o.predict_ugroup(stripped), g.predict_ugroup(stripped))
