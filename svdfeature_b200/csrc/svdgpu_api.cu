@@ -560,6 +560,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_urgent_gap")) h->own_urgent_gap = (int)std::max<long long>(0, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_batch")) h->own_batch = (int)std::max<long long>(1, std::min<long long>(v, 32));
   else if (!strcmp(name, "own_stats")) h->own_stats = v ? 1 : 0;
+  else if (!strcmp(name, "own_poll_ns")) h->own_poll_ns = (int)std::max<long long>(0, std::min<long long>(v, 100000));
   else if (!strcmp(name, "own_spare_sms")) h->own_spare_sms = (int)std::max<long long>(0, std::min<long long>(v, 64));
   else if (!strcmp(name, "own_depth")) h->own_depth = v >= 16 ? 16 : 8;
   else if (!strcmp(name, "own_fast")) h->own_fast = v ? 1 : 0;

@@ -145,6 +145,7 @@ struct svdgpu {
   int own_reverse = 1;       // option "own_reverse": busiest owners on the highest warp ids (the arbiter prefers them)
   int own_spare_sms = 16;    // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
                              // fills of the next chunk (k_own then runs on num_sm - this many CTAs)
+  int own_poll_ns = 50;      // option "own_poll_ns": loader warps sleep this long between polls without progress
   int own_stats = 0;         // option "own_stats": k_own records per-owner cycle counters (svdgpu_own_stats)
   OwnScratch own;
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves

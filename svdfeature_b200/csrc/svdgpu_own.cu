@@ -150,6 +150,7 @@ struct OwnArgs {
   unsigned *abort_flag;
   long long *stats;  // option "own_stats": per owner {cycles, cycles waiting for a slot, cycles in flushes, waits} or null
   int flags;         // OWN_F_*
+  unsigned poll_ns;  // loader warps: sleep between polls when no lane made progress
 };
 enum { OWN_F_ACQUIRE = 1,   // loaders poll with ld.acquire.gpu (LDG + CCTL.IVALL) instead of ld.relaxed.gpu
        OWN_F_REVERSE = 2 }; // busiest owners on the highest warp ids of a CTA
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
         idle = 0;
       } else {
         ++idle;
-        if (idle > 4) __nanosleep(idle < 64 ? 20 : 100);
+        if (idle > 2) __nanosleep(a.poll_ns);
       }
       if ((it & 63u) == 63u && ld_relaxed_u32(a.abort_flag)) break;
     }
@@ -542,17 +543,16 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       x.ub = lds32f(sa + ROW + 4u * ((x.e0.x + koff) & 3u));
     };
     float4 &wi0 = wi[0];
-    // one link; returns false when the launch is being aborted
+    // One link.  Everything that is not arithmetic of this instance -- the publish fence, a next
+    // entry that has not landed, a change of item -- sits behind ONE rarely taken branch at the
+    // end; the item row of `cur` is in registers when the link starts.  Returns false when the
+    // launch is being aborted.
     auto link = [&](Link &cur, Link &nxt, int j) -> bool {
       const int j1 = j + 1, s1 = j1 & (D - 1);
       const unsigned par1 = (unsigned)(j1 >> LOG_D) & 1u;
       const bool more = j1 < n;
       const bool nready = more && mbar_test_s(full_s + 8u * (unsigned)s1, par1);
       read_link(s1, nxt, nready ? 1u : 0u);  // (not landed yet: read again below)
-      if (cur.e0.w != cur_item) {
-        put_item();
-        get_item(cur.e0.w, cur.e1.x);
-      }
       const float uval = __uint_as_float(cur.e1.y), ival = __uint_as_float(cur.e1.z), label = __uint_as_float(cur.e0.z);
       const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
       const float4 tu = f4_add_scaled(f4_zero(), cur.wu, um, false);  // prepare_tmp, base.h:354-381
@@ -600,12 +600,19 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
         my_t = cur.e0.y + 1u;
       }
       ++pend;
-      if ((cur.e1.w & 1u) || pend >= B) flush();
-      if (more && !nready) {
-        if (!wait_full(s1, par1)) return false;
-        read_link(s1, nxt);
-        __syncwarp();
-        if (lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
+      const bool publish = (cur.e1.w & 1u) || pend >= B;
+      if (publish || (more && (!nready || nxt.e0.w != cur_item))) {
+        if (publish) flush();
+        if (more && !nready) {
+          if (!wait_full(s1, par1)) return false;
+          read_link(s1, nxt);
+          __syncwarp();
+          if (lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
+        }
+        if (more && nxt.e0.w != cur_item) {
+          put_item();
+          get_item(nxt.e0.w, nxt.e1.x);
+        }
       }
       return true;
     };
@@ -614,6 +621,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       read_link(0, la);
       __syncwarp();
       if (lane0) mbar_arrive_s(empty_s);
+      get_item(la.e0.w, la.e1.x);
       for (int j = 0; j < n; j += 2) {
         if (!link(la, lb, j)) break;
         if (j + 1 < n && !link(lb, la, j + 1)) break;
@@ -893,6 +901,7 @@ static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   a.err_flag = h->d_err;
   a.abort_flag = h->d_abort;
   a.flags = (h->own_acquire ? OWN_F_ACQUIRE : 0) | (h->own_reverse ? OWN_F_REVERSE : 0);
+  a.poll_ns = (unsigned)h->own_poll_ns;
   a.stats = nullptr;
   if (h->own_stats) {
     if (own_reserve(h, h->own.stats, (size_t)p.num_owner * 4 * sizeof(long long))) return 1;
