@@ -78,9 +78,15 @@ def marginals(seed=10):
     return ucdf, icdf, iperm
 
 
-def gen_rows_torch(n, seed, device, rank=0, world=1):
-    """(row_ptr, label, index, value) as torch tensors on `device`: the rows of rank `rank`'s user
-    shard (hash partition by user id mod world), user ids already local to the shard."""
+def gen_rows_torch(n, seed, device, rank=0, world=1, shard=False, planted=False):
+    """(row_ptr, label, index, value) as torch tensors on `device`.
+    shard=False (weak scaling): n rows over NUM_USER users -- with world > 1 the global population is
+    NUM_USER * world users, rank r owns the users congruent to r mod world and stores them under the
+    local index id // world, i.e. every rank trains the same per-GPU problem as the single-GPU run.
+    shard=True (strong scaling): the GLOBAL stream of n rows is generated (same seed on every rank)
+    and the rows of this rank's users (user id mod world == rank) are kept, global user ids.
+    planted=True: labels = 3.6 + <p_user, q_item> + N(0, 0.5): a rank-8 signal a model can learn, so
+    that held-out RMSE says something (the BASELINE labels are noise independent of user and item)."""
     import torch
 
     ucdf, icdf, iperm = marginals()
@@ -89,12 +95,20 @@ def gen_rows_torch(n, seed, device, rank=0, world=1):
     ucdf_t = torch.from_numpy(ucdf).to(device)
     icdf_t = torch.from_numpy(icdf).to(device)
     iperm_t = torch.from_numpy(iperm.astype(np.int64)).to(device)
-    # weak scaling: the global population is NUM_USER * world users; rank r owns the users whose id
-    # is congruent to r mod world and stores them under the local index id // world, so every rank
-    # trains NUM_USER local users -- the same per-GPU problem as the single-GPU run
     u = torch.searchsorted(ucdf_t, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=NUM_USER - 1)
     it = iperm_t[torch.searchsorted(icdf_t, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=NUM_ITEM - 1)]
-    lab = torch.clamp(torch.round(3.6 + 1.1 * torch.randn(n, generator=g, device=device)), 1, 5).float()
+    if planted:
+        gp = torch.Generator(device=device)
+        gp.manual_seed(4242)  # the planted factors do not depend on the stream's seed
+        P = torch.randn(NUM_USER, 8, generator=gp, device=device) * 0.6
+        Q = torch.randn(NUM_ITEM, 8, generator=gp, device=device) * 0.6
+        lab = (3.6 + (P[u] * Q[it]).sum(1) + 0.5 * torch.randn(n, generator=g, device=device)).float()
+    else:
+        lab = torch.clamp(torch.round(3.6 + 1.1 * torch.randn(n, generator=g, device=device)), 1, 5).float()
+    if shard and world > 1:
+        keep = (u % world) == rank
+        u, it, lab = u[keep], it[keep], lab[keep]
+        n = int(u.numel())
     index = torch.stack([u, it], 1).reshape(-1).to(torch.int32)  # ids < 2^31: same bits as uint32
     value = torch.ones(2 * n, device=device, dtype=torch.float32)
     base = torch.arange(n, device=device, dtype=torch.int64) * 2
@@ -296,6 +310,71 @@ def workload_config(rows_per_step):
             "hparams": HP}
 
 
+def convergence_leg(args, api, torch, dist, dev, stream, rank, world, local, W0, epochs=3, heldout=1_000_000):
+    """Planted rank-8 signal (labels = 3.6 + <p_u, q_i> + N(0, 0.5)), `--convergence-rows` ratings split by
+    user hash over the ranks, ordered mode, item side all-reduced E times per epoch: held-out RMSE of the
+    completed model (svdgpu_allgather_users) beside the single-GPU ordered run of the same stream on rank 0
+    (= the reference's sequential loop) and the noise floor."""
+    n, rows_model = args.convergence_rows, NUM_USER + NUM_ITEM
+    E = max(4, args.exchanges_per_step)
+    scale = args.allreduce_scale if args.allreduce_scale > 0 else 1.0 / world
+
+    def to_np(ts):
+        return tuple(t.cpu().numpy() for t in ts)
+
+    def trainer():
+        g = api.SvdGpu(NUM_USER, NUM_ITEM, K, device=local)
+        g.set_hparams(**HP)
+        g.set_mode(api.MODE_EXACT)
+        g.set_stream(stream.cuda_stream)
+        g.upload(np.zeros(rows_model, np.float32), W0, np.zeros(1, np.float32))
+        return g
+
+    test = to_np(gen_rows_torch(heldout, seed=777, device=dev, planted=True))
+    out = {"rows": n, "epochs": epochs, "exchanges_per_epoch": E, "scale": scale, "noise_floor_rmse": 0.5,
+           "labels": "planted rank-8 signal + N(0, 0.5); held-out = %d fresh ratings" % heldout}
+    # sharded run
+    mine = to_np(gen_rows_torch(n, seed=99, device=dev, rank=rank, world=world, shard=True, planted=True))
+    m = len(mine[1])
+    g = trainer()
+    ids = [api.comm_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    g.comm_init(world, rank, ids[0])
+    g.allreduce_items(scale)
+    cuts = [(m * e) // E for e in range(E + 1)]
+    bs = [g.batch_create((mine[0][3 * a:3 * b + 1] - mine[0][3 * a], mine[1][a:b], mine[2][2 * a:2 * b], mine[3][2 * a:2 * b]))
+          for a, b in zip(cuts[:-1], cuts[1:])]
+    curve = []
+    for _ in range(epochs):
+        for b in bs:
+            g.batch_update(b)
+            g.allreduce_items(scale)
+        g.allgather_users()
+        sse, cnt = g.eval_csr(test)
+        curve.append(float(np.sqrt(sse / max(cnt, 1))))
+    for b in bs:
+        b.close()
+    g.close()
+    out["heldout_rmse_by_epoch_sharded"] = curve
+    dist.barrier()
+    # the single-GPU ordered run of the same global stream (rank 0 only)
+    if rank == 0:
+        full = to_np(gen_rows_torch(n, seed=99, device=dev, planted=True))
+        g = trainer()
+        b = g.batch_create(full)
+        curve1 = []
+        for _ in range(epochs):
+            g.batch_update(b)
+            sse, cnt = g.eval_csr(test)
+            curve1.append(float(np.sqrt(sse / max(cnt, 1))))
+        b.close()
+        g.close()
+        out["heldout_rmse_by_epoch_single_gpu_ordered"] = curve1
+        out["gap_last_epoch"] = curve[-1] - curve1[-1]
+    dist.barrier()
+    return out
+
+
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
@@ -317,6 +396,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to svdgpu_set_option")
     ap.add_argument("--allreduce-every", type=int, default=1)
+    ap.add_argument("--allreduce-scale", type=float, default=1.0, help="factor on the summed deltas; 0 = mean (1/world)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every rank trains its own 480k users / rows-per-step ratings (the global problem "
+                         "grows with N); strong = the stated config (480k users, rows-per-step ratings) split over the ranks")
+    ap.add_argument("--exchanges-per-step", type=int, default=1,
+                    help="strong scaling: a step's shard is trained in this many resident batches, the item side "
+                         "all-reduced after each")
+    ap.add_argument("--convergence-rows", type=int, default=20_000_000,
+                    help="N>1: rows of the planted-signal convergence leg (0 = skip it)")
     ap.add_argument("--e2e-chunk-rows", type=int, default=1 << 22, help="rows per launch of the ordered e2e call")
     args = ap.parse_args()
 
@@ -351,11 +439,20 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
+    strong = world > 1 and args.scaling == "strong"
     rows = args.rows_per_step
     nchunk = max(1, min(TOTAL_ROWS // rows, args.steps + args.warmup))
     total = rows * nchunk
+    global_rows = rows * (1 if strong else world)  # ratings all ranks train per step
     t_setup = time.perf_counter()
-    rp, lab, idx, val = gen_rows_torch(total, seed=10 + rank, device=dev, rank=rank, world=world)
+    if strong:
+        # the stated problem (480k users, rows-per-step ratings per step) split by user hash: every rank
+        # generates the same global stream and keeps the rows of its users; one resident chunk per rank
+        rp, lab, idx, val = gen_rows_torch(rows, seed=10, device=dev, rank=rank, world=world, shard=True)
+        rows, nchunk = int(lab.numel()), 1
+        total = rows
+    else:
+        rp, lab, idx, val = gen_rows_torch(total, seed=10 + rank, device=dev, rank=rank, world=world)
     # the C ABI takes host pointers: stage the stream in pinned host memory once
     host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (rp, lab, idx, val)]
     torch.cuda.synchronize()
@@ -388,39 +485,51 @@ def main():
 
         # ---- resident batches (value) ----
         t_b = time.perf_counter()
+        # a step = one chunk of `rows` ratings; with --exchanges-per-step E (strong scaling) the chunk is
+        # trained in E pieces and the item side is all-reduced after each
+        E = max(1, args.exchanges_per_step) if strong else 1
+        cuts = [[c * rows + (rows * e) // E for e in range(E + 1)] for c in range(nchunk)]
         if mode == "exact":  # the ordered mode trains whole resident batches (its plan is per batch)
             batches = []
             for c in range(nchunk):
-                sl = (h_rp[3 * c * rows:3 * (c + 1) * rows + 1] - int(h_rp[3 * c * rows])).contiguous().numpy()
-                batches.append(g.batch_create((sl, h_lab[c * rows:(c + 1) * rows].numpy(),
-                                               h_idx[2 * c * rows:2 * (c + 1) * rows].numpy(),
-                                               h_val[2 * c * rows:2 * (c + 1) * rows].numpy())))
+                for e in range(E):
+                    a, b = cuts[c][e], cuts[c][e + 1]
+                    sl = (h_rp[3 * a:3 * b + 1] - int(h_rp[3 * a])).contiguous().numpy()
+                    batches.append(g.batch_create((sl, h_lab[a:b].numpy(), h_idx[2 * a:2 * b].numpy(),
+                                                   h_val[2 * a:2 * b].numpy())))
 
-            def step(s):
-                g.batch_update(batches[s % nchunk])
+            def piece(s, e):
+                g.batch_update(batches[(s % nchunk) * E + e])
         else:
             batches = [g.batch_create((h_rp, h_lab, h_idx, h_val))]
 
-            def step(s):
+            def piece(s, e):
                 c = s % nchunk
-                g.batch_update(batches[0], c * rows, (c + 1) * rows)
+                g.batch_update(batches[0], cuts[c][e], cuts[c][e + 1])
+
+        def step(s):
+            for e in range(E):
+                piece(s, e)
+                if E > 1:
+                    exchange()
         g.sync()
         log("[rank %d] %s: %d rows resident in %d batch(es), %.2f s" % (rank, mode, total, len(batches), time.perf_counter() - t_b))
 
-        xchg = [None]
-
         def exchange():
             if use_allreduce:
-                xchg[0].sync()  # pack item-side deltas, ONE NCCL all-reduce, apply (svdfeature_b200/parallel.py)
+                # pack the item-side deltas, ONE ncclAllReduce on the launch stream, apply: all inside
+                # the library (svdgpu_allreduce_items, svdgpu_comm.cu)
+                g.allreduce_items(args.allreduce_scale if args.allreduce_scale > 0 else 1.0 / world)
 
         with torch.cuda.stream(stream):
             if use_allreduce:
-                from svdfeature_b200 import parallel
-
-                xchg[0] = parallel.ItemExchange(g, dist, dev, scale=1.0)
+                ids = [api.comm_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                g.comm_init(world, rank, ids[0])
+                exchange()  # (first call: snapshot of the replicated slabs)
             for s in range(warmup):
                 step(s)
-                if (s + 1) % args.allreduce_every == 0:
+                if E == 1 and (s + 1) % args.allreduce_every == 0:
                     exchange()
             g.sync()
             clocks = ClockSampler(local)
@@ -433,9 +542,10 @@ def main():
             l0, o0 = g.counter("kernel_launches"), g.counter("own_launches")
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
+            c0, b0 = g.counter("collectives"), g.counter("collective_bytes")
             for s in range(steps):
                 step(warmup + s)
-                if (s + 1) % args.allreduce_every == 0:
+                if E == 1 and (s + 1) % args.allreduce_every == 0:
                     exchange()
             ev1.record(stream)
             g.sync()
@@ -446,6 +556,8 @@ def main():
             ms = ev0.elapsed_time(ev1)
             res["launches"] = g.counter("kernel_launches") - l0
             res["own_launches"] = g.counter("own_launches") - o0
+            res["collectives"] = g.counter("collectives") - c0
+            res["collective_bytes"] = g.counter("collective_bytes") - b0
 
             # kernel-only duration of the training launches (roofline numerator), same stream
             kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -464,14 +576,15 @@ def main():
                 xe1.record(stream)
                 g.sync()
                 torch.cuda.synchronize()
+                res["exchange_ms"] = xe0.elapsed_time(xe1) / 5
                 log("[rank %d] %s kernel-only %.3f ms/step, exchange-only %.3f ms, timed loop %.3f ms/step"
-                    % (rank, mode, res["kms"], xe0.elapsed_time(xe1) / 5, ms / steps))
+                    % (rank, mode, res["kms"], res["exchange_ms"], ms / steps))
         if dist:
             tt = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         res["ms"] = ms
-        res["value"] = world * rows * steps / (ms * 1e-3)
+        res["value"] = global_rows * steps / (ms * 1e-3)
 
         # ---- the ordered mode's plan: what rebuilding it every step would cost ----
         if mode == "exact" and res["own_launches"] > 0:
@@ -484,7 +597,7 @@ def main():
             plan_ms = 1e3 * (time.perf_counter() - t0) / ksteps
             res["plan"] = {"ms_per_batch": plan_ms, "what": "device: shape/bound checks, item and user histograms, two radix sorts "
                            "(by user: tickets; by owner: queues), queue entries; host: LPT of the item counts",
-                           "value_with_plan_rebuilt_every_step": world * rows / ((ms / steps + plan_ms) * 1e-3)}
+                           "value_with_plan_rebuilt_every_step": global_rows / ((ms / steps + plan_ms * E) * 1e-3)}
 
         # ---- end to end through the C ABI with host buffers ----
         if want_e2e:
@@ -515,7 +628,7 @@ def main():
                     tt = torch.tensor([dt], device=dev, dtype=torch.float64)
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                     dt = float(tt.item())
-                return {"value": world * rows * steps / dt, "unit": "instances/s",
+                return {"value": global_rows * steps / dt, "unit": "instances/s",
                         "h2d_bytes_per_step": (g.counter("h2d_bytes") - h0) // steps,
                         "d2h_bytes_per_step": (g.counter("d2h_bytes") - d0) // steps}
 
@@ -560,6 +673,14 @@ def main():
             second = {"error": "%s: %s" % (type(e).__name__, e)}
     ms, kms, value, launches, clk, e2e = (main_res["ms"], main_res["kms"], main_res["value"], main_res["launches"],
                                           main_res["clocks"], main_res.get("e2e"))
+
+    # ---- N > 1: does the sharded run still learn what the single-GPU ordered run learns? ----
+    conv = None
+    if world > 1 and args.convergence_rows > 0:
+        try:
+            conv = convergence_leg(args, api, torch, dist, dev, stream, rank, world, local, W0)
+        except Exception as e:  # a diagnostic leg must not cost the run its line
+            conv = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if dist:
         dist.barrier()
@@ -612,7 +733,7 @@ def main():
     line = {
         "metric": "sgd_training_instances_per_sec", "value": value, "unit": "instances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg, "mode": ("ordered: bit-identical to the reference's sequential loop (k_own, item-owner warps)"
                                 if args.mode == "exact" else "hogwild: no ordering between the instances of a launch"),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
@@ -632,9 +753,25 @@ def main():
     if parity:
         line["parity"] = parity
     if world > 1:
-        line["config"]["parallelism"] = ("user-hash shards x%d (global problem %d users x %d items, %d ratings per step; "
-                                         "each rank owns %d users), item-side delta allreduce (NCCL) every %d step(s)"
-                                         % (world, NUM_USER * world, NUM_ITEM, rows * world, NUM_USER, args.allreduce_every))
+        if strong:
+            line["config"]["parallelism"] = (
+                "strong scaling: the stated problem (%d users x %d items, %d ratings per step) split by user id mod %d; "
+                "a step's shard is trained in %d piece(s), the item side all-reduced (NCCL, inside the library) after each"
+                % (NUM_USER, NUM_ITEM, global_rows, world, max(1, args.exchanges_per_step)))
+        else:
+            line["config"]["parallelism"] = (
+                "weak scaling: user-hash shards x%d (global problem %d users x %d items, %d ratings per step; each rank "
+                "owns %d users), item-side delta allreduce (NCCL, inside the library) every %d step(s)"
+                % (world, NUM_USER * world, NUM_ITEM, global_rows, NUM_USER, args.allreduce_every))
+        ncoll = max(1, main_res.get("collectives", 0))
+        line["exchange"] = {"collectives_per_step": main_res.get("collectives", 0) / args.steps,
+                            "message_bytes": main_res.get("collective_bytes", 0) // ncoll,
+                            "ms_per_exchange": main_res.get("exchange_ms"),
+                            "scale": args.allreduce_scale if args.allreduce_scale > 0 else 1.0 / world,
+                            "what": "delta = current - snapshot of W_item, i_bias, g_bias packed into one buffer, ONE ncclAllReduce(sum) "
+                                    "on the launch stream, current = snapshot + scale * sum (svdgpu_allreduce_items)"}
+        if conv is not None:
+            line["convergence"] = conv
     emit(line)
     if dist:
         dist.destroy_process_group()

@@ -277,6 +277,7 @@ int svdgpu_sync(svdgpu_t *h);
 int svdgpu_timer_start(svdgpu_t *h);
 int svdgpu_timer_stop(svdgpu_t *h, float *elapsed_ms);
 /* "kernel_launches", "instances", "h2d_bytes", "d2h_bytes", "num_sm", "lanes", "own_launches", "own_rows",
+ * "collectives", "collective_bytes" (NCCL all-reduces issued by the handle and the bytes they reduced),
  * "ingest_read_us", "ingest_call_us" (bulk ingest: time reading the file / inside the hot-path calls) */
 long long svdgpu_get_counter(const svdgpu_t *h, const char *name);
 /* Diagnostics of the last item-owner launch (option "own_stats" = 1 before it): per owner warp
@@ -295,6 +296,29 @@ int svdgpu_items_snapshot(svdgpu_t *h);
 int svdgpu_items_pack_delta(svdgpu_t *h, void **dev_ptr, size_t *num_floats);
 /* current = snapshot + scale * (reduced delta); then re-snapshot. */
 int svdgpu_items_apply_delta(svdgpu_t *h, float scale);
+
+
+/* ---- multi-GPU: the exchange itself (NCCL over NVLink, bound at run time) -------------------
+ * One handle per GPU -- one process per GPU, or several handles in one process.  The reference has
+ * no distributed code; these entry points serve its training loop (svd_feature.cpp:231-247) when
+ * it runs once per GPU on the rows of that GPU's users (user id mod world == rank).
+ *
+ * svdgpu_comm_id: rank 0 makes the 128-byte rendezvous id (ncclGetUniqueId) and hands it to the
+ * other ranks by any means (a file, MPI, torch.distributed); svdgpu_comm_init joins (collective). */
+int svdgpu_comm_id(char *id128);
+int svdgpu_comm_init(svdgpu_t *h, int world, int rank, const char *id128);
+int svdgpu_comm_destroy(svdgpu_t *h);
+int svdgpu_comm_rank(const svdgpu_t *h, int *world, int *rank);
+/* Exchange the replicated slabs: delta = current - snapshot, ONE ncclAllReduce(sum) on the launch
+ * stream, current = snapshot + scale * sum, re-snapshot (scale 1 keeps the whole step mass of all
+ * ranks, 1/world averages).  The first call only takes the snapshot.  Collective. */
+int svdgpu_allreduce_items(svdgpu_t *h, float scale);
+/* Complete the user side on every rank (before save_model / evaluation): rows of users other ranks
+ * own are zeroed and the user slab is summed in place.  Collective. */
+int svdgpu_allgather_users(svdgpu_t *h);
+/* Several handles of ONE process (hs[i] on its own device): the same exchange as one NCCL group;
+ * communicators are created on first use (ncclCommInitAll).   */
+int svdgpu_allreduce_items_group(svdgpu_t **hs, int n, float scale);
 
 #ifdef __cplusplus
 }

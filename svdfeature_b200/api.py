@@ -90,6 +90,13 @@ SVDGPU_SYMBOLS = {
     "svdgpu_items_snapshot": (C.c_int, [_vp]),
     "svdgpu_items_pack_delta": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "svdgpu_items_apply_delta": (C.c_int, [_vp, C.c_float]),
+    "svdgpu_comm_id": (C.c_int, [_vp]),
+    "svdgpu_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "svdgpu_comm_destroy": (C.c_int, [_vp]),
+    "svdgpu_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "svdgpu_allreduce_items": (C.c_int, [_vp, C.c_float]),
+    "svdgpu_allgather_users": (C.c_int, [_vp]),
+    "svdgpu_allreduce_items_group": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_float]),
 }
 
 _lib = None
@@ -416,6 +423,18 @@ class SvdGpu:
         self._ck(self.lib.svdgpu_items_pack_delta(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    # the exchange inside the library (NCCL)
+    def comm_init(self, world, rank, id_bytes):
+        """Join the communicator: id_bytes = the 128 bytes of comm_id() made on rank 0."""
+        buf = C.create_string_buffer(bytes(id_bytes), 128) if id_bytes is not None else None
+        self._ck(self.lib.svdgpu_comm_init(self.h, world, rank, buf))
+
+    def allreduce_items(self, scale=1.0):
+        self._ck(self.lib.svdgpu_allreduce_items(self.h, scale))
+
+    def allgather_users(self):
+        self._ck(self.lib.svdgpu_allgather_users(self.h))
+
     def items_apply_delta(self, scale=1.0):
         self._ck(self.lib.svdgpu_items_apply_delta(self.h, scale))
 
@@ -423,6 +442,15 @@ class SvdGpu:
 # ---------------------------------------------------------------------------
 # the C++ ISVDTrainer implementation behind the svdtr_* shim
 # ---------------------------------------------------------------------------
+def comm_id():
+    """The 128-byte NCCL rendezvous id (call on rank 0, hand the bytes to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.svdgpu_comm_id(buf) != 0:
+        raise SvdGpuError((lib.svdgpu_last_error(None) or b"").decode())
+    return buf.raw
+
+
 def load_trainer_library():
     global _tlib
     if _tlib is None:

@@ -40,7 +40,7 @@ def _sources(*names):
     return [os.path.join(CSRC, n) for n in names]
 
 
-GPU_UNITS = ["svdgpu_api.cu", "svdgpu_stream.cu", "svdgpu_mf.cu", "svdgpu_ordered.cu", "svdgpu_own.cu", "svdgpu_ingest.cu", "svdgpu_pairs.cu", "svdgpu_svdpp.cu",
+GPU_UNITS = ["svdgpu_api.cu", "svdgpu_stream.cu", "svdgpu_mf.cu", "svdgpu_ordered.cu", "svdgpu_own.cu", "svdgpu_comm.cu", "svdgpu_ingest.cu", "svdgpu_pairs.cu", "svdgpu_svdpp.cu",
              "svdgpu_rank.cu"]
 GPU_HEADERS = ["svdgpu_internal.h", "svdgpu_device.cuh", "svdgpu_fb.cuh", "svdgpu_scan.h", "svdgpu_ownplan.h"]
 
@@ -72,7 +72,7 @@ def build_gpu(force=False, verbose=False):
         if verbose:
             print("\n".join(logs))
     if procs or not os.path.exists(LIB_GPU):
-        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-o", LIB_GPU] + objs)
+        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-o", LIB_GPU] + objs + ["-ldl"])
     return LIB_GPU
 
 

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 namespace {
 
@@ -177,6 +178,14 @@ class GpuSVDFeature : public ISVDTrainer {
       else apex_utils::error("gpu:mode must be exact or hogwild");
     }
     if (!strcmp("gpu:batch", name)) batch_rows_ = atoi(val) > 0 ? atoi(val) : batch_rows_;
+    // multi-GPU: one process of the unchanged driver per GPU, every one reading the same input;
+    // a process trains the rows of its users (first user feature mod world == rank) and the item
+    // side is all-reduced over NCCL (svdgpu_comm.cu)
+    if (!strcmp("gpu:world", name)) world_ = atoi(val) > 0 ? atoi(val) : 1;
+    if (!strcmp("gpu:rank", name)) rank_ = atoi(val);
+    if (!strcmp("gpu:nccl_id", name)) nccl_id_file_ = val;
+    if (!strcmp("gpu:allreduce_rows", name)) xchg_rows_ = atoll(val) > 0 ? atoll(val) : xchg_rows_;
+    if (!strcmp("gpu:allreduce_scale", name)) xchg_scale_ = !strcmp(val, "mean") ? -1.0f : (float)atof(val);
     if (!strncmp("gpu:opt:", name, 8)) options_.push_back(std::make_pair(std::string(name + 8), atoll(val)));
     if (h_) {
       flush();  // rows staged so far were handed over under the old hyper-parameters (the reference applies them per row)
@@ -231,6 +240,10 @@ class GpuSVDFeature : public ISVDTrainer {
 
   virtual void save_model(FILE *fo) {  // model.h:638-660
     flush();
+    if (h_ && world_ > 1 && comm_on_) {  // every process saves at the same points of the driver's loop
+      exchange();
+      check(h_, svdgpu_allgather_users(h_));  // the file holds every user's rows, whoever trained them
+    }
     if (h_) check(h_, svdgpu_download_model(h_, ui_bias_.data(), W_.data(), (size_t)pitch_, g_bias_.data()));
     fwrite(&mp_, sizeof(ModelHeader), 1, fo);
     write_1d(&ui_bias_[ustart_], mp_.num_user, fo);
@@ -279,6 +292,7 @@ class GpuSVDFeature : public ISVDTrainer {
     load_side_features(0, name_feat_user_);  // base.h:152-153
     load_side_features(1, name_feat_item_);
     upload();
+    join_comm();
     init_end_ = 1;
   }
 
@@ -294,13 +308,18 @@ class GpuSVDFeature : public ISVDTrainer {
       if (h_) push_hparams();
     }
   }
-  virtual void finish_round(void) { flush(); }
+  virtual void finish_round(void) {
+    flush();
+    exchange();  // (every process finishes the round: the collective lines up)
+  }
 
   virtual void update(const SVDFeatureCSR::Elem &feature) {  // base.h:464-466
     apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
     if (svdpp_) apex_utils::error("GPU trainer: a user-grouped model takes SVDPlusBlock input");
-    rows_.push(feature);  // the Elem aliases the loader's buffer: copy now (apex_buffer_loader.h:212-226)
+    if (mine(feature))
+      rows_.push(feature);  // the Elem aliases the loader's buffer: copy now (apex_buffer_loader.h:212-226)
     if (rows_.num_row() >= batch_rows_) flush();
+    tick();
   }
   virtual float predict(const SVDFeatureCSR::Elem &feature) {  // base.h:467-469
     apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
@@ -317,9 +336,12 @@ class GpuSVDFeature : public ISVDTrainer {
   virtual void update(const SVDPlusBlock &data) {  // base.h:568-582
     apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
     if (!svdpp_) apex_utils::error("GPU trainer: a random-order model takes SVDFeatureCSR::Elem input");
-    push_block(data);
+    // (a user's blocks follow each other and carry the user in their rows: the whole unit goes to one process)
+    if (data.data.num_row == 0 || mine(data.data[0])) push_block(data);
     const bool closed = data.extend_tag == svdpp_tag::DEFAULT || data.extend_tag == svdpp_tag::END_TAG;
     if (closed && rows_.num_row() >= batch_rows_) flush();
+    if (closed) tick(data.data.num_row);
+    else seen_ += data.data.num_row;
   }
   virtual void predict(std::vector<float> &pred, const SVDPlusBlock &data) {  // base.h:583-591
     apex_utils::assert_true(init_end_ != 0, "predict before init_trainer");
@@ -348,6 +370,10 @@ class GpuSVDFeature : public ISVDTrainer {
     apex_utils::assert_true(init_end_ != 0, "update before init_trainer");
     if (svdpp_) apex_utils::error("GPU trainer: a user-grouped model takes SVDPlusBlock input");
     flush();
+    if (world_ > 1) {  // this process's share of the batch, through the staging path
+      for (int r = 0; r < c.num_row; ++r) update(c[r]);
+      return;
+    }
     check(h_, svdgpu_update_csr(h_, c.num_row, c.row_ptr, c.row_label, c.feat_index, c.feat_value));
   }
   void predict_batch(const SVDFeatureCSR &c, float *out) {
@@ -434,6 +460,58 @@ class GpuSVDFeature : public ISVDTrainer {
     fclose(fi);
     check(h_, svdgpu_set_side_features(h_, which, (int)rp.size() - 1, rp.data(), idx.data(), val.data()));
   }
+  // ---- multi-GPU (gpu:world > 1) ---------------------------------------------------------
+  bool mine(const SVDFeatureCSR::Elem &e) const {
+    if (world_ <= 1) return true;
+    const unsigned u = e.num_ufactor > 0 ? e.index_ufactor[0] : 0u;  // rows without a user feature: rank 0
+    return (int)(u % (unsigned)world_) == rank_;
+  }
+  // `n` more rows of the COMMON input stream have gone by: every process counts all of them, so
+  // the exchange points are the same everywhere whatever share of the rows a process keeps
+  void tick(long long n = 1) {
+    if (world_ <= 1) return;
+    const long long before = seen_ / xchg_rows_;
+    seen_ += n;
+    if (seen_ / xchg_rows_ != before) {
+      flush();
+      exchange();
+    }
+  }
+  void exchange() {
+    if (world_ <= 1 || !h_ || !comm_on_) return;
+    check(h_, svdgpu_allreduce_items(h_, xchg_scale_ < 0.0f ? 1.0f / (float)world_ : xchg_scale_));
+  }
+  // rank 0 makes the NCCL id and leaves it in the file gpu:nccl_id names; the others wait for it
+  void join_comm() {
+    if (world_ <= 1 || comm_on_) return;
+    apex_utils::assert_true(rank_ >= 0 && rank_ < world_, "gpu:rank must be in [0, gpu:world)");
+    apex_utils::assert_true(!nccl_id_file_.empty(), "gpu:world > 1 needs gpu:nccl_id=<file shared by the processes>");
+    char id[128];
+    if (rank_ == 0) {
+      check(h_, svdgpu_comm_id(id));
+      const std::string tmp = nccl_id_file_ + ".tmp";
+      FILE *fo = fopen(tmp.c_str(), "wb");
+      apex_utils::assert_true(fo != NULL, "can not write gpu:nccl_id file");
+      fwrite(id, 1, sizeof(id), fo);
+      fclose(fo);
+      apex_utils::assert_true(rename(tmp.c_str(), nccl_id_file_.c_str()) == 0, "can not publish gpu:nccl_id file");
+    } else {
+      bool got = false;
+      for (int t = 0; t < 6000 && !got; ++t) {  // up to 10 minutes
+        FILE *fi = fopen(nccl_id_file_.c_str(), "rb");
+        if (fi) {
+          got = fread(id, 1, sizeof(id), fi) == sizeof(id);
+          fclose(fi);
+        }
+        if (!got) usleep(100000);
+      }
+      apex_utils::assert_true(got, "gpu:nccl_id file did not appear");
+    }
+    check(h_, svdgpu_comm_init(h_, world_, rank_, id));
+    comm_on_ = true;
+    exchange();  // (first call: snapshot of the replicated slabs)
+  }
+
   void push_hparams() {
     hp_.base_score = mp_.base_score;
     hp_.user_nonnegative = mp_.user_nonnegative;
@@ -554,6 +632,12 @@ class GpuSVDFeature : public ISVDTrainer {
   std::vector<int> blk_row_off_, blk_fb_off_, blk_tag_;
   std::vector<unsigned> fb_index_;
   std::vector<float> fb_value_;
+  // multi-GPU
+  int world_ = 1, rank_ = 0;
+  bool comm_on_ = false;
+  std::string nccl_id_file_;
+  long long xchg_rows_ = 1 << 22, seen_ = 0;  // exchange every this many rows of the common stream
+  float xchg_scale_ = 1.0f;                   // < 0: mean over the processes
   // feedback list of the last DEFAULT / START block handed to predict (base.h:583-591)
   std::vector<unsigned> pred_fb_index_;
   std::vector<float> pred_fb_value_;

@@ -470,6 +470,7 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
 void svdgpu_destroy(svdgpu_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  svdgpu_comm_destroy(h);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->plan_stream) cudaStreamSynchronize(h->plan_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -699,6 +700,8 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
   if (!strcmp(name, "h2d_bytes")) return h->n_h2d;
   if (!strcmp(name, "d2h_bytes")) return h->n_d2h;
   if (!strcmp(name, "num_sm")) return h->num_sm;
+  if (!strcmp(name, "collectives")) return h->n_coll;  // NCCL all-reduces issued by svdgpu_allreduce_items / _allgather_users
+  if (!strcmp(name, "collective_bytes")) return h->n_coll_bytes;
   if (!strcmp(name, "own_launches")) return h->n_own;  // ordered mode: launches of the item-owner kernel
   if (!strcmp(name, "own_rows")) return h->n_own_rows;
   if (!strcmp(name, "ingest_read_us")) return (long long)(h->ingest_read_s * 1e6);  // file -> pinned chunk

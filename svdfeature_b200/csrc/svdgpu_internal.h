@@ -80,6 +80,7 @@ struct Geometry {
 }  // namespace svdk
 
 struct svdgpu_rank_state;  // svdgpu_rank.cu
+struct svdgpu_comm;        // svdgpu_comm.cu: NCCL communicator of a handle
 
 struct svdgpu {
   svdgpu_shape shape;
@@ -168,6 +169,8 @@ struct svdgpu {
   svdgpu_rank_state *rank = nullptr;
   int rank_force_sort = 0;  // option "rank_force_sort": top-k by the radix sort even for small top_k (testing)
   // multi-GPU exchange
+  svdgpu_comm *comm = nullptr;
+  long long n_coll = 0, n_coll_bytes = 0;  // NCCL collectives issued and the bytes they reduced
   svdk::DeltaPlan plan;
   float *d_snap = nullptr, *d_delta = nullptr;
   // host scratch for tickets

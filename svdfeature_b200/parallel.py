@@ -59,13 +59,24 @@ def exchange_deltas(delta, dist, scale=1.0):
 
 
 class ItemExchange:
-    """snapshot -> [train steps] -> sync() on an api.SvdGpu trainer."""
+    """snapshot -> [train steps] -> sync() on an api.SvdGpu trainer, with the all-reduce done by
+    torch.distributed (any backend).  The production path is the library's own exchange
+    (api.SvdGpu.comm_init / allreduce_items: NCCL on the trainer's launch stream, svdgpu_comm.cu);
+    this class remains for backends NCCL does not cover (the gloo tests).
+
+    pack and apply run on the trainer's launch stream, the all-reduce on torch's current stream: the
+    two are ordered here by synchronising each before the other continues."""
 
     def __init__(self, trainer, dist, device, scale=1.0):
         self.g, self.dist, self.device, self.scale = trainer, dist, device, scale
         self.g.items_snapshot()
 
     def sync(self):
+        import torch
+
         ptr, n = self.g.items_pack_delta()
+        self.g.sync()  # the packed buffer is complete before the collective reads it
         s = exchange_deltas(device_tensor(ptr, n, self.device), self.dist, self.scale)
+        if torch.device(self.device).type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()  # ... and reduced before it is applied
         self.g.items_apply_delta(s)

@@ -42,7 +42,7 @@ class _FakeGpu:
     """What bench.py calls on api.SvdGpu; predictions are the base score."""
 
     def __init__(self, *a, **k):
-        self.c = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0, "own_launches": 0}
+        self.c = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0, "own_launches": 0, "collectives": 0, "collective_bytes": 0}
         self.compact = 1
         self.mode = 1
 
