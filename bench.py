@@ -85,7 +85,7 @@ def gen_rows_torch(n, seed, device, rank=0, world=1, shard=False, planted=False)
     local index id // world, i.e. every rank trains the same per-GPU problem as the single-GPU run.
     shard=True (strong scaling): the GLOBAL stream of n rows is generated (same seed on every rank)
     and the rows of this rank's users (user id mod world == rank) are kept, global user ids.
-    planted=True: labels = 3.6 + <p_user, q_item> + N(0, 0.5): a rank-8 signal a model can learn, so
+    planted=True: labels = 3.6 + b_user + b_item + <p_user, q_item> + N(0, 0.5): biases and a rank-8 signal a model can learn, so
     that held-out RMSE says something (the BASELINE labels are noise independent of user and item)."""
     import torch
 
@@ -100,9 +100,11 @@ def gen_rows_torch(n, seed, device, rank=0, world=1, shard=False, planted=False)
     if planted:
         gp = torch.Generator(device=device)
         gp.manual_seed(4242)  # the planted factors do not depend on the stream's seed
-        P = torch.randn(NUM_USER, 8, generator=gp, device=device) * 0.6
-        Q = torch.randn(NUM_ITEM, 8, generator=gp, device=device) * 0.6
-        lab = (3.6 + (P[u] * Q[it]).sum(1) + 0.5 * torch.randn(n, generator=g, device=device)).float()
+        P = torch.randn(NUM_USER, 8, generator=gp, device=device) * 0.4
+        Q = torch.randn(NUM_ITEM, 8, generator=gp, device=device) * 0.4
+        bu = torch.randn(NUM_USER, generator=gp, device=device) * 0.6
+        bi = torch.randn(NUM_ITEM, generator=gp, device=device) * 0.6
+        lab = (3.6 + bu[u] + bi[it] + (P[u] * Q[it]).sum(1) + 0.5 * torch.randn(n, generator=g, device=device)).float()
     else:
         lab = torch.clamp(torch.round(3.6 + 1.1 * torch.randn(n, generator=g, device=device)), 1, 5).float()
     if shard and world > 1:
@@ -310,8 +312,8 @@ def workload_config(rows_per_step):
             "hparams": HP}
 
 
-def convergence_leg(args, api, torch, dist, dev, stream, rank, world, local, W0, epochs=3, heldout=1_000_000):
-    """Planted rank-8 signal (labels = 3.6 + <p_u, q_i> + N(0, 0.5)), `--convergence-rows` ratings split by
+def convergence_leg(args, api, torch, dist, dev, stream, rank, world, local, W0, epochs=5, heldout=1_000_000):
+    """Planted signal (labels = 3.6 + b_u + b_i + <p_u, q_i> + N(0, 0.5)), `--convergence-rows` ratings split by
     user hash over the ranks, ordered mode, item side all-reduced E times per epoch: held-out RMSE of the
     completed model (svdgpu_allgather_users) beside the single-GPU ordered run of the same stream on rank 0
     (= the reference's sequential loop) and the noise floor."""
@@ -332,7 +334,7 @@ def convergence_leg(args, api, torch, dist, dev, stream, rank, world, local, W0,
 
     test = to_np(gen_rows_torch(heldout, seed=777, device=dev, planted=True))
     out = {"rows": n, "epochs": epochs, "exchanges_per_epoch": E, "scale": scale, "noise_floor_rmse": 0.5,
-           "labels": "planted rank-8 signal + N(0, 0.5); held-out = %d fresh ratings" % heldout}
+           "labels": "planted user/item biases + rank-8 signal + N(0, 0.5), label std 1.08; held-out = %d fresh ratings" % heldout}
     # sharded run
     mine = to_np(gen_rows_torch(n, seed=99, device=dev, rank=rank, world=world, shard=True, planted=True))
     m = len(mine[1])

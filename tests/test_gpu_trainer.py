@@ -116,3 +116,25 @@ def test_split_user_predict_uses_the_start_blocks_feedback(native, bulk, tmp_pat
             t.finish_round()
     assert o.model_bytes(tmp_path) == g.model_bytes(tmp_path)
     assert np.array_equal(o.predict_ugroup(stripped), g.predict_ugroup(stripped))
+
+
+@pytest.mark.parametrize("mode", ["exact", "hogwild"])
+def test_ml100k_convergence_band(native, mode, tmp_path):
+    """demo/basicMF on MovieLens-100K through the ISVDTrainer seam, 40 rounds (SURVEY.md section 4 iii).
+    Ordered mode: the reference's test RMSE after every recorded round and its model file, bit for bit
+    (every round is one k_own launch).  Hogwild: the same curve to 5e-3."""
+    import _ml100k
+
+    train, test, truth, gold = _ml100k.load()
+    want = {int(k): v for k, v in gold["test_rmse_after_round"].items()}
+    g = native.GpuTrainer(0, 0, 0, dict(gold["params"], **{"gpu:mode": mode}))
+    curve, sha = _ml100k.run(g, train, test, truth, set(want), gold["seed"], tmp_path)
+    g.close()
+    if mode == "exact":
+        for r, v in want.items():
+            assert abs(curve[r] - v) < 1e-9, (r, curve[r], v)
+        assert sha == gold["model_sha256_after_round_40"]
+    else:
+        for r, v in want.items():
+            assert abs(curve[r] - v) < 5e-3, (r, curve[r], v)
+        assert curve[40] < curve[10] < curve[1] < curve[0]

@@ -114,3 +114,18 @@ def test_oracle_reproduces_reference_cli_run(tmp_path):
     assert hashlib.sha256(blob).hexdigest() == meta["sha256"]
     m = parse_model(blob)
     assert m["W_user"].shape == (943, 64) and m["W_item"].shape == (1682, 64)
+
+
+def test_oracle_reproduces_the_ml100k_convergence_curve(tmp_path):
+    """demo/basicMF on MovieLens-100K, 40 rounds, k = 64.  The plain-C oracle
+    lands on the compiled reference's test RMSE after every recorded round (0.9327 after round 40) and
+    on its model file, bit for bit."""
+    import _ml100k
+
+    train, test, truth, gold = _ml100k.load()
+    want = {int(k): v for k, v in gold["test_rmse_after_round"].items()}
+    curve, sha = _ml100k.run(COracle(0, 0, 0, gold["params"]), train, test, truth, set(want), gold["seed"], tmp_path)
+    assert abs(want[40] - 0.9327) < 1e-3 and want[0] > 1.2  # the band SURVEY quotes
+    for r, v in want.items():
+        assert abs(curve[r] - v) < 1e-9, (r, curve[r], v)
+    assert sha == gold["model_sha256_after_round_40"]
