@@ -29,10 +29,14 @@ k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch
              ISVDTrainer seam on the GPU in both modes: RMSE / max-abs of the predictions
              against the reference's own (ordered mode: 0.0; Hogwild: its measured distance)
 
-N>1 (torchrun): users are hash-partitioned (user mod N) so user rows are private to a
-rank; item rows/bias are replicated and their deltas are all-reduced over NCCL every
-step.  Weak scaling: the global problem is 480k*N users x 18k items with 100M*N ratings;
-every rank owns 480k users (local indices) and processes --rows-per-step rows per step.
+N>1 (torchrun): users are hash-partitioned (user id mod N), so user rows are private to a rank;
+item rows / biases are replicated and their deltas are all-reduced over NCCL inside the library
+(svdgpu_allreduce_items).  Default = STRONG scaling of the stated config: the 480k x 18k problem
+with 100M ratings per step is split over the ranks, a step's shard is trained in
+--exchanges-per-step pieces with one exchange after each (`scaling`: "strong").  --scaling weak:
+every rank trains its own 480k users / rows-per-step ratings (global problem N times larger).
+The `convergence` object (N>1) compares held-out RMSE on a planted-signal stream with the
+single-GPU ordered run.
 """
 import argparse
 import json
@@ -398,11 +402,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to svdgpu_set_option")
     ap.add_argument("--allreduce-every", type=int, default=1)
-    ap.add_argument("--allreduce-scale", type=float, default=1.0, help="factor on the summed deltas; 0 = mean (1/world)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+    ap.add_argument("--allreduce-scale", type=float, default=0.0,
+                    help="factor on the summed item-side deltas; 0 = mean (1/world), the default: it tracks the single-GPU "
+                         "run at any exchange frequency, the plain sum only when exchanges are frequent "
+                         "(profiles/r2_convergence_sweep.jsonl)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N>1: weak = every rank trains its own 480k users / rows-per-step ratings (the global problem "
                          "grows with N); strong = the stated config (480k users, rows-per-step ratings) split over the ranks")
-    ap.add_argument("--exchanges-per-step", type=int, default=1,
+    ap.add_argument("--exchanges-per-step", type=int, default=4,
                     help="strong scaling: a step's shard is trained in this many resident batches, the item side "
                          "all-reduced after each")
     ap.add_argument("--convergence-rows", type=int, default=20_000_000,

@@ -637,7 +637,8 @@ class GpuSVDFeature : public ISVDTrainer {
   bool comm_on_ = false;
   std::string nccl_id_file_;
   long long xchg_rows_ = 1 << 22, seen_ = 0;  // exchange every this many rows of the common stream
-  float xchg_scale_ = 1.0f;                   // < 0: mean over the processes
+  float xchg_scale_ = -1.0f;                  // < 0: mean over the processes (the default: tracks the sequential run at
+                                              // any exchange frequency, profiles/r2_convergence_sweep.jsonl)
   // feedback list of the last DEFAULT / START block handed to predict (base.h:583-591)
   std::vector<unsigned> pred_fb_index_;
   std::vector<float> pred_fb_value_;
