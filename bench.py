@@ -31,10 +31,10 @@ k=64, 100M synthetic ratings; one STEP = one pass of the hot path over one batch
 
 N>1 (torchrun): users are hash-partitioned (user id mod N), so user rows are private to a rank;
 item rows / biases are replicated and their deltas are all-reduced over NCCL inside the library
-(svdgpu_allreduce_items).  Default = STRONG scaling of the stated config: the 480k x 18k problem
-with 100M ratings per step is split over the ranks, a step's shard is trained in
---exchanges-per-step pieces with one exchange after each (`scaling`: "strong").  --scaling weak:
-every rank trains its own 480k users / rows-per-step ratings (global problem N times larger).
+(svdgpu_allreduce_items).  The headline is WEAK scaling (every rank trains its own 480k users /
+rows-per-step ratings per step; `scaling`: "weak"); the same line carries `strong_scaling`: the
+stated config (480k x 18k, 100M ratings per step) split over the ranks, a step's shard trained in
+--exchanges-per-step pieces with one exchange after each (--scaling strong makes it the headline).
 The `convergence` object (N>1) compares held-out RMSE on a planted-signal stream with the
 single-GPU ordered run.
 """
@@ -406,7 +406,8 @@ def main():
                     help="factor on the summed item-side deltas; 0 = mean (1/world), the default: it tracks the single-GPU "
                          "run at any exchange frequency, the plain sum only when exchanges are frequent "
                          "(profiles/r2_convergence_sweep.jsonl)")
-    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+    ap.add_argument("--no-strong", action="store_true", help="N>1, weak headline: skip the strong-scaling leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every rank trains its own 480k users / rows-per-step ratings (the global problem "
                          "grows with N); strong = the stated config (480k users, rows-per-step ratings) split over the ranks")
     ap.add_argument("--exchanges-per-step", type=int, default=4,
@@ -448,40 +449,49 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    strong = world > 1 and args.scaling == "strong"
-    rows = args.rows_per_step
-    nchunk = max(1, min(TOTAL_ROWS // rows, args.steps + args.warmup))
-    total = rows * nchunk
-    global_rows = rows * (1 if strong else world)  # ratings all ranks train per step
+    import types
+
+    def make_data(strong):
+        """The rating stream of this rank, staged in pinned host memory (the C ABI takes host pointers)."""
+        D = types.SimpleNamespace(strong=strong)
+        rows = args.rows_per_step
+        D.nchunk = max(1, min(TOTAL_ROWS // rows, args.steps + args.warmup))
+        D.global_rows = rows * (1 if strong else world)  # ratings all ranks train per step
+        if strong:
+            # the stated problem (480k users, rows-per-step ratings per step) split by user hash: every rank
+            # generates the same global stream and keeps the rows of its users; one resident chunk per rank
+            ts = gen_rows_torch(rows, seed=10, device=dev, rank=rank, world=world, shard=True)
+            D.rows, D.nchunk = int(ts[1].numel()), 1
+        else:
+            ts = gen_rows_torch(rows * D.nchunk, seed=10 + rank, device=dev, rank=rank, world=world)
+            D.rows = rows
+        D.total = D.rows * D.nchunk
+        D.h_rp, D.h_lab, D.h_idx, D.h_val = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in ts]
+        torch.cuda.synchronize()
+        del ts
+        torch.cuda.empty_cache()
+        probe_n, check_n = 1024, min(D.rows, 1_000_000)
+        D.probe = (D.h_rp[:3 * probe_n + 1].numpy(), D.h_lab[:probe_n].numpy(), D.h_idx.numpy(), D.h_val.numpy())
+        D.check = (D.h_rp[:3 * check_n + 1].numpy(), D.h_lab[:check_n].numpy(), D.h_idx.numpy(), D.h_val.numpy())
+        return D
+
     t_setup = time.perf_counter()
-    if strong:
-        # the stated problem (480k users, rows-per-step ratings per step) split by user hash: every rank
-        # generates the same global stream and keeps the rows of its users; one resident chunk per rank
-        rp, lab, idx, val = gen_rows_torch(rows, seed=10, device=dev, rank=rank, world=world, shard=True)
-        rows, nchunk = int(lab.numel()), 1
-        total = rows
-    else:
-        rp, lab, idx, val = gen_rows_torch(total, seed=10 + rank, device=dev, rank=rank, world=world)
-    # the C ABI takes host pointers: stage the stream in pinned host memory once
-    host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in (rp, lab, idx, val)]
-    torch.cuda.synchronize()
-    del rp, lab, idx, val
-    torch.cuda.empty_cache()
-    h_rp, h_lab, h_idx, h_val = host
+    main_strong = world > 1 and args.scaling == "strong"
+    data_main = make_data(main_strong)
+    rows, global_rows, strong = data_main.rows, data_main.global_rows, main_strong
+    h_idx = data_main.h_idx
 
     stream = torch.cuda.Stream(device=dev)
     rng = np.random.default_rng(10)
     rows_model = NUM_USER + NUM_ITEM
     W0 = (rng.standard_normal((rows_model, K)) * 0.01).astype(np.float32)  # N(0, 0.01^2) as rand_init
     use_allreduce = world > 1
-    probe_n = 1024
-    probe = (h_rp[:3 * probe_n + 1].numpy(), h_lab[:probe_n].numpy(), h_idx.numpy(), h_val.numpy())
-    check_n = min(rows, 1_000_000)  # rows of the post-run model check
-    check = (h_rp[:3 * check_n + 1].numpy(), h_lab[:check_n].numpy(), h_idx.numpy(), h_val.numpy())
 
-    def measure(mode, steps, warmup, want_e2e):
-        """One trainer in `mode` ("exact" = ordered, "hogwild"): resident `value`, kernel-only time,
-        e2e through host buffers, and the state of the model afterwards."""
+    def measure(D, mode, steps, warmup, want_e2e):
+        """One trainer in `mode` ("exact" = ordered, "hogwild") on the stream D: resident `value`,
+        kernel-only time, e2e through host buffers, and the state of the model afterwards."""
+        rows, nchunk, total, global_rows, strong = D.rows, D.nchunk, D.total, D.global_rows, D.strong
+        h_rp, h_lab, h_idx, h_val, probe, check = D.h_rp, D.h_lab, D.h_idx, D.h_val, D.probe, D.check
         g = api.SvdGpu(NUM_USER, NUM_ITEM, K, device=local)
         g.set_hparams(**HP)
         g.set_mode(api.MODE_HOGWILD if mode == "hogwild" else api.MODE_EXACT)
@@ -673,13 +683,21 @@ def main():
         g.close()
         return res
 
-    main_res = measure(args.mode, args.steps, args.warmup, not args.no_e2e)
+    main_res = measure(data_main, args.mode, args.steps, args.warmup, not args.no_e2e)
     second = None
     if args.mode == "exact" and not args.no_secondary:
         try:
-            second = measure("hogwild", max(1, min(args.steps, 10)), 3, not args.no_e2e and world == 1)
+            second = measure(data_main, "hogwild", max(1, min(args.steps, 10)), 3, not args.no_e2e and world == 1)
         except Exception as e:  # the secondary must not cost the run its line
             second = {"error": "%s: %s" % (type(e).__name__, e)}
+    # N > 1, weak headline: the stated config (fixed total problem) split over the ranks, same run
+    other = None
+    if world > 1 and not main_strong and not args.no_strong:
+        try:
+            del data_main.h_rp, data_main.h_lab, data_main.h_val
+            other = measure(make_data(True), args.mode, max(1, min(args.steps, 5)), 3, False)
+        except Exception as e:
+            other = {"error": "%s: %s" % (type(e).__name__, e)}
     ms, kms, value, launches, clk, e2e = (main_res["ms"], main_res["kms"], main_res["value"], main_res["launches"],
                                           main_res["clocks"], main_res.get("e2e"))
 
@@ -781,6 +799,18 @@ def main():
                                     "on the launch stream, current = snapshot + scale * sum (svdgpu_allreduce_items)"}
         if conv is not None:
             line["convergence"] = conv
+        if other is not None:
+            if "error" in other:
+                line["strong_scaling"] = other
+            else:
+                line["strong_scaling"] = {
+                    "what": "the stated config (480k users x 18k items, %d ratings per step) split by user id mod %d, a step's "
+                            "shard trained in %d pieces with the item side all-reduced after each; bounded by the chain of "
+                            "the heaviest USER (its ratings stay on one rank and hand the user row from owner to owner)"
+                            % (args.rows_per_step, world, max(1, args.exchanges_per_step)),
+                    "value": other["value"], "ms_per_step": other["ms"] / max(1, min(args.steps, 5)),
+                    "collectives_per_step": other.get("collectives", 0) / max(1, min(args.steps, 5)),
+                    "model_check": other.get("model_check")}
     emit(line)
     if dist:
         dist.destroy_process_group()

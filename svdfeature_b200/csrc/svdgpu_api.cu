@@ -812,7 +812,9 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     int hw = (int)std::thread::hardware_concurrency(), lw = 1;
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) lw = std::max(1, atoi(e));
     scan_threads = std::min(16, std::max(1, hw) / lw - 1);
-    if (scan_threads < 5) scan_threads = 0;
+    // (the ordered mode spends ~1 ns per row in its kernel: there even two threads keep ahead of it,
+    // and what they save is host memory bandwidth the ranks of one box share)
+    if (scan_threads < (exact ? 2 : 5)) scan_threads = 0;
   }
   const bool compact = h->compact_h2d && scan_threads > 0 && (!exact || own_ok) && !sides_on(h) && num_row >= h->compact_min_rows;
   svdscan::ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
