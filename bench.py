@@ -272,6 +272,33 @@ def parity_leg(yard, kind, device):
     return out
 
 
+def seam_leg(device, rows):
+    """SURVEY hard part 2: the reference's per-instance virtual call.  `rows` ratings are handed to the GPU
+    trainer one ISVDTrainer::update(Elem) at a time (what svd_feature.cpp:231-247 does; the trainer stages
+    gpu:batch rows and flushes them to svdgpu_update_csr), wall clock including the final flush."""
+    from svdfeature_b200 import api
+
+    data = gen_rows_numpy(rows, seed=11)
+    out = {"rows": rows, "what": "ISVDTrainer::update(const SVDFeatureCSR::Elem&) per rating through the C++ GpuSVDFeature "
+                                 "(gpu:batch = 2^20 rows staged per flush), one host thread"}
+    for mode in ("exact", "hogwild"):
+        params = dict(num_user=NUM_USER, num_item=NUM_ITEM, num_factor=K, **HP)
+        params["gpu:device"] = device
+        params["gpu:mode"] = mode
+        t = api.GpuTrainer(0, 0, 0, params, bulk=False)
+        t.init(10)
+        warm = 1 << 20
+        t.update_csr((data[0][:3 * warm + 1], data[1][:warm], data[2], data[3]))
+        t.finish_round()
+        t0 = time.perf_counter()
+        t.update_csr(data)
+        t.finish_round()
+        t.predict_csr((data[0][:4], data[1][:1], data[2], data[3]))  # (synchronises)
+        out["ordered" if mode == "exact" else mode] = rows / (time.perf_counter() - t0)
+        t.close()
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -399,6 +426,8 @@ def main():
     ap.add_argument("--parity-rows", type=int, default=2_000_000,
                     help="rows of the cpu_baseline sample that are also trained on the GPU and compared (N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seam-rows", type=int, default=10_000_000,
+                    help="N=1: ratings of the per-Elem seam leg (ISVDTrainer::update one rating at a time); 0 = skip")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to svdgpu_set_option")
     ap.add_argument("--allreduce-every", type=int, default=1)
@@ -756,6 +785,12 @@ def main():
                "sample": "first %d ratings of the same stream, ISVDTrainer::update loop, %.1f s, 1 thread of %d host cores"
                          % (args.cpu_rows, dt, os.cpu_count())}
 
+    seam = None
+    if world == 1 and args.seam_rows > 0:
+        try:
+            seam = seam_leg(local, args.seam_rows)
+        except Exception as e:  # a diagnostic leg must not cost the run its line
+            seam = {"error": "%s: %s" % (type(e).__name__, e)}
     cfg = workload_config(rows)
     line = {
         "metric": "sgd_training_instances_per_sec", "value": value, "unit": "instances/s", "n_gpus": world,
@@ -768,6 +803,8 @@ def main():
     }
     if "plan" in main_res:
         line["plan"] = main_res["plan"]
+    if seam is not None:
+        line["seam"] = seam
     if second is not None:
         if "error" in second:
             line["hogwild"] = second

@@ -118,6 +118,9 @@ class _FakeTrainer:
     def predict_csr(self, csr):
         return np.full(len(csr[1]), 3.6, np.float32)
 
+    def finish_round(self):
+        pass
+
     def close(self):
         pass
 
@@ -146,7 +149,7 @@ def test_bench_main_runs_against_stand_ins(monkeypatch, capfd):
     monkeypatch.setattr(bench, "TOTAL_ROWS", 40000)
     monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--rows-per-step", "20000",
-                                      "--cpu-rows", "30000", "--parity-rows", "5000"])
+                                      "--cpu-rows", "30000", "--parity-rows", "5000", "--seam-rows", "3000"])
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     capfd.readouterr()
@@ -166,6 +169,7 @@ def test_bench_main_runs_against_stand_ins(monkeypatch, capfd):
     assert d["model_check"]["finite"] is True and abs(d["model_check"]["rmse_vs_labels"] - 1.1) < 1e-6
     assert d["hogwild"]["value"] > 0 and d["hogwild"]["roofline"]["kernel"] == "k_mf"
     assert "mode" not in d["config"] and d["config"]["rows_per_step"] == 20000
+    assert d["seam"]["ordered"] > 0 and d["seam"]["hogwild"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 20000 * 12 and d["e2e"]["full_copy"]["h2d_bytes_per_step"] == 20000 * 32
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1

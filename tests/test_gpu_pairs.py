@@ -1,7 +1,13 @@
-"""GPU: pairwise-rank sample generation on the device against the semantics of
-PairwiseRankGenerator (apex_svd_data.cpp:812-1025).  The reference's rand() shuffles cannot be
-reproduced, so parity is structural: which rows may pair, how many pairs a block gets, that every
-negative is used once per cycle, and the merged feature lists (restated here in numpy)."""
+"""GPU: pairwise-rank sample generation on the device against PairwiseRankGenerator
+(apex_svd_data.cpp:812-1025).  The reference's rand() shuffles cannot be reproduced on a GPU, so
+parity has two parts:
+  * PINNED to the compiled reference (tests/golden/pairs_ref.npz, recorded from the unmodified
+    generator by tests/golden/make_pairs_golden.py): the number of rows every block yields under
+    every parameter set, and -- on blocks of one positive and one negative row, where rand() has no
+    say -- the emitted rows bit for bit (genpair, merge, dropped zero-valued user features, the label
+    rule, the pointwise variant, both sampling methods);
+  * structural, against the same semantics restated in numpy below: which rows may pair, that every
+    negative is used once per cycle, the merged feature lists of every emitted pair."""
 import numpy as np
 import pytest
 
@@ -204,3 +210,46 @@ def test_training_on_device_pairs_learns_the_ranking(native):
         pairs.close()
     after = auc()
     assert abs(before - 0.5) < 0.05 and after > 0.75, (before, after)
+
+
+PAIR_PARAMS = {  # name -> device sampler keywords (the reference's parameters: tests/golden/make_pairs_golden.py)
+    "default": {}, "num5": {"num": 5}, "num5_max3": {"num": 5, "maxn": 3}, "pointwise": {"num": 2, "pointwise": 1},
+    "bounds": {"pos_lowerb": 0.4, "neg_upperb": 0.2}, "cmp": {"method": 1}, "cmp_gap": {"method": 1, "gap": 0.6},
+    "cmp_pointwise": {"method": 1, "pointwise": 1},
+}
+
+
+def _golden_ug(z, pre):
+    return tuple(z["%s_%s" % (pre, n)] for n in ("bro", "bfo", "tag", "fi", "fv", "rp", "lab", "idx", "val"))
+
+
+@pytest.mark.parametrize("name", sorted(PAIR_PARAMS))
+def test_device_sampler_is_pinned_to_the_compiled_reference(native, name):
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pairs_ref.npz"))
+    g = native.SvdGpu(200, 200, 8, num_global=8, num_ufeedback=1, no_user_bias=1, active_type=3, format_type=1)
+    g.set_hparams(learning_rate=0.01, base_score=0.0)
+    g.set_mode(native.MODE_HOGWILD)
+    kw = PAIR_PARAMS[name]
+    # (1) rows per block on the general blocks: exactly the reference's
+    gen = _golden_ug(z, "general")
+    src = g.batch_create(gen[5:], ugroup=gen[:5])
+    for seed in (1, 2):
+        bro = g.batch_download(g.batch_sample_pairs(src, seed=seed, **kw))[0]
+        assert np.array_equal(np.diff(bro), z["cnt_" + name]), name
+    assert z["cnt_" + name].sum() > 250
+    src.close()
+    # (2) one positive + one negative per block: the reference's rows, bit for bit
+    duo = _golden_ug(z, "duo")
+    src = g.batch_create(duo[5:], ugroup=duo[:5])
+    bro, rp, lab, idx, val = g.batch_download(g.batch_sample_pairs(src, seed=3, **kw))
+    want = [z["duo_out_%s_%s" % (name, n)] for n in ("bro", "rp", "lab", "idx", "val")]
+    assert np.array_equal(bro, want[0])
+    assert np.array_equal(rp, want[1])
+    assert np.array_equal(lab, want[2])
+    assert np.array_equal(idx, want[3])
+    assert np.array_equal(val.view(np.uint32), want[4].view(np.uint32))  # the merged values, to the bit
+    assert len(lab) >= 120
+    src.close()
+    g.close()
