@@ -19,6 +19,7 @@
 
 #include "svdgpu.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -71,31 +72,56 @@ void check(svdgpu_t *h, int rc) {
   if (rc != 0) apex_utils::error(svdgpu_last_error(h));
 }
 
-// growable SoA staging for the per-row / per-block API
+// growable SoA staging for the per-row / per-block API.  push() is the per-instance cost of the
+// reference's calling convention (one virtual update(Elem) per rating, svd_feature.cpp:231-247): the
+// arrays grow geometrically and a row is appended with plain stores (no per-segment vector::insert).
 struct CsrStage {
   std::vector<int> row_ptr;
   std::vector<float> label;
   std::vector<unsigned> index;
   std::vector<float> value;
-  CsrStage() { row_ptr.push_back(0); }
+  size_t nrow_ = 0, nval_ = 0;  // used prefixes of the arrays (their size() is the capacity in use + slack)
+  CsrStage() { row_ptr.assign(1, 0); }
   void clear() {
-    row_ptr.assign(1, 0);
+    nrow_ = nval_ = 0;
+    row_ptr.resize(1);
+    row_ptr[0] = 0;
     label.clear();
     index.clear();
     value.clear();
   }
-  int num_row() const { return (int)label.size(); }
+  int num_row() const { return (int)nrow_; }
+  void reserve_rows(size_t rows, size_t vals_per_row) {
+    row_ptr.reserve(3 * rows + 1);
+    label.reserve(rows);
+    index.reserve(rows * vals_per_row);
+    value.reserve(rows * vals_per_row);
+  }
   void push(const apex_svd::SVDFeatureCSR::Elem &e) {
-    label.push_back(e.label);
-    index.insert(index.end(), e.index_global, e.index_global + e.num_global);
-    value.insert(value.end(), e.value_global, e.value_global + e.num_global);
-    row_ptr.push_back((int)index.size());
-    index.insert(index.end(), e.index_ufactor, e.index_ufactor + e.num_ufactor);
-    value.insert(value.end(), e.value_ufactor, e.value_ufactor + e.num_ufactor);
-    row_ptr.push_back((int)index.size());
-    index.insert(index.end(), e.index_ifactor, e.index_ifactor + e.num_ifactor);
-    value.insert(value.end(), e.value_ifactor, e.value_ifactor + e.num_ifactor);
-    row_ptr.push_back((int)index.size());
+    const size_t n = (size_t)e.num_global + (size_t)e.num_ufactor + (size_t)e.num_ifactor;
+    if (label.size() < nrow_ + 1) {
+      const size_t cap = std::max<size_t>(1024, 2 * (nrow_ + 1));
+      label.resize(cap);
+      row_ptr.resize(3 * cap + 1);
+    }
+    if (index.size() < nval_ + n) {
+      const size_t cap = std::max<size_t>(4096, 2 * (nval_ + n));
+      index.resize(cap);
+      value.resize(cap);
+    }
+    label[nrow_] = e.label;
+    unsigned *ix = index.data() + nval_;
+    float *vl = value.data() + nval_;
+    int *rp = row_ptr.data() + 3 * nrow_;  // rp[0] is this row's first position, already set
+    size_t k = 0;
+    for (int i = 0; i < e.num_global; ++i, ++k) ix[k] = e.index_global[i], vl[k] = e.value_global[i];
+    rp[1] = (int)(nval_ + k);
+    for (int i = 0; i < e.num_ufactor; ++i, ++k) ix[k] = e.index_ufactor[i], vl[k] = e.value_ufactor[i];
+    rp[2] = (int)(nval_ + k);
+    for (int i = 0; i < e.num_ifactor; ++i, ++k) ix[k] = e.index_ifactor[i], vl[k] = e.value_ifactor[i];
+    rp[3] = (int)(nval_ + k);
+    nval_ += n;
+    nrow_ += 1;
   }
 };
 
@@ -535,11 +561,14 @@ class GpuSVDFeature : public ISVDTrainer {
   void keep_open_run(int nb) {
     const int r0 = blk_row_off_[(size_t)nb], f0 = blk_fb_off_[(size_t)nb], v0 = rows_.row_ptr[3 * (size_t)r0];
     CsrStage rest;
-    rest.label.assign(rows_.label.begin() + r0, rows_.label.end());
-    rest.index.assign(rows_.index.begin() + v0, rows_.index.end());
-    rest.value.assign(rows_.value.begin() + v0, rows_.value.end());
+    const size_t nr = rows_.nrow_, nv = rows_.nval_;
+    rest.label.assign(rows_.label.begin() + r0, rows_.label.begin() + nr);
+    rest.index.assign(rows_.index.begin() + v0, rows_.index.begin() + nv);
+    rest.value.assign(rows_.value.begin() + v0, rows_.value.begin() + nv);
     rest.row_ptr.clear();
-    for (size_t i = 3 * (size_t)r0; i < rows_.row_ptr.size(); ++i) rest.row_ptr.push_back(rows_.row_ptr[i] - v0);
+    for (size_t i = 3 * (size_t)r0; i <= 3 * nr; ++i) rest.row_ptr.push_back(rows_.row_ptr[i] - v0);
+    rest.nrow_ = nr - (size_t)r0;
+    rest.nval_ = nv - (size_t)v0;
     rows_ = rest;
     std::vector<int> bro(1, 0), bfo(1, 0);
     for (size_t b = (size_t)nb + 1; b < blk_row_off_.size(); ++b) {
