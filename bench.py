@@ -426,6 +426,8 @@ def main():
     ap.add_argument("--parity-rows", type=int, default=2_000_000,
                     help="rows of the cpu_baseline sample that are also trained on the GPU and compared (N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="N=1: skip the kernel-resident runs of configs[2..4] (SVD++ blocks, pairwise rows, neighbourhood rows)")
     ap.add_argument("--seam-rows", type=int, default=10_000_000,
                     help="N=1: ratings of the per-Elem seam leg (ISVDTrainer::update one rating at a time); 0 = skip")
     ap.add_argument("--no-e2e", action="store_true")
@@ -773,6 +775,18 @@ def main():
         return r
 
     roofline = roof(kms, args.mode)
+    # the L2 read rate (a 48 MB buffer streamed 40 times): the second roofline of the Hogwild gather kernel, whose
+    # 128 MB model is almost L2-resident (DRAM moves 157 of the 1072 algorithmic bytes per instance)
+    l2_peak = None
+    try:
+        gp = api.SvdGpu(16, 16, 4, device=local)
+        l2_peak = {"read_gbs": gp.microbench(0, 48 << 20, 40), "copy_gbs": gp.microbench(1, 24 << 20, 40),
+                   "hbm_read_gbs": gp.microbench(0, 4 << 30, 2),
+                   "how": "svdgpu_microbench: 16-byte ld.global.cg over 48 MB x 40 passes (L2-resident), copy of 24 MB "
+                          "(read+write), and the same read over 4 GB (HBM)"}
+        gp.close()
+    except Exception as e:
+        l2_peak = {"error": "%s: %s" % (type(e).__name__, e)}
     cpu = parity = None
     if not args.no_cpu_baseline:
         v, kind, dt, yard = time_cpu(args.cpu_rows, 1_000_000, 0 if world > 1 else args.parity_rows)
@@ -791,6 +805,24 @@ def main():
             seam = seam_leg(local, args.seam_rows)
         except Exception as e:  # a diagnostic leg must not cost the run its line
             seam = {"error": "%s: %s" % (type(e).__name__, e)}
+    # the other single-GPU BASELINE configs, kernel-resident, scaled down (tools/bench_configs.py)
+    others = None
+    if world == 1 and not args.no_other_configs:
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_configs.py"), "c3", "c4", "c5", "--scale", "0.25"],
+                               capture_output=True, text=True, timeout=240)
+            others = []
+            for l in p.stdout.splitlines():
+                if l.startswith("{"):
+                    d = json.loads(l)
+                    others.append({"config": d.get("config"), "mode": "hogwild", "rows": d.get("rows", d.get("pairs")),
+                                   "value": 1e6 * d["ginst_s"], "unit": "instances/s",
+                                   "algorithmic_gbs": d.get("algorithmic_gbs"), "bytes_per_row": d.get("bytes_per_row"),
+                                   "frac_of_hbm_peak": (d.get("algorithmic_gbs") or 0.0) / peak})
+            if p.returncode != 0 and not others:
+                others = {"error": p.stderr[-300:]}
+        except Exception as e:  # a side measurement must not cost the run its line
+            others = {"error": "%s: %s" % (type(e).__name__, e)}
     cfg = workload_config(rows)
     line = {
         "metric": "sgd_training_instances_per_sec", "value": value, "unit": "instances/s", "n_gpus": world,
@@ -805,6 +837,8 @@ def main():
         line["plan"] = main_res["plan"]
     if seam is not None:
         line["seam"] = seam
+    if others is not None:
+        line["other_configs"] = others
     if second is not None:
         if "error" in second:
             line["hogwild"] = second
@@ -812,7 +846,9 @@ def main():
             line["hogwild"] = {"what": "secondary: the throughput mode on the same workload; NOT within the north star's 1e-4 "
                                        "of the sequential order (see parity.hogwild)",
                                "value": second["value"], "ms_per_step": second["ms"] / max(1, min(args.steps, 10)),
-                               "e2e": second.get("e2e"), "roofline": roof(second["kms"], "hogwild"),
+                               "e2e": second.get("e2e"), "roofline": dict(roof(second["kms"], "hogwild"), **(
+                                   {"l2_peak": l2_peak, "l2_frac": roof(second["kms"], "hogwild")["achieved"] / l2_peak["read_gbs"]}
+                                   if l2_peak and "read_gbs" in l2_peak else {"l2_peak": l2_peak})),
                                "gpu_launches": int(second["launches"]), "model_check": second.get("model_check")}
     if parity:
         line["parity"] = parity

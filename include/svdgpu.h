@@ -284,6 +284,10 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name);
  * {cycles in its queue loop, cycles waiting for a ring slot, cycles in publish fences, number of
  * waits}; out holds 4 * cap_owners values, *num_owner receives the owner count. */
 int svdgpu_own_stats(svdgpu_t *h, long long *out, int cap_owners, int *num_owner);
+/* Bandwidth probe on this handle's device and stream: which = 0 streams `bytes` of device memory
+ * `iters` times with 16-byte loads, 1 copies it (read + write counted).  A buffer that fits L2
+ * (<= 64 MB) measures the L2 rate the gather kernels live on, a multi-GB one the HBM rate. */
+int svdgpu_microbench(svdgpu_t *h, int which, size_t bytes, int iters, double *gbytes_per_s);
 /* device pointers of the model slabs (for peer / collective plumbing): 0 ui_bias,
  * 1 W_uiset, 2 g_bias; *pitch_floats receives the device row stride */
 void *svdgpu_device_ptr(svdgpu_t *h, int which, size_t *pitch_floats);

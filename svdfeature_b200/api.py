@@ -86,6 +86,7 @@ SVDGPU_SYMBOLS = {
     "svdgpu_timer_stop": (C.c_int, [_vp, _f32p]),
     "svdgpu_get_counter": (C.c_longlong, [_vp, C.c_char_p]),
     "svdgpu_own_stats": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "svdgpu_microbench": (C.c_int, [_vp, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "svdgpu_device_ptr": (_vp, [_vp, C.c_int, C.POINTER(C.c_size_t)]),
     "svdgpu_items_snapshot": (C.c_int, [_vp]),
     "svdgpu_items_pack_delta": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
@@ -408,6 +409,12 @@ class SvdGpu:
         out = np.zeros((n.value, 4), np.int64)
         self._ck(self.lib.svdgpu_own_stats(self.h, out.ctypes.data, n.value, C.byref(n)))
         return out
+
+    def microbench(self, which, nbytes, iters):
+        """GB/s of a streaming read (which=0) or copy (1) over `nbytes` of device memory, `iters` passes."""
+        out = C.c_double()
+        self._ck(self.lib.svdgpu_microbench(self.h, which, nbytes, iters, C.byref(out)))
+        return out.value
 
     def device_ptr(self, which):
         pitch = C.c_size_t()

@@ -56,6 +56,25 @@ __global__ void k_sse(const float *__restrict__ pred, const float *__restrict__ 
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(acc + 1, (double)n);
 }
 
+// L2 / HBM bandwidth probes (svdgpu_microbench): every thread streams float4s of a buffer `iters`
+// times; a buffer that fits the 126 MB L2 measures the L2 read rate the gather kernels live on
+// (the 128 MB model of configs[1] is almost L2-resident), a larger one the HBM read rate.
+__global__ void k_probe_read(const float4 *__restrict__ p, long long n4, int iters, float *sink) {
+  float acc = 0.0f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; ++it)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = __ldcg(p + i);
+      acc += v.x + v.y + v.z + v.w;
+    }
+  if (acc == 12345.678f) *sink = acc;  // (keeps the loads alive)
+}
+__global__ void k_probe_copy(const float4 *__restrict__ src, float4 *__restrict__ dst, long long n4, int iters) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; ++it)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) __stcg(dst + i, __ldcg(src + i));
+}
+
 namespace {
 
 // squared-error accumulation of one predicted chunk (only while an svdgpu_eval_* call is active)
@@ -723,6 +742,37 @@ int svdgpu_own_stats(svdgpu_t *h, long long *out, int cap_owners, int *num_owner
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaMemcpy(out, h->own.stats.p, (size_t)W * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   }
+  return 0;
+}
+
+int svdgpu_microbench(svdgpu_t *h, int which, size_t bytes, int iters, double *gbytes_per_s) {
+  if (!h || !gbytes_per_s) return 1;
+  if (which != 0 && which != 1) return fail(h, "microbench: which must be 0 (read) or 1 (copy)");
+  if (bytes < 1024 || iters < 1) return fail(h, "microbench: bad size");
+  CU(h, cudaSetDevice(h->device));
+  const long long n4 = (long long)(bytes / 16);
+  float4 *a = nullptr, *b = nullptr;
+  float *sink = nullptr;
+  CU(h, cudaMalloc(&a, (size_t)n4 * 16));
+  CU(h, cudaMalloc(&sink, 4));
+  if (which == 1) CU(h, cudaMalloc(&b, (size_t)n4 * 16));
+  CU(h, cudaMemsetAsync(a, 0, (size_t)n4 * 16, h->stream));
+  const int grid = h->num_sm * 8, block = 512;
+  for (int rep = 0; rep < 2; ++rep) {  // the first pass warms L2 and the clocks
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    if (which == 0) k_probe_read<<<grid, block, 0, h->stream>>>(a, n4, iters, sink);
+    else k_probe_copy<<<grid, block, 0, h->stream>>>(a, b, n4, iters);
+    CU(h, cudaGetLastError());
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    CU(h, cudaEventSynchronize(h->ev1));
+  }
+  float ms = 0.0f;
+  CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->n_launch += 2;
+  *gbytes_per_s = (double)n4 * 16.0 * iters * (which == 1 ? 2.0 : 1.0) / (ms * 1e-3) / 1e9;
+  cudaFree(a);
+  cudaFree(b);
+  cudaFree(sink);
   return 0;
 }
 

@@ -77,6 +77,9 @@ class _FakeGpu:
         n = len(csr[1])
         return 1.21 * n, n
 
+    def microbench(self, which, nbytes, iters):
+        return 20000.0
+
     def download(self):
         return np.zeros(4, np.float32), np.zeros((4, 2), np.float32), np.zeros(1, np.float32)
 
@@ -149,7 +152,8 @@ def test_bench_main_runs_against_stand_ins(monkeypatch, capfd):
     monkeypatch.setattr(bench, "TOTAL_ROWS", 40000)
     monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--rows-per-step", "20000",
-                                      "--cpu-rows", "30000", "--parity-rows", "5000", "--seam-rows", "3000"])
+                                      "--cpu-rows", "30000", "--parity-rows", "5000", "--seam-rows", "3000",
+                                      "--no-other-configs"])
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     capfd.readouterr()
