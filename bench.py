@@ -816,7 +816,7 @@ def main():
                 if l.startswith("{"):
                     d = json.loads(l)
                     others.append({"config": d.get("config"), "mode": "hogwild", "rows": d.get("rows", d.get("pairs")),
-                                   "value": 1e6 * d["ginst_s"], "unit": "instances/s",
+                                   "value": 1e9 * d["ginst_s"], "unit": "instances/s",
                                    "algorithmic_gbs": d.get("algorithmic_gbs"), "bytes_per_row": d.get("bytes_per_row"),
                                    "frac_of_hbm_peak": (d.get("algorithmic_gbs") or 0.0) / peak})
             if p.returncode != 0 and not others:
