@@ -580,6 +580,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_urgent_gap")) h->own_urgent_gap = (int)std::max<long long>(0, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_batch")) h->own_batch = (int)std::max<long long>(1, std::min<long long>(v, 32));
   else if (!strcmp(name, "own_stats")) h->own_stats = v ? 1 : 0;
+  else if (!strcmp(name, "own_partner")) h->own_partner = v ? 1 : 0;
   else if (!strcmp(name, "own_poll_ns")) h->own_poll_ns = (int)std::max<long long>(0, std::min<long long>(v, 100000));
   else if (!strcmp(name, "own_spare_sms")) h->own_spare_sms = (int)std::max<long long>(0, std::min<long long>(v, 64));
   else if (!strcmp(name, "own_depth")) h->own_depth = v >= 16 ? 16 : 8;
@@ -735,7 +736,7 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
 int svdgpu_own_stats(svdgpu_t *h, long long *out, int cap_owners, int *num_owner) {
   if (!h || !num_owner) return 1;
   CU(h, cudaSetDevice(h->device));
-  const int W = h->num_sm * svdk::own_owners_per_cta();
+  const int W = h->own.stats_owners;
   *num_owner = W;
   if (!h->own.stats.p) return fail(h, "own_stats: set option own_stats before the ordered launch");
   if (out && cap_owners >= W) {

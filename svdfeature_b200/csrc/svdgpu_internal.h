@@ -28,11 +28,13 @@ struct OwnPlan {
   DevBuf entries, queue_off, item_off, items, batch;
   HostBuf stage;  // pinned source of the small host-made arrays
   int num_owner = 0;
+  int per_cta = 0;  // owners per CTA the plan was dealt for (12: k_own, 8: k_own2)
   long long rows = 0, max_load = 0;
   bool valid = false;
 };
 struct OwnScratch {
   DevBuf cnt_item, cnt_user, start_user, flag, keyA, keyB, valA, valB, key_item, tick, tmp, item_owner, item_slot, stats;
+  int stats_owners = 0;   // owners of the launch the stats buffer describes
   void *h_cnt = nullptr;  // pinned: item counts + flag word
   size_t h_cnt_cap = 0;
   cudaEvent_t ev = nullptr;
@@ -147,6 +149,7 @@ struct svdgpu {
   int own_spare_sms = 16;    // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
                              // fills of the next chunk (k_own then runs on num_sm - this many CTAs)
   int own_poll_ns = 50;      // option "own_poll_ns": loader warps sleep this long between polls without progress
+  int own_partner = 1;       // option "own_partner": split link (k_own2: owner + partner warp) where the shape allows
   int own_stats = 0;         // option "own_stats": k_own records per-owner cycle counters (svdgpu_own_stats)
   OwnScratch own;
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
@@ -222,7 +225,7 @@ int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, b
 int launch_exact(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1);
 // ordered mode with item-owner warps (svdgpu_own.cu)
 bool own_supported(const svdgpu *h);
-int own_owners_per_cta();
+int own_owners_per_cta(const svdgpu *h);
 // ctas: CTAs (= SMs) the launch will occupy, 12 owners each; 0 = every SM
 int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cudaStream_t st, int *bad, int ctas = 0);
 int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st);

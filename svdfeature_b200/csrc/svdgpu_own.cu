@@ -146,6 +146,7 @@ struct OwnArgs {
   int S;                  // item rows an owner keeps in shared memory (the rest stay in L2)
   unsigned region_bytes;  // shared memory per owner
   unsigned off_items, off_ibias, off_dot, off_bars;
+  unsigned off_hand;      // k_own2: the owner -> partner hand-off slots
   int *err_flag;
   unsigned *abort_flag;
   long long *stats;  // option "own_stats": per owner {cycles, cycles waiting for a slot, cycles in flushes, waits} or null
@@ -284,31 +285,18 @@ __device__ __forceinline__ void own_step(const Group<32, VEC> &g, const DevModel
   ib = __fmul_rn(__fadd_rn(ib, si), hp.dib);
 }
 
-// CH > 0: rows of exactly CH chunks, linear loss (fast link); CH = 0: any row width up to
-// 32*VEC chunks, any loss.  D = ring slots per owner (a power of two).
-template <int CH, int VEC, int D>
-__global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
-  extern __shared__ __align__(128) unsigned char own_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Loader lane (c, s) of a CTA with C owners: feeds ring slot s of owner c.  `t` = index of the thread
+// among the CTA's loader threads.
+template <int D>
+__device__ __forceinline__ void own_loader(const OwnArgs &a, unsigned char *own_smem, int t, int C) {
   const DevModel &m = a.m;
   const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
-  const int S = a.S;
-  // every owner's barriers: full[D] then empty[D], one arrival each
-  if (warp < OWN_C) {
-    uint64_t *bars = reinterpret_cast<uint64_t *>(own_smem + (size_t)warp * a.region_bytes + a.off_bars);
-    for (int i = lane; i < 2 * D; i += 32) mbar_init(bars + i, 1);
-  }
-  mbar_fence_init();
-  __syncthreads();
   unsigned *const ver = m.ver_ui + m.user_off;
-
-  if (warp >= OWN_C) {
     // =========================== loader lane: ring slot s of owner c ===========================
     // Per iteration ONE round trip to L2 for the whole warp: the poll of the version the current
     // entry waits for and the fetch of the entry after it are issued together, consumed together.
-    const int t = (int)threadIdx.x - OWN_C * 32;
     const int c = t / D, s = t % D;
-    const int w = ((a.flags & OWN_F_REVERSE) ? OWN_C - 1 - c : c) * (int)gridDim.x + (int)blockIdx.x;
+    const int w = ((a.flags & OWN_F_REVERSE) ? C - 1 - c : c) * (int)gridDim.x + (int)blockIdx.x;
     unsigned char *reg = own_smem + (size_t)c * a.region_bytes;
     unsigned char *slot = reg + (size_t)s * slot_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(reg + a.off_bars) + s;
@@ -374,6 +362,28 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       }
       if ((it & 63u) == 63u && ld_relaxed_u32(a.abort_flag)) break;
     }
+}
+
+// CH > 0: rows of exactly CH chunks, linear loss (fast link); CH = 0: any row width up to
+// 32*VEC chunks, any loss.  D = ring slots per owner (a power of two).
+template <int CH, int VEC, int D>
+__global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
+  extern __shared__ __align__(128) unsigned char own_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DevModel &m = a.m;
+  const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
+  const int S = a.S;
+  // every owner's barriers: full[D] then empty[D], one arrival each
+  if (warp < OWN_C) {
+    uint64_t *bars = reinterpret_cast<uint64_t *>(own_smem + (size_t)warp * a.region_bytes + a.off_bars);
+    for (int i = lane; i < 2 * D; i += 32) mbar_init(bars + i, 1);
+  }
+  mbar_fence_init();
+  __syncthreads();
+  unsigned *const ver = m.ver_ui + m.user_off;
+
+  if (warp >= OWN_C) {
+    own_loader<D>(a, own_smem, (int)threadIdx.x - OWN_C * 32, OWN_C);
     return;
   }
 
@@ -693,6 +703,294 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// k_own2 -- the same scheme with the link split over TWO warps (rows of CH chunks, linear loss).
+//
+// What makes the launch long is the chain of one item's updates, and only half of a link is on
+// that chain: the dot, the error and the new ITEM row.  The new USER row, its stores and the
+// publish fences are not -- nothing of the next link needs them.  Here the owner warp does the
+// first half and hands {ti = the item row the user row needs, lr*err} to its PARTNER warp through a
+// small shared-memory ring; the partner reads the user row and the entry out of the same ring
+// slot the owner used, forms and stores the new user row and bias, and publishes versions: in
+// batches while it is behind the owner, at once whenever it has caught up (it would block
+// anyway) -- so a user row is published as soon as there is nothing better to do, and no "returns
+// soon" flag is needed.  The ring slot is released by the partner, the last one to read it.
+// 8 owners + 8 partners + 2 loader warps per CTA.
+// ---------------------------------------------------------------------------
+constexpr int OWN2_C = 8;   // owners per CTA
+constexpr int OWN2_H = 4;   // hand-off slots per owner
+constexpr int own2_threads(int D) { return (2 * OWN2_C + OWN2_C * D / 32) * 32; }
+
+template <int CH, int D>
+__global__ void __launch_bounds__(own2_threads(D), 1) k_own2(const OwnArgs a) {
+  extern __shared__ __align__(128) unsigned char own_smem[];
+  constexpr int C = OWN2_C, H = OWN2_H;
+  constexpr int LOG_D = D == 16 ? 4 : 3;
+  constexpr unsigned ROW = CH * 16u, SLOT = ROW + OWN_SLOT_EXTRA, DOTROW = 36u * 4u, DOTBUF = 4u * DOTROW;
+  constexpr unsigned HSLOT = 32u * 16u + 16u;  // every lane's float4 (lanes >= CH: never read) + {lr*err}
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DevModel &m = a.m;
+  const int S = a.S;
+  // barriers of an owner: full[D], empty[D] (ring; one arrival each), hfull[H] (32 arrivals: every lane of
+  // the owner after its own store), hempty[H] (one arrival: the partner)
+  if (warp < C) {
+    uint64_t *bars = reinterpret_cast<uint64_t *>(own_smem + (size_t)warp * a.region_bytes + a.off_bars);
+    for (int i = lane; i < 2 * D + 2 * H; i += 32) mbar_init(bars + i, (i >= 2 * D && i < 2 * D + H) ? 32 : 1);
+  }
+  mbar_fence_init();
+  __syncthreads();
+  if (warp >= 2 * C) {
+    own_loader<D>(a, own_smem, (int)threadIdx.x - 2 * C * 32, C);
+    return;
+  }
+  // owner c and its partner sit on different schedulers (warp ids c and C + (c + C - 2) % C)
+  const bool is_owner = warp < C;
+  const int c = is_owner ? warp : (warp - C + 2) % C;
+  const int w = ((a.flags & OWN_F_REVERSE) ? C - 1 - c : c) * (int)gridDim.x + (int)blockIdx.x;
+  unsigned char *reg = own_smem + (size_t)c * a.region_bytes;
+  const unsigned reg_s = pin(smem_u32(reg));
+  const unsigned full_s = pin(reg_s + a.off_bars), empty_s = pin(reg_s + a.off_bars + 8u * D);
+  const unsigned hfull_s = pin(reg_s + a.off_bars + 16u * D), hempty_s = pin(reg_s + a.off_bars + 16u * D + 8u * H);
+  const unsigned hand_s = pin(reg_s + a.off_hand);
+  const unsigned lane16 = pin(16u * (unsigned)lane);
+  const unsigned koff = pin((unsigned)m.user_off & 3u);
+  const bool lane0 = lane == 0;
+  const int q0 = a.queue_off[w], n = a.queue_off[w + 1] - q0;
+  (void)q0;
+  // wait until barrier `bar` has completed the phase of parity `par`; false: the launch is being aborted
+  auto wait_bar = [&](unsigned bar, unsigned par) -> bool {
+    const long long t0 = clock64();
+    for (unsigned it = 0;; ++it) {
+      unsigned ok;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(ok)
+          : "r"(bar), "r"(par), "r"(100000u)
+          : "memory");
+      if (ok) return true;
+      if ((it & 63u) == 63u) {
+        if (ld_relaxed_u32(a.abort_flag)) return false;
+        if (clock64() - t0 > OWN_TIMEOUT) {
+          if (lane0) {
+            atomicCAS(a.err_flag, 0, ERR_TIMEOUT);
+            st_relaxed_u32(a.abort_flag, 1u);
+          }
+          return false;
+        }
+      }
+    }
+  };
+
+  if (!is_owner) {
+    // ================================ partner warp ==========================================
+    char *const wbase = pin(reinterpret_cast<char *>(m.W + (size_t)m.user_off * (size_t)m.pitch) + 16 * lane);
+    float *const bbase = pin(m.bias + m.user_off);
+    unsigned *const pver = pin(m.ver_ui + m.user_off);
+    const float du = pin(a.hp.du_skip ? 1.0f : a.hp.du), dub = pin(a.hp.dub);
+    const bool has_ub = pin((unsigned)(m.no_user_bias == 0)) != 0u;
+    const bool row_lane = lane < CH, st_ub = has_ub && lane0;
+    const int B = a.batch[w];
+    int pend = 0;
+    unsigned my_u = 0, my_t = 0;
+    auto flush = [&]() {  // publish the user rows written since the last flush: one release fence
+      if (pend) {
+        __syncwarp();  // the row stores of all lanes happen-before the releases (cumulative)
+        if (lane < pend) st_release_u32(pver + my_u, my_t);
+        pend = 0;
+      }
+    };
+    for (int j = 0; j < n; ++j) {
+      const int hs = j & (H - 1), s = j & (D - 1);
+      const unsigned hb = hfull_s + 8u * (unsigned)hs, hpar = (unsigned)(j / H) & 1u;
+      if (!mbar_test_s(hb, hpar)) {
+        flush();  // caught up with the owner: publish now, then wait for the next hand-off
+        if (!wait_bar(hb, hpar)) break;
+      }
+      // (the owner has consumed ring slot s, so its bulk copy has landed; test it all the same: this
+      // warp's own acquire on the barrier the TMA unit completed)
+      if (!mbar_test_s(full_s + 8u * (unsigned)s, (unsigned)(j >> LOG_D) & 1u) &&
+          !wait_bar(full_s + 8u * (unsigned)s, (unsigned)(j >> LOG_D) & 1u))
+        break;
+      const unsigned ha = hand_s + (unsigned)hs * HSLOT, sa = reg_s + (unsigned)s * SLOT;
+      const float4 ti = lds128f(ha + lane16);
+      const float lrerr = lds32f(ha + 32u * 16u);
+      const uint4 e0 = lds128u(sa + ROW + 16u), e1 = lds128u(sa + ROW + 32u);
+      const float4 wu = lds128f(sa + lane16);
+      const float ub = lds32f(sa + ROW + 4u * ((e0.x + koff) & 3u));
+      __syncwarp();
+      if (lane0) {  // both slots may be refilled
+        mbar_arrive_s(hempty_s + 8u * (unsigned)hs);
+        mbar_arrive_s(empty_s + 8u * (unsigned)s);
+      }
+      const float uval = __uint_as_float(e1.y);
+      const float su = __fmul_rn(lrerr, uval);  // base.h:391
+      const float sum_ = scalar_is_one(su) ? 1.0f : su;
+      const float4 nwu = f4_scale(f4_add_scaled(wu, ti, sum_, false), du);  // update_no_decay + regularize(after)
+      const unsigned user = e0.x;
+      if (row_lane) stcg4(reinterpret_cast<float *>(wbase + (size_t)user * ROW), nwu);
+      if (st_ub) __stcg(bbase + user, __fmul_rn(__fadd_rn(ub, su), dub));
+      if (lane == pend) {
+        my_u = user;
+        my_t = e0.y + 1u;
+      }
+      if (++pend >= B) flush();
+    }
+    flush();
+    return;
+  }
+
+  // ================================ owner warp ================================================
+  float *items_s = reinterpret_cast<float *>(reg + a.off_items);
+  float *ibias_s = reinterpret_cast<float *>(reg + a.off_ibias);
+  const int it0 = a.item_off[w], nit = a.item_off[w + 1] - it0, nres = min(nit, S);
+  const bool row_lane = lane < CH;
+  for (int sl = 0; sl < nres; ++sl) {  // the owner's most popular item rows live in shared memory for the launch
+    const size_t row = (size_t)m.item_off + a.items[it0 + sl];
+    if (row_lane) *reinterpret_cast<float4 *>(items_s + (size_t)sl * m.pitch + 4 * lane) = ldcg4(m.W + row * (size_t)m.pitch + 4 * lane);
+    if (lane0) ibias_s[sl] = __ldcg(m.bias + row);
+  }
+  __syncwarp();
+  float4 wi = f4_zero();
+  float ib = 0.0f;
+  unsigned cur_item = 0xffffffffu, cur_slot = 0;
+  auto put_item = [&]() {  // the current item row leaves the registers
+    if (cur_item == 0xffffffffu) return;
+    if ((int)cur_slot < S) {
+      if (row_lane) *reinterpret_cast<float4 *>(items_s + (size_t)cur_slot * m.pitch + 4 * lane) = wi;
+      if (lane0) ibias_s[cur_slot] = ib;
+    } else {
+      if (row_lane) stcg4(m.W + ((size_t)m.item_off + cur_item) * (size_t)m.pitch + 4 * lane, wi);
+      if (lane0) __stcg(m.bias + m.item_off + cur_item, ib);
+    }
+    __syncwarp();
+  };
+  auto get_item = [&](unsigned item, unsigned sl) {
+    if ((int)sl < S) {
+      wi = row_lane ? *reinterpret_cast<const float4 *>(items_s + (size_t)sl * m.pitch + 4 * lane) : f4_zero();
+      ib = ibias_s[sl];
+    } else {
+      wi = row_lane ? ldcg4(m.W + ((size_t)m.item_off + item) * (size_t)m.pitch + 4 * lane) : f4_zero();
+      ib = __ldcg(m.bias + m.item_off + item);
+    }
+    cur_item = item;
+    cur_slot = sl;
+  };
+  const unsigned dot_w = pin(reg_s + a.off_dot + 4u * (unsigned)lane);             // this lane's column of the products
+  const unsigned dot_r = pin(reg_s + a.off_dot + DOTROW * ((unsigned)lane & 3u));  // the row this lane adds up
+  const float lr = pin(a.hp.lr), dib = pin(a.hp.dib), pdi = pin(a.hp.di_skip ? 1.0f : a.hp.di);
+  const double base = pin((double)a.hp.base_score);
+  const bool has_ub = pin((unsigned)(m.no_user_bias == 0)) != 0u;
+  long long st_wait = 0, st_nwait = 0;
+  const long long st_begin = clock64();
+  struct Link {
+    uint4 e0, e1;  // {user, ticket, label, item}, {slot, uval, ival, flags}
+    float4 wu;
+    float ub;
+  };
+  auto read_link = [&](int s, Link &x, unsigned landed = 1u) {  // (`landed` enters the address: see k_own)
+    const unsigned sa = reg_s + landed * ((unsigned)s * SLOT);
+    x.e0 = lds128u(sa + ROW + 16u);
+    x.e1 = lds128u(sa + ROW + 32u);
+    x.wu = lds128f(sa + lane16);
+    x.ub = lds32f(sa + ROW + 4u * ((x.e0.x + koff) & 3u));
+  };
+  auto link = [&](Link &cur, Link &nxt, int j) -> bool {
+    const int j1 = j + 1, s1 = j1 & (D - 1), hs = j & (H - 1);
+    const unsigned par1 = (unsigned)(j1 >> LOG_D) & 1u;
+    const bool more = j1 < n;
+    const bool nready = more && mbar_test_s(full_s + 8u * (unsigned)s1, par1);
+    // hand-off slot hs is free once the partner has read link j - H out of it (a fresh barrier passes parity 1)
+    const bool hfree = mbar_test_s(hempty_s + 8u * (unsigned)hs, ((unsigned)(j / H) & 1u) ^ 1u);
+    read_link(s1, nxt, nready ? 1u : 0u);  // (not landed yet: read again below)
+    const float uval = __uint_as_float(cur.e1.y), ival = __uint_as_float(cur.e1.z), label = __uint_as_float(cur.e0.z);
+    const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
+    const float4 tu = f4_add_scaled(f4_zero(), cur.wu, um, false);  // prepare_tmp, base.h:354-381
+    const float4 ti = f4_add_scaled(f4_zero(), wi, im, false);
+    const unsigned dw = dot_w + ((unsigned)j & 1u) * DOTBUF, dr = dot_r + ((unsigned)j & 1u) * DOTBUF;
+    sts32f(dw, __fmul_rn(tu.x, ti.x));
+    sts32f(dw + DOTROW, __fmul_rn(tu.y, ti.y));
+    sts32f(dw + 2u * DOTROW, __fmul_rn(tu.z, ti.z));
+    sts32f(dw + 3u * DOTROW, __fmul_rn(tu.w, ti.w));
+    double bsum = 0.0;  // calc_bias, base.h:313-353 (needs no dot: off the chain)
+    if (has_ub) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, cur.ub));
+    bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
+    const double s0 = __dadd_rn(base, bsum);
+    __syncwarp();
+    float acc = 0.0f;
+    float4 q[CH / 4];
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) q[i] = lds128f(dr + 16u * i);  // (all in flight before the first add)
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+      acc = __fadd_rn(acc, q[i].x);
+      acc = __fadd_rn(acc, q[i].y);
+      acc = __fadd_rn(acc, q[i].z);
+      acc = __fadd_rn(acc, q[i].w);
+    }
+    const float l0 = __shfl_sync(0xffffffffu, acc, 0), l1 = __shfl_sync(0xffffffffu, acc, 1),
+                l2 = __shfl_sync(0xffffffffu, acc, 2), l3 = __shfl_sync(0xffffffffu, acc, 3);
+    const float d = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
+    const float p = (float)__dadd_rn(s0, (double)d);  // pred, base.h:445-454 (linear: map_active is the identity)
+    const float err = __fsub_rn(label, p);           // cal_grad, model.h:132-156
+    const float lrerr = __fmul_rn(lr, err);
+    const float si = __fmul_rn(lrerr, ival);  // base.h:412
+    const float sim = scalar_is_one(si) ? 1.0f : si;
+    wi = f4_scale(f4_add_scaled(wi, tu, sim, false), pdi);  // update_no_decay + regularize(after), item side
+    ib = __fmul_rn(__fadd_rn(ib, si), dib);
+    // everything rare behind one branch: hand-off slot still in use, next entry not landed, change of item
+    if (!hfree || (more && (!nready || nxt.e0.w != cur_item))) {
+      if (!hfree) {
+        const long long t0 = clock64();
+        if (!wait_bar(hempty_s + 8u * (unsigned)hs, ((unsigned)(j / H) & 1u) ^ 1u)) return false;
+        st_wait += clock64() - t0;
+      }
+      if (more && !nready) {
+        const long long t0 = clock64();
+        if (!wait_bar(full_s + 8u * (unsigned)s1, par1)) return false;
+        st_wait += clock64() - t0;
+        ++st_nwait;
+        read_link(s1, nxt);
+      }
+      if (more && nxt.e0.w != cur_item) {
+        // (the hand-off below still needs ti of THIS link: it is in registers already)
+        put_item();
+        get_item(nxt.e0.w, nxt.e1.x);
+      }
+    }
+    // the user-side half of the link goes to the partner: ti and lr*err
+    const unsigned ha = hand_s + (unsigned)hs * HSLOT;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ha + lane16), "f"(ti.x), "f"(ti.y), "f"(ti.z), "f"(ti.w) : "memory");
+    if (lane0) sts32f(ha + 32u * 16u, lrerr);
+    mbar_arrive_s(hfull_s + 8u * (unsigned)hs);  // (all 32 lanes arrive, each after its own store)
+    return true;
+  };
+  Link la, lb;
+  if (n > 0 && wait_bar(full_s, 0u)) {
+    read_link(0, la);
+    get_item(la.e0.w, la.e1.x);
+    for (int j = 0; j < n; j += 2) {
+      if (!link(la, lb, j)) break;
+      if (j + 1 < n && !link(lb, la, j + 1)) break;
+    }
+  }
+  put_item();
+  if (a.stats && lane0) {
+    a.stats[4 * w + 0] = clock64() - st_begin;
+    a.stats[4 * w + 1] = st_wait;
+    a.stats[4 * w + 2] = 0;
+    a.stats[4 * w + 3] = st_nwait;
+  }
+  for (int sl = 0; sl < nres; ++sl) {  // resident item rows go home
+    const size_t row = (size_t)m.item_off + a.items[it0 + sl];
+    if (row_lane) stcg4(m.W + row * (size_t)m.pitch + 4 * lane, *reinterpret_cast<const float4 *>(items_s + (size_t)sl * m.pitch + 4 * lane));
+    if (lane0) __stcg(m.bias + row, ibias_s[sl]);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static int own_reserve(svdgpu *h, DevBuf &b, size_t bytes) {
@@ -712,7 +1010,12 @@ static int bits_for(unsigned n) {  // key bits needed for values < n
   return b;
 }
 
-int own_owners_per_cta() { return OWN_C; }
+// the split link (k_own2) covers linear loss and rows of exactly 4 / 8 / 16 / 32 chunks
+static bool own_fast_shape(const svdgpu *h) {
+  const int chunks = h->dm.pitch / 4;
+  return h->own_fast && h->dm.active_type == 0 && h->dm.k == h->dm.pitch && (chunks == 4 || chunks == 8 || chunks == 16 || chunks == 32);
+}
+int own_owners_per_cta(const svdgpu *h) { return (h->own_partner && own_fast_shape(h)) ? OWN2_C : OWN_C; }
 
 bool own_supported(const svdgpu *h) {
   // plain L2 decay only (the other regularisers keep k_exact), rows of at most 256 floats
@@ -755,7 +1058,8 @@ int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cuda
   OwnScratch &s = h->own;
   const DevModel &m = h->dm;
   if (ctas <= 0 || ctas > h->num_sm) ctas = h->num_sm;
-  const int W = ctas * OWN_C;
+  const int per_cta = own_owners_per_cta(h);
+  const int W = ctas * per_cta;
   const size_t nn = (size_t)n;
   if (own_reserve(h, s.cnt_item, (size_t)m.num_item * 4) || own_reserve(h, s.cnt_user, (size_t)m.num_user * 4) ||
       own_reserve(h, s.start_user, (size_t)m.num_user * 4) || own_reserve(h, s.flag, 4) ||
@@ -864,6 +1168,7 @@ int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cuda
     h->n_launch += 3;
   }
   p.num_owner = W;
+  p.per_cta = per_cta;
   p.rows = n;
   p.max_load = hp.max_load;
   p.valid = true;
@@ -907,6 +1212,7 @@ static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
     if (own_reserve(h, h->own.stats, (size_t)p.num_owner * 4 * sizeof(long long))) return 1;
     CU(h, cudaMemsetAsync(h->own.stats.p, 0, (size_t)p.num_owner * 4 * sizeof(long long), st));
     a.stats = (long long *)h->own.stats.p;
+    h->own.stats_owners = p.num_owner;
   }
   const size_t smem = (size_t)a.region_bytes * OWN_C;
   auto k = k_own<CH, VEC, D>;
@@ -922,6 +1228,58 @@ static int own_launch_as(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   return 0;
 }
 
+template <int CH>
+static int own_launch2(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
+  constexpr int D = 8;
+  const DevModel &m = h->dm;
+  const unsigned row_bytes = (unsigned)m.pitch * 4u, slot_bytes = row_bytes + OWN_SLOT_EXTRA;
+  const unsigned ring = D * slot_bytes, dot = 2u * 4u * 36u * 4u, hand = OWN2_H * (32u * 16u + 16u);
+  const unsigned bars = (2u * D + 2u * OWN2_H) * 8u;
+  int max_smem = 0;
+  CU(h, cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const long long fixed = (long long)ring + dot + hand + bars + 128;
+  long long S = ((long long)max_smem / OWN2_C - fixed) / (long long)(row_bytes + 4);
+  S = std::min<long long>(S, h->own_slots > 0 ? h->own_slots : 32);
+  if (S < 0) return fail(h, "ordered mode: shared memory too small for k_own2 at num_factor %d", m.k);
+  OwnArgs a;
+  a.m = m;
+  a.hp = h->dhp;
+  a.entries = (const uint4 *)p.entries.p;
+  a.queue_off = (const int *)p.queue_off.p;
+  a.item_off = (const int *)p.item_off.p;
+  a.items = (const unsigned *)p.items.p;
+  a.batch = (const int *)p.batch.p;
+  a.S = (int)S;
+  a.off_items = ring;
+  a.off_ibias = a.off_items + (unsigned)S * row_bytes;
+  a.off_dot = (a.off_ibias + (unsigned)S * 4u + 15u) & ~15u;
+  a.off_hand = a.off_dot + dot;
+  a.off_bars = a.off_hand + hand;
+  a.region_bytes = (a.off_bars + bars + 127u) & ~127u;
+  a.err_flag = h->d_err;
+  a.abort_flag = h->d_abort;
+  a.flags = (h->own_acquire ? OWN_F_ACQUIRE : 0) | (h->own_reverse ? OWN_F_REVERSE : 0);
+  a.poll_ns = (unsigned)h->own_poll_ns;
+  a.stats = nullptr;
+  if (h->own_stats) {
+    if (own_reserve(h, h->own.stats, (size_t)p.num_owner * 4 * sizeof(long long))) return 1;
+    CU(h, cudaMemsetAsync(h->own.stats.p, 0, (size_t)p.num_owner * 4 * sizeof(long long), st));
+    a.stats = (long long *)h->own.stats.p;
+    h->own.stats_owners = p.num_owner;
+  }
+  const size_t smem = (size_t)a.region_bytes * OWN2_C;
+  auto k = k_own2<CH, D>;
+  CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(h, cudaMemsetAsync(m.ver_ui + m.user_off, 0, sizeof(unsigned) * (size_t)m.num_user, st));
+  CU(h, cudaMemsetAsync(h->d_abort, 0, sizeof(unsigned), st));
+  void *args[] = {&a};
+  CU(h, cudaLaunchCooperativeKernel((void *)k, dim3(p.num_owner / OWN2_C), dim3(own2_threads(D)), args, smem, st));
+  h->n_launch++;
+  h->n_own++;
+  h->n_own_rows += p.rows;
+  return 0;
+}
+
 template <int CH, int VEC>
 static int own_launch_d(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   if (h->own_depth == 16 && h->dm.pitch <= 128) return own_launch_as<CH, VEC, 16>(h, p, st);
@@ -930,10 +1288,18 @@ static int own_launch_d(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
 
 int launch_own(svdgpu *h, const OwnPlan &p, cudaStream_t st) {
   if (!p.valid) return fail(h, "ordered mode: no owner plan");
-  if (p.num_owner <= 0 || p.num_owner % OWN_C || p.num_owner > h->num_sm * OWN_C)
+  if (p.num_owner <= 0 || p.per_cta <= 0 || p.num_owner % p.per_cta || p.num_owner > h->num_sm * p.per_cta)
     return fail(h, "ordered mode: plan was built for another device");
   const DevModel &m = h->dm;
   const int chunks = m.pitch / 4;
+  if (p.per_cta == OWN2_C) {  // planned for the split link (owner + partner warps)
+    if (!own_fast_shape(h)) return fail(h, "ordered mode: the plan was built for k_own2; re-create the batch after changing own_fast");
+    if (chunks == 16) return own_launch2<16>(h, p, st);
+    if (chunks == 32) return own_launch2<32>(h, p, st);
+    if (chunks == 8) return own_launch2<8>(h, p, st);
+    return own_launch2<4>(h, p, st);
+  }
+  if (p.per_cta != OWN_C) return fail(h, "ordered mode: plan was built by another version of the library");
   // the fast link: linear loss, rows of exactly 4 / 8 / 16 / 32 chunks (num_factor 16, 32, 64, 128)
   if (h->own_fast && m.active_type == 0 && m.k == m.pitch) {
     if (chunks == 16) return own_launch_d<16, 1>(h, p, st);

@@ -793,6 +793,7 @@ def test_exact_owner_matches_oracle(native, k, resident):
 
 
 @pytest.mark.parametrize("options", [dict(own_slots=1), dict(own_batch=1), dict(own_batch=32, own_urgent_gap=0),
+                                     dict(own_partner=0), dict(own_partner=0, own_slots=1), dict(own_fast=0),
                                      dict(own_urgent_gap=1 << 30), dict(own_min_rows=1, chunk_rows=37),
                                      dict(own_min_rows=1, chunk_rows=1)])
 def test_exact_owner_options_do_not_change_the_result(native, options):
@@ -885,7 +886,8 @@ def test_exact_owner_equals_exact_kernel_and_falls_back(native):
 
 @pytest.mark.parametrize("compact", [0, 1])
 @pytest.mark.parametrize("pinned", [False, True])
-def test_exact_owner_host_call_at_scale(native, compact, pinned):
+@pytest.mark.parametrize("partner", [1, 0])
+def test_exact_owner_host_call_at_scale(native, compact, pinned, partner):
     """The ordered host-pointer call the trainer seam uses (several chunks in flight, the compact
     H2D path, pageable and pinned caller arrays) on a model larger than L2's hot set: bit-identical
     to the sequential oracle."""
@@ -893,7 +895,8 @@ def test_exact_owner_host_call_at_scale(native, compact, pinned):
     params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.005, wd_user=0.004, wd_item=0.004,
                   base_score=3.6)
     data = synth.basic_mf(n, nu, ni, seed=41, zipf_q=20.0)
-    opts = {"chunk_rows": 150000, "compact_h2d": compact, "compact_min_rows": 1, "scan_threads": 4}
+    opts = {"chunk_rows": 150000, "compact_h2d": compact, "compact_min_rows": 1, "scan_threads": 4,
+            "own_partner": partner}  # 1: k_own2 (owner + partner warps), 0: k_own
     for kv in os.environ.get("SVDGPU_TEST_OPTS", "").split():
         opts[kv.split("=")[0]] = int(kv.split("=")[1])
     o, g = _own_setup(native, params, options=opts)
