@@ -940,31 +940,32 @@ __global__ void __launch_bounds__(own2_threads(D), 1) k_own2(const OwnArgs a) {
     const float sim = scalar_is_one(si) ? 1.0f : si;
     wi = f4_scale(f4_add_scaled(wi, tu, sim, false), pdi);  // update_no_decay + regularize(after), item side
     ib = __fmul_rn(__fadd_rn(ib, si), dib);
-    // everything rare behind one branch: hand-off slot still in use, next entry not landed, change of item
-    if (!hfree || (more && (!nready || nxt.e0.w != cur_item))) {
-      if (!hfree) {
-        const long long t0 = clock64();
-        if (!wait_bar(hempty_s + 8u * (unsigned)hs, ((unsigned)(j / H) & 1u) ^ 1u)) return false;
-        st_wait += clock64() - t0;
-      }
-      if (more && !nready) {
+    // The user-side half of the link goes to the partner: ti and lr*err.  This comes BEFORE any wait
+    // for the next entry: that entry may be the same user again, whose version only the partner
+    // can publish -- once it has been handed this link.
+    if (!hfree) {  // (the partner is H links behind: rare)
+      const long long t0 = clock64();
+      if (!wait_bar(hempty_s + 8u * (unsigned)hs, ((unsigned)(j / H) & 1u) ^ 1u)) return false;
+      st_wait += clock64() - t0;
+    }
+    const unsigned ha = hand_s + (unsigned)hs * HSLOT;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ha + lane16), "f"(ti.x), "f"(ti.y), "f"(ti.z), "f"(ti.w) : "memory");
+    if (lane0) sts32f(ha + 32u * 16u, lrerr);
+    mbar_arrive_s(hfull_s + 8u * (unsigned)hs);  // (all 32 lanes arrive, each after its own store)
+    // everything else that is rare behind one branch: next entry not landed, change of item
+    if (more && (!nready || nxt.e0.w != cur_item)) {
+      if (!nready) {
         const long long t0 = clock64();
         if (!wait_bar(full_s + 8u * (unsigned)s1, par1)) return false;
         st_wait += clock64() - t0;
         ++st_nwait;
         read_link(s1, nxt);
       }
-      if (more && nxt.e0.w != cur_item) {
-        // (the hand-off below still needs ti of THIS link: it is in registers already)
+      if (nxt.e0.w != cur_item) {
         put_item();
         get_item(nxt.e0.w, nxt.e1.x);
       }
     }
-    // the user-side half of the link goes to the partner: ti and lr*err
-    const unsigned ha = hand_s + (unsigned)hs * HSLOT;
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ha + lane16), "f"(ti.x), "f"(ti.y), "f"(ti.z), "f"(ti.w) : "memory");
-    if (lane0) sts32f(ha + 32u * 16u, lrerr);
-    mbar_arrive_s(hfull_s + 8u * (unsigned)hs);  // (all 32 lanes arrive, each after its own store)
     return true;
   };
   Link la, lb;
