@@ -107,7 +107,9 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   publishes the busiest owner holds back per release fence, <= 32),
  *                   "own_urgent_gap" (4096: a user whose next rating follows within this many rows
  *                   is published at once), "own_slots" (0 = auto: item rows per owner kept in
- *                   shared memory, <= 32; the rest of an owner's rows stay in L2) */
+ *                   shared memory, <= 32; the rest of an owner's rows stay in L2), "own_partner" (0; 1 = the
+ *                   variant that splits a link over an owner and a partner warp, k_own2: same results,
+ *                   measured slower on configs[1]) */
 int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
 int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);

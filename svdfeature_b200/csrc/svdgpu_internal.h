@@ -149,7 +149,9 @@ struct svdgpu {
   int own_spare_sms = 16;    // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
                              // fills of the next chunk (k_own then runs on num_sm - this many CTAs)
   int own_poll_ns = 50;      // option "own_poll_ns": loader warps sleep this long between polls without progress
-  int own_partner = 1;       // option "own_partner": split link (k_own2: owner + partner warp) where the shape allows
+  int own_partner = 0;       // option "own_partner": 1 = split link (k_own2: owner + partner warp) where the shape allows.
+                             // Measured, 20 M rows of configs[1]: 22.4 ms against k_own's 19.9 ms (the partner releases the
+                             // ring slots later, the hot owners wait for them; alone on the GPU a link takes 0.304 vs 0.316 us)
   int own_stats = 0;         // option "own_stats": k_own records per-owner cycle counters (svdgpu_own_stats)
   OwnScratch own;
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
