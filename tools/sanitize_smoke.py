@@ -53,4 +53,21 @@ for mode in (api.MODE_HOGWILD, api.MODE_EXACT):
     g.items_apply_delta(1.0)
     g.sync()
     g.close()
+# ordered mode through the item-owner kernels: resident batch + host call, the fast link (k = 64, 128),
+# the generic link (k = 20), few shared-memory item slots, the split link (k_own2)
+for k, opts in ((64, {}), (128, {"own_slots": 2}), (20, {}), (64, {"own_partner": 1}), (16, {"own_partner": 1, "chunk_rows": 6000})):
+    g = api.SvdGpu(1501, 301, k)
+    g.set_hparams(learning_rate=0.005, wd_user=0.004, wd_item=0.004, wd_user_bias=0.001, base_score=3.6)
+    g.set_mode(api.MODE_EXACT)
+    for name, v in opts.items():
+        g.set_option(name, v)
+    model(g, 1501 + 301, k, 0)
+    d = synth.basic_mf(15013, 1501, 301, seed=5, zipf_q=3.0)
+    b = g.batch_create(d)
+    g.batch_update(b)
+    g.update_csr(d)
+    g.sync()
+    assert g.counter("own_launches") >= 2, g.counter("own_launches")
+    b.close()
+    g.close()
 print("sanitize_smoke done")
