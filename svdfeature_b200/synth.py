@@ -80,6 +80,24 @@ def ratings(n, num_user, num_item, seed=10, zipf_s=1.0, zipf_q=70.0, user_sigma=
     return u, i, lab
 
 
+def planted_mf(n, num_user, num_item, seed=10, rank=8, factor_scale=0.4, bias_scale=0.6, noise=0.5, **kw):
+    """basic-MF rows whose labels carry a signal a model can learn: label = 3.6 + b_user + b_item +
+    <p_user, q_item> + N(0, noise).  The planted parameters depend on (num_user, num_item, rank) only, not on
+    `seed`, so a training stream (seed a) and a held-out stream (seed b) share them.  With the defaults the
+    label std is 1.08 and the noise floor of the held-out RMSE is 0.5.  (BASELINE's own labels are noise
+    independent of user and item: nothing to learn, held-out RMSE cannot tell a good run from a bad one.)"""
+    u, i, _ = ratings(n, num_user, num_item, seed, **kw)
+    pr = np.random.default_rng(4242)
+    P = pr.standard_normal((num_user, rank)).astype(np.float32) * factor_scale
+    Q = pr.standard_normal((num_item, rank)).astype(np.float32) * factor_scale
+    bu = pr.standard_normal(num_user).astype(np.float32) * bias_scale
+    bi = pr.standard_normal(num_item).astype(np.float32) * bias_scale
+    rng = np.random.default_rng(seed + 7)
+    lab = (3.6 + bu[u] + bi[i] + np.einsum("nk,nk->n", P[u], Q[i]) + noise * rng.standard_normal(n)).astype(np.float32)
+    ones = np.ones(n, np.float32)
+    return fixed_csr(lab, uidx=u, uval=ones, iidx=i, ival=ones)
+
+
 def basic_mf(n, num_user, num_item, seed=10, **kw):
     """configs[0]/[1]: one user feature, one item feature, values 1 (demo/basicMF)."""
     u, i, lab = ratings(n, num_user, num_item, seed, **kw)

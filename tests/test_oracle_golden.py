@@ -129,3 +129,22 @@ def test_oracle_reproduces_the_ml100k_convergence_curve(tmp_path):
     for r, v in want.items():
         assert abs(curve[r] - v) < 1e-9, (r, curve[r], v)
     assert sha == gold["model_sha256_after_round_40"]
+
+
+def test_planted_signal_is_learnable_by_the_sequential_loop():
+    """synth.planted_mf: the oracle's held-out RMSE falls epoch by epoch towards the 0.5 noise floor (on the
+    BASELINE noise labels it cannot fall at all), so convergence tests built on it can discriminate."""
+    from svdfeature_b200 import synth
+
+    nu, ni = 2000, 300
+    params = dict(num_user=nu, num_item=ni, num_factor=16, learning_rate=0.01, wd_user=0.004, wd_item=0.004, base_score=3.6)
+    train = synth.planted_mf(200000, nu, ni, seed=1)
+    held = synth.planted_mf(20000, nu, ni, seed=2)
+    assert abs(float(held[1].std()) - 1.08) < 0.08
+    o = COracle(0, 0, 0, params)
+    o.init(10)
+    curve = []
+    for _ in range(4):
+        o.update_csr(train)
+        curve.append(float(np.sqrt(np.mean((o.predict_csr(held) - held[1]) ** 2))))
+    assert curve[0] < 0.95 and curve[3] < curve[2] < curve[1] < curve[0] and curve[3] < 0.72, curve
