@@ -97,6 +97,12 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   feature counts, nor its values when all are 1.0f; host threads ("scan_threads",
  *                   0 = this process's share of the cores, at most 16; fewer than 5: no scan) verify every element while earlier chunks are copied, the
  *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
+ *   "hogwild_safety": Hogwild stability guard, per mille (default 1000; 0 = off).  N instances in flight that
+ *                   touch a row with probability p apply ~N*p stale steps of size lr to it at once; beyond
+ *                   N*p*lr ~ 2 asynchronous SGD on that row diverges.  Training launches of the fast passes
+ *                   keep at most safety / (lr * share of the hottest item) instances in flight (the share is
+ *                   measured on the device: once per resident batch, on the first chunk of a host call);
+ *                   counters "inflight_cap", "hot_item_ppm".  configs[1] is far below the bound: no effect.
  *   "exact_opt"   : ordered kernel hand-off variants, bit mask (default 5): 1 release without a
  *                   per-lane fence, 2 poll back to back, 4 instance slice staged in shared memory
  *   "exact_owner" : 1 (default): in the ordered mode, launches made only of basic-MF rows (0 | 1 | 1

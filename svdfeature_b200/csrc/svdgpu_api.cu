@@ -75,7 +75,60 @@ __global__ void k_probe_copy(const float4 *__restrict__ src, float4 *__restrict_
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) __stcg(dst + i, __ldcg(src + i));
 }
 
+// Hogwild stability guard: how often does the most frequent item occur among rows [r0, r0+n)?
+__global__ void k_item_hist(DevCsr csr, int r0, int n, unsigned num_item, unsigned *cnt) {
+  const unsigned *idx = csr.index - csr.val_base;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = r0 + i;
+    const int a = csr.row_ptr[3 * r + 2], b = csr.row_ptr[3 * r + 3];
+    if (a < csr.val_base || b > csr.val_end || b - a > 64) continue;  // (bad rows are the kernels' business)
+    for (int f = a; f < b; ++f)
+      if (idx[f] < num_item) atomicAdd(cnt + idx[f], 1u);
+  }
+}
+__global__ void k_max_u32(const unsigned *cnt, unsigned n, unsigned *out) {
+  unsigned m = 0;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, cnt[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 namespace {
+
+// share of the hottest item among the rows (one small sync; resident batches measure once)
+int hot_fraction(svdgpu *h, const DevCsr &csr, int r0, int n, double *frac) {
+  *frac = 0.0;
+  const size_t ni = (size_t)h->shape.num_item;
+  if (n <= 0 || ni == 0) return 0;
+  if (h->hist_cap < (ni + 1) * 4) {
+    if (h->d_hist) CU(h, cudaFree(h->d_hist));
+    h->d_hist = nullptr;
+    h->hist_cap = 0;
+    CU(h, cudaMalloc(&h->d_hist, (ni + 1) * 4 + 64));
+    h->hist_cap = (ni + 1) * 4;
+  }
+  CU(h, cudaMemsetAsync(h->d_hist, 0, (ni + 1) * 4, h->stream));
+  k_item_hist<<<(int)std::min<long long>(h->num_sm * 16, ((long long)n + 255) / 256), 256, 0, h->stream>>>(
+      csr, r0, n, (unsigned)ni, h->d_hist);
+  k_max_u32<<<std::min<int>(h->num_sm * 4, (int)((ni + 255) / 256)), 256, 0, h->stream>>>(h->d_hist, (unsigned)ni, h->d_hist + ni);
+  CU(h, cudaGetLastError());
+  h->n_launch += 2;
+  unsigned mx = 0;
+  CU(h, cudaMemcpyAsync(&mx, h->d_hist + ni, 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->n_d2h += 4;
+  *frac = (double)mx / (double)n;
+  return 0;
+}
+// cap on the instances a Hogwild training launch keeps in flight (0 = none)
+void set_inflight_cap(svdgpu *h, double hot_frac) {
+  h->hot_frac = hot_frac;
+  h->inflight_cap = 0;
+  const double lr = (double)h->hp.learning_rate;
+  if (h->hog_safety_permille <= 0 || !(hot_frac > 0.0) || !(lr > 0.0)) return;
+  const double cap = 1e-3 * h->hog_safety_permille / (lr * hot_frac);
+  h->inflight_cap = cap > 4e18 ? 0 : std::max<long long>(64, (long long)cap);
+}
 
 // squared-error accumulation of one predicted chunk (only while an svdgpu_eval_* call is active)
 int eval_chunk(svdgpu *h, const float *pred, const float *label, int n) {
@@ -502,6 +555,7 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->d_err);
   cudaFree(h->d_counter);
   cudaFree(h->d_abort);
+  cudaFree(h->d_hist);
   own_scratch_free(h->own);
   for (int i = 0; i < svdgpu::NSLOT; ++i) own_plan_free(h->slot[i].own);
   cudaFree(h->d_eval);
@@ -579,6 +633,7 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_min_rows")) h->own_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_urgent_gap")) h->own_urgent_gap = (int)std::max<long long>(0, std::min<long long>(v, 1LL << 30));
   else if (!strcmp(name, "own_batch")) h->own_batch = (int)std::max<long long>(1, std::min<long long>(v, 32));
+  else if (!strcmp(name, "hogwild_safety")) h->hog_safety_permille = (int)std::max<long long>(0, std::min<long long>(v, 1000000));
   else if (!strcmp(name, "own_stats")) h->own_stats = v ? 1 : 0;
   else if (!strcmp(name, "own_partner")) h->own_partner = v ? 1 : 0;
   else if (!strcmp(name, "own_poll_ns")) h->own_poll_ns = (int)std::max<long long>(0, std::min<long long>(v, 100000));
@@ -720,6 +775,8 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
   if (!strcmp(name, "h2d_bytes")) return h->n_h2d;
   if (!strcmp(name, "d2h_bytes")) return h->n_d2h;
   if (!strcmp(name, "num_sm")) return h->num_sm;
+  if (!strcmp(name, "inflight_cap")) return h->inflight_cap;  // Hogwild guard of the last training launch (0 = none)
+  if (!strcmp(name, "hot_item_ppm")) return (long long)(h->hot_frac * 1e6);
   if (!strcmp(name, "collectives")) return h->n_coll;  // NCCL all-reduces issued by svdgpu_allreduce_items / _allgather_users
   if (!strcmp(name, "collective_bytes")) return h->n_coll_bytes;
   if (!strcmp(name, "own_launches")) return h->n_own;  // ordered mode: launches of the item-owner kernel
@@ -868,6 +925,7 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     if (scan_threads < (exact ? 2 : 5)) scan_threads = 0;
   }
   const bool compact = h->compact_h2d && scan_threads > 0 && (!exact || own_ok) && !sides_on(h) && num_row >= h->compact_min_rows;
+  if (h->hog_safety_permille <= 0) h->inflight_cap = 0;
   svdscan::ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
   if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value, scan_threads);
   for (int r0 = 0, ci = 0; r0 < num_row; r0 += h->chunk_rows, ++ci) {
@@ -965,6 +1023,11 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
         pred = (float *)s.d_pred.p;
       }
       if (slot_copied(h, s)) return 1;
+      if (train && ci == 0 && h->hog_safety_permille > 0) {  // Hogwild guard: the first chunk speaks for the call
+        double hf = 0.0;
+        if (hot_fraction(h, csr, 0, n, &hf)) return 1;
+        set_inflight_cap(h, hf);
+      }
       if (launch_stream(h, geo, csr, 0, n, train, pred)) return 1;
       if (!train && eval_chunk(h, pred, csr.label, n)) return 1;
       if (!train && out) {
@@ -1371,6 +1434,12 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
       if (launch_exact(h, geo, batch_csr(b), begin, end)) return 1;
     }
   } else {
+    if (h->hog_safety_permille > 0) {  // Hogwild guard: the batch's hottest item, measured once
+      if (b->hot_frac < 0.0 && hot_fraction(h, batch_csr(b), 0, b->num_row, &b->hot_frac)) return 1;
+      set_inflight_cap(h, b->hot_frac);
+    } else {
+      h->inflight_cap = 0;
+    }
     if (launch_stream(h, geo, batch_csr(b), begin, end, true, (float *)nullptr)) return 1;
   }
   h->n_inst += end - begin;

@@ -157,6 +157,15 @@ struct svdgpu {
   unsigned *d_abort = nullptr;  // k_own: set when a wait timed out, every warp leaves
   int exact_opt = 5;   // option "exact_opt": k_exact hand-off variants (bit mask, svdgpu_ordered.cu):
                        // 1 no per-lane fence before the release, 2 spin before sleeping, 4 staged slice
+  // Hogwild stability guard: N instances in flight that touch a row with probability p apply ~N*p stale
+  // steps of size lr to it at once; beyond N*p*lr ~ 2 asynchronous SGD on that row diverges (measured: NaN at
+  // k = 32, lr = 0.01, 3000 items -- tools/hogwild_stability.py).  Training launches are capped at
+  // inflight_cap = hog_safety / (lr * share of the hottest item), 0 = no cap.
+  long long inflight_cap = 0;
+  int hog_safety_permille = 1000;  // option "hogwild_safety" (per mille; 0 disables the guard)
+  unsigned *d_hist = nullptr;      // item histogram + max word of the guard
+  size_t hist_cap = 0;
+  double hot_frac = -1.0;          // share of the hottest item in the last measured launch
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
   static constexpr int NSLOT = 3;
   Slot slot[NSLOT];
@@ -191,6 +200,7 @@ struct svdgpu_batch {
   long long num_val = 0;
   DevBuf d_rp, d_label, d_index, d_value, d_value2, d_ticket, d_pred;
   bool has_ticket = false, has_value2 = false;
+  double hot_frac = -1.0;  // share of the hottest item among the batch's rows (Hogwild guard), -1: not measured yet
   OwnPlan own;  // ordered mode through k_own: the batch's owner plan (valid when the rows qualify)
   // user-group structure
   bool ugroup = false, has_fb = false;

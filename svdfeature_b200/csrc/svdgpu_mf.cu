@@ -535,6 +535,11 @@ static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool trai
     const size_t smem = mf_smem_bytes<L, V, ED, DEPTH, NI, NG, LATEB>();                         \
     CU(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     if (grid_for(h, k, MF_THREADS, (ntile + MF_WARPS - 1) / MF_WARPS, &grid, smem)) return 1;    \
+    /* Hogwild stability: at most h->inflight_cap instances in flight (svdgpu_api.cu, hot_cap) */ \
+    if (TR && h->inflight_cap > 0) {                                                             \
+      const long long per_cta = (long long)MF_WARPS * (32 / L) * DEPTH;                          \
+      if ((long long)grid * per_cta > h->inflight_cap) grid = (int)std::max<long long>(1, h->inflight_cap / per_cta); \
+    }                                                                                            \
     k<<<grid, MF_THREADS, smem, h->stream>>>(h->dm, h->dhp, csr, r0, r1, h->scatter_user,        \
                                              h->scatter_item, pred, h->d_row_mask,               \
                                              flag_out, flag_gate);                               \
@@ -558,7 +563,10 @@ static int launch_mf_geo(svdgpu *h, const DevCsr &csr, int r0, int r1, bool trai
 int launch_mf(svdgpu *h, const Geometry &g, const DevCsr &csr, int r0, int r1, bool train, float *pred,
               int which, unsigned *flag_out, const unsigned *flag_gate) {
   // tuning knobs (options "ring_depth", "mf_ctas"): ring depth 2 or 4, 2 or 3 CTAs per SM
-  const int depth = h->ring_depth == 2 ? 2 : 4;
+  int depth = h->ring_depth == 2 ? 2 : 4;
+  // a capped launch first halves the ring (half the instances in flight at nearly the same speed), then
+  // shrinks the grid
+  if (train && h->inflight_cap > 0 && h->inflight_cap < (long long)h->num_sm * 2 * MF_WARPS * (32 / g.lanes) * 4) depth = 2;
   const int minb = h->mf_ctas == 3 ? 3 : 2;
 #define GEO(L, V)                                                                                      \
   if (g.lanes == L && g.vec == V) {                                                                    \

@@ -144,7 +144,10 @@ def test_ml100k_convergence_band(native, mode, tmp_path):
 
 def test_planted_signal_heldout_rmse_both_modes(native):
     """Convergence on labels that carry a signal (synth.planted_mf): the ordered mode's held-out curve IS the
-    sequential loop's (identical predictions); Hogwild's stays within 5e-3 of it at every epoch."""
+    sequential loop's (identical predictions); Hogwild's stays within 5e-3 of it at every epoch.  This shape
+    (k = 32: eight instances per warp; lr = 0.01; 3000 items) is where an uncapped Hogwild launch diverged to
+    NaN -- 76k instances in flight x 0.37 % on the hottest item x lr = 2.8 -- before the stability guard
+    (option hogwild_safety) bounded the instances in flight (tools/hogwild_stability.py)."""
     from svdfeature_b200 import synth
 
     nu, ni = 60000, 3000
@@ -165,6 +168,7 @@ def test_planted_signal_heldout_rmse_both_modes(native):
             curves[name].append(float(np.sqrt(np.mean((p - held[1]) ** 2))))
         preds[name] = p
     assert np.array_equal(preds["oracle"], preds["exact"])
+    assert np.isfinite(preds["hogwild"]).all()
     assert curves["oracle"][2] < curves["oracle"][0] < 1.0  # it learns
     for a, b in zip(curves["oracle"], curves["hogwild"]):
         assert abs(a - b) < 5e-3, (curves["oracle"], curves["hogwild"])
