@@ -642,6 +642,8 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_fast")) h->own_fast = v ? 1 : 0;
   else if (!strcmp(name, "own_acquire")) h->own_acquire = v ? 1 : 0;
   else if (!strcmp(name, "own_reverse")) h->own_reverse = v ? 1 : 0;
+  else if (!strcmp(name, "own_isolate")) h->own_isolate = v < 0 ? 0 : v;
+  else if (!strcmp(name, "own_isolate_full")) h->own_isolate_full = v < 0 ? 0 : v;
   else if (!strcmp(name, "own_slots")) h->own_slots = (int)std::max<long long>(0, std::min<long long>(v, 32));
   else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
   else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));

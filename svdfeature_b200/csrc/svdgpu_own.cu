@@ -538,52 +538,89 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
     const bool st_ub = has_ub && lane0;
     struct Link {
       uint4 e0, e1;  // {user, ticket, label, item}, {slot, uval, ival, flags}
-      float4 wu;
-      float ub;
+      float4 wu, tu; // the user row (this lane's chunk) and uval * row (prepare_tmp, base.h:354-381)
+      float ub, um, im;  // the user bias; uval, ival with "is one" folded in (below)
     };
-    // `landed` = what the barrier test returned, 1 or 0: it enters the address (0: the owner's first
-    // slot, whose content is then discarded), so the reads cannot be issued before the test has
-    // answered.  (Reads issued unconditionally behind a test_wait may be performed BEFORE it: they
-    // then see the slot as it was, while the test already sees the bulk copy complete.)
-    auto read_link = [&](int s, Link &x, unsigned landed = 1u) {
-      const unsigned sa = reg_s + landed * ((unsigned)s * SLOT);
+    // What is known of an entry before its link starts -- everything but the item row -- is worked out when
+    // the entry is read, one link ahead and off the chain.
+    auto finish_link = [&](Link &x) {
+      const float uval = __uint_as_float(x.e1.y), ival = __uint_as_float(x.e1.z);
+      x.um = scalar_is_one(uval) ? 1.0f : uval;
+      x.im = scalar_is_one(ival) ? 1.0f : ival;
+      x.tu = f4_add_scaled(f4_zero(), x.wu, x.um, false);
+    };
+    auto read_link = [&](int s, Link &x) {
+      const unsigned sa = reg_s + (unsigned)s * SLOT;
       x.e0 = lds128u(sa + ROW + 16u);
       x.e1 = lds128u(sa + ROW + 32u);
       x.wu = lds128f(sa + lane16);
       x.ub = lds32f(sa + ROW + 4u * ((x.e0.x + koff) & 3u));
+      finish_link(x);
     };
     float4 &wi0 = wi[0];
-    // One link.  Everything that is not arithmetic of this instance -- the publish fence, a next
-    // entry that has not landed, a change of item -- sits behind ONE rarely taken branch at the
-    // end; the item row of `cur` is in registers when the link starts.  Returns false when the
-    // launch is being aborted.
-    auto link = [&](Link &cur, Link &nxt, int j) -> bool {
-      const int j1 = j + 1, s1 = j1 & (D - 1);
-      const unsigned par1 = (unsigned)(j1 >> LOG_D) & 1u;
-      const bool more = j1 < n;
-      const bool nready = more && mbar_test_s(full_s + 8u * (unsigned)s1, par1);
-      read_link(s1, nxt, nready ? 1u : 0u);  // (not landed yet: read again below)
-      const float uval = __uint_as_float(cur.e1.y), ival = __uint_as_float(cur.e1.z), label = __uint_as_float(cur.e0.z);
-      const float um = scalar_is_one(uval) ? 1.0f : uval, im = scalar_is_one(ival) ? 1.0f : ival;
-      const float4 tu = f4_add_scaled(f4_zero(), cur.wu, um, false);  // prepare_tmp, base.h:354-381
-      const float4 ti = f4_add_scaled(f4_zero(), wi0, im, false);
+    // What a link can ask for besides its arithmetic; anything set ends the inner loop below.
+    // (a change of item is reported beside these, in `evx`)
+    enum : unsigned { EV_PUBLISH = 1u, EV_LAST = 2u, EV_WAIT = 4u };
+    // `rdy`: has the entry after the current one landed?  The barrier test takes ~150 cycles to answer
+    // (B300_MICROARCH.md: test_wait 149), so it is made one link ahead: link j consumes the answer for entry
+    // j+1 that link j-1 asked for, and asks for entry j+2.  "Not yet" sends the owner to the blocking wait
+    // (which looks again), so a stale "no" costs a detour, never a wrong read.
+    // Asking and reading the answer are two statements around one predicate register of this function, so that
+    // the link's work stands between them (as one statement the answer is consumed at once: a 150-cycle stall).
+    unsigned rdy = 0u, evx = 0u;
+    const unsigned lane0i = lane0 ? 1u : 0u;
+    auto test_entry = [&](int e) -> unsigned {
+      return e < n && mbar_test_s(full_s + 8u * (unsigned)(e & (D - 1)), (unsigned)(e >> LOG_D) & 1u) ? 1u : 0u;
+    };
+    asm volatile(".reg .pred own_landed;");
+    auto ask_entry = [&](int e) {  // (past the end of the queue: some barrier of the ring, answer unused)
+      asm volatile("mbarrier.test_wait.parity.shared::cta.b64 own_landed, [%0], %1;" ::"r"(full_s + 8u * (unsigned)(e & (D - 1))),
+                   "r"((unsigned)(e >> LOG_D) & 1u)
+                   : "memory");
+    };
+    auto answer = [&]() -> unsigned {
+      unsigned ok;
+      asm volatile("selp.u32 %0, 1, 0, own_landed;" : "=r"(ok)::"memory");
+      return ok;
+    };
+    // One link: the arithmetic of `cur` (whose item row is in registers), its user row stored, the next
+    // entry read out of its ring slot into `nxt` if it has landed.  Straight-line code; the warp issues in
+    // order, so the statements stand in the order the chain wants them:
+    //   1. the barrier test for the entry after the next is asked for; the products of the dot go to shared
+    //      memory -- only the item row is new to this link;
+    //   2. the off-chain sums;
+    //   3. the transposed products come back, the next entry is read behind them;
+    //   4. the adds of the dot, the error, the two new rows.
+    auto body = [&](Link &cur, Link &nxt, int j) -> unsigned {
+      ask_entry(j + 2);
+      const float4 ti = f4_add_scaled(f4_zero(), wi0, cur.im, false);  // prepare_tmp, base.h:354-381
       const unsigned dw = dot_w + ((unsigned)j & 1u) * DOTBUF, dr = dot_r + ((unsigned)j & 1u) * DOTBUF;
-      sts32f(dw, __fmul_rn(tu.x, ti.x));
-      sts32f(dw + DOTROW, __fmul_rn(tu.y, ti.y));
-      sts32f(dw + 2u * DOTROW, __fmul_rn(tu.z, ti.z));
-      sts32f(dw + 3u * DOTROW, __fmul_rn(tu.w, ti.w));
+      sts32f(dw, __fmul_rn(cur.tu.x, ti.x));
+      sts32f(dw + DOTROW, __fmul_rn(cur.tu.y, ti.y));
+      sts32f(dw + 2u * DOTROW, __fmul_rn(cur.tu.z, ti.z));
+      sts32f(dw + 3u * DOTROW, __fmul_rn(cur.tu.w, ti.w));
+      // (flags as integers, not predicates: the few predicate registers are left to the barrier test, whose
+      // answer must stay in one from here to the end of the link)
+      const int j1 = j + 1, s1 = j1 & (D - 1);
+      const unsigned more = (unsigned)(j1 - n) >> 31;  // 1: there is a next entry
+      const unsigned nready = more & rdy;              // 1: ... and it has landed
+      const float uval = __uint_as_float(cur.e1.y), ival = __uint_as_float(cur.e1.z), label = __uint_as_float(cur.e0.z);
       double bsum = 0.0;  // calc_bias, base.h:313-353 (needs no dot: off the chain)
       if (has_ub) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, cur.ub));
       bsum = __dadd_rn(bsum, (double)__fmul_rn(ival, ib));
       const double s0 = __dadd_rn(base, bsum);
       __syncwarp();
-      // every lane has read the next entry out of its ring slot by now: the slot may be refilled
-      if (nready && lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
-      float acc = 0.0f;
       constexpr int NQ = CH ? CH / 4 : 1;
       float4 q[NQ];
 #pragma unroll
       for (int i = 0; i < NQ; ++i) q[i] = lds128f(dr + 16u * i);  // (all in flight before the first add)
+      // the answer of the test enters the address: these reads cannot be issued before it (not landed: the
+      // owner's first slot is read and the result discarded)
+      const unsigned sa = reg_s + nready * ((unsigned)s1 * SLOT);
+      nxt.e0 = lds128u(sa + ROW + 16u);
+      nxt.e1 = lds128u(sa + ROW + 32u);
+      nxt.wu = lds128f(sa + lane16);
+      float acc = 0.0f;
 #pragma unroll
       for (int i = 0; i < NQ; ++i) {
         acc = __fadd_rn(acc, q[i].x);
@@ -593,13 +630,18 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       }
       const float l0 = __shfl_sync(0xffffffffu, acc, 0), l1 = __shfl_sync(0xffffffffu, acc, 1),
                   l2 = __shfl_sync(0xffffffffu, acc, 2), l3 = __shfl_sync(0xffffffffu, acc, 3);
+      nxt.ub = lds32f(sa + ROW + 4u * ((nxt.e0.x + koff) & 3u));
+      finish_link(nxt);
+      __syncwarp();
+      // every lane has read the next entry out of its ring slot: the slot may be refilled
+      if (nready + lane0i == 2u) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
       const float d = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
       const float p = (float)__dadd_rn(s0, (double)d);  // pred, base.h:445-454 (linear: map_active is the identity)
       const float err = __fsub_rn(label, p);           // cal_grad, model.h:132-156
       const float lrerr = __fmul_rn(lr, err);
       const float su = __fmul_rn(lrerr, uval), si = __fmul_rn(lrerr, ival);  // base.h:391,412
       const float sum_ = scalar_is_one(su) ? 1.0f : su, sim = scalar_is_one(si) ? 1.0f : si;
-      wi0 = f4_scale(f4_add_scaled(wi0, tu, sim, false), pdi);  // update_no_decay + regularize(after)
+      wi0 = f4_scale(f4_add_scaled(wi0, cur.tu, sim, false), pdi);  // update_no_decay + regularize(after)
       ib = __fmul_rn(__fadd_rn(ib, si), dib);
       const float4 nwu = f4_scale(f4_add_scaled(cur.wu, ti, sum_, false), pdu);
       const unsigned user = cur.e0.x;
@@ -610,21 +652,12 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
         my_t = cur.e0.y + 1u;
       }
       ++pend;
-      const bool publish = (cur.e1.w & 1u) || pend >= B;
-      if (publish || (more && (!nready || nxt.e0.w != cur_item))) {
-        if (publish) flush();
-        if (more && !nready) {
-          if (!wait_full(s1, par1)) return false;
-          read_link(s1, nxt);
-          __syncwarp();
-          if (lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s1);
-        }
-        if (more && nxt.e0.w != cur_item) {
-          put_item();
-          get_item(nxt.e0.w, nxt.e1.x);
-        }
-      }
-      return true;
+      evx = (0u - nready) & (nxt.e0.w ^ cur_item);  // non-zero: the next entry is of another item
+      const unsigned ev = (cur.e1.w & 1u) | ((unsigned)(B - 1 - pend) >> 31)   // EV_PUBLISH: asked for, or the batch is full
+                          | ((more ^ 1u) << 1)                                  // EV_LAST
+                          | ((more & (rdy ^ 1u)) << 2);                         // EV_WAIT
+      rdy = ((unsigned)(j + 2 - n) >> 31) & answer();
+      return ev;
     };
     Link la, lb;
     if (n > 0 && wait_full(0, 0u)) {
@@ -632,9 +665,39 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       __syncwarp();
       if (lane0) mbar_arrive_s(empty_s);
       get_item(la.e0.w, la.e1.x);
-      for (int j = 0; j < n; j += 2) {
-        if (!link(la, lb, j)) break;
-        if (j + 1 < n && !link(lb, la, j + 1)) break;
+      rdy = test_entry(1);
+      // The inner loop is nothing but links (two per trip: `la` and `lb` swap roles, no register moves);
+      // whatever else has to happen -- the publish fence, a next entry that has not landed, a change of
+      // item, the end of the queue -- leaves it, is dealt with here, and re-enters with the current entry in `la`.
+      for (int j = 0;;) {
+        unsigned ev;
+        for (;;) {
+          ev = body(la, lb, j);
+          if (ev | evx) {
+            la = lb;
+            break;
+          }
+          ++j;
+          ev = body(lb, la, j);
+          if (ev | evx) break;
+          ++j;
+        }
+        if (ev & EV_PUBLISH) flush();
+        if (ev & EV_LAST) break;
+        ++j;
+        if (ev & EV_WAIT) {
+          st_nwait += 1LL << 32;  // (own_stats: upper half = how often the next entry had not landed one link ahead)
+          const int s = j & (D - 1);
+          if (!wait_full(s, (unsigned)(j >> LOG_D) & 1u)) break;
+          read_link(s, la);
+          __syncwarp();
+          if (lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s);
+          rdy = test_entry(j + 1);  // (the answer the skipped link would have asked for may be stale)
+        }
+        if (la.e0.w != cur_item) {
+          put_item();
+          get_item(la.e0.w, la.e1.x);
+        }
       }
     }
   } else {
@@ -1121,7 +1184,28 @@ int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cuda
     return 0;  // not for k_own (the caller reports bound errors / falls back to k_exact)
   }
   svdown::HostPlan hp;
-  svdown::assign(hc, m.num_item, W, h->own_batch, hp);
+  // The chain of the hottest item is what the whole launch waits for, and a link of it is slower in company:
+  // measured per link (20 M rows, hottest item 51 080), 0.27 us with the SM to itself, 0.32 us with the other
+  // eleven owner warps at work but nobody on its issue port (warps w, w+4, w+8 share one: warp id mod 4),
+  // 0.36-0.37 us with two busy neighbours there.  So the owners of hot items (more than own_isolate % of the
+  // mean owner load) get the port to themselves, and those within reach of the longest chain (own_isolate_full %
+  // of it, at most an eighth of the SMs) a whole SM; the warps so closed get no items.  (k_own's mapping: owner
+  // o is warp OWN_C-1 - o/ctas, or o/ctas without own_reverse, of block o % ctas; LPT gives the r-th most
+  // popular item to owner r.)
+  std::vector<char> closed;
+  if (h->own_isolate > 0 && per_cta == OWN_C) {
+    const int hot = std::min(svdown::hot_owners(hc, m.num_item, W, h->own_isolate), ctas);
+    const int full = h->own_isolate_full > 0
+                         ? std::min(std::min(svdown::top_owners(hc, m.num_item, h->own_isolate_full), hot), std::max(ctas / 8, 1))
+                         : 0;
+    if (hot > 0) {
+      closed.assign((size_t)W, 0);
+      for (int o = 0; o < hot; ++o)
+        for (int c = 1; c < OWN_C; ++c)
+          if (c % 4 == 0 || o < full) closed[(size_t)c * ctas + o] = 1;  // (c % 4 == 0: same port under either mapping)
+    }
+  }
+  svdown::assign(hc, m.num_item, W, h->own_batch, hp, closed.empty() ? nullptr : &closed);
   if (own_reserve(h, p.queue_off, (size_t)(W + 1) * 4) || own_reserve(h, p.item_off, (size_t)(W + 1) * 4) ||
       own_reserve(h, p.items, std::max<size_t>(hp.items.size(), 1) * 4) || own_reserve(h, p.batch, (size_t)W * 4) ||
       own_reserve(h, p.entries, nn * sizeof(OwnEntry)))

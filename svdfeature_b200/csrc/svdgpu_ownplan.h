@@ -37,7 +37,11 @@ struct HostPlan {
 // max_batch: how many user-row version publishes the most loaded owner may collect before one
 // release fence; slower owners hold back proportionally fewer, so the delay is about the same
 // stretch of the input order for everybody.
-inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_batch, HostPlan &p) {
+// closed (optional, [num_owner]): owners that get no items -- the warps that would share an issue port with
+// the owner of a very hot item (hot_owners below; the mapping owner -> warp is the kernel's, so the caller
+// marks them).
+inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_batch, HostPlan &p,
+                   const std::vector<char> *closed = nullptr) {
   p.num_owner = num_owner;
   p.item_owner.assign((size_t)num_item, -1);
   p.item_slot.assign((size_t)num_item, 0u);
@@ -48,7 +52,8 @@ inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_bat
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
   typedef std::pair<int64_t, int> Load;  // (rows, owner): smallest load first, then smallest owner id
   std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-  for (int w = 0; w < num_owner; ++w) heap.push(Load(0, w));
+  for (int w = 0; w < num_owner; ++w)
+    if (!closed || !(*closed)[(size_t)w]) heap.push(Load(0, w));
   std::vector<int64_t> load((size_t)num_owner, 0);
   std::vector<int> nitem((size_t)num_owner, 0);
   for (int i : order) {
@@ -76,6 +81,30 @@ inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_bat
     const int64_t b = p.max_load > 0 ? (int64_t)max_batch * load[(size_t)w] / p.max_load : 1;
     p.batch[(size_t)w] = (int)std::max<int64_t>(1, std::min<int64_t>(b, max_batch));
   }
+}
+
+// How many of the most popular items carry more than `percent` % of an owner's mean load each: LPT gives
+// the r-th most popular item to owner r, so these are owners 0 .. hot_owners-1, with one item each, and
+// their chains are what the launch waits for.
+inline int hot_owners(const unsigned *cnt, int num_item, int num_owner, int percent) {
+  int64_t total = 0;
+  for (int i = 0; i < num_item; ++i) total += cnt[i];
+  if (total == 0 || num_owner <= 0) return 0;
+  int hot = 0;
+  for (int i = 0; i < num_item; ++i)
+    if ((int64_t)cnt[i] * num_owner * 100 > total * percent) ++hot;
+  return std::min(hot, num_owner);
+}
+
+// ... and how many items carry at least `percent` % of the most popular item's count: the chains within
+// reach of the longest one.
+inline int top_owners(const unsigned *cnt, int num_item, int percent) {
+  unsigned mx = 0;
+  for (int i = 0; i < num_item; ++i) mx = std::max(mx, cnt[i]);
+  int top = 0;
+  for (int i = 0; i < num_item; ++i)
+    if (cnt[i] > 0 && (uint64_t)cnt[i] * 100u >= (uint64_t)mx * (unsigned)percent) ++top;
+  return top;
 }
 
 }  // namespace svdown

@@ -2,7 +2,8 @@
 reason and the instructions that collect the most samples.  Used on k_own with every rating on
 ONE item (tools/own_study.py ... ni=1): a single owner warp is then active, so the samples are the
 stall profile of the chain link itself.
-usage: python tools/ncu_source_top.py gpurun_out/x.ncu-rep [marker-instruction] [min-executions]"""
+usage: python tools/ncu_source_top.py gpurun_out/x.ncu-rep [marker-instruction] [min-executions] [all]
+("all": every instruction of the hot loop in program order, not only the 40 with the most samples)"""
 import csv
 import subprocess
 import sys
@@ -30,7 +31,8 @@ print("by reason:", ", ".join("%s %.1f%%" % (k[6:], 100.0 * v / max(tot, 1)) for
 hot = [(n, r) for n, r in part if int(r[ix["Instructions Executed"]]) >= min_ex]
 per = sum(int(r[ix["Instructions Executed"]]) for _, r in hot) / max(1, max(int(r[ix["Instructions Executed"]]) for _, r in hot))
 print("instructions executed >= %d times: %d (%.1f per trip of the hottest)" % (min_ex, len(hot), per))
-for n, r in sorted(sorted(hot, key=lambda x: -int(x[1][ix["# Samples"]]))[:40]):
+show = hot if "all" in sys.argv[4:] else sorted(hot, key=lambda x: -int(x[1][ix["# Samples"]]))[:40]
+for n, r in sorted(show):
     st = {c[6:]: int(r[ix[c]]) for c in stall_cols if int(r[ix[c]]) > 0}
     top = sorted(st.items(), key=lambda x: -x[1])[:2]
     print("%5d  %-60s %6s %9s  %s" % (n, r[ix["Source"]].strip()[:60], r[ix["# Samples"]], r[ix["Instructions Executed"]], top))

@@ -86,10 +86,11 @@ if "stats" in FLAGS:
     rep = dict(ms_with_stats=ms1, mhz_assumed=1965)
     for name, sel in (("slowest16", order[:16]), ("owners0_15", np.arange(16)), ("median16", order[len(order) // 2 - 8:len(order) // 2 + 8])):
         rep[name] = dict(owner=sel.tolist(), us_total=(st[sel, 0] / 1965).round(0).tolist(), us_wait=(st[sel, 1] / 1965).round(0).tolist(),
-                         us_flush=(st[sel, 2] / 1965).round(0).tolist(), waits=st[sel, 3].tolist())
+                         us_flush=(st[sel, 2] / 1965).round(0).tolist(), waits=(st[sel, 3] & 0xffffffff).tolist(),
+                         not_landed=(st[sel, 3] >> 32).tolist())
     rep["all"] = dict(us_total_max=float(st[:, 0].max() / 1965), us_total_mean=float(st[:, 0].mean() / 1965),
                       us_wait_mean=float(st[:, 1].mean() / 1965), us_flush_mean=float(st[:, 2].mean() / 1965),
-                      waits_total=int(st[:, 3].sum()))
+                      waits_total=int((st[:, 3] & 0xffffffff).sum()), not_landed_total=int((st[:, 3] >> 32).sum()))
     print(json.dumps(rep), flush=True)
     out.write(json.dumps(rep) + "\n")
     g.set_option("own_stats", 0)
