@@ -109,13 +109,18 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   features) under plain L2 decay take the item-owner kernel (k_own: every item row
  *                   stays on one warp, user rows travel under version counters; bit-identical to
  *                   k_exact and to the reference); 0 keeps every row in k_exact.  Tuning:
- *                   "own_min_rows" (4096: smaller launches keep k_exact), "own_batch" (32: version
+ *                   "own_min_rows" (4096: smaller launches keep k_exact), "own_batch" (24: version
  *                   publishes the busiest owner holds back per release fence, <= 32),
  *                   "own_urgent_gap" (4096: a user whose next rating follows within this many rows
  *                   is published at once), "own_slots" (0 = auto: item rows per owner kept in
  *                   shared memory, <= 32; the rest of an owner's rows stay in L2), "own_partner" (0; 1 = the
  *                   variant that splits a link over an owner and a partner warp, k_own2: same results,
- *                   measured slower on configs[1]) */
+ *                   measured slower on configs[1]), "own_isolate" (200: an item that
+ *                   carries more than this % of the mean owner load gets the issue port of its owner warp
+ *                   to itself -- the two owner warps that share the port stay empty; 0 = off) and
+ *                   "own_isolate_full" (75: ... and one within this % of the hottest item's count a whole
+ *                   SM, for at most an eighth of the SMs; 0 = off): the chain of the hottest item is what
+ *                   the launch waits for, and a link of it is slower in company */
 int svdgpu_set_option(svdgpu_t *h, const char *name, long long value);
 /* Launch on this CUDA stream (a cudaStream_t) instead of the handle's own. */
 int svdgpu_set_stream(svdgpu_t *h, void *cuda_stream);

@@ -140,7 +140,7 @@ struct svdgpu {
   int own_min_rows = 4096;   // option "own_min_rows": launches with fewer rows keep k_exact (no plan to build)
   int own_urgent_gap = 4096;   // option "own_urgent_gap": a user whose next rating follows within this many rows
                                // is published at once instead of with the owner's batch
-  int own_batch = 32;        // option "own_batch": version publishes the most loaded owner holds back (<= 32)
+  int own_batch = 24;        // option "own_batch": version publishes the most loaded owner holds back (<= 32)
   int own_slots = 0;         // option "own_slots": item rows an owner keeps in shared memory (0 = auto, <= 32)
   int own_depth = 8;         // option "own_depth": ring slots per owner (8 or 16)
   int own_fast = 1;          // option "own_fast": 0 keeps the generic link for every shape (testing)

@@ -26,6 +26,19 @@ extern "C" long long own_assign(const unsigned *cnt, int num_item, int num_owner
   for (int w = 0; w < num_owner; ++w) batch[w] = p.batch[w];
   return p.max_load;
 }
+extern "C" int own_hot_owners(const unsigned *cnt, int num_item, int num_owner, int percent) {
+  return svdown::hot_owners(cnt, num_item, num_owner, percent);
+}
+extern "C" int own_top_owners(const unsigned *cnt, int num_item, int percent) { return svdown::top_owners(cnt, num_item, percent); }
+extern "C" long long own_assign_closed(const unsigned *cnt, int num_item, int num_owner, const char *closed, int *item_owner,
+                                       int *queue_off) {
+  svdown::HostPlan p;
+  std::vector<char> c(closed, closed + num_owner);
+  svdown::assign(cnt, num_item, num_owner, 16, p, &c);
+  for (int i = 0; i < num_item; ++i) item_owner[i] = p.item_owner[i];
+  for (int w = 0; w <= num_owner; ++w) queue_off[w] = p.queue_off[w];
+  return p.max_load;
+}
 """
 
 
@@ -174,3 +187,26 @@ def test_protocol_reproduces_the_sequential_order(lib, seed):
         assert idle_rounds < 200, "deadlock"
     for log in user_log + item_log:
         assert log == sorted(log)  # every row saw its writers in input order
+
+
+def test_closed_owners_get_nothing_and_hot_items_are_counted(lib):
+    """Issue-port / SM isolation of the hot chains (svdgpu_own.cu, own_plan_build): owners marked closed get no
+    items, everything else is dealt out as before; hot_owners / top_owners count the items that qualify."""
+    ni, num_owner = 400, 48
+    cnt = (100000.0 / (np.arange(ni) + 3.0)).astype(np.uint32)  # Zipf-like, item 0 the hottest
+    total = int(cnt.sum())
+    hot = lib.own_hot_owners(cnt.ctypes.data, ni, num_owner, 200)
+    assert hot == int((cnt.astype(np.int64) * num_owner * 100 > total * 200).sum()) and 0 < hot < num_owner
+    top = lib.own_top_owners(cnt.ctypes.data, ni, 75)
+    assert top == int((cnt >= 0.75 * cnt.max()).sum()) and top >= 1
+    assert lib.own_hot_owners(np.full(ni, 50, np.uint32).ctypes.data, ni, num_owner, 200) == 0  # flat popularity: nobody is hot
+    closed = np.zeros(num_owner, np.int8)
+    closed[[5, 17, 40]] = 1
+    owner = np.zeros(ni, np.int32)
+    qo = np.zeros(num_owner + 1, np.int32)
+    lib.own_assign_closed.restype = C.c_longlong
+    ml = lib.own_assign_closed(cnt.ctypes.data, ni, num_owner, closed.ctypes.data, owner.ctypes.data, qo.ctypes.data)
+    loads = np.diff(qo)
+    assert np.all(loads[closed == 1] == 0) and not np.isin(owner, [5, 17, 40]).any()
+    assert loads.sum() == total and ml == loads.max() == cnt.max()
+    assert np.array_equal(owner[:5], np.arange(5)) and owner[5] == 6  # the r-th hottest item on the r-th open owner
