@@ -95,11 +95,14 @@ __global__ void k_max_u32(const unsigned *cnt, unsigned n, unsigned *out) {
 
 namespace {
 
-// share of the hottest item among the rows (one small sync; resident batches measure once)
-int hot_fraction(svdgpu *h, const DevCsr &csr, int r0, int n, double *frac) {
-  *frac = 0.0;
+// share of the hottest item among the rows: the measurement is enqueued on the launch stream and lands in
+// pinned memory {count of the hottest item, rows}; `wait` makes the caller wait for it (one small sync)
+int hot_measure(svdgpu *h, const DevCsr &csr, int r0, int n, bool wait, double *frac) {
   const size_t ni = (size_t)h->shape.num_item;
-  if (n <= 0 || ni == 0) return 0;
+  if (n <= 0 || ni == 0) {
+    if (frac) *frac = 0.0;
+    return 0;
+  }
   if (h->hist_cap < (ni + 1) * 4) {
     if (h->d_hist) CU(h, cudaFree(h->d_hist));
     h->d_hist = nullptr;
@@ -107,17 +110,40 @@ int hot_fraction(svdgpu *h, const DevCsr &csr, int r0, int n, double *frac) {
     CU(h, cudaMalloc(&h->d_hist, (ni + 1) * 4 + 64));
     h->hist_cap = (ni + 1) * 4;
   }
+  if (!h->h_hot) {
+    CU(h, cudaMallocHost(&h->h_hot, 2 * sizeof(unsigned)));
+    CU(h, cudaEventCreateWithFlags(&h->ev_hot, cudaEventDisableTiming));
+  }
   CU(h, cudaMemsetAsync(h->d_hist, 0, (ni + 1) * 4, h->stream));
   k_item_hist<<<(int)std::min<long long>(h->num_sm * 16, ((long long)n + 255) / 256), 256, 0, h->stream>>>(
       csr, r0, n, (unsigned)ni, h->d_hist);
   k_max_u32<<<std::min<int>(h->num_sm * 4, (int)((ni + 255) / 256)), 256, 0, h->stream>>>(h->d_hist, (unsigned)ni, h->d_hist + ni);
   CU(h, cudaGetLastError());
   h->n_launch += 2;
-  unsigned mx = 0;
-  CU(h, cudaMemcpyAsync(&mx, h->d_hist + ni, 4, cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpyAsync(h->h_hot, h->d_hist + ni, 4, cudaMemcpyDeviceToHost, h->stream));
+  h->h_hot[1] = (unsigned)n;
   h->n_d2h += 4;
-  *frac = (double)mx / (double)n;
+  if (!wait) {
+    CU(h, cudaEventRecord(h->ev_hot, h->stream));
+    h->hot_pending = 1;
+    return 0;
+  }
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->hot_pending = 0;
+  if (frac) *frac = (double)h->h_hot[0] / (double)n;
+  return 0;
+}
+// Host-pointer Hogwild training calls: the first call measures its first chunk and waits for the answer; every
+// later call uses the share the call before it measured and enqueues a measurement of its own (no sync: a
+// stream of small calls -- the per-instance seam flushing 2^20 rows at a time -- would otherwise drain the
+// device once per call).
+int hot_for_call(svdgpu *h, const DevCsr &csr, int n) {
+  if (h->hot_pending && cudaEventQuery(h->ev_hot) == cudaSuccess) {
+    h->hot_pending = 0;
+    if (h->h_hot[1]) h->hot_call = (double)h->h_hot[0] / (double)h->h_hot[1];
+  }
+  if (h->hot_call < 0.0) return hot_measure(h, csr, 0, n, true, &h->hot_call);
+  if (!h->hot_pending) return hot_measure(h, csr, 0, n, false, nullptr);
   return 0;
 }
 // cap on the instances a Hogwild training launch keeps in flight (0 = none)
@@ -556,6 +582,8 @@ void svdgpu_destroy(svdgpu_t *h) {
   cudaFree(h->d_counter);
   cudaFree(h->d_abort);
   cudaFree(h->d_hist);
+  if (h->h_hot) cudaFreeHost(h->h_hot);
+  if (h->ev_hot) cudaEventDestroy(h->ev_hot);
   own_scratch_free(h->own);
   for (int i = 0; i < svdgpu::NSLOT; ++i) own_plan_free(h->slot[i].own);
   cudaFree(h->d_eval);
@@ -1026,9 +1054,8 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
       }
       if (slot_copied(h, s)) return 1;
       if (train && ci == 0 && h->hog_safety_permille > 0) {  // Hogwild guard: the first chunk speaks for the call
-        double hf = 0.0;
-        if (hot_fraction(h, csr, 0, n, &hf)) return 1;
-        set_inflight_cap(h, hf);
+        if (hot_for_call(h, csr, n)) return 1;
+        set_inflight_cap(h, h->hot_call);
       }
       if (launch_stream(h, geo, csr, 0, n, train, pred)) return 1;
       if (!train && eval_chunk(h, pred, csr.label, n)) return 1;
@@ -1437,7 +1464,7 @@ int svdgpu_batch_update(svdgpu_t *h, svdgpu_batch_t *b, int begin, int end) {
     }
   } else {
     if (h->hog_safety_permille > 0) {  // Hogwild guard: the batch's hottest item, measured once
-      if (b->hot_frac < 0.0 && hot_fraction(h, batch_csr(b), 0, b->num_row, &b->hot_frac)) return 1;
+      if (b->hot_frac < 0.0 && hot_measure(h, batch_csr(b), 0, b->num_row, true, &b->hot_frac)) return 1;
       set_inflight_cap(h, b->hot_frac);
     } else {
       h->inflight_cap = 0;

@@ -148,7 +148,7 @@ struct svdgpu {
   int own_isolate = 200;     // option "own_isolate": owners of items above this % of the mean owner load get an issue port to themselves (0: off)
   int own_isolate_full = 75; // option "own_isolate_full": ... and those above this % of the hottest item's count a whole SM (0: off)
   int own_reverse = 1;       // option "own_reverse": busiest owners on the highest warp ids (the arbiter prefers them)
-  int own_spare_sms = 16;    // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
+  int own_spare_sms = 8;     // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
                              // fills of the next chunk (k_own then runs on num_sm - this many CTAs)
   int own_poll_ns = 50;      // option "own_poll_ns": loader warps sleep this long between polls without progress
   int own_partner = 0;       // option "own_partner": 1 = split link (k_own2: owner + partner warp) where the shape allows.
@@ -167,7 +167,11 @@ struct svdgpu {
   int hog_safety_permille = 1000;  // option "hogwild_safety" (per mille; 0 disables the guard)
   unsigned *d_hist = nullptr;      // item histogram + max word of the guard
   size_t hist_cap = 0;
-  double hot_frac = -1.0;          // share of the hottest item in the last measured launch
+  double hot_frac = -1.0;          // share of the hottest item the current cap was derived from
+  double hot_call = -1.0;          // ... as last measured on a host-pointer call (-1: never)
+  unsigned *h_hot = nullptr;       // pinned {count of the hottest item, rows} of the measurement in flight
+  cudaEvent_t ev_hot = nullptr;
+  int hot_pending = 0;
   int mf_ctas = 0;     // option "mf_ctas": k_mf CTAs per SM the register allocation aims at (0 = default 2)
   static constexpr int NSLOT = 3;
   Slot slot[NSLOT];
