@@ -97,6 +97,8 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   feature counts, nor its values when all are 1.0f; host threads ("scan_threads",
  *                   0 = this process's share of the cores, at most 16; fewer than 5: no scan) verify every element while earlier chunks are copied, the
  *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
+ *                   2: ordered-mode calls as well (measured slower there: the item-owner kernel, not the
+ *                   bus, sets the pace); 0: never.
  *   "hogwild_safety": Hogwild stability guard, per mille (default 1000; 0 = off).  N instances in flight that
  *                   touch a row with probability p apply ~N*p stale steps of size lr to it at once; beyond
  *                   N*p*lr ~ 2 asynchronous SGD on that row diverges.  Training launches of the fast passes
@@ -115,7 +117,10 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   is published at once), "own_slots" (0 = auto: item rows per owner kept in
  *                   shared memory, <= 32; the rest of an owner's rows stay in L2), "own_partner" (0; 1 = the
  *                   variant that splits a link over an owner and a partner warp, k_own2: same results,
- *                   measured slower on configs[1]), "own_isolate" (200: an item that
+ *                   measured slower on configs[1]), "own_redeal" (25: a plan keeps the
+ *                   deal of items to owners of the plan before it while the heaviest owner stays within this %
+ *                   of the mean -- a host-pointer call plans every chunk, and dealing anew costs the host
+ *                   2.3 ms; 0 = deal every time; counters "own_deals", "own_redeals"), "own_isolate" (200: an item that
  *                   carries more than this % of the mean owner load gets the issue port of its owner warp
  *                   to itself -- the two owner warps that share the port stay empty; 0 = off) and
  *                   "own_isolate_full" (75: ... and one within this % of the hottest item's count a whole

@@ -512,13 +512,18 @@ int svdgpu_create(svdgpu_t **out, const svdgpu_shape *shape, int device) {
   cudaDeviceProp prop;
   CUC(cudaGetDeviceProperties(&prop, device));
   h->num_sm = prop.multiProcessorCount;
-  CUC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  // The launch stream outranks the plan stream: an ordered host-pointer call plans chunk c+1 beside the k_own
+  // launch of chunk c, and the cooperative launch of chunk c+1 needs its SMs all at once -- the blocks of a plan
+  // kernel already queued for chunk c+2 must not be handed them first.
+  int prio_least = 0, prio_greatest = 0;
+  CUC(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUC(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_greatest));
   h->stream = h->own_stream;
   CUC(cudaEventCreate(&h->ev0));
   CUC(cudaEventCreate(&h->ev1));
   CUC(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
   CUC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  CUC(cudaStreamCreateWithFlags(&h->plan_stream, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithPriority(&h->plan_stream, cudaStreamNonBlocking, prio_least));
   CUC(cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming));
   for (int i = 0; i < svdgpu::NSLOT; ++i) {
     CUC(cudaEventCreateWithFlags(&h->slot[i].done, cudaEventDisableTiming));
@@ -671,9 +676,11 @@ int svdgpu_set_option(svdgpu_t *h, const char *name, long long v) {
   else if (!strcmp(name, "own_acquire")) h->own_acquire = v ? 1 : 0;
   else if (!strcmp(name, "own_reverse")) h->own_reverse = v ? 1 : 0;
   else if (!strcmp(name, "own_isolate")) h->own_isolate = v < 0 ? 0 : v;
+  else if (!strcmp(name, "own_redeal")) h->own_redeal = v < 0 ? 0 : v;
+  else if (!strcmp(name, "own_plan_beside")) h->own_plan_beside = v ? 1 : 0;
   else if (!strcmp(name, "own_isolate_full")) h->own_isolate_full = v < 0 ? 0 : v;
   else if (!strcmp(name, "own_slots")) h->own_slots = (int)std::max<long long>(0, std::min<long long>(v, 32));
-  else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v ? 1 : 0;
+  else if (!strcmp(name, "compact_h2d")) h->compact_h2d = v < 0 ? 0 : v > 2 ? 2 : (int)v;
   else if (!strcmp(name, "scan_threads")) h->scan_threads = (int)std::max<long long>(0, std::min<long long>(v, 256));
   else if (!strcmp(name, "compact_min_rows")) h->compact_min_rows = (int)std::max<long long>(1, std::min<long long>(v, 1LL << 30));
   else return fail(h, "unknown option '%s'", name);
@@ -811,6 +818,10 @@ long long svdgpu_get_counter(const svdgpu_t *h, const char *name) {
   if (!strcmp(name, "collective_bytes")) return h->n_coll_bytes;
   if (!strcmp(name, "own_launches")) return h->n_own;  // ordered mode: launches of the item-owner kernel
   if (!strcmp(name, "own_rows")) return h->n_own_rows;
+  if (!strcmp(name, "own_deals")) return h->n_deal;      // plans that dealt the items out to owners (host LPT)
+  if (!strcmp(name, "own_redeals")) return h->n_redeal;  // plans that carried the previous deal over
+  if (!strcmp(name, "own_lpt_us")) return h->own_lpt_us;          // plan: host time dealing the items out
+  if (!strcmp(name, "own_cntwait_us")) return h->own_cntwait_us;  // plan: host time waiting for the item counts
   if (!strcmp(name, "ingest_read_us")) return (long long)(h->ingest_read_s * 1e6);  // file -> pinned chunk
   if (!strcmp(name, "ingest_call_us")) return (long long)(h->ingest_call_s * 1e6);  // hot-path calls
   if (!strcmp(name, "lanes")) {
@@ -911,6 +922,10 @@ static int plan_on_side(svdgpu *h, const DevCsr &csr, int n, OwnPlan &p, int *ba
     after = h->ev_plan;
   }
   CU(h, cudaStreamWaitEvent(h->plan_stream, after, 0));
+  if (!h->own_plan_beside) {  // (experiment: the plan only starts when the launch stream has drained)
+    CU(h, cudaEventRecord(h->ev_plan, h->stream));
+    CU(h, cudaStreamWaitEvent(h->plan_stream, h->ev_plan, 0));
+  }
   if (own_plan_build(h, csr, 0, n, p, h->plan_stream, bad, ctas)) return 1;
   CU(h, cudaEventRecord(done, h->plan_stream));
   CU(h, cudaStreamWaitEvent(h->stream, done, 0));
@@ -954,7 +969,11 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     // and what they save is host memory bandwidth the ranks of one box share)
     if (scan_threads < (exact ? 2 : 5)) scan_threads = 0;
   }
-  const bool compact = h->compact_h2d && scan_threads > 0 && (!exact || own_ok) && !sides_on(h) && num_row >= h->compact_min_rows;
+  // (the ordered mode only on request: its kernel, not the bus, sets the pace -- 32 B per row cross in 0.6 ns,
+  // a row trains in 0.8 ns -- and measured, the chunks' plans interleave better with the copies taking their time:
+  // 1.01 G inst/s with everything copied against 0.83 G with the compact path)
+  const bool compact = (exact ? h->compact_h2d >= 2 && own_ok : h->compact_h2d >= 1) && scan_threads > 0 && !sides_on(h) &&
+                       num_row >= h->compact_min_rows;
   if (h->hog_safety_permille <= 0) h->inflight_cap = 0;
   svdscan::ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
   if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value, scan_threads);

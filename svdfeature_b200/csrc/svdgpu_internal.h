@@ -32,12 +32,18 @@ struct OwnPlan {
   long long rows = 0, max_load = 0;
   bool valid = false;
 };
+namespace svdown {
+struct HostPlan;
+}
 struct OwnScratch {
   DevBuf cnt_item, cnt_user, start_user, flag, keyA, keyB, valA, valB, key_item, tick, tmp, item_owner, item_slot, stats;
   int stats_owners = 0;   // owners of the launch the stats buffer describes
   void *h_cnt = nullptr;  // pinned: item counts + flag word
   size_t h_cnt_cap = 0;
   cudaEvent_t ev = nullptr;
+  svdown::HostPlan *deal = nullptr;  // the last deal of items to owners (svdgpu_ownplan.h), carried over between plans
+  int deal_ctas = 0;                 // ... and what it was made for
+  long long deal_key = 0;
 };
 
 // One staging slot for host-pointer calls: pinned mirrors + device arrays.
@@ -130,7 +136,7 @@ struct svdgpu {
                        // depth 2 / two CTAs per SM (1.17 G inst/s: the pass is short of warps, not of bytes in flight)
   int stream_tile = 0; // option "stream_tile": rows per tile of the generic pass (0 = auto: 64 / 32 / 16 / 8 by row width)
   int ring_depth = 0;  // option "ring_depth": k_mf ring depth (0 = default 4)
-  int compact_h2d = 1;  // option "compact_h2d": Hogwild / predict host-pointer calls do not copy a chunk's
+  int compact_h2d = 1;  // option "compact_h2d" (1: Hogwild / predict, 2: ordered host-pointer calls too): they do not copy a chunk's
                         // row_ptr when every row has the same feature counts, nor its values when all are 1.0f
                         // (checked on host threads while earlier chunks are copied; rebuilt on the device)
   int scan_threads = 0;            // option "scan_threads": host threads of that check (0 = min(cores, 16))
@@ -146,6 +152,8 @@ struct svdgpu {
   int own_fast = 1;          // option "own_fast": 0 keeps the generic link for every shape (testing)
   int own_acquire = 0;       // option "own_acquire": loaders poll versions with ld.acquire.gpu (adds CCTL.IVALL per poll)
   int own_isolate = 200;     // option "own_isolate": owners of items above this % of the mean owner load get an issue port to themselves (0: off)
+  int own_plan_beside = 1;   // option "own_plan_beside": host-pointer calls build the plan of chunk c+1 while k_own trains chunk c (0: after it; measured slower)
+  int own_redeal = 25;       // option "own_redeal": a plan keeps the previous plan's deal of items to owners while its heaviest owner is within this % of the best possible (0: deal every time)
   int own_isolate_full = 75; // option "own_isolate_full": ... and those above this % of the hottest item's count a whole SM (0: off)
   int own_reverse = 1;       // option "own_reverse": busiest owners on the highest warp ids (the arbiter prefers them)
   int own_spare_sms = 8;     // option "own_spare_sms": SMs an ordered host-pointer call leaves to the plan kernels and
@@ -198,6 +206,8 @@ struct svdgpu {
   std::string err;
   long long n_launch = 0, n_inst = 0, n_h2d = 0, n_d2h = 0;
   long long n_own = 0, n_own_rows = 0;  // k_own launches and the rows they trained
+  long long n_deal = 0, n_redeal = 0;  // plans that dealt the items out anew / carried the deal over
+  long long own_lpt_us = 0, own_cntwait_us = 0;  // plan: host time dealing items out / waiting for the item counts
 };
 
 // an instance batch resident in HBM (svdgpu_batch_create / svdgpu_batch_sample_pairs)

@@ -33,6 +33,7 @@
 
 #include <cub/cub.cuh>
 
+#include <chrono>
 #include <cstring>
 
 namespace svdk {
@@ -561,28 +562,33 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
     // What a link can ask for besides its arithmetic; anything set ends the inner loop below.
     // (a change of item is reported beside these, in `evx`)
     enum : unsigned { EV_PUBLISH = 1u, EV_LAST = 2u, EV_WAIT = 4u };
-    // `rdy`: has the entry after the current one landed?  The barrier test takes ~150 cycles to answer
-    // (B300_MICROARCH.md: test_wait 149), so it is made one link ahead: link j consumes the answer for entry
-    // j+1 that link j-1 asked for, and asks for entry j+2.  "Not yet" sends the owner to the blocking wait
-    // (which looks again), so a stale "no" costs a detour, never a wrong read.
-    // Asking and reading the answer are two statements around one predicate register of this function, so that
-    // the link's work stands between them (as one statement the answer is consumed at once: a 150-cycle stall).
-    unsigned rdy = 0u, evx = 0u;
+    // Has the entry after the current one landed?  The barrier test takes ~150 cycles to answer
+    // (B300_MICROARCH.md: test_wait 149), so it is made one link ahead: link j asks for entry j+2 when it
+    // starts, and reads -- where it is about to read entry j+1 out of its slot -- what link j-1 asked for.
+    // "Not yet" sends the owner to the blocking wait (which looks again), so a stale "no" costs a detour,
+    // never a wrong read.  Asking and reading the answer are two statements around a predicate register of
+    // this function, so that the links' work stands between them (as one statement the answer is consumed at
+    // once: a 150-cycle stall); two registers, one per link of a loop trip, since two questions are open.
+    unsigned evx = 0u;
     const unsigned lane0i = lane0 ? 1u : 0u;
-    auto test_entry = [&](int e) -> unsigned {
-      return e < n && mbar_test_s(full_s + 8u * (unsigned)(e & (D - 1)), (unsigned)(e >> LOG_D) & 1u) ? 1u : 0u;
+    asm volatile(".reg .pred own_landed0, own_landed1;");
+    auto ask_entry = [&](auto which, int e) {  // (past the end of the queue: some barrier of the ring, answer unused)
+      const unsigned bar = full_s + 8u * (unsigned)(e & (D - 1)), par = (unsigned)(e >> LOG_D) & 1u;
+      if (decltype(which)::value == 0)
+        asm volatile("mbarrier.test_wait.parity.shared::cta.b64 own_landed0, [%0], %1;" ::"r"(bar), "r"(par) : "memory");
+      else
+        asm volatile("mbarrier.test_wait.parity.shared::cta.b64 own_landed1, [%0], %1;" ::"r"(bar), "r"(par) : "memory");
     };
-    asm volatile(".reg .pred own_landed;");
-    auto ask_entry = [&](int e) {  // (past the end of the queue: some barrier of the ring, answer unused)
-      asm volatile("mbarrier.test_wait.parity.shared::cta.b64 own_landed, [%0], %1;" ::"r"(full_s + 8u * (unsigned)(e & (D - 1))),
-                   "r"((unsigned)(e >> LOG_D) & 1u)
-                   : "memory");
-    };
-    auto answer = [&]() -> unsigned {
+    auto answer = [&](auto which) -> unsigned {
       unsigned ok;
-      asm volatile("selp.u32 %0, 1, 0, own_landed;" : "=r"(ok)::"memory");
+      if (decltype(which)::value == 0)
+        asm volatile("selp.u32 %0, 1, 0, own_landed0;" : "=r"(ok)::"memory");
+      else
+        asm volatile("selp.u32 %0, 1, 0, own_landed1;" : "=r"(ok)::"memory");
       return ok;
     };
+    typedef std::integral_constant<int, 0> P0;
+    typedef std::integral_constant<int, 1> P1;
     // One link: the arithmetic of `cur` (whose item row is in registers), its user row stored, the next
     // entry read out of its ring slot into `nxt` if it has landed.  Straight-line code; the warp issues in
     // order, so the statements stand in the order the chain wants them:
@@ -591,8 +597,8 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
     //   2. the off-chain sums;
     //   3. the transposed products come back, the next entry is read behind them;
     //   4. the adds of the dot, the error, the two new rows.
-    auto body = [&](Link &cur, Link &nxt, int j) -> unsigned {
-      ask_entry(j + 2);
+    auto body = [&](auto mine, auto other, Link &cur, Link &nxt, int j) -> unsigned {
+      ask_entry(mine, j + 2);
       const float4 ti = f4_add_scaled(f4_zero(), wi0, cur.im, false);  // prepare_tmp, base.h:354-381
       const unsigned dw = dot_w + ((unsigned)j & 1u) * DOTBUF, dr = dot_r + ((unsigned)j & 1u) * DOTBUF;
       sts32f(dw, __fmul_rn(cur.tu.x, ti.x));
@@ -603,7 +609,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       // answer must stay in one from here to the end of the link)
       const int j1 = j + 1, s1 = j1 & (D - 1);
       const unsigned more = (unsigned)(j1 - n) >> 31;  // 1: there is a next entry
-      const unsigned nready = more & rdy;              // 1: ... and it has landed
+      const unsigned nready = more & answer(other);    // 1: ... and it has landed (asked by the link before)
       const float uval = __uint_as_float(cur.e1.y), ival = __uint_as_float(cur.e1.z), label = __uint_as_float(cur.e0.z);
       double bsum = 0.0;  // calc_bias, base.h:313-353 (needs no dot: off the chain)
       if (has_ub) bsum = __dadd_rn(bsum, (double)__fmul_rn(uval, cur.ub));
@@ -655,8 +661,7 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       evx = (0u - nready) & (nxt.e0.w ^ cur_item);  // non-zero: the next entry is of another item
       const unsigned ev = (cur.e1.w & 1u) | ((unsigned)(B - 1 - pend) >> 31)   // EV_PUBLISH: asked for, or the batch is full
                           | ((more ^ 1u) << 1)                                  // EV_LAST
-                          | ((more & (rdy ^ 1u)) << 2);                         // EV_WAIT
-      rdy = ((unsigned)(j + 2 - n) >> 31) & answer();
+                          | ((more & (nready ^ 1u)) << 2);                      // EV_WAIT
       return ev;
     };
     Link la, lb;
@@ -665,20 +670,20 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
       __syncwarp();
       if (lane0) mbar_arrive_s(empty_s);
       get_item(la.e0.w, la.e1.x);
-      rdy = test_entry(1);
+      ask_entry(P1(), 1);
       // The inner loop is nothing but links (two per trip: `la` and `lb` swap roles, no register moves);
       // whatever else has to happen -- the publish fence, a next entry that has not landed, a change of
       // item, the end of the queue -- leaves it, is dealt with here, and re-enters with the current entry in `la`.
       for (int j = 0;;) {
         unsigned ev;
         for (;;) {
-          ev = body(la, lb, j);
+          ev = body(P0(), P1(), la, lb, j);
           if (ev | evx) {
             la = lb;
             break;
           }
           ++j;
-          ev = body(lb, la, j);
+          ev = body(P1(), P0(), lb, la, j);
           if (ev | evx) break;
           ++j;
         }
@@ -692,8 +697,8 @@ __global__ void __launch_bounds__(own_threads(D), 1) k_own(const OwnArgs a) {
           read_link(s, la);
           __syncwarp();
           if (lane0) mbar_arrive_s(empty_s + 8u * (unsigned)s);
-          rdy = test_entry(j + 1);  // (the answer the skipped link would have asked for may be stale)
         }
+        ask_entry(P1(), j + 1);  // (the first link of a trip reads this register)
         if (la.e0.w != cur_item) {
           put_item();
           get_item(la.e0.w, la.e1.x);
@@ -1111,6 +1116,8 @@ void own_scratch_free(OwnScratch &s) {
   s.h_cnt_cap = 0;
   if (s.ev) cudaEventDestroy(s.ev);
   s.ev = nullptr;
+  delete s.deal;
+  s.deal = nullptr;
 }
 
 // Build the plan of rows [r0, r0+n) of a device CSR on `st`.  Returns non-zero on failure (message
@@ -1176,14 +1183,27 @@ int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cuda
   }
 
   // host: deal the items out
+  const auto t_wait0 = std::chrono::steady_clock::now();
   CU(h, cudaEventSynchronize(s.ev));
+  const auto t_lpt0 = std::chrono::steady_clock::now();
+  h->own_cntwait_us += std::chrono::duration_cast<std::chrono::microseconds>(t_lpt0 - t_wait0).count();
   const unsigned *hc = (const unsigned *)s.h_cnt;
   const int fl = (int)hc[m.num_item];
   if (fl) {
     if (bad) *bad = fl;
     return 0;  // not for k_own (the caller reports bound errors / falls back to k_exact)
   }
-  svdown::HostPlan hp;
+  // The deal of items to owners is carried over from the plan before while it stays a good one for the new
+  // counts (svdown::redeal; the options that shape a deal are part of its key): a host-pointer call plans every
+  // chunk, and dealing anew costs the host 2.3 ms of a 3.6 ms chunk.
+  if (!s.deal) s.deal = new svdown::HostPlan();
+  svdown::HostPlan &hp = *s.deal;
+  const long long deal_key = (long long)h->own_batch | ((long long)h->own_isolate << 8) | ((long long)h->own_isolate_full << 24) |
+                             ((long long)per_cta << 40) | ((long long)m.num_item << 44);
+  const bool carried = h->own_redeal > 0 && s.deal_ctas == ctas && s.deal_key == deal_key && hp.age < 64 &&
+                       svdown::redeal(hc, m.num_item, h->own_batch, h->own_redeal, hp);
+  if (carried) ++h->n_redeal;
+  else {
   // The chain of the hottest item is what the whole launch waits for, and a link of it is slower in company:
   // measured per link (20 M rows, hottest item 51 080), 0.27 us with the SM to itself, 0.32 us with the other
   // eleven owner warps at work but nobody on its issue port (warps w, w+4, w+8 share one: warp id mod 4),
@@ -1205,7 +1225,12 @@ int own_plan_build(svdgpu *h, const DevCsr &csr, int r0, int n, OwnPlan &p, cuda
           if (c % 4 == 0 || o < full) closed[(size_t)c * ctas + o] = 1;  // (c % 4 == 0: same port under either mapping)
     }
   }
-  svdown::assign(hc, m.num_item, W, h->own_batch, hp, closed.empty() ? nullptr : &closed);
+  svdown::assign(hc, m.num_item, W, h->own_batch, hp, closed.empty() ? nullptr : &closed, h->own_redeal > 0);
+  s.deal_ctas = ctas;
+  s.deal_key = deal_key;
+  ++h->n_deal;
+  }
+  h->own_lpt_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_lpt0).count();
   if (own_reserve(h, p.queue_off, (size_t)(W + 1) * 4) || own_reserve(h, p.item_off, (size_t)(W + 1) * 4) ||
       own_reserve(h, p.items, std::max<size_t>(hp.items.size(), 1) * 4) || own_reserve(h, p.batch, (size_t)W * 4) ||
       own_reserve(h, p.entries, nn * sizeof(OwnEntry)))

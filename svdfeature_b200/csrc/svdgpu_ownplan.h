@@ -30,6 +30,8 @@ struct HostPlan {
   std::vector<unsigned> items;       // items by owner, most popular first (slot order)
   std::vector<int> batch;            // [num_owner] user-row publishes an owner may hold back
   int64_t max_load = 0;
+  int num_open = 0;                  // owners that take items (num_owner - closed ones)
+  int age = 0;                       // redeal() calls since the deal was made
 };
 
 // cnt[i] = ratings of item i in the batch.  Owner w of the launch is warp (w / grid) of block
@@ -40,9 +42,12 @@ struct HostPlan {
 // closed (optional, [num_owner]): owners that get no items -- the warps that would share an issue port with
 // the owner of a very hot item (hot_owners below; the mapping owner -> warp is the kernel's, so the caller
 // marks them).
+// deal_all: items the batch never touches get an owner too (round robin over the lighter owners, behind the
+// owner's popular items), so that redeal() can carry the deal over to a batch that does touch them.
 inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_batch, HostPlan &p,
-                   const std::vector<char> *closed = nullptr) {
+                   const std::vector<char> *closed = nullptr, bool deal_all = false) {
   p.num_owner = num_owner;
+  p.age = 0;
   p.item_owner.assign((size_t)num_item, -1);
   p.item_slot.assign((size_t)num_item, 0u);
   std::vector<int> order;
@@ -52,8 +57,13 @@ inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_bat
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
   typedef std::pair<int64_t, int> Load;  // (rows, owner): smallest load first, then smallest owner id
   std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  std::vector<int> open;
   for (int w = 0; w < num_owner; ++w)
-    if (!closed || !(*closed)[(size_t)w]) heap.push(Load(0, w));
+    if (!closed || !(*closed)[(size_t)w]) {
+      heap.push(Load(0, w));
+      open.push_back(w);
+    }
+  p.num_open = (int)open.size();
   std::vector<int64_t> load((size_t)num_owner, 0);
   std::vector<int> nitem((size_t)num_owner, 0);
   for (int i : order) {
@@ -64,6 +74,23 @@ inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_bat
     l.first += cnt[i];
     load[(size_t)l.second] = l.first;
     heap.push(l);
+  }
+  if (deal_all && !open.empty()) {
+    // (to owners that carry no more than the mean: the owner of a hot item keeps its chain to itself)
+    int64_t total = 0;
+    for (int w : open) total += load[(size_t)w];
+    std::vector<int> light;
+    for (int w : open)
+      if (load[(size_t)w] * (int64_t)open.size() <= total) light.push_back(w);
+    if (!light.empty()) open.swap(light);
+    size_t rr = 0;
+    for (int i = 0; i < num_item; ++i)
+      if (cnt[i] == 0) {
+        const int w = open[rr++ % open.size()];
+        p.item_owner[(size_t)i] = w;
+        p.item_slot[(size_t)i] = (unsigned)nitem[(size_t)w]++;
+        order.push_back(i);
+      }
   }
   p.queue_off.assign((size_t)num_owner + 1, 0);
   p.item_off.assign((size_t)num_owner + 1, 0);
@@ -81,6 +108,39 @@ inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_bat
     const int64_t b = p.max_load > 0 ? (int64_t)max_batch * load[(size_t)w] / p.max_load : 1;
     p.batch[(size_t)w] = (int)std::max<int64_t>(1, std::min<int64_t>(b, max_batch));
   }
+}
+
+// Carry the deal of an earlier batch over to new counts: same owners, same item lists; only the queue
+// offsets, the loads and the batch sizes are recomputed (microseconds instead of the milliseconds of a new
+// deal -- a host-pointer call plans every chunk).  Any deal is a CORRECT one; this one is kept as long as it is
+// a good one: every touched item has an owner, and the heaviest owner carries no more than the hottest item
+// alone, or slack_percent % above the mean of the open owners.  false: deal again.
+inline bool redeal(const unsigned *cnt, int num_item, int max_batch, int slack_percent, HostPlan &p) {
+  const int num_owner = p.num_owner;
+  if (num_owner <= 0 || p.num_open <= 0 || (int)p.item_owner.size() != num_item) return false;
+  std::vector<int64_t> load((size_t)num_owner, 0);
+  int64_t total = 0;
+  unsigned mx = 0;
+  for (int i = 0; i < num_item; ++i) {
+    const unsigned c = cnt[i];
+    if (!c) continue;
+    const int w = p.item_owner[(size_t)i];
+    if (w < 0) return false;
+    load[(size_t)w] += c;
+    total += c;
+    mx = std::max(mx, c);
+  }
+  const int64_t max_load = *std::max_element(load.begin(), load.end());
+  const int64_t mean = (total + p.num_open - 1) / p.num_open;
+  if (max_load > std::max<int64_t>(mx, mean * (100 + slack_percent) / 100)) return false;
+  p.max_load = max_load;
+  for (int w = 0; w < num_owner; ++w) {
+    p.queue_off[(size_t)w + 1] = p.queue_off[(size_t)w] + (int)load[(size_t)w];
+    const int64_t b = max_load > 0 ? (int64_t)max_batch * load[(size_t)w] / max_load : 1;
+    p.batch[(size_t)w] = (int)std::max<int64_t>(1, std::min<int64_t>(b, max_batch));
+  }
+  ++p.age;
+  return true;
 }
 
 // How many of the most popular items carry more than `percent` % of an owner's mean load each: LPT gives

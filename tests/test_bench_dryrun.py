@@ -42,7 +42,8 @@ class _FakeGpu:
     """What bench.py calls on api.SvdGpu; predictions are the base score."""
 
     def __init__(self, *a, **k):
-        self.c = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0, "own_launches": 0, "collectives": 0, "collective_bytes": 0}
+        self.c = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0, "own_launches": 0, "collectives": 0, "collective_bytes": 0,
+                  "own_deals": 0, "own_redeals": 0, "own_lpt_us": 0, "own_cntwait_us": 0}
         self.compact = 1
         self.mode = 1
 
@@ -85,7 +86,8 @@ class _FakeGpu:
 
     def update_csr(self, csr):
         n = len(csr[1])
-        self.c["h2d_bytes"] += n * (12 if self.compact else 32)
+        compact = self.compact >= (2 if self.mode == 0 else 1)  # (the ordered mode copies everything unless asked)
+        self.c["h2d_bytes"] += n * (12 if compact else 32)
 
     def predict_csr(self, csr):
         n = len(csr[1])
@@ -174,7 +176,9 @@ def test_bench_main_runs_against_stand_ins(monkeypatch, capfd):
     assert d["hogwild"]["value"] > 0 and d["hogwild"]["roofline"]["kernel"] == "k_mf"
     assert "mode" not in d["config"] and d["config"]["rows_per_step"] == 20000
     assert d["seam"]["ordered"] > 0 and d["seam"]["hogwild"] > 0
-    assert d["e2e"]["h2d_bytes_per_step"] == 20000 * 12 and d["e2e"]["full_copy"]["h2d_bytes_per_step"] == 20000 * 32
+    assert d["e2e"]["h2d_bytes_per_step"] == 20000 * 32 and d["e2e"]["compact_h2d"]["h2d_bytes_per_step"] == 20000 * 12
+    assert d["hogwild"]["e2e"]["h2d_bytes_per_step"] == 20000 * 12 and d["hogwild"]["e2e"]["full_copy"]["h2d_bytes_per_step"] == 20000 * 32
+    assert d["e2e"]["plans_per_step"]["dealt_anew"] == 0
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
     assert "error" not in d["parity"]

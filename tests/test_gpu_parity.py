@@ -895,7 +895,7 @@ def test_exact_owner_host_call_at_scale(native, compact, pinned, partner):
     params = dict(num_user=nu, num_item=ni, num_factor=k, learning_rate=0.005, wd_user=0.004, wd_item=0.004,
                   base_score=3.6)
     data = synth.basic_mf(n, nu, ni, seed=41, zipf_q=20.0)
-    opts = {"chunk_rows": 150000, "compact_h2d": compact, "compact_min_rows": 1, "scan_threads": 4,
+    opts = {"chunk_rows": 150000, "compact_h2d": 2 * compact, "compact_min_rows": 1, "scan_threads": 4,  # (2: ordered calls too)
             "own_partner": partner}  # 1: k_own2 (owner + partner warps), 0: k_own
     for kv in os.environ.get("SVDGPU_TEST_OPTS", "").split():
         opts[kv.split("=")[0]] = int(kv.split("=")[1])
@@ -914,4 +914,6 @@ def test_exact_owner_host_call_at_scale(native, compact, pinned, partner):
     o.update_csr(data)
     g.update_csr(gdata)
     assert _maxdiff(o, g) == 0.0
+    # every chunk was planned: its items dealt out anew, or the deal of the chunk before carried over
+    assert g.counter("own_deals") + g.counter("own_redeals") == 2 * ((n + 149999) // 150000) and g.counter("own_deals") >= 1
     g.close()

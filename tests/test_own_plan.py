@@ -30,6 +30,18 @@ extern "C" int own_hot_owners(const unsigned *cnt, int num_item, int num_owner, 
   return svdown::hot_owners(cnt, num_item, num_owner, percent);
 }
 extern "C" int own_top_owners(const unsigned *cnt, int num_item, int percent) { return svdown::top_owners(cnt, num_item, percent); }
+// deal on cnt_a (all items get owners), carry over to cnt_b: returns 1 if carried; outputs describe the plan for cnt_b
+extern "C" int own_redeal(const unsigned *cnt_a, const unsigned *cnt_b, int num_item, int num_owner, int slack, int *item_owner,
+                          int *queue_off, int *batch, long long *max_load) {
+  svdown::HostPlan p;
+  svdown::assign(cnt_a, num_item, num_owner, 16, p, nullptr, true);
+  const int ok = svdown::redeal(cnt_b, num_item, 16, slack, p) ? 1 : 0;
+  for (int i = 0; i < num_item; ++i) item_owner[i] = p.item_owner[i];
+  for (int w = 0; w <= num_owner; ++w) queue_off[w] = p.queue_off[w];
+  for (int w = 0; w < num_owner; ++w) batch[w] = p.batch[w];
+  *max_load = p.max_load;
+  return ok;
+}
 extern "C" long long own_assign_closed(const unsigned *cnt, int num_item, int num_owner, const char *closed, int *item_owner,
                                        int *queue_off) {
   svdown::HostPlan p;
@@ -53,6 +65,11 @@ def lib(tmp_path_factory):
     lib = C.CDLL(str(so))
     lib.own_assign.restype = C.c_longlong
     lib.own_assign.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    lib.own_hot_owners.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.own_top_owners.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.own_assign_closed.restype = C.c_longlong
+    lib.own_assign_closed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.own_redeal.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -204,9 +221,37 @@ def test_closed_owners_get_nothing_and_hot_items_are_counted(lib):
     closed[[5, 17, 40]] = 1
     owner = np.zeros(ni, np.int32)
     qo = np.zeros(num_owner + 1, np.int32)
-    lib.own_assign_closed.restype = C.c_longlong
     ml = lib.own_assign_closed(cnt.ctypes.data, ni, num_owner, closed.ctypes.data, owner.ctypes.data, qo.ctypes.data)
     loads = np.diff(qo)
     assert np.all(loads[closed == 1] == 0) and not np.isin(owner, [5, 17, 40]).any()
     assert loads.sum() == total and ml == loads.max() == cnt.max()
     assert np.array_equal(owner[:5], np.arange(5)) and owner[5] == 6  # the r-th hottest item on the r-th open owner
+
+
+def test_redeal_carries_a_deal_over_while_it_is_good(lib):
+    """svdown::redeal: the same owners for new counts of the same distribution (queue offsets, loads and batch
+    sizes follow the new counts; items the first batch never touched have owners too); refused when the
+    popularity has moved."""
+    ni, num_owner = 600, 32
+    rng = np.random.default_rng(5)
+    p = 1.0 / (np.arange(ni) + 5.0)
+    p /= p.sum()
+    a = rng.multinomial(200000, p).astype(np.uint32)
+    b = rng.multinomial(200000, p).astype(np.uint32)
+    a[-40:] = 0  # untouched by the first batch, touched by the second
+    owner = np.zeros(ni, np.int32)
+    qo = np.zeros(num_owner + 1, np.int32)
+    batch = np.zeros(num_owner, np.int32)
+    ml = C.c_longlong(0)
+    ok = lib.own_redeal(a.ctypes.data, b.ctypes.data, ni, num_owner, 25, owner.ctypes.data, qo.ctypes.data, batch.ctypes.data,
+                        C.byref(ml))
+    assert ok == 1 and np.all(owner >= 0)
+    loads = np.bincount(owner, weights=b, minlength=num_owner).astype(np.int64)
+    assert np.array_equal(np.diff(qo), loads) and ml.value == loads.max()
+    assert loads.max() <= max(b.max(), 1.25 * np.ceil(b.sum() / num_owner))
+    assert batch.min() >= 1 and batch.max() == 16 and batch[np.argmax(loads)] == 16
+    # the popularity moves to the other end of the catalogue: the old deal piles the load on a few owners
+    moved = b[::-1].copy()
+    ok = lib.own_redeal(a.ctypes.data, moved.ctypes.data, ni, num_owner, 25, owner.ctypes.data, qo.ctypes.data,
+                        batch.ctypes.data, C.byref(ml))
+    assert ok == 0

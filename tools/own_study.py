@@ -95,13 +95,15 @@ if "stats" in FLAGS:
     out.write(json.dumps(rep) + "\n")
     g.set_option("own_stats", 0)
 # host-pointer call (plan per chunk inside the call)
-for chunk in (() if "nohost" in FLAGS else (1 << 20, 1 << 23)):
+for chunk in (() if "nohost" in FLAGS else (1 << 20, 1 << 22, 1 << 23)):
     g.set_option("chunk_rows", chunk)
+    c0 = (g.counter("own_lpt_us"), g.counter("own_cntwait_us"))
     t0 = time.perf_counter()
     g.update_csr(data)
     g.sync()
     dt = time.perf_counter() - t0
-    line = dict(host_call_rows=N, chunk_rows=chunk, s=dt, minst_s=N / dt / 1e6)
+    line = dict(host_call_rows=N, chunk_rows=chunk, s=dt, minst_s=N / dt / 1e6, plan_host_lpt_ms=(g.counter("own_lpt_us") - c0[0]) / 1e3,
+                plan_host_wait_counts_ms=(g.counter("own_cntwait_us") - c0[1]) / 1e3)
     print(json.dumps(line), flush=True)
     out.write(json.dumps(line) + "\n")
 b.close()
