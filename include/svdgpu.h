@@ -97,8 +97,9 @@ int svdgpu_set_mode(svdgpu_t *h, int mode);
  *                   feature counts, nor its values when all are 1.0f; host threads ("scan_threads",
  *                   0 = this process's share of the cores, at most 16; fewer than 5: no scan) verify every element while earlier chunks are copied, the
  *                   arrays are rebuilt on the device.  What the kernels read is identical either way.
- *                   2: ordered-mode calls as well (measured slower there: the item-owner kernel, not the
- *                   bus, sets the pace); 0: never.
+ *                   Ordered-mode calls take this path when four or more ranks share the host
+ *                   (LOCAL_WORLD_SIZE) or with 2 (alone the item-owner kernel, not the bus, sets the pace,
+ *                   and copying everything measured faster); 0: never.
  *   "hogwild_safety": Hogwild stability guard, per mille (default 1000; 0 = off).  N instances in flight that
  *                   touch a row with probability p apply ~N*p stale steps of size lr to it at once; beyond
  *                   N*p*lr ~ 2 asynchronous SGD on that row diverges.  Training launches of the fast passes

@@ -969,11 +969,14 @@ static int run_csr_host(svdgpu_t *h, int num_row, const int *row_ptr, const floa
     // and what they save is host memory bandwidth the ranks of one box share)
     if (scan_threads < (exact ? 2 : 5)) scan_threads = 0;
   }
-  // (the ordered mode only on request: its kernel, not the bus, sets the pace -- 32 B per row cross in 0.6 ns,
-  // a row trains in 0.8 ns -- and measured, the chunks' plans interleave better with the copies taking their time:
-  // 1.01 G inst/s with everything copied against 0.83 G with the compact path)
-  const bool compact = (exact ? h->compact_h2d >= 2 && own_ok : h->compact_h2d >= 1) && scan_threads > 0 && !sides_on(h) &&
-                       num_row >= h->compact_min_rows;
+  // (The ordered mode: on request, or when four or more ranks share the host.  Alone its kernel, not the bus, sets
+  // the pace -- 32 B per row cross in 0.6 ns, a row trains in 0.8 ns -- and measured, the chunks' plans interleave
+  // better with the copies taking their time: 1.01 G inst/s with everything copied against 0.82 G compact at N=1,
+  // 2.01 against 1.63 G at N=2; eight ranks on one host are short of host bandwidth: 5.25 against 5.68 G.)
+  int local_world = 1;
+  if (const char *e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
+  const bool compact = (exact ? own_ok && (h->compact_h2d >= 2 || (h->compact_h2d == 1 && local_world >= 4)) : h->compact_h2d >= 1) &&
+                       scan_threads > 0 && !sides_on(h) && num_row >= h->compact_min_rows;
   if (h->hog_safety_permille <= 0) h->inflight_cap = 0;
   svdscan::ScanPool pool(compact ? nchunk : 0);  // (joined on every way out of this function)
   if (compact) pool.start(num_row, h->chunk_rows, row_ptr, value, scan_threads);
