@@ -795,10 +795,14 @@ def test_exact_owner_matches_oracle(native, k, resident):
 @pytest.mark.parametrize("options", [dict(own_slots=1), dict(own_batch=1), dict(own_batch=32, own_urgent_gap=0),
                                      dict(own_partner=0), dict(own_partner=0, own_slots=1), dict(own_fast=0),
                                      dict(own_urgent_gap=1 << 30), dict(own_min_rows=1, chunk_rows=37),
-                                     dict(own_min_rows=1, chunk_rows=1)])
+                                     dict(own_min_rows=1, chunk_rows=1), dict(own_isolate=0), dict(own_isolate=1, own_isolate_full=1),
+                                     dict(own_redeal=0, chunk_rows=5000), dict(own_redeal=1000, chunk_rows=5000),
+                                     dict(own_plan_beside=0, chunk_rows=5000)])
 def test_exact_owner_options_do_not_change_the_result(native, options):
     """Item rows beyond an owner's shared-memory slots (own_slots=1: most of them live in L2),
-    publish batching, the urgent-publish rule and tiny launches: all bit-identical."""
+    publish batching, the urgent-publish rule, tiny launches, hot items with an issue port or a whole SM to
+    themselves (own_isolate=1: every item counts as hot), the deal of items to owners made anew for every
+    chunk or carried over whatever the balance (own_redeal=1000): all bit-identical."""
     nu, ni, n = 500, 2000, 20000 if options.get("chunk_rows", 0) != 1 else 300
     params = dict(num_user=nu, num_item=ni, num_factor=32, learning_rate=0.02, wd_user=0.004, wd_item=0.003,
                   wd_user_bias=0.001, wd_item_bias=0.002, base_score=3.6)
@@ -809,7 +813,41 @@ def test_exact_owner_options_do_not_change_the_result(native, options):
     g.sync()
     assert g.counter("own_rows") == n
     assert _maxdiff(o, g) == 0.0
+    if options.get("own_redeal") == 1000:
+        assert g.counter("own_deals") == 1 and g.counter("own_redeals") == 3
+    if options.get("own_redeal") == 0:
+        assert g.counter("own_deals") == 4 and g.counter("own_redeals") == 0
     g.close()
+
+
+def test_hogwild_guard_caps_the_instances_in_flight(native):
+    """Option hogwild_safety: a Hogwild training launch keeps at most
+    safety / (lr x share of the hottest item) instances in flight; the share is measured on the device."""
+    nu, ni, n = 20000, 300, 400000
+    data = synth.basic_mf(n, nu, ni, seed=7, zipf_q=2.0)
+    share = np.bincount(data[2][1::2]).max() / n
+    for safety, lr in ((1000, 0.01), (500, 0.02), (0, 0.01)):
+        g = native.SvdGpu(num_user=nu, num_item=ni, num_factor=32)
+        g.set_hparams(learning_rate=lr, wd_user=0.004, wd_item=0.004, base_score=3.6)
+        g.set_mode(native.MODE_HOGWILD)
+        g.set_option("hogwild_safety", safety)
+        rng = np.random.default_rng(1)
+        g.upload(np.zeros(nu + ni, np.float32), (rng.standard_normal((nu + ni, 32)) * 0.01).astype(np.float32), np.zeros(1, np.float32))
+        b = g.batch_create(data)
+        g.batch_update(b)
+        g.sync()
+        cap = g.counter("inflight_cap")
+        if safety:
+            assert abs(g.counter("hot_item_ppm") - 1e6 * share) <= 1
+            assert abs(cap - 1e-3 * safety / (lr * share)) <= 1
+            assert all(np.isfinite(a).all() for a in g.download()), (safety, lr)
+        else:
+            assert cap == 0  # (and this launch may well diverge: 38k instances in flight x share x lr >> 2)
+        g.update_csr(data)  # the host-pointer call measures its first chunk
+        g.sync()
+        assert (g.counter("inflight_cap") > 0) == (safety > 0)
+        b.close()
+        g.close()
 
 
 def test_exact_owner_values_bias_switch_and_sigmoid(native):
