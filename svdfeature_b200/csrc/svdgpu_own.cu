@@ -15,19 +15,23 @@
 //     carries a ticket (= number of earlier instances of its user) and its user row may only be
 //     fetched once the counter has reached it.  Checking, waiting and fetching is done by LOADER
 //     lanes, never by the owner: loader lane (c, s) feeds ring slot s of owner c -- it reads the
-//     queue entry, polls the version (ld.acquire.gpu), and when the row is final issues one TMA
+//     queue entry, polls the version (ld.relaxed.gpu), and when the row is final issues one TMA
 //     bulk copy (cp.async.bulk, 256 B at k = 64) that lands in the slot and completes its
 //     mbarrier.  The owner only ever waits on shared memory;
 //   * an owner publishes the user rows it has written with one release per BATCH of instances
 //     (st.release.gpu of ticket+1; the fence is what costs), at once when the plan says the user
 //     comes back soon, and always before it blocks -- so the oldest unfinished instance of the
-//     whole launch can always proceed (all CTAs are co-resident: cooperative launch).
+//     whole launch can always proceed (all CTAs are co-resident: cooperative launch);
+//   * the launch lasts as long as the chain of the hottest item, and a link of that chain is slower in
+//     company: the owners of hot items get their issue port, the hottest ones their SM, to themselves (the
+//     warps that would share it are dealt no items: own_plan_build below).
 //
 // Arithmetic = process_instance (svdgpu_device.cuh) specialised to the shape (0 | 1 | 1) with
 // plain L2 decay: the same operations in the same order, the reference's dot order included.
 //
 // The plan (queues, tickets, item lists) is built on the device from the CSR batch: two radix
-// sorts (by user for the tickets, by owner for the queues) around a host LPT of the item counts.
+// sorts (by user for the tickets, by owner for the queues) around a host LPT of the item counts -- or,
+// for the chunks of a host-pointer call, around the deal of the chunk before while it stays balanced.
 #include "svdgpu_internal.h"
 #include "svdgpu_ownplan.h"
 
