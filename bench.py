@@ -60,8 +60,8 @@ BYTES_PER_INSTANCE = 8 * K * 2 + 8 * 2 + 16 + 8 * 2  # = 1072, SURVEY.md section
 # `ncu --set full` (profiles/r1_kmf_v5_100M_ncu_full_summary.txt): 7.549 GB + 8.126 GB
 NCU_DRAM_BYTES_PER_INSTANCE = (7.548526e9 + 8.126198e9) / 100e6
 # the same for ONE k_own launch (ordered mode); None until the capture is committed
-NCU_OWN_DRAM_BYTES_PER_INSTANCE = (9.126184e9 + 8.464127e9) / 100e6
-NCU_OWN_TRAFFIC_SOURCE = ("ncu --set full, profiles/r2_kown_100M_ncu_full_summary.txt (175.9 B/instance: user rows stream "
+NCU_OWN_DRAM_BYTES_PER_INSTANCE = (9.135374e9 + 8.447472e9) / 100e6
+NCU_OWN_TRAFFIC_SOURCE = ("ncu --set full, profiles/r2_kown_100M_ncu_full_summary.txt (175.8 B/instance: user rows stream "
                           "through L2/HBM once per rating, item rows stay in shared memory; the queue entries add 32 B)")
 
 
