@@ -50,30 +50,59 @@ inline void assign(const unsigned *cnt, int num_item, int num_owner, int max_bat
   p.age = 0;
   p.item_owner.assign((size_t)num_item, -1);
   p.item_slot.assign((size_t)num_item, 0u);
-  std::vector<int> order;
+  // items by decreasing count, ties by increasing index: a stable LSD radix sort (3 passes of 11 bits) of the
+  // touched items on the key ~count
+  std::vector<int> order, tmp_order;
   order.reserve((size_t)num_item);
   for (int i = 0; i < num_item; ++i)
     if (cnt[i] > 0) order.push_back(i);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
-  typedef std::pair<int64_t, int> Load;  // (rows, owner): smallest load first, then smallest owner id
-  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  {
+    tmp_order.resize(order.size());
+    std::vector<unsigned> hist(2048);
+    for (int pass = 0; pass < 3; ++pass) {
+      const int shift = 11 * pass;
+      std::fill(hist.begin(), hist.end(), 0u);
+      for (int i : order) ++hist[(~cnt[i] >> shift) & 2047u];
+      unsigned run = 0;
+      for (unsigned &hv : hist) {
+        const unsigned c = hv;
+        hv = run;
+        run += c;
+      }
+      for (int i : order) tmp_order[hist[(~cnt[i] >> shift) & 2047u]++] = i;
+      order.swap(tmp_order);
+    }
+  }
+  // binary min-heap of (rows, owner) packed into one word (rows << 32 | owner: smallest load first, then
+  // smallest owner id; a plan covers fewer than 2^31 rows); an item goes to the top, whose load grows, and the
+  // top sinks back into place (one sift instead of a pop and a push).
   std::vector<int> open;
   for (int w = 0; w < num_owner; ++w)
-    if (!closed || !(*closed)[(size_t)w]) {
-      heap.push(Load(0, w));
-      open.push_back(w);
-    }
+    if (!closed || !(*closed)[(size_t)w]) open.push_back(w);
   p.num_open = (int)open.size();
   std::vector<int64_t> load((size_t)num_owner, 0);
   std::vector<int> nitem((size_t)num_owner, 0);
+  std::vector<uint64_t> heap;
+  heap.reserve(open.size());
+  for (int w : open) heap.push_back((uint64_t)(unsigned)w);  // (ascending owner ids with equal loads: already a heap)
+  const size_t hn = heap.size();
   for (int i : order) {
-    Load l = heap.top();
-    heap.pop();
-    p.item_owner[(size_t)i] = l.second;
-    p.item_slot[(size_t)i] = (unsigned)nitem[(size_t)l.second]++;
-    l.first += cnt[i];
-    load[(size_t)l.second] = l.first;
-    heap.push(l);
+    if (!hn) break;
+    const int w = (int)(heap[0] & 0xffffffffu);
+    p.item_owner[(size_t)i] = w;
+    p.item_slot[(size_t)i] = (unsigned)nitem[(size_t)w]++;
+    load[(size_t)w] += cnt[i];
+    const uint64_t l = ((uint64_t)load[(size_t)w] << 32) | (uint64_t)(unsigned)w;
+    size_t at = 0;
+    for (;;) {
+      size_t c = 2 * at + 1;
+      if (c >= hn) break;
+      if (c + 1 < hn && heap[c + 1] < heap[c]) ++c;
+      if (heap[c] >= l) break;
+      heap[at] = heap[c];
+      at = c;
+    }
+    heap[at] = l;
   }
   if (deal_all && !open.empty()) {
     // (to owners that carry no more than the mean: the owner of a hot item keeps its chain to itself)
